@@ -1,0 +1,158 @@
+/*
+ * maicos_b200 -- C ABI of the B200-native MAICoS hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy types.
+ * The Python host layer (maicos_b200/_cabi.py) binds exactly these symbols with
+ * ctypes; a MAICoS maintainer would bind the same symbols from
+ * src/maicos/lib/math.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MB200_E* code on failure;
+ *     mb200_last_error() returns the message of the last failure on this thread.
+ *   - "host" pointers are ordinary (pageable or pinned) CPU memory; the library does
+ *     the host<->device copies.  "dev" pointers are CUDA device pointers on the
+ *     context's device (e.g. torch.Tensor.data_ptr()).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     MB200_ENODEVICE.
+ *   - outputs are written in the layout of the reference (row-major, float64 sums,
+ *     int64 counts).
+ *
+ * Reference file:line citations are relative to /root/reference (MAICoS v0.11.2).
+ */
+#ifndef MAICOS_B200_H
+#define MAICOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_OK 0
+#define MB200_EINVAL (-1)
+#define MB200_ENODEVICE (-2)
+#define MB200_ECUDA (-3)
+#define MB200_ENOMEM (-4)
+
+typedef struct mb200_ctx mb200_ctx;
+
+/* ---- library / context -------------------------------------------------------- */
+
+/* ABI version of this header (bumped on any signature change). */
+int mb200_abi_version(void);
+/* Message of the last error raised on the calling thread ("" if none). */
+const char *mb200_last_error(void);
+/* Number of visible CUDA devices (0 when there is no driver / no GPU). */
+int mb200_device_count(void);
+/* One context per (process, device): owns a stream, workspaces and the q-plan cache. */
+int mb200_ctx_create(int device, mb200_ctx **out);
+void mb200_ctx_destroy(mb200_ctx *ctx);
+/* Block until all work queued on the context's stream has finished. */
+int mb200_ctx_synchronize(mb200_ctx *ctx);
+/* The context's cudaStream_t as an integer (for torch.cuda.ExternalStream / events). */
+uint64_t mb200_ctx_stream(mb200_ctx *ctx);
+/* Statistics of the last S(q) call on this context (for bench.py / DESIGN.md):
+ *   out[0] = kernels launched, out[1] = n_valid q, out[2] = CTAs of the contraction kernel,
+ *   out[3] = DMMA tile-steps issued (8x8x4 MMAs), out[4] = atom*q evaluations,
+ *   out[5] = last contraction-kernel time in ns (0 unless timing enabled),
+ *   out[6] = k-splits, out[7] = warp tiles in the plan. */
+int mb200_ctx_stats(mb200_ctx *ctx, int64_t out[8]);
+/* Enable (1) / disable (0) CUDA-event timing of the contraction kernel inside calls. */
+int mb200_ctx_set_timing(mb200_ctx *ctx, int enable);
+/* Total kernels launched by this context since creation. */
+int64_t mb200_ctx_launch_count(mb200_ctx *ctx);
+
+/* ---- path 1: reciprocal-space structure factor -------------------------------- */
+
+/* maxn[i] = (int)ceil(qmax / (float)(2*pi/dimensions[i]))
+ * replaces: src/maicos/lib/_cmath.pyx:93-96 (NB the float32 cast of q_factor). */
+int mb200_sfactor_maxn(const double dimensions[3], double qmax, int32_t maxn[3]);
+
+/* Drop-in for `_cmath.structure_factor` (src/maicos/lib/_cmath.pyx:21-126, re-exported
+ * at src/maicos/lib/math.py:15; callers saxs.py:197-205, diporderstructurefactor.py:121-129).
+ *   positions : host float64, element (j, d) at positions[j*stride_atom + d*stride_xyz]
+ *   weights   : host float64 [n_atoms]
+ *   scattering_vectors, structure_factors : host float64 [maxn0*maxn1*maxn2], C order,
+ *               exactly 0.0 in rejected cells (callers use S != 0 as the validity mask).
+ * Acceptance test per cell is the reference's: h+k+l != 0, qmin <= |q| <= qmax,
+ * thetamin <= acos(qz/|q|) <= thetamax (radians, inclusive).  */
+int mb200_structure_factor(mb200_ctx *ctx, const double *positions, int64_t stride_atom,
+                           int64_t stride_xyz, int64_t n_atoms, const double dimensions[3],
+                           double qmin, double qmax, double thetamin, double thetamax,
+                           const double *weights, double *scattering_vectors,
+                           double *structure_factors);
+
+/* Same contraction, restricted to a block of the q-plan ("q-vector blocks as the second
+ * axis for single huge frames"): only CTA tile groups g with g % n_blocks == block are
+ * computed; all other cells are returned as 0, so summing the outputs of all blocks
+ * (e.g. an NCCL allreduce over ranks) reproduces mb200_structure_factor. */
+int mb200_structure_factor_block(mb200_ctx *ctx, const double *positions, int64_t stride_atom,
+                                 int64_t stride_xyz, int64_t n_atoms,
+                                 const double dimensions[3], double qmin, double qmax,
+                                 double thetamin, double thetamax, const double *weights,
+                                 int32_t block, int32_t n_blocks, double *scattering_vectors,
+                                 double *structure_factors);
+
+/* Fused Saxs frame body (replaces the per-group loop of Saxs._single_frame,
+ * src/maicos/modules/saxs.py:191-235, bin_spectrum=True): for every frame f and element
+ * group g: wrap positions to [-L/2, L/2] in float32 (saxs.py:193-195), S over the valid
+ * q set of that frame's box, I = f_g(|q|)^2 * S (math.py:623-702), then the three |q|
+ * histograms (saxs.py:222-233) over entries with S != 0.
+ *   positions   : float32 [n_frames][n_atoms_total][3] (host, or device if positions_on_device)
+ *   boxes       : host float32 [n_frames][3] box lengths (ts.dimensions[:3])
+ *   group_index : host int32, concatenated atom indices of the groups
+ *   group_ptr   : host int64 [n_groups+1] offsets into group_index
+ *   cm_params   : host float64 [n_groups][2][10] = up to two (multiplicity, a1..a4, b1..b4, c)
+ *                 Cromer-Mann sets per group (second set for united atoms CHn/NHn, else mult 0)
+ *   pack_atoms  : apply AtomGroup.wrap(compound="atoms") (x -= floor(x/L)*L, float32) first
+ *   q-plan block selection as in mb200_structure_factor_block (use block=0, n_blocks=1).
+ * outputs (host):
+ *   s_binned, i_binned : float64 [n_frames][n_groups][n_bins]
+ *   bincount           : int64   [n_frames][n_groups][n_bins]  (entries with S != 0)  */
+int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int positions_on_device,
+                      int64_t n_frames, int64_t n_atoms_total, const float *boxes,
+                      const int32_t *group_index, const int64_t *group_ptr, int32_t n_groups,
+                      const double *cm_params, double qmin, double qmax, double thetamin,
+                      double thetamax, int32_t n_bins, int pack_atoms, int32_t block,
+                      int32_t n_blocks, double *s_binned, double *i_binned, int64_t *bincount);
+
+/* Fused DiporderStructureFactor frame body (replaces
+ * src/maicos/modules/diporderstructurefactor.py:105-150): three weight sets on identical
+ * positions share one set of phase tables; per frame and component S is binned by |q|.
+ *   positions : host float64 [n_frames][n][3] (compound centres)
+ *   weights   : host float64 [n_frames][3][n]
+ *   boxes     : host float64 [n_frames][3]
+ * outputs (host): s_binned float64 [n_frames][3][n_bins] (sum of S per bin),
+ *                 bincount int64 [n_frames][3][n_bins] (entries with S != 0).  */
+int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const double *weights,
+                       int64_t n_frames, int64_t n, const double *boxes, double qmin,
+                       double qmax, int32_t n_bins, int32_t block, int32_t n_blocks,
+                       double *s_binned, int64_t *bincount);
+
+/* ---- path 2: weighted slab / shell histograms --------------------------------- */
+
+#define MB200_GEOM_PLANAR 0   /* np.histogram(pos[:, dim])            core/planar.py:235-243   */
+#define MB200_GEOM_CYLINDER 1 /* transform_cylinder + np.histogram2d  core/cylinder.py:229-243 */
+#define MB200_GEOM_SPHERE 2   /* transform_sphere + np.histogram      core/sphere.py:215-223   */
+
+/* Fused weighted + count histogram of ProfileBase._single_frame (core/base.py:815-818),
+ * batched over frames.  numpy semantics (numpy/lib/_histograms_impl.py:816-873, 1037-1069):
+ * x is promoted to float64, values outside [edges[0], edges[n_bins]] are dropped, the right
+ * edge is inclusive, the bin is the one with edges[i] <= x < edges[i+1].
+ *   positions : float32 or float64 [n_frames][n][3] (host or device)
+ *   weights   : float64 [n] (weights_per_frame=0) or [n_frames][n] (=1), or NULL
+ *   edges     : host float64 [n_frames][n_bins+1]  (np.linspace of the frame's range)
+ *   center    : host float64 [n_frames][3] box centre (cylinder / sphere), may be NULL for planar
+ *   zrange    : host float64 [n_frames][2] axial window (cylinder only), else NULL
+ * outputs (host): hist_w float64 [n_frames][n_bins] (NULL-able when weights NULL),
+ *                 hist_c int64 [n_frames][n_bins].  */
+int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *positions, int pos_is_f32,
+                       int positions_on_device, int64_t n_frames, int64_t n, int dim,
+                       const double *weights, int weights_per_frame, int weights_on_device,
+                       const double *edges, int32_t n_bins, const double *center,
+                       const double *zrange, double *hist_w, int64_t *hist_c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAICOS_B200_H */

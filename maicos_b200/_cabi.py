@@ -1,0 +1,179 @@
+"""ctypes binding of ``libmaicos_b200.so`` -- the C ABI declared in ``include/maicos_b200.h``.
+
+The library is the only compute path of this package.  There is **no CPU fallback**: if the
+shared object is missing, or no CUDA device is visible, every compute call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from pathlib import Path
+
+import numpy as np
+
+_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libmaicos_b200.so"
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_i32_p = ctypes.POINTER(ctypes.c_int32)
+c_i64_p = ctypes.POINTER(ctypes.c_int64)
+
+#: every symbol ``include/maicos_b200.h`` declares -> (restype, argtypes)
+SIGNATURES = {
+    "mb200_abi_version": (ctypes.c_int, []),
+    "mb200_last_error": (ctypes.c_char_p, []),
+    "mb200_device_count": (ctypes.c_int, []),
+    "mb200_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "mb200_ctx_destroy": (None, [ctypes.c_void_p]),
+    "mb200_ctx_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
+    "mb200_ctx_stream": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "mb200_ctx_stats": (ctypes.c_int, [ctypes.c_void_p, c_i64_p]),
+    "mb200_ctx_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "mb200_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "mb200_sfactor_maxn": (ctypes.c_int, [c_double_p, ctypes.c_double, c_i32_p]),
+    "mb200_structure_factor": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_double_p,
+         ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "mb200_structure_factor_block": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_double_p,
+         ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
+         ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "mb200_saxs_frames": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_double, ctypes.c_double,
+         ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_int, ctypes.c_int32, ctypes.c_int32,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "mb200_dipsf_frames": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+         ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+         ctypes.c_void_p],
+    ),
+    "mb200_profile_hist": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+         ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+         ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+}
+
+_lib = None
+_lock = threading.Lock()
+_contexts: dict[int, "Context"] = {}
+
+
+class MB200Error(RuntimeError):
+    """Raised when a C-ABI call fails (message from ``mb200_last_error``)."""
+
+
+def library_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library and bind every declared symbol (no compute, no GPU needed)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not _LIB_PATH.exists():
+            raise MB200Error(
+                f"{_LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or `make -C maicos_b200/csrc`. maicos_b200 has no CPU fallback."
+            )
+        lib = ctypes.CDLL(str(_LIB_PATH))
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export it
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        msg = load().mb200_last_error().decode("utf8", "replace")
+        raise MB200Error(f"libmaicos_b200 error {rc}: {msg}")
+
+
+def device_count() -> int:
+    return int(load().mb200_device_count())
+
+
+class Context:
+    """One per (process, device); owns the stream, workspaces and the q-plan cache."""
+
+    def __init__(self, device: int):
+        lib = load()
+        handle = ctypes.c_void_p()
+        _check(lib.mb200_ctx_create(int(device), ctypes.byref(handle)))
+        self._h = handle
+        self.device = int(device)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self) -> None:
+        _check(load().mb200_ctx_synchronize(self._h))
+
+    def set_timing(self, enable: bool) -> None:
+        _check(load().mb200_ctx_set_timing(self._h, int(bool(enable))))
+
+    def stats(self) -> dict:
+        out = (ctypes.c_int64 * 8)()
+        _check(load().mb200_ctx_stats(self._h, out))
+        keys = ["launches", "n_valid_q", "ctas", "dmma_steps", "atom_q", "contract_ns", "k_splits", "warp_tiles"]
+        return dict(zip(keys, [int(v) for v in out]))
+
+    def launch_count(self) -> int:
+        return int(load().mb200_ctx_launch_count(self._h))
+
+    def close(self) -> None:
+        if self._h is not None and self._h.value:
+            load().mb200_ctx_destroy(self._h)
+            self._h = None
+
+
+def default_device() -> int:
+    """LOCAL_RANK under torchrun (one process per GPU), else MAICOS_B200_DEVICE, else 0."""
+    for var in ("MAICOS_B200_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(var)
+        if v is not None and v != "":
+            return int(v)
+    return 0
+
+
+def context(device: int | None = None) -> Context:
+    """Cached context for ``device``; raises :class:`MB200Error` when no GPU is visible."""
+    if device is None:
+        device = default_device()
+    with _lock:
+        ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        with _lock:
+            _contexts[device] = ctx
+    return ctx
+
+
+def ptr(a: np.ndarray | None):
+    """Raw data pointer of a numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def check(rc: int) -> None:
+    _check(rc)

@@ -1,0 +1,115 @@
+// Shared host-side plumbing of libmaicos_b200: error reporting, grow-only device /
+// pinned buffers and the per-device context behind the C ABI (include/maicos_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <list>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/maicos_b200.h"
+
+namespace mb200 {
+
+extern thread_local std::string g_last_error;
+
+inline int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define MB_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return ::mb200::fail(_e == cudaErrorMemoryAllocation ? MB200_ENOMEM : MB200_ECUDA, \
+                                 "CUDA error '%s' in %s (%s:%d)", cudaGetErrorString(_e),  \
+                                 #expr, __FILE__, __LINE__);                               \
+    } while (0)
+
+#define MB_TRY(expr)                \
+    do {                            \
+        int _rc = (expr);           \
+        if (_rc != MB200_OK) return _rc; \
+    } while (0)
+
+// Grow-only device buffer.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return MB200_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(MB200_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return MB200_OK;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+// Grow-only pinned host buffer (staging for async H2D / D2H).
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return MB200_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(MB200_ENOMEM, "cudaMallocHost(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return MB200_OK;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+    ~PinBuf() {
+        if (p) cudaFreeHost(p);
+    }
+};
+
+struct SfPlan;  // sfactor.cu
+
+}  // namespace mb200
+
+struct mb200_ctx {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false;
+    int64_t launches = 0;
+    int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // S(q) workspaces
+    mb200::DevBuf d_pos, d_w, d_idx, d_tables, d_amp, d_sval, d_jobs, d_segs, d_items, d_out, d_ff2;
+    mb200::PinBuf h_stage, h_out;
+    // histogram workspaces
+    mb200::DevBuf d_hpos, d_hw, d_hedges, d_hpar, d_hout;
+    std::list<std::shared_ptr<mb200::SfPlan>> plans;  // small LRU cache keyed by box + q window
+    ~mb200_ctx();
+};

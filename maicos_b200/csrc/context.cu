@@ -1,0 +1,82 @@
+// Context / library-level entry points of the C ABI (include/maicos_b200.h).
+#include "common.cuh"
+
+namespace mb200 {
+thread_local std::string g_last_error;
+}
+using namespace mb200;
+
+mb200_ctx::~mb200_ctx() {
+    plans.clear();
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+extern "C" int mb200_abi_version(void) { return 1; }
+
+extern "C" const char *mb200_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int mb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int mb200_ctx_create(int device, mb200_ctx **out) {
+    if (!out) return fail(MB200_EINVAL, "null output pointer");
+    *out = nullptr;
+    int n = mb200_device_count();
+    if (n <= 0) return fail(MB200_ENODEVICE, "no CUDA device visible: maicos_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(MB200_EINVAL, "device %d out of range (have %d)", device, n);
+    MB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(MB200_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    mb200_ctx *ctx = new mb200_ctx();
+    ctx->device = device;
+    ctx->n_sm = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail(MB200_ECUDA, "context creation failed: %s", cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return MB200_OK;
+}
+
+extern "C" void mb200_ctx_destroy(mb200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int mb200_ctx_synchronize(mb200_ctx *ctx) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MB200_OK;
+}
+
+extern "C" uint64_t mb200_ctx_stream(mb200_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+
+extern "C" int mb200_ctx_stats(mb200_ctx *ctx, int64_t out[8]) {
+    if (!ctx || !out) return fail(MB200_EINVAL, "null argument");
+    for (int i = 0; i < 8; ++i) out[i] = ctx->stats[i];
+    return MB200_OK;
+}
+
+extern "C" int mb200_ctx_set_timing(mb200_ctx *ctx, int enable) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    ctx->timing = enable != 0;
+    return MB200_OK;
+}
+
+extern "C" int64_t mb200_ctx_launch_count(mb200_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,1015 @@
+// S(q) engine of libmaicos_b200 (sm_100a).
+//
+// Replaces the reference's only native kernel, `_cmath.structure_factor`
+// (/root/reference/src/maicos/lib/_cmath.pyx:21-126), and the per-frame bodies built on it
+// (modules/saxs.py:175-241, modules/diporderstructurefactor.py:93-155).
+//
+// Formulation.  With fractional coordinates u = r/L the phase of Miller vector (h,k,l) on atom
+// j factorises:  exp(i q.r_j) = Ex_j[h] * Ey_j[k] * Ez_j[l],  E*_j[n] = exp(2 pi i n u*_j).
+// The complex amplitudes  A[(h,k), l] = sum_j (w_j Ex_j[h] Ey_j[k]) * Ez_j[l]  are therefore a
+// dense complex contraction over atoms (M = (h,k) pairs, N = l, K = atoms).  It is evaluated
+// in FP64 on the DMMA pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; measured 37.0 TFLOP/s on
+// B200 vs 33 TFLOP/s for scalar DFMA, tools/microbench) with the 3-multiplication complex
+// product:  T1 = sum Pr*Zr, T2 = sum Pi*Zi, T3 = sum (Pr+Pi)*(Zr+Zi),
+//           Re A = T1 - T2, Im A = T3 - T1 - T2     (3 real MACs per atom*q instead of 4).
+//
+// Kernels
+//   k_sf_tables  : per-atom per-axis phase tables Ex (weighted), Ey, Ez by complex recurrence,
+//                  re-seeded with an exact sincospi every 8 steps.  [row][atom] double2.
+//   k_sf_contract: one CTA (4 warps) per (segment, atom range, tile group).  cp.async stages
+//                  8-atom slices of the needed table rows into shared memory (3-deep), the CTA
+//                  forms the P = Ex*Ey rows once per slice (3 planes), every warp owns a
+//                  32 (hk) x 16 (l) tile = 4x2 DMMA tiles x 3 planes held in registers.
+//                  8x8 DMMA tiles entirely outside the q-sphere are skipped (warp-uniform mask).
+//   k_sf_svalues / k_sf_binned: sum the per-split partial amplitudes in fixed order, S = |A|^2,
+//                  then either the compact S list (dense cube is scattered on the host) or the
+//                  |q| histograms (S, f^2 S, count of S != 0) with one CTA per (segment, bin)
+//                  and a fixed-order reduction -> bitwise reproducible run to run.
+#include <algorithm>
+#include <cmath>
+#include <map>
+
+#include "common.cuh"
+
+namespace mb200 {
+
+// ------------------------------------------------------------------------------------------
+// tiling constants
+// ------------------------------------------------------------------------------------------
+constexpr int KT = 8;          // atoms per pipeline stage (two DMMA k-steps of 4)
+constexpr int WPC = 4;         // warps per CTA
+constexpr int NTHREADS = WPC * 32;
+constexpr int MAXX = 4;        // distinct (h,k) quads (4h x 8k = 32 rows) a CTA may stage
+constexpr int MAXY = 4;        // distinct l-pairs (16 l) a CTA may stage
+constexpr int QH = 4, QK = 8;  // quad shape
+constexpr int NL = 16;         // l extent of a warp tile
+constexpr int RAWROW = 9;      // double2 per staged table row: 8 atoms + 1 pad (bank spread)
+constexpr int XY_ROWS = MAXX * (QH + QK);  // 48
+constexpr int Z_ROWS = MAXY * NL;          // 64
+constexpr int X_ROWS = MAXX * 32;          // 128
+constexpr int SMEM_RAWXY = 2 * XY_ROWS * RAWROW * 16;   // 13824
+constexpr int SMEM_RAWZ = 3 * Z_ROWS * RAWROW * 16;     // 27648
+constexpr int SMEM_X = 2 * 3 * X_ROWS * KT * 8;         // 49152
+constexpr int SMEM_PTR = (XY_ROWS + Z_ROWS) * 8;        // 896
+constexpr int SMEM_TOTAL = SMEM_RAWXY + SMEM_RAWZ + SMEM_X + SMEM_PTR;
+
+struct __align__(16) TileGroupDesc {
+    int16_t xh0[MAXX];
+    int16_t xk0[MAXX];
+    int16_t yl0[MAXY];
+    uint8_t wx[WPC];
+    uint8_t wy[WPC];
+    uint8_t wmask[WPC];
+    int32_t n_warp, n_x, n_y, wt0;
+    int32_t pad[3];
+};
+static_assert(sizeof(TileGroupDesc) == 64, "TileGroupDesc layout");
+
+struct SegDesc {
+    const double2 *ex, *ey, *ez;   // phase tables [row][ld]
+    double2 *amp;                  // partial amplitudes [n_split][n_wt][512]
+    const TileGroupDesc *tgs;      // plan tile groups (device)
+    const int32_t *ent_amp;        // plan entries -> index into a [n_wt][512] amplitude block
+    const int32_t *bin_start;      // [n_bins+1] entry ranges per |q| bin (entries sorted by bin)
+    const double *ff2;             // [n_valid] squared form factor per entry (may be null)
+    int32_t ld, n_split, n_wt, n_valid;
+};
+
+struct ItemDesc {
+    int32_t seg, tg, j0, j1, split;
+};
+
+struct TableJob {
+    const void *pos;       // float32 or float64 coordinates
+    const int32_t *index;  // optional gather indices
+    const double *weights; // optional weights (null = 1)
+    double2 *tab[3];       // outputs (null = skip axis)
+    int64_t stride_atom, stride_xyz;
+    double box[3];
+    float boxf[3];
+    int32_t n, ld, rows[3];
+    int32_t is_f32, wrap_mode;  // wrap_mode: 0 none, 1 saxs float32 wrap, 2 pack + saxs wrap
+};
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// k_sf_tables: phase tables
+//   grid = (ceil(ld/128), 3, n_jobs); thread = one atom on one axis.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ jobs) {
+    const TableJob &jb = jobs[blockIdx.z];
+    const int axis = blockIdx.y;
+    double2 *tab = jb.tab[axis];
+    if (tab == nullptr) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= jb.ld) return;
+    const int rows = jb.rows[axis];
+    if (j >= jb.n) {  // zero padding up to the leading dimension
+        for (int r = 0; r < rows; ++r) tab[(size_t)r * jb.ld + j] = make_double2(0.0, 0.0);
+        return;
+    }
+    const int64_t a = jb.index ? (int64_t)jb.index[j] : (int64_t)j;
+    double u;
+    if (jb.is_f32) {
+        float p = reinterpret_cast<const float *>(jb.pos)[a * jb.stride_atom + axis * jb.stride_xyz];
+        const float L = jb.boxf[axis];
+        if (jb.wrap_mode == 2)  // AtomGroup.wrap(compound="atoms"): x -= floor(x/L)*L in float32
+            p = __fsub_rn(p, __fmul_rn(floorf(__fdiv_rn(p, L)), L));
+        if (jb.wrap_mode >= 1)  // saxs.py:193-195: pos - box*round(pos/box), float32 arithmetic
+            p = __fsub_rn(p, __fmul_rn(L, rintf(__fdiv_rn(p, L))));
+        u = (double)p / (double)L;
+    } else {
+        double p = reinterpret_cast<const double *>(jb.pos)[a * jb.stride_atom + axis * jb.stride_xyz];
+        u = p / jb.box[axis];
+    }
+    const double w = (axis == 0 && jb.weights) ? jb.weights[j] : 1.0;
+    double s1, c1;
+    {
+        double t = u - rint(u);
+        sincospi(2.0 * t, &s1, &c1);
+    }
+    double cr = 1.0, ci = 0.0;
+    for (int r = 0; r < rows; ++r) {
+        if ((r & 7) == 0) {  // exact re-seed: limits recurrence drift to 7 steps
+            double t = (double)r * u;
+            t -= rint(t);
+            sincospi(2.0 * t, &ci, &cr);
+        }
+        tab[(size_t)r * jb.ld + j] = make_double2(w * cr, w * ci);
+        const double nr = cr * c1 - ci * s1;
+        const double ni = cr * s1 + ci * c1;
+        cr = nr;
+        ci = ni;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_sf_contract: the DMMA contraction
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 2)
+k_sf_contract(const ItemDesc *__restrict__ items, const SegDesc *__restrict__ segs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double2 *rawxy = reinterpret_cast<double2 *>(smem);                       // [2][XY_ROWS][RAWROW]
+    double2 *rawz = reinterpret_cast<double2 *>(smem + SMEM_RAWXY);           // [3][Z_ROWS][RAWROW]
+    double *xbuf = reinterpret_cast<double *>(smem + SMEM_RAWXY + SMEM_RAWZ); // [2][3][X_ROWS][KT]
+    const double2 **rowptr =
+        reinterpret_cast<const double2 **>(smem + SMEM_RAWXY + SMEM_RAWZ + SMEM_X);  // [XY_ROWS + Z_ROWS]
+
+    const ItemDesc it = items[blockIdx.x];
+    const SegDesc &sg = segs[it.seg];
+    const TileGroupDesc tg = sg.tgs[it.tg];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int ld = sg.ld;
+
+    // source row pointers (at atom j0) of every staged row; compacted: x-slot rows, then z rows
+    const int n_xy = tg.n_x * (QH + QK);
+    const int n_z = tg.n_y * NL;
+    for (int r = tid; r < n_xy + n_z; r += NTHREADS) {
+        const double2 *p;
+        if (r < n_xy) {
+            const int xs = r / (QH + QK), q = r % (QH + QK);
+            p = (q < QH) ? sg.ex + (size_t)(tg.xh0[xs] + q) * ld
+                         : sg.ey + (size_t)(tg.xk0[xs] + (q - QH)) * ld;
+        } else {
+            const int rz = r - n_xy;
+            p = sg.ez + (size_t)(tg.yl0[rz / NL] + (rz % NL)) * ld;
+        }
+        rowptr[r < n_xy ? r : XY_ROWS + (r - n_xy)] = p + it.j0;
+    }
+    __syncthreads();
+
+    const int n_stage = (it.j1 - it.j0) / KT;
+    const int n_chunk_xy = n_xy * KT, n_chunk_z = n_z * KT;
+
+    auto issue = [&](int t) {  // cp.async stage t -> rawxy[t&1], rawz[t%3]
+        if (t < n_stage) {
+            double2 *dxy = rawxy + (t & 1) * (XY_ROWS * RAWROW);
+            double2 *dz = rawz + (t % 3) * (Z_ROWS * RAWROW);
+            const int off = t * KT;
+            for (int q = tid; q < n_chunk_xy; q += NTHREADS) {
+                const int r = q >> 3, c = q & 7;
+                cp_async16(dxy + r * RAWROW + c, rowptr[r] + off + c);
+            }
+            for (int q = tid; q < n_chunk_z; q += NTHREADS) {
+                const int r = q >> 3, c = q & 7;
+                cp_async16(dz + r * RAWROW + c, rowptr[XY_ROWS + r] + off + c);
+            }
+        }
+        cp_async_commit();
+    };
+    auto build = [&](int t) {  // P rows of stage t: rawxy[t&1] -> xbuf[t&1] (planes Pr, Pi, Pr+Pi)
+        const double2 *sxy = rawxy + (t & 1) * (XY_ROWS * RAWROW);
+        double *xb = xbuf + (t & 1) * (3 * X_ROWS * KT);
+        const int n_ent = tg.n_x * 32 * 4;
+        for (int e = tid; e < n_ent; e += NTHREADS) {
+            const int row = e >> 2, ap = e & 3;
+            const int xs = row >> 5, r = row & 31;
+            const double2 *pex = sxy + (xs * (QH + QK) + (r >> 3)) * RAWROW + 2 * ap;
+            const double2 *pey = sxy + (xs * (QH + QK) + QH + (r & 7)) * RAWROW + 2 * ap;
+            const double2 a0 = pex[0], a1 = pex[1], b0 = pey[0], b1 = pey[1];
+            double2 pr, pi, ps;
+            pr.x = a0.x * b0.x - a0.y * b0.y;
+            pi.x = a0.x * b0.y + a0.y * b0.x;
+            pr.y = a1.x * b1.x - a1.y * b1.y;
+            pi.y = a1.x * b1.y + a1.y * b1.x;
+            ps.x = pr.x + pi.x;
+            ps.y = pr.y + pi.y;
+            double *dst = xb + row * KT + 2 * ap;
+            *reinterpret_cast<double2 *>(dst) = pr;
+            *reinterpret_cast<double2 *>(dst + X_ROWS * KT) = pi;
+            *reinterpret_cast<double2 *>(dst + 2 * X_ROWS * KT) = ps;
+        }
+    };
+
+    // accumulators: [mt][nt] x planes (T1,T2,T3) x {c0,c1}
+    double acc[4][2][3][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int p = 0; p < 3; ++p) acc[mt][nt][p][0] = acc[mt][nt][p][1] = 0.0;
+
+    const bool active = warp < tg.n_warp;
+    const int wx = active ? tg.wx[warp] : 0, wy = active ? tg.wy[warp] : 0;
+    const unsigned wmask = active ? tg.wmask[warp] : 0u;
+
+    // prologue
+    issue(0);
+    issue(1);
+    cp_async_wait<1>();
+    __syncthreads();
+    build(0);
+
+    for (int t = 0; t < n_stage; ++t) {
+        cp_async_wait<0>();
+        __syncthreads();  // stage t+1 raw + X(t) visible; everyone is done with MMA(t-1)/build(t)
+        issue(t + 2);
+        if (t + 1 < n_stage) build(t + 1);
+
+        if (wmask) {
+            const double *xb = xbuf + (t & 1) * (3 * X_ROWS * KT) + (wx * 32 + g) * KT + 2 * tig;
+            const double2 *sz = rawz + (t % 3) * (Z_ROWS * RAWROW) + (wy * NL + g) * RAWROW + 2 * tig;
+            double br[2][2], bi[2][2], bs[2][2];  // [nt][kstep]
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const double2 z0 = sz[nt * 8 * RAWROW], z1 = sz[nt * 8 * RAWROW + 1];
+                br[nt][0] = z0.x; bi[nt][0] = z0.y; bs[nt][0] = z0.x + z0.y;
+                br[nt][1] = z1.x; bi[nt][1] = z1.y; bs[nt][1] = z1.x + z1.y;
+            }
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                if ((wmask >> (2 * mt)) & 3u) {
+                    const double2 ar = *reinterpret_cast<const double2 *>(xb + mt * 8 * KT);
+                    const double2 ai = *reinterpret_cast<const double2 *>(xb + mt * 8 * KT + X_ROWS * KT);
+                    const double2 as = *reinterpret_cast<const double2 *>(xb + mt * 8 * KT + 2 * X_ROWS * KT);
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        if ((wmask >> (2 * mt + nt)) & 1u) {
+                            dmma(acc[mt][nt][0][0], acc[mt][nt][0][1], ar.x, br[nt][0]);
+                            dmma(acc[mt][nt][1][0], acc[mt][nt][1][1], ai.x, bi[nt][0]);
+                            dmma(acc[mt][nt][2][0], acc[mt][nt][2][1], as.x, bs[nt][0]);
+                            dmma(acc[mt][nt][0][0], acc[mt][nt][0][1], ar.y, br[nt][1]);
+                            dmma(acc[mt][nt][1][0], acc[mt][nt][1][1], ai.y, bi[nt][1]);
+                            dmma(acc[mt][nt][2][0], acc[mt][nt][2][1], as.y, bs[nt][1]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: Re = T1 - T2, Im = T3 - T1 - T2 -> amp[split][wt][row][col]
+    if (wmask) {
+        double2 *out = sg.amp + ((size_t)it.split * sg.n_wt + tg.wt0 + warp) * 512;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                if ((wmask >> (2 * mt + nt)) & 1u) {
+                    const int row = mt * 8 + g, col = nt * 8 + 2 * tig;
+                    double2 v0, v1;
+                    v0.x = acc[mt][nt][0][0] - acc[mt][nt][1][0];
+                    v0.y = acc[mt][nt][2][0] - acc[mt][nt][0][0] - acc[mt][nt][1][0];
+                    v1.x = acc[mt][nt][0][1] - acc[mt][nt][1][1];
+                    v1.y = acc[mt][nt][2][1] - acc[mt][nt][0][1] - acc[mt][nt][1][1];
+                    out[row * 16 + col] = v0;
+                    out[row * 16 + col + 1] = v1;
+                }
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// finalisers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double s_of_entry(const SegDesc &sg, int e) {
+    const int ai = sg.ent_amp[e];
+    double re = 0.0, im = 0.0;
+    const size_t stride = (size_t)sg.n_wt * 512;
+    for (int s = 0; s < sg.n_split; ++s) {  // fixed order -> reproducible
+        const double2 v = sg.amp[s * stride + ai];
+        re += v.x;
+        im += v.y;
+    }
+    return re * re + im * im;
+}
+
+// compact S list: svals[seg][e]
+__global__ void __launch_bounds__(256) k_sf_svalues(const SegDesc *__restrict__ segs, double *__restrict__ svals,
+                                                   int sval_stride) {
+    const SegDesc &sg = segs[blockIdx.y];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < sg.n_valid) svals[(size_t)blockIdx.y * sval_stride + e] = s_of_entry(sg, e);
+}
+
+// |q| histograms: one CTA per (bin, segment); out[seg][{S, f2S}][n_bins], cnt[seg][n_bins]
+__global__ void __launch_bounds__(128) k_sf_binned(const SegDesc *__restrict__ segs, double *__restrict__ out_s,
+                                                  double *__restrict__ out_i, long long *__restrict__ out_c,
+                                                  int n_bins) {
+    const SegDesc &sg = segs[blockIdx.y];
+    const int b = blockIdx.x;
+    const int e0 = sg.bin_start[b], e1 = sg.bin_start[b + 1];
+    double s = 0.0, si = 0.0;
+    long long c = 0;
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const double v = s_of_entry(sg, e);
+        s += v;
+        if (sg.ff2) si += sg.ff2[e] * v;
+        c += (v != 0.0);
+    }
+    __shared__ double sh_s[4], sh_i[4];
+    __shared__ long long sh_c[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        si += __shfl_down_sync(0xffffffffu, si, o);
+        c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sh_s[threadIdx.x >> 5] = s;
+        sh_i[threadIdx.x >> 5] = si;
+        sh_c[threadIdx.x >> 5] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t o = (size_t)blockIdx.y * n_bins + b;
+        out_s[o] = (sh_s[0] + sh_s[1]) + (sh_s[2] + sh_s[3]);
+        if (out_i) out_i[o] = (sh_i[0] + sh_i[1]) + (sh_i[2] + sh_i[3]);
+        out_c[o] = sh_c[0] + sh_c[1] + sh_c[2] + sh_c[3];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host: q-plan
+// ------------------------------------------------------------------------------------------
+struct SfPlan {
+    // key
+    double dims[3], qmin, qmax, thmin, thmax;
+    int32_t n_bins;  // 0: entries in C order of the cube; >0: entries sorted by |q| bin
+    // geometry
+    int32_t maxn[3];
+    int32_t rows[3];  // padded table rows
+    // entries (valid q vectors)
+    std::vector<int32_t> cell;     // h*maxn1*maxn2 + k*maxn2 + l
+    std::vector<double> qrr;       // |q|
+    std::vector<int32_t> ent_amp;  // index into [n_wt][512]
+    std::vector<int32_t> bin_start;
+    // tiles
+    std::vector<TileGroupDesc> tgs;
+    int32_t n_wt = 0;
+    int64_t n_mma_tiles = 0;  // valid 8x8 DMMA tiles
+    // device copies
+    DevBuf d_tgs, d_ent_amp, d_bin_start, d_ff2;
+    std::vector<double> ff2_key;  // cm params the cached ff2 was built for
+    int32_t ff2_groups = 0;
+};
+
+static void sfactor_maxn_host(const double *dims, double qmax, int32_t *maxn) {
+    for (int i = 0; i < 3; ++i) {
+        const double q_factor = 2 * M_PI / dims[i];
+        // _cmath.pyx:96: the divisor is cast to float32 before the (double) division
+        maxn[i] = (int32_t)std::ceil(qmax / (double)(float)q_factor);
+    }
+}
+
+// numpy.histogram uniform-bin index for x in [first, last] (numpy/lib/_histograms_impl.py:840-873)
+static inline int32_t numpy_bin(double x, double first, double last, int32_t n, const std::vector<double> &edges) {
+    const double denom = last - first;
+    double f = ((x - first) / denom) * (double)n;
+    int64_t idx = (int64_t)f;
+    if (idx == n) idx -= 1;
+    if (x < edges[idx]) idx -= 1;
+    if (x >= edges[idx + 1] && idx != n - 1) idx += 1;
+    return (int32_t)idx;
+}
+
+static int build_plan(const double *dims, double qmin, double qmax, double thmin, double thmax, int32_t n_bins,
+                      std::shared_ptr<SfPlan> &out) {
+    auto pl = std::make_shared<SfPlan>();
+    for (int i = 0; i < 3; ++i) pl->dims[i] = dims[i];
+    pl->qmin = qmin; pl->qmax = qmax; pl->thmin = thmin; pl->thmax = thmax; pl->n_bins = n_bins;
+    sfactor_maxn_host(dims, qmax, pl->maxn);
+    const int m0 = std::max(pl->maxn[0], 0), m1 = std::max(pl->maxn[1], 0), m2 = std::max(pl->maxn[2], 0);
+    pl->maxn[0] = m0; pl->maxn[1] = m1; pl->maxn[2] = m2;
+    if (m0 > 30000 || m1 > 30000 || m2 > 30000 || (double)m0 * m1 * m2 > 2.0e9)
+        return fail(MB200_EINVAL, "q-range too large for this box: maxn = (%d, %d, %d)", m0, m1, m2);
+    pl->rows[0] = (m0 + QH - 1) / QH * QH;
+    pl->rows[1] = (m1 + QK - 1) / QK * QK;
+    pl->rows[2] = (m2 + NL - 1) / NL * NL;
+    double qf[3];
+    for (int i = 0; i < 3; ++i) qf[i] = 2 * M_PI / dims[i];
+
+    const size_t cells = (size_t)m0 * m1 * m2;
+    std::vector<double> qcube(cells, 0.0);  // 0 = rejected
+    const bool need_theta = !(thmin <= 0.0 && thmax >= 1.5707963267948968);
+    for (int h = 0; h < m0; ++h) {
+        const double qx = h * qf[0];
+        for (int k = 0; k < m1; ++k) {
+            const double qy = k * qf[1];
+            for (int l = 0; l < m2; ++l) {
+                if (h + k + l == 0) continue;
+                const double qz = l * qf[2];
+                const double qrr = std::sqrt(qx * qx + qy * qy + qz * qz);
+                if (!(qrr >= qmin && qrr <= qmax)) continue;
+                if (need_theta) {
+                    const double theta = std::acos(qz / qrr);
+                    if (!(theta >= thmin && theta <= thmax)) continue;
+                }
+                qcube[((size_t)h * m1 + k) * m2 + l] = qrr;
+            }
+        }
+    }
+    // warp tiles: (quad, l-pair) with at least one valid q; DMMA-tile validity mask
+    const int nqh = pl->rows[0] / QH, nqk = pl->rows[1] / QK, nlp = pl->rows[2] / NL;
+    std::vector<int32_t> wt_of((size_t)nqh * nqk * nlp, -1);
+    struct WT { int16_t h0, k0, l0; uint8_t mask; };
+    std::vector<WT> wts;
+    for (int a = 0; a < nqh; ++a)
+        for (int b = 0; b < nqk; ++b)
+            for (int c = 0; c < nlp; ++c) {
+                unsigned mask = 0;
+                for (int mt = 0; mt < 4; ++mt) {
+                    const int h = a * QH + mt;
+                    if (h >= m0) continue;
+                    for (int nt = 0; nt < 2; ++nt) {
+                        bool any = false;
+                        for (int kk = 0; kk < QK && !any; ++kk) {
+                            const int k = b * QK + kk;
+                            if (k >= m1) break;
+                            for (int ll = 0; ll < 8; ++ll) {
+                                const int l = c * NL + nt * 8 + ll;
+                                if (l >= m2) break;
+                                if (qcube[((size_t)h * m1 + k) * m2 + l] != 0.0) { any = true; break; }
+                            }
+                        }
+                        if (any) mask |= 1u << (2 * mt + nt);
+                    }
+                }
+                if (mask) {
+                    wt_of[((size_t)a * nqk + b) * nlp + c] = (int32_t)wts.size();
+                    wts.push_back({(int16_t)(a * QH), (int16_t)(b * QK), (int16_t)(c * NL), (uint8_t)mask});
+                    pl->n_mma_tiles += __builtin_popcount(mask);
+                }
+            }
+    pl->n_wt = (int32_t)wts.size();
+    // pack consecutive warp tiles into CTAs
+    for (size_t i = 0; i < wts.size(); i += WPC) {
+        TileGroupDesc tg;
+        std::memset(&tg, 0, sizeof(tg));
+        tg.wt0 = (int32_t)i;
+        tg.n_warp = (int32_t)std::min<size_t>(WPC, wts.size() - i);
+        for (int w = 0; w < tg.n_warp; ++w) {
+            const WT &t = wts[i + w];
+            int xs = -1, ys = -1;
+            for (int s = 0; s < tg.n_x; ++s)
+                if (tg.xh0[s] == t.h0 && tg.xk0[s] == t.k0) xs = s;
+            if (xs < 0) { xs = tg.n_x++; tg.xh0[xs] = t.h0; tg.xk0[xs] = t.k0; }
+            for (int s = 0; s < tg.n_y; ++s)
+                if (tg.yl0[s] == t.l0) ys = s;
+            if (ys < 0) { ys = tg.n_y++; tg.yl0[ys] = t.l0; }
+            tg.wx[w] = (uint8_t)xs; tg.wy[w] = (uint8_t)ys; tg.wmask[w] = t.mask;
+        }
+        pl->tgs.push_back(tg);
+    }
+    // entries
+    std::vector<int32_t> cell; std::vector<double> qv; std::vector<int32_t> amp;
+    for (int h = 0; h < m0; ++h)
+        for (int k = 0; k < m1; ++k)
+            for (int l = 0; l < m2; ++l) {
+                const size_t ci = ((size_t)h * m1 + k) * m2 + l;
+                if (qcube[ci] == 0.0) continue;
+                const int32_t wt = wt_of[((size_t)(h / QH) * nqk + (k / QK)) * nlp + (l / NL)];
+                cell.push_back((int32_t)ci);
+                qv.push_back(qcube[ci]);
+                amp.push_back((wt * 32 + (h % QH) * 8 + (k % QK)) * 16 + (l % NL));
+            }
+    const size_t nv = cell.size();
+    if (n_bins > 0) {
+        // np.histogram(a=|q|, bins=n_bins, range=(qmin, qmax)) -- saxs.py:222-233
+        double first = qmin, last = qmax;
+        if (first == last) { first -= 0.5; last += 0.5; }
+        std::vector<double> edges(n_bins + 1);
+        const double step = (last - first) / (double)n_bins;  // np.linspace
+        for (int i = 0; i <= n_bins; ++i) edges[i] = (double)i * step + first;
+        edges[n_bins] = last;
+        std::vector<int32_t> bin(nv);
+        std::vector<int32_t> count(n_bins + 1, 0);
+        for (size_t e = 0; e < nv; ++e) {
+            bin[e] = numpy_bin(qv[e], first, last, n_bins, edges);
+            count[bin[e] + 1]++;
+        }
+        for (int b = 0; b < n_bins; ++b) count[b + 1] += count[b];
+        pl->bin_start = count;
+        std::vector<int32_t> pos(count.begin(), count.end() - 1);
+        pl->cell.resize(nv); pl->qrr.resize(nv); pl->ent_amp.resize(nv);
+        for (size_t e = 0; e < nv; ++e) {  // stable counting sort by bin
+            const int32_t d = pos[bin[e]]++;
+            pl->cell[d] = cell[e]; pl->qrr[d] = qv[e]; pl->ent_amp[d] = amp[e];
+        }
+    } else {
+        pl->cell.swap(cell); pl->qrr.swap(qv); pl->ent_amp.swap(amp);
+    }
+    out = pl;
+    return MB200_OK;
+}
+
+static int upload_plan(mb200_ctx *ctx, SfPlan &pl) {
+    if (!pl.tgs.empty()) {
+        MB_TRY(pl.d_tgs.ensure(pl.tgs.size() * sizeof(TileGroupDesc)));
+        MB_CUDA(cudaMemcpyAsync(pl.d_tgs.p, pl.tgs.data(), pl.tgs.size() * sizeof(TileGroupDesc),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!pl.ent_amp.empty()) {
+        MB_TRY(pl.d_ent_amp.ensure(pl.ent_amp.size() * 4));
+        MB_CUDA(cudaMemcpyAsync(pl.d_ent_amp.p, pl.ent_amp.data(), pl.ent_amp.size() * 4, cudaMemcpyHostToDevice,
+                                ctx->stream));
+    }
+    if (!pl.bin_start.empty()) {
+        MB_TRY(pl.d_bin_start.ensure(pl.bin_start.size() * 4));
+        MB_CUDA(cudaMemcpyAsync(pl.d_bin_start.p, pl.bin_start.data(), pl.bin_start.size() * 4,
+                                cudaMemcpyHostToDevice, ctx->stream));
+    }
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors may be read again only after this
+    return MB200_OK;
+}
+
+static int get_plan(mb200_ctx *ctx, const double *dims, double qmin, double qmax, double thmin, double thmax,
+                    int32_t n_bins, std::shared_ptr<SfPlan> &out) {
+    for (auto it = ctx->plans.begin(); it != ctx->plans.end(); ++it) {
+        SfPlan &p = **it;
+        if (p.dims[0] == dims[0] && p.dims[1] == dims[1] && p.dims[2] == dims[2] && p.qmin == qmin &&
+            p.qmax == qmax && p.thmin == thmin && p.thmax == thmax && p.n_bins == n_bins) {
+            out = *it;
+            ctx->plans.splice(ctx->plans.begin(), ctx->plans, it);
+            return MB200_OK;
+        }
+    }
+    MB_TRY(build_plan(dims, qmin, qmax, thmin, thmax, n_bins, out));
+    MB_TRY(upload_plan(ctx, *out));
+    ctx->plans.push_front(out);
+    while (ctx->plans.size() > 64) ctx->plans.pop_back();
+    return MB200_OK;
+}
+
+// Squared form factor per entry and group (lib/math.py:692-700): f = sum_i a_i exp(-b_i (q/4pi)^2) + c,
+// up to two element sets per group for united atoms (math.py:671-684).
+static int plan_ff2(mb200_ctx *ctx, SfPlan &pl, const double *cm, int n_groups) {
+    std::vector<double> key(cm, cm + (size_t)n_groups * 20);
+    if (pl.ff2_groups == n_groups && pl.ff2_key == key) return MB200_OK;
+    const size_t nv = pl.qrr.size();
+    std::vector<double> ff2((size_t)n_groups * nv);
+    for (int gidx = 0; gidx < n_groups; ++gidx)
+        for (size_t e = 0; e < nv; ++e) {
+            const double q = pl.qrr[e] / (4 * M_PI);
+            const double q2 = q * q;
+            double f = 0.0;
+            for (int s = 0; s < 2; ++s) {
+                const double *p = cm + ((size_t)gidx * 2 + s) * 10;
+                if (p[0] == 0.0) continue;
+                double fs = 0.0;
+                for (int i = 0; i < 4; ++i) fs += p[1 + i] * std::exp(-p[5 + i] * q2);
+                f += p[0] * (fs + p[9]);
+            }
+            ff2[(size_t)gidx * nv + e] = f * f;
+        }
+    if (!ff2.empty()) {
+        MB_TRY(pl.d_ff2.ensure(ff2.size() * 8));
+        MB_CUDA(cudaMemcpyAsync(pl.d_ff2.p, ff2.data(), ff2.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    pl.ff2_key.swap(key);
+    pl.ff2_groups = n_groups;
+    return MB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host: engine
+// ------------------------------------------------------------------------------------------
+struct SegSpec {       // one contraction problem (one reference structure_factor call)
+    SfPlan *plan;
+    TableJob job;       // table inputs (tab pointers filled by the engine)
+    int share_yz_with;  // >= 0: reuse Ey/Ez tables of that earlier segment (same positions)
+    int ff2_group;      // index into plan ff2, -1 none
+};
+
+static bool g_smem_attr_set = false;
+
+// Runs tables + contraction for all segments; leaves SegDesc array on the device (ctx->d_segs).
+static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t block, int32_t n_blocks,
+                        std::vector<SegDesc> &segs_host) {
+    const int ns = (int)specs.size();
+    segs_host.assign(ns, SegDesc());
+    if (ns == 0) return MB200_OK;
+    if (n_blocks < 1 || block < 0 || block >= n_blocks) return fail(MB200_EINVAL, "invalid q-block %d of %d", block, n_blocks);
+
+    // ---- table workspace layout
+    size_t tab_elems = 0;
+    std::vector<size_t> off_x(ns), off_y(ns), off_z(ns);
+    for (int s = 0; s < ns; ++s) {
+        SegSpec &sp = specs[s];
+        const int ld = (sp.job.n + KT - 1) / KT * KT;
+        sp.job.ld = ld;
+        for (int a = 0; a < 3; ++a) sp.job.rows[a] = sp.plan->rows[a];
+        off_x[s] = tab_elems; tab_elems += (size_t)sp.plan->rows[0] * ld;
+        if (sp.share_yz_with >= 0) {
+            off_y[s] = off_y[sp.share_yz_with]; off_z[s] = off_z[sp.share_yz_with];
+        } else {
+            off_y[s] = tab_elems; tab_elems += (size_t)sp.plan->rows[1] * ld;
+            off_z[s] = tab_elems; tab_elems += (size_t)sp.plan->rows[2] * ld;
+        }
+    }
+    MB_TRY(ctx->d_tables.ensure(std::max<size_t>(tab_elems, 1) * 16));
+    double2 *tab = ctx->d_tables.as<double2>();
+
+    // ---- split / item plan
+    int64_t total_tg = 0;
+    for (int s = 0; s < ns; ++s) {
+        const int ntg = (int)specs[s].plan->tgs.size();
+        for (int g = 0; g < ntg; ++g) total_tg += (g % n_blocks == block) && specs[s].job.ld > 0;
+    }
+    const int64_t target_ctas = (int64_t)ctx->n_sm * 2 * 4;  // ~4 waves of 2 CTAs/SM
+    std::vector<ItemDesc> items;
+    size_t amp_elems = 0;
+    std::vector<size_t> off_amp(ns);
+    int64_t mma_steps = 0, atomq = 0;
+    int max_split = 1;
+    for (int s = 0; s < ns; ++s) {
+        SegSpec &sp = specs[s];
+        const int ld = sp.job.ld;
+        const int n_stage_total = ld / KT;
+        int n_split = 1;
+        if (total_tg > 0 && total_tg < target_ctas) n_split = (int)((target_ctas + total_tg - 1) / total_tg);
+        n_split = std::max(1, std::min(n_split, n_stage_total / 32));  // >= 256 atoms per split
+        const int stages_per = n_split ? (n_stage_total + n_split - 1) / n_split : 0;
+        if (stages_per > 0) n_split = (n_stage_total + stages_per - 1) / stages_per;
+        max_split = std::max(max_split, n_split);
+        off_amp[s] = amp_elems;
+        amp_elems += (size_t)n_split * sp.plan->n_wt * 512;
+        SegDesc &sd = segs_host[s];
+        sd.ld = ld; sd.n_split = n_split; sd.n_wt = sp.plan->n_wt; sd.n_valid = (int32_t)sp.plan->cell.size();
+        sd.tgs = sp.plan->d_tgs.as<TileGroupDesc>();
+        sd.ent_amp = sp.plan->d_ent_amp.as<int32_t>();
+        sd.bin_start = sp.plan->d_bin_start.as<int32_t>();
+        sd.ff2 = (sp.ff2_group >= 0 && sp.plan->d_ff2.p) ? sp.plan->d_ff2.as<double>() + (size_t)sp.ff2_group * sd.n_valid : nullptr;
+        sd.ex = tab + off_x[s]; sd.ey = tab + off_y[s]; sd.ez = tab + off_z[s];
+        sp.job.tab[0] = tab + off_x[s];
+        sp.job.tab[1] = sp.share_yz_with >= 0 ? nullptr : tab + off_y[s];
+        sp.job.tab[2] = sp.share_yz_with >= 0 ? nullptr : tab + off_z[s];
+        if (ld == 0) continue;
+        const int ntg = (int)sp.plan->tgs.size();
+        for (int sp_i = 0; sp_i < n_split; ++sp_i) {
+            const int j0 = sp_i * stages_per * KT, j1 = std::min(ld, (sp_i + 1) * stages_per * KT);
+            if (j1 <= j0) continue;
+            for (int g = 0; g < ntg; ++g) {
+                if (g % n_blocks != block) continue;
+                items.push_back({s, g, j0, j1, sp_i});
+                int tiles = 0;
+                for (int w = 0; w < sp.plan->tgs[g].n_warp; ++w) tiles += __builtin_popcount(sp.plan->tgs[g].wmask[w]);
+                mma_steps += (int64_t)tiles * 3 * ((j1 - j0) / 4);
+            }
+        }
+        atomq += (int64_t)sp.job.n * sd.n_valid;
+    }
+    MB_TRY(ctx->d_amp.ensure(std::max<size_t>(amp_elems, 1) * 16));
+    for (int s = 0; s < ns; ++s) segs_host[s].amp = ctx->d_amp.as<double2>() + off_amp[s];
+    if (n_blocks > 1 && amp_elems) {
+        MB_CUDA(cudaMemsetAsync(ctx->d_amp.p, 0, amp_elems * 16, ctx->stream));
+    } else {
+        // splits beyond a segment's populated range never exist; unowned tiles never read. Zero-length
+        // segments (n = 0) are never written, so clear their amplitude blocks.
+        for (int s = 0; s < ns; ++s)
+            if (specs[s].job.ld == 0 && specs[s].plan->n_wt)
+                MB_CUDA(cudaMemsetAsync(segs_host[s].amp, 0, (size_t)segs_host[s].n_split * specs[s].plan->n_wt * 512 * 16, ctx->stream));
+    }
+
+    // ---- upload descriptors (pinned staging keeps the copies asynchronous and ordered)
+    const size_t b_jobs = (size_t)ns * sizeof(TableJob), b_segs = (size_t)ns * sizeof(SegDesc),
+                 b_items = items.size() * sizeof(ItemDesc);
+    MB_TRY(ctx->h_stage.ensure(b_jobs + b_segs + b_items + 64));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));  // previous call may still read the staging buffer
+    char *hs = ctx->h_stage.as<char>();
+    for (int s = 0; s < ns; ++s) std::memcpy(hs + (size_t)s * sizeof(TableJob), &specs[s].job, sizeof(TableJob));
+    std::memcpy(hs + b_jobs, segs_host.data(), b_segs);
+    if (b_items) std::memcpy(hs + b_jobs + b_segs, items.data(), b_items);
+    MB_TRY(ctx->d_jobs.ensure(b_jobs));
+    MB_TRY(ctx->d_segs.ensure(b_segs));
+    MB_TRY(ctx->d_items.ensure(std::max<size_t>(b_items, 16)));
+    MB_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, hs, b_jobs, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(cudaMemcpyAsync(ctx->d_segs.p, hs + b_jobs, b_segs, cudaMemcpyHostToDevice, ctx->stream));
+    if (b_items)
+        MB_CUDA(cudaMemcpyAsync(ctx->d_items.p, hs + b_jobs + b_segs, b_items, cudaMemcpyHostToDevice, ctx->stream));
+
+    // ---- launch
+    int max_ld = 0;
+    for (int s = 0; s < ns; ++s) max_ld = std::max(max_ld, specs[s].job.ld);
+    int64_t launched = 0;
+    if (max_ld > 0) {
+        dim3 grid((max_ld + 127) / 128, 3, ns);
+        k_sf_tables<<<grid, 128, 0, ctx->stream>>>(ctx->d_jobs.as<TableJob>());
+        MB_CUDA(cudaGetLastError());
+        ++launched;
+    }
+    if (!items.empty()) {
+        if (!g_smem_attr_set) {
+            MB_CUDA(cudaFuncSetAttribute(k_sf_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+            g_smem_attr_set = true;
+        }
+        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        k_sf_contract<<<(unsigned)items.size(), NTHREADS, SMEM_TOTAL, ctx->stream>>>(ctx->d_items.as<ItemDesc>(),
+                                                                                  ctx->d_segs.as<SegDesc>());
+        MB_CUDA(cudaGetLastError());
+        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        ++launched;
+    }
+    ctx->launches += launched;
+    ctx->stats[0] = launched;
+    ctx->stats[1] = ns ? (int64_t)specs[0].plan->cell.size() : 0;
+    ctx->stats[2] = (int64_t)items.size();
+    ctx->stats[3] = mma_steps;
+    ctx->stats[4] = atomq;
+    ctx->stats[6] = max_split;
+    ctx->stats[7] = ns ? specs[0].plan->n_wt : 0;
+    return MB200_OK;
+}
+
+static int finish_timing(mb200_ctx *ctx) {
+    ctx->stats[5] = 0;
+    if (ctx->timing && ctx->stats[2] > 0) {
+        float ms = 0.f;
+        MB_CUDA(cudaEventSynchronize(ctx->ev1));
+        MB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->stats[5] = (int64_t)(ms * 1.0e6);
+    }
+    return MB200_OK;
+}
+
+}  // namespace mb200
+
+using namespace mb200;
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" int mb200_sfactor_maxn(const double dimensions[3], double qmax, int32_t maxn[3]) {
+    if (!dimensions || !maxn) return fail(MB200_EINVAL, "null argument");
+    sfactor_maxn_host(dimensions, qmax, maxn);
+    return MB200_OK;
+}
+
+extern "C" int mb200_structure_factor_block(mb200_ctx *ctx, const double *positions, int64_t stride_atom,
+                                            int64_t stride_xyz, int64_t n_atoms, const double dimensions[3],
+                                            double qmin, double qmax, double thetamin, double thetamax,
+                                            const double *weights, int32_t block, int32_t n_blocks,
+                                            double *scattering_vectors, double *structure_factors) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    if (!dimensions || !scattering_vectors || !structure_factors || n_atoms < 0 || (n_atoms && (!positions || !weights)))
+        return fail(MB200_EINVAL, "invalid argument to mb200_structure_factor");
+    if (n_atoms > 2000000000LL) return fail(MB200_EINVAL, "too many atoms");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    std::shared_ptr<SfPlan> plan;
+    MB_TRY(get_plan(ctx, dimensions, qmin, qmax, thetamin, thetamax, 0, plan));
+    const size_t cells = (size_t)plan->maxn[0] * plan->maxn[1] * plan->maxn[2];
+    std::memset(scattering_vectors, 0, cells * 8);
+    std::memset(structure_factors, 0, cells * 8);
+    const size_t nv = plan->cell.size();
+    for (size_t e = 0; e < nv; ++e) scattering_vectors[plan->cell[e]] = plan->qrr[e];
+    if (nv == 0) return MB200_OK;
+
+    // stage inputs: positions compacted to [n][3] f64, weights [n]
+    const size_t n = (size_t)n_atoms;
+    MB_TRY(ctx->h_out.ensure(std::max<size_t>(n * 32, nv * 8) + 64));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    double *hp = ctx->h_out.as<double>();
+    for (size_t j = 0; j < n; ++j)
+        for (int d = 0; d < 3; ++d) hp[j * 3 + d] = positions[(int64_t)j * stride_atom + d * stride_xyz];
+    if (n) std::memcpy(hp + n * 3, weights, n * 8);
+    MB_TRY(ctx->d_pos.ensure(std::max<size_t>(n, 1) * 32));
+    if (n) MB_CUDA(cudaMemcpyAsync(ctx->d_pos.p, hp, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+
+    std::vector<SegSpec> specs(1);
+    SegSpec &sp = specs[0];
+    sp.plan = plan.get(); sp.share_yz_with = -1; sp.ff2_group = -1;
+    std::memset(&sp.job, 0, sizeof(TableJob));
+    sp.job.pos = ctx->d_pos.p; sp.job.index = nullptr;
+    sp.job.weights = ctx->d_pos.as<double>() + n * 3;
+    sp.job.stride_atom = 3; sp.job.stride_xyz = 1;
+    for (int d = 0; d < 3; ++d) { sp.job.box[d] = dimensions[d]; sp.job.boxf[d] = (float)dimensions[d]; }
+    sp.job.n = (int32_t)n; sp.job.is_f32 = 0; sp.job.wrap_mode = 0;
+    std::vector<SegDesc> segs;
+    MB_TRY(run_segments(ctx, specs, block, n_blocks, segs));
+
+    MB_TRY(ctx->d_sval.ensure(nv * 8));
+    dim3 grid((unsigned)((nv + 255) / 256), 1);
+    k_sf_svalues<<<grid, 256, 0, ctx->stream>>>(ctx->d_segs.as<SegDesc>(), ctx->d_sval.as<double>(), (int)nv);
+    MB_CUDA(cudaGetLastError());
+    ctx->launches += 1; ctx->stats[0] += 1;
+    MB_CUDA(cudaMemcpyAsync(hp, ctx->d_sval.p, nv * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MB_TRY(finish_timing(ctx));
+    for (size_t e = 0; e < nv; ++e) structure_factors[plan->cell[e]] = hp[e];
+    return MB200_OK;
+}
+
+extern "C" int mb200_structure_factor(mb200_ctx *ctx, const double *positions, int64_t stride_atom, int64_t stride_xyz,
+                                      int64_t n_atoms, const double dimensions[3], double qmin, double qmax,
+                                      double thetamin, double thetamax, const double *weights,
+                                      double *scattering_vectors, double *structure_factors) {
+    return mb200_structure_factor_block(ctx, positions, stride_atom, stride_xyz, n_atoms, dimensions, qmin, qmax,
+                                        thetamin, thetamax, weights, 0, 1, scattering_vectors, structure_factors);
+}
+
+extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                                 int64_t n_atoms_total, const float *boxes, const int32_t *group_index,
+                                 const int64_t *group_ptr, int32_t n_groups, const double *cm_params, double qmin,
+                                 double qmax, double thetamin, double thetamax, int32_t n_bins, int pack_atoms,
+                                 int32_t block, int32_t n_blocks, double *s_binned, double *i_binned,
+                                 int64_t *bincount) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    if (n_frames < 0 || n_groups < 0 || n_bins <= 0 || !boxes || !group_ptr || !cm_params || !s_binned || !i_binned ||
+        !bincount || (n_atoms_total && !positions))
+        return fail(MB200_EINVAL, "invalid argument to mb200_saxs_frames");
+    if (n_frames == 0 || n_groups == 0) return MB200_OK;
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const size_t n_idx = (size_t)group_ptr[n_groups];
+    for (int gi = 0; gi < n_groups; ++gi)
+        if (group_ptr[gi + 1] < group_ptr[gi]) return fail(MB200_EINVAL, "group_ptr must be non-decreasing");
+    for (size_t i = 0; i < n_idx; ++i)
+        if (group_index[i] < 0 || group_index[i] >= n_atoms_total) return fail(MB200_EINVAL, "group index out of range");
+
+    // group indices -> device
+    MB_TRY(ctx->d_idx.ensure(std::max<size_t>(n_idx, 1) * 4));
+    if (n_idx) MB_CUDA(cudaMemcpyAsync(ctx->d_idx.p, group_index, n_idx * 4, cudaMemcpyHostToDevice, ctx->stream));
+
+    // frames are processed in chunks bounded by the table workspace
+    const size_t frame_elems = (size_t)n_atoms_total * 3;
+    size_t done = 0;
+    while (done < (size_t)n_frames) {
+        // chunk size: keep tables under ~12 GB
+        size_t chunk = 0, tab_bytes = 0;
+        std::vector<std::shared_ptr<SfPlan>> plans;
+        while (done + chunk < (size_t)n_frames) {
+            const float *bx = boxes + (done + chunk) * 3;
+            double dims[3] = {(double)bx[0], (double)bx[1], (double)bx[2]};
+            std::shared_ptr<SfPlan> pl;
+            MB_TRY(get_plan(ctx, dims, qmin, qmax, thetamin, thetamax, n_bins, pl));
+            size_t fb = 0;
+            for (int gi = 0; gi < n_groups; ++gi) {
+                const size_t ld = ((size_t)(group_ptr[gi + 1] - group_ptr[gi]) + KT - 1) / KT * KT;
+                fb += ld * (size_t)(pl->rows[0] + pl->rows[1] + pl->rows[2]) * 16;
+            }
+            if (chunk > 0 && tab_bytes + fb > ((size_t)12 << 30)) break;
+            tab_bytes += fb;
+            plans.push_back(pl);
+            ++chunk;
+            if (chunk >= 256) break;
+        }
+        for (auto &pl : plans) MB_TRY(plan_ff2(ctx, *pl, cm_params, n_groups));
+
+        const float *dpos;
+        if (positions_on_device) {
+            dpos = positions + done * frame_elems;
+        } else {
+            MB_TRY(ctx->d_pos.ensure(std::max<size_t>(chunk * frame_elems, 1) * 4));
+            if (frame_elems)
+                MB_CUDA(cudaMemcpyAsync(ctx->d_pos.p, positions + done * frame_elems, chunk * frame_elems * 4,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+            dpos = ctx->d_pos.as<float>();
+        }
+        std::vector<SegSpec> specs(chunk * n_groups);
+        for (size_t f = 0; f < chunk; ++f)
+            for (int gi = 0; gi < n_groups; ++gi) {
+                SegSpec &sp = specs[f * n_groups + gi];
+                sp.plan = plans[f].get(); sp.share_yz_with = -1; sp.ff2_group = gi;
+                std::memset(&sp.job, 0, sizeof(TableJob));
+                sp.job.pos = dpos + f * frame_elems;
+                sp.job.index = ctx->d_idx.as<int32_t>() + group_ptr[gi];
+                sp.job.weights = nullptr;
+                sp.job.stride_atom = 3; sp.job.stride_xyz = 1;
+                const float *bx = boxes + (done + f) * 3;
+                for (int d = 0; d < 3; ++d) { sp.job.boxf[d] = bx[d]; sp.job.box[d] = (double)bx[d]; }
+                sp.job.n = (int32_t)(group_ptr[gi + 1] - group_ptr[gi]);
+                sp.job.is_f32 = 1; sp.job.wrap_mode = pack_atoms ? 2 : 1;
+            }
+        std::vector<SegDesc> segs;
+        MB_TRY(run_segments(ctx, specs, block, n_blocks, segs));
+        const size_t ns = specs.size();
+        const size_t ob = ns * (size_t)n_bins;
+        MB_TRY(ctx->d_out.ensure(ob * 24));
+        double *d_s = ctx->d_out.as<double>(), *d_i = d_s + ob;
+        long long *d_c = reinterpret_cast<long long *>(d_i + ob);
+        dim3 grid((unsigned)n_bins, (unsigned)ns);
+        k_sf_binned<<<grid, 128, 0, ctx->stream>>>(ctx->d_segs.as<SegDesc>(), d_s, d_i, d_c, n_bins);
+        MB_CUDA(cudaGetLastError());
+        ctx->launches += 1; ctx->stats[0] += 1;
+        const size_t oo = done * (size_t)n_groups * n_bins;
+        MB_CUDA(cudaMemcpyAsync(s_binned + oo, d_s, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MB_CUDA(cudaMemcpyAsync(i_binned + oo, d_i, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MB_CUDA(cudaMemcpyAsync(bincount + oo, d_c, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MB_CUDA(cudaStreamSynchronize(ctx->stream));
+        MB_TRY(finish_timing(ctx));
+        done += chunk;
+    }
+    return MB200_OK;
+}
+
+extern "C" int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const double *weights, int64_t n_frames,
+                                  int64_t n, const double *boxes, double qmin, double qmax, int32_t n_bins,
+                                  int32_t block, int32_t n_blocks, double *s_binned, int64_t *bincount) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    if (n_frames < 0 || n < 0 || n_bins <= 0 || !boxes || !s_binned || !bincount || (n && (!positions || !weights)))
+        return fail(MB200_EINVAL, "invalid argument to mb200_dipsf_frames");
+    if (n_frames == 0) return MB200_OK;
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const size_t nn = (size_t)n;
+    size_t done = 0;
+    while (done < (size_t)n_frames) {
+        size_t chunk = 0, tab_bytes = 0;
+        std::vector<std::shared_ptr<SfPlan>> plans;
+        while (done + chunk < (size_t)n_frames) {
+            std::shared_ptr<SfPlan> pl;
+            MB_TRY(get_plan(ctx, boxes + (done + chunk) * 3, qmin, qmax, 0.0, M_PI, n_bins, pl));
+            const size_t ld = (nn + KT - 1) / KT * KT;
+            const size_t fb = ld * (size_t)(3 * pl->rows[0] + pl->rows[1] + pl->rows[2]) * 16;
+            if (chunk > 0 && tab_bytes + fb > ((size_t)12 << 30)) break;
+            tab_bytes += fb;
+            plans.push_back(pl);
+            if (++chunk >= 64) break;
+        }
+        // inputs: positions [chunk][n][3], weights [chunk][3][n]
+        MB_TRY(ctx->d_pos.ensure(std::max<size_t>(chunk * nn, 1) * 48));
+        double *dp = ctx->d_pos.as<double>(), *dw = dp + chunk * nn * 3;
+        if (nn) {
+            MB_CUDA(cudaMemcpyAsync(dp, positions + done * nn * 3, chunk * nn * 24, cudaMemcpyHostToDevice, ctx->stream));
+            MB_CUDA(cudaMemcpyAsync(dw, weights + done * nn * 3, chunk * nn * 24, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        std::vector<SegSpec> specs(chunk * 3);
+        for (size_t f = 0; f < chunk; ++f)
+            for (int c = 0; c < 3; ++c) {
+                SegSpec &sp = specs[f * 3 + c];
+                sp.plan = plans[f].get(); sp.share_yz_with = c == 0 ? -1 : (int)(f * 3); sp.ff2_group = -1;
+                std::memset(&sp.job, 0, sizeof(TableJob));
+                sp.job.pos = dp + f * nn * 3; sp.job.index = nullptr;
+                sp.job.weights = dw + (f * 3 + c) * nn;
+                sp.job.stride_atom = 3; sp.job.stride_xyz = 1;
+                for (int d = 0; d < 3; ++d) { sp.job.box[d] = boxes[(done + f) * 3 + d]; sp.job.boxf[d] = (float)sp.job.box[d]; }
+                sp.job.n = (int32_t)nn; sp.job.is_f32 = 0; sp.job.wrap_mode = 0;
+            }
+        std::vector<SegDesc> segs;
+        MB_TRY(run_segments(ctx, specs, block, n_blocks, segs));
+        const size_t ns = specs.size(), ob = ns * (size_t)n_bins;
+        MB_TRY(ctx->d_out.ensure(ob * 16));
+        double *d_s = ctx->d_out.as<double>();
+        long long *d_c = reinterpret_cast<long long *>(d_s + ob);
+        dim3 grid((unsigned)n_bins, (unsigned)ns);
+        k_sf_binned<<<grid, 128, 0, ctx->stream>>>(ctx->d_segs.as<SegDesc>(), d_s, nullptr, d_c, n_bins);
+        MB_CUDA(cudaGetLastError());
+        ctx->launches += 1; ctx->stats[0] += 1;
+        const size_t oo = done * 3 * (size_t)n_bins;
+        MB_CUDA(cudaMemcpyAsync(s_binned + oo, d_s, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MB_CUDA(cudaMemcpyAsync(bincount + oo, d_c, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MB_CUDA(cudaStreamSynchronize(ctx->stream));
+        MB_TRY(finish_timing(ctx));
+        done += chunk;
+    }
+    return MB200_OK;
+}
