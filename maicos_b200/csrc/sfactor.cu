@@ -39,6 +39,7 @@ namespace mb200 {
 constexpr int KT = 8;          // atoms per pipeline stage (two DMMA k-steps of 4)
 constexpr int WPC = 4;         // warps per CTA
 constexpr int NTHREADS = WPC * 32;
+constexpr int NSTAGE = 4;      // cp.async ring depth
 constexpr int MAXX = 4;        // distinct (h,k) quads (4h x 8k = 32 rows) a CTA may stage
 constexpr int MAXY = 4;        // distinct l-pairs (16 l) a CTA may stage
 constexpr int QH = 4, QK = 8;  // quad shape
@@ -46,12 +47,10 @@ constexpr int NL = 16;         // l extent of a warp tile
 constexpr int RAWROW = 9;      // double2 per staged table row: 8 atoms + 1 pad (bank spread)
 constexpr int XY_ROWS = MAXX * (QH + QK);  // 48
 constexpr int Z_ROWS = MAXY * NL;          // 64
-constexpr int X_ROWS = MAXX * 32;          // 128
-constexpr int SMEM_RAWXY = 2 * XY_ROWS * RAWROW * 16;   // 13824
-constexpr int SMEM_RAWZ = 3 * Z_ROWS * RAWROW * 16;     // 27648
-constexpr int SMEM_X = 2 * 3 * X_ROWS * KT * 8;         // 49152
-constexpr int SMEM_PTR = (XY_ROWS + Z_ROWS) * 8;        // 896
-constexpr int SMEM_TOTAL = SMEM_RAWXY + SMEM_RAWZ + SMEM_X + SMEM_PTR;
+constexpr int ST_ROWS = XY_ROWS + Z_ROWS;  // 112 rows per stage
+constexpr int SMEM_STAGE = ST_ROWS * RAWROW * 16;       // 16128
+constexpr int SMEM_PTR = ST_ROWS * 8;                   // 896
+constexpr int SMEM_TOTAL = NSTAGE * SMEM_STAGE + SMEM_PTR + 16;
 
 struct __align__(16) TileGroupDesc {
     int16_t xh0[MAXX];
@@ -95,9 +94,12 @@ struct TableJob {
 // device helpers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-        : "+d"(c0), "+d"(c1)
-        : "d"(a), "d"(b));
+    // volatile: keeps the issue order written below (dependent DMMAs six instructions apart);
+    // without it nvcc pairs the two k-steps of an accumulator back to back and every second
+    // DMMA waits for the full latency of the first (ncu: profiles/r01_notes.md).
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
 }
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -161,161 +163,163 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// k_sf_contract: the DMMA contraction
+// k_sf_contract: the DMMA contraction (persistent CTAs, dynamic item queue)
+//
+//   per stage (8 atoms) a CTA stages, with cp.async, the table rows its warps need:
+//     Ex rows h0..h0+3 and Ey rows k0..k0+7 of each of its (h,k) quads, Ez rows l0..l0+15 of
+//     each of its l-pairs; [row][8 atoms + pad] double2, NSTAGE-deep ring, one barrier per stage.
+//   every warp owns a 32 (hk) x 16 (l) tile: 4 x 2 DMMA tiles x 3 planes of accumulators.
+//   A fragments P = Ex*Ey (and Pr+Pi) are formed in registers from the staged rows, B fragments
+//   are the staged Ez rows (and Zr+Zi); k index of the MMA = atom.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 2)
-k_sf_contract(const ItemDesc *__restrict__ items, const SegDesc *__restrict__ segs) {
+__global__ void __launch_bounds__(NTHREADS, 3)
+k_sf_contract(const ItemDesc *__restrict__ items, int n_items, const SegDesc *__restrict__ segs,
+              int *__restrict__ counter) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double2 *rawxy = reinterpret_cast<double2 *>(smem);                       // [2][XY_ROWS][RAWROW]
-    double2 *rawz = reinterpret_cast<double2 *>(smem + SMEM_RAWXY);           // [3][Z_ROWS][RAWROW]
-    double *xbuf = reinterpret_cast<double *>(smem + SMEM_RAWXY + SMEM_RAWZ); // [2][3][X_ROWS][KT]
-    const double2 **rowptr =
-        reinterpret_cast<const double2 **>(smem + SMEM_RAWXY + SMEM_RAWZ + SMEM_X);  // [XY_ROWS + Z_ROWS]
+    double2 *raw = reinterpret_cast<double2 *>(smem);  // [NSTAGE][ST_ROWS][RAWROW]
+    const double2 **rowptr = reinterpret_cast<const double2 **>(smem + NSTAGE * SMEM_STAGE);  // [ST_ROWS]
+    int *s_item = reinterpret_cast<int *>(smem + NSTAGE * SMEM_STAGE + SMEM_PTR);
 
-    const ItemDesc it = items[blockIdx.x];
-    const SegDesc &sg = segs[it.seg];
-    const TileGroupDesc tg = sg.tgs[it.tg];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tig = lane & 3;
-    const int ld = sg.ld;
 
-    // source row pointers (at atom j0) of every staged row; compacted: x-slot rows, then z rows
-    const int n_xy = tg.n_x * (QH + QK);
-    const int n_z = tg.n_y * NL;
-    for (int r = tid; r < n_xy + n_z; r += NTHREADS) {
-        const double2 *p;
-        if (r < n_xy) {
-            const int xs = r / (QH + QK), q = r % (QH + QK);
-            p = (q < QH) ? sg.ex + (size_t)(tg.xh0[xs] + q) * ld
-                         : sg.ey + (size_t)(tg.xk0[xs] + (q - QH)) * ld;
-        } else {
-            const int rz = r - n_xy;
-            p = sg.ez + (size_t)(tg.yl0[rz / NL] + (rz % NL)) * ld;
-        }
-        rowptr[r < n_xy ? r : XY_ROWS + (r - n_xy)] = p + it.j0;
-    }
-    __syncthreads();
+    for (;;) {
+        if (tid == 0) *s_item = atomicAdd(counter, 1);
+        __syncthreads();
+        const int item = *s_item;
+        if (item >= n_items) break;
 
-    const int n_stage = (it.j1 - it.j0) / KT;
-    const int n_chunk_xy = n_xy * KT, n_chunk_z = n_z * KT;
+        const ItemDesc it = items[item];
+        const SegDesc &sg = segs[it.seg];
+        const TileGroupDesc *tg = sg.tgs + it.tg;
+        const int ld = sg.ld;
+        const int n_x = tg->n_x, n_y = tg->n_y;
 
-    auto issue = [&](int t) {  // cp.async stage t -> rawxy[t&1], rawz[t%3]
-        if (t < n_stage) {
-            double2 *dxy = rawxy + (t & 1) * (XY_ROWS * RAWROW);
-            double2 *dz = rawz + (t % 3) * (Z_ROWS * RAWROW);
-            const int off = t * KT;
-            for (int q = tid; q < n_chunk_xy; q += NTHREADS) {
-                const int r = q >> 3, c = q & 7;
-                cp_async16(dxy + r * RAWROW + c, rowptr[r] + off + c);
+        // source row pointers (at atom j0) of every staged row: x-slot rows (4 Ex + 8 Ey), then Ez rows
+        const int n_xy = n_x * (QH + QK);
+        const int n_rows = n_xy + n_y * NL;
+        for (int r = tid; r < n_rows; r += NTHREADS) {
+            const double2 *p;
+            if (r < n_xy) {
+                const int xs = r / (QH + QK), q = r % (QH + QK);
+                p = (q < QH) ? sg.ex + (size_t)(tg->xh0[xs] + q) * ld
+                             : sg.ey + (size_t)(tg->xk0[xs] + (q - QH)) * ld;
+            } else {
+                const int rz = r - n_xy;
+                p = sg.ez + (size_t)(tg->yl0[rz / NL] + (rz % NL)) * ld;
             }
-            for (int q = tid; q < n_chunk_z; q += NTHREADS) {
-                const int r = q >> 3, c = q & 7;
-                cp_async16(dz + r * RAWROW + c, rowptr[XY_ROWS + r] + off + c);
-            }
+            rowptr[r] = p + it.j0;
         }
-        cp_async_commit();
-    };
-    auto build = [&](int t) {  // P rows of stage t: rawxy[t&1] -> xbuf[t&1] (planes Pr, Pi, Pr+Pi)
-        const double2 *sxy = rawxy + (t & 1) * (XY_ROWS * RAWROW);
-        double *xb = xbuf + (t & 1) * (3 * X_ROWS * KT);
-        const int n_ent = tg.n_x * 32 * 4;
-        for (int e = tid; e < n_ent; e += NTHREADS) {
-            const int row = e >> 2, ap = e & 3;
-            const int xs = row >> 5, r = row & 31;
-            const double2 *pex = sxy + (xs * (QH + QK) + (r >> 3)) * RAWROW + 2 * ap;
-            const double2 *pey = sxy + (xs * (QH + QK) + QH + (r & 7)) * RAWROW + 2 * ap;
-            const double2 a0 = pex[0], a1 = pex[1], b0 = pey[0], b1 = pey[1];
-            double2 pr, pi, ps;
-            pr.x = a0.x * b0.x - a0.y * b0.y;
-            pi.x = a0.x * b0.y + a0.y * b0.x;
-            pr.y = a1.x * b1.x - a1.y * b1.y;
-            pi.y = a1.x * b1.y + a1.y * b1.x;
-            ps.x = pr.x + pi.x;
-            ps.y = pr.y + pi.y;
-            double *dst = xb + row * KT + 2 * ap;
-            *reinterpret_cast<double2 *>(dst) = pr;
-            *reinterpret_cast<double2 *>(dst + X_ROWS * KT) = pi;
-            *reinterpret_cast<double2 *>(dst + 2 * X_ROWS * KT) = ps;
-        }
-    };
+        const bool active = warp < tg->n_warp;
+        const int wx = active ? tg->wx[warp] : 0, wy = active ? tg->wy[warp] : 0;
+        const unsigned wmask = active ? tg->wmask[warp] : 0u;
+        __syncthreads();
 
-    // accumulators: [mt][nt] x planes (T1,T2,T3) x {c0,c1}
-    double acc[4][2][3][2];
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int p = 0; p < 3; ++p) acc[mt][nt][p][0] = acc[mt][nt][p][1] = 0.0;
+        const int n_stage = (it.j1 - it.j0) / KT;
+        const int n_chunk = n_rows * KT;
 
-    const bool active = warp < tg.n_warp;
-    const int wx = active ? tg.wx[warp] : 0, wy = active ? tg.wy[warp] : 0;
-    const unsigned wmask = active ? tg.wmask[warp] : 0u;
-
-    // prologue
-    issue(0);
-    issue(1);
-    cp_async_wait<1>();
-    __syncthreads();
-    build(0);
-
-    for (int t = 0; t < n_stage; ++t) {
-        cp_async_wait<0>();
-        __syncthreads();  // stage t+1 raw + X(t) visible; everyone is done with MMA(t-1)/build(t)
-        issue(t + 2);
-        if (t + 1 < n_stage) build(t + 1);
-
-        if (wmask) {
-            const double *xb = xbuf + (t & 1) * (3 * X_ROWS * KT) + (wx * 32 + g) * KT + 2 * tig;
-            const double2 *sz = rawz + (t % 3) * (Z_ROWS * RAWROW) + (wy * NL + g) * RAWROW + 2 * tig;
-            double br[2][2], bi[2][2], bs[2][2];  // [nt][kstep]
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                const double2 z0 = sz[nt * 8 * RAWROW], z1 = sz[nt * 8 * RAWROW + 1];
-                br[nt][0] = z0.x; bi[nt][0] = z0.y; bs[nt][0] = z0.x + z0.y;
-                br[nt][1] = z1.x; bi[nt][1] = z1.y; bs[nt][1] = z1.x + z1.y;
+        auto issue = [&](int t) {  // cp.async stage t -> ring slot t % NSTAGE
+            if (t < n_stage) {
+                double2 *dst = raw + (t % NSTAGE) * (ST_ROWS * RAWROW);
+                const int off = t * KT;
+                for (int q = tid; q < n_chunk; q += NTHREADS) {
+                    const int r = q >> 3, c = q & 7;
+                    cp_async16(dst + r * RAWROW + c, rowptr[r] + off + c);
+                }
             }
+            cp_async_commit();
+        };
+
+        // accumulators: [mt][nt] x planes (T1,T2,T3) x {c0,c1}
+        double acc[4][2][3][2];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
-                if ((wmask >> (2 * mt)) & 3u) {
-                    const double2 ar = *reinterpret_cast<const double2 *>(xb + mt * 8 * KT);
-                    const double2 ai = *reinterpret_cast<const double2 *>(xb + mt * 8 * KT + X_ROWS * KT);
-                    const double2 as = *reinterpret_cast<const double2 *>(xb + mt * 8 * KT + 2 * X_ROWS * KT);
+        for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) {
-                        if ((wmask >> (2 * mt + nt)) & 1u) {
-                            dmma(acc[mt][nt][0][0], acc[mt][nt][0][1], ar.x, br[nt][0]);
-                            dmma(acc[mt][nt][1][0], acc[mt][nt][1][1], ai.x, bi[nt][0]);
-                            dmma(acc[mt][nt][2][0], acc[mt][nt][2][1], as.x, bs[nt][0]);
-                            dmma(acc[mt][nt][0][0], acc[mt][nt][0][1], ar.y, br[nt][1]);
-                            dmma(acc[mt][nt][1][0], acc[mt][nt][1][1], ai.y, bi[nt][1]);
-                            dmma(acc[mt][nt][2][0], acc[mt][nt][2][1], as.y, bs[nt][1]);
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int p = 0; p < 3; ++p) acc[mt][nt][p][0] = acc[mt][nt][p][1] = 0.0;
+
+        issue(0);
+        issue(1);
+        issue(2);
+        // per-thread fragment offsets inside a stage (double2 units)
+        const int off_ex = (wx * (QH + QK)) * RAWROW + 2 * tig;
+        const int off_ey = (wx * (QH + QK) + QH + g) * RAWROW + 2 * tig;
+        const int off_ez = (n_xy + wy * NL + g) * RAWROW + 2 * tig;
+
+        for (int t = 0; t < n_stage; ++t) {
+            cp_async_wait<NSTAGE - 2>();
+            __syncthreads();  // stage t visible to all; every warp is done with stage t-1
+            issue(t + NSTAGE - 1);
+
+            if (wmask) {
+                const double2 *st = raw + (t % NSTAGE) * (ST_ROWS * RAWROW);
+                double br[2][2], bi[2][2], bs[2][2];  // [nt][kstep]
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const double2 z0 = st[off_ez + nt * 8 * RAWROW], z1 = st[off_ez + nt * 8 * RAWROW + 1];
+                    br[nt][0] = z0.x; bi[nt][0] = z0.y; bs[nt][0] = z0.x + z0.y;
+                    br[nt][1] = z1.x; bi[nt][1] = z1.y; bs[nt][1] = z1.x + z1.y;
+                }
+                const double2 y0 = st[off_ey], y1 = st[off_ey + 1];
+                double2 xn0 = st[off_ex], xn1 = st[off_ex + 1];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    const double2 x0 = xn0, x1 = xn1;
+                    if (mt < 3) {  // prefetch the next Ex row while this row's DMMAs issue
+                        xn0 = st[off_ex + (mt + 1) * RAWROW];
+                        xn1 = st[off_ex + (mt + 1) * RAWROW + 1];
+                    }
+                    if ((wmask >> (2 * mt)) & 3u) {
+                        const double pr0 = x0.x * y0.x - x0.y * y0.y, pi0 = x0.x * y0.y + x0.y * y0.x;
+                        const double pr1 = x1.x * y1.x - x1.y * y1.y, pi1 = x1.x * y1.y + x1.y * y1.x;
+                        const double ps0 = pr0 + pi0, ps1 = pr1 + pi1;
+                        const bool v0 = (wmask >> (2 * mt)) & 1u, v1 = (wmask >> (2 * mt + 1)) & 1u;
+                        if (v0) {
+                            dmma(acc[mt][0][0][0], acc[mt][0][0][1], pr0, br[0][0]);
+                            dmma(acc[mt][0][1][0], acc[mt][0][1][1], pi0, bi[0][0]);
+                            dmma(acc[mt][0][2][0], acc[mt][0][2][1], ps0, bs[0][0]);
+                        }
+                        if (v1) {
+                            dmma(acc[mt][1][0][0], acc[mt][1][0][1], pr0, br[1][0]);
+                            dmma(acc[mt][1][1][0], acc[mt][1][1][1], pi0, bi[1][0]);
+                            dmma(acc[mt][1][2][0], acc[mt][1][2][1], ps0, bs[1][0]);
+                        }
+                        if (v0) {
+                            dmma(acc[mt][0][0][0], acc[mt][0][0][1], pr1, br[0][1]);
+                            dmma(acc[mt][0][1][0], acc[mt][0][1][1], pi1, bi[0][1]);
+                            dmma(acc[mt][0][2][0], acc[mt][0][2][1], ps1, bs[0][1]);
+                        }
+                        if (v1) {
+                            dmma(acc[mt][1][0][0], acc[mt][1][0][1], pr1, br[1][1]);
+                            dmma(acc[mt][1][1][0], acc[mt][1][1][1], pi1, bi[1][1]);
+                            dmma(acc[mt][1][2][0], acc[mt][1][2][1], ps1, bs[1][1]);
                         }
                     }
                 }
             }
         }
-    }
-    cp_async_wait<0>();
+        cp_async_wait<0>();
 
-    // epilogue: Re = T1 - T2, Im = T3 - T1 - T2 -> amp[split][wt][row][col]
-    if (wmask) {
-        double2 *out = sg.amp + ((size_t)it.split * sg.n_wt + tg.wt0 + warp) * 512;
+        // epilogue: Re = T1 - T2, Im = T3 - T1 - T2 -> amp[split][wt][row][col]
+        if (wmask) {
+            double2 *out = sg.amp + ((size_t)it.split * sg.n_wt + tg->wt0 + warp) * 512;
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+            for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                if ((wmask >> (2 * mt + nt)) & 1u) {
-                    const int row = mt * 8 + g, col = nt * 8 + 2 * tig;
-                    double2 v0, v1;
-                    v0.x = acc[mt][nt][0][0] - acc[mt][nt][1][0];
-                    v0.y = acc[mt][nt][2][0] - acc[mt][nt][0][0] - acc[mt][nt][1][0];
-                    v1.x = acc[mt][nt][0][1] - acc[mt][nt][1][1];
-                    v1.y = acc[mt][nt][2][1] - acc[mt][nt][0][1] - acc[mt][nt][1][1];
-                    out[row * 16 + col] = v0;
-                    out[row * 16 + col + 1] = v1;
+                for (int nt = 0; nt < 2; ++nt) {
+                    if ((wmask >> (2 * mt + nt)) & 1u) {
+                        const int row = mt * 8 + g, col = nt * 8 + 2 * tig;
+                        double2 v0, v1;
+                        v0.x = acc[mt][nt][0][0] - acc[mt][nt][1][0];
+                        v0.y = acc[mt][nt][2][0] - acc[mt][nt][0][0] - acc[mt][nt][1][0];
+                        v1.x = acc[mt][nt][0][1] - acc[mt][nt][1][1];
+                        v1.y = acc[mt][nt][2][1] - acc[mt][nt][0][1] - acc[mt][nt][1][1];
+                        out[row * 16 + col] = v0;
+                        out[row * 16 + col + 1] = v1;
+                    }
                 }
-            }
+        }
     }
 }
 
@@ -667,7 +671,7 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
         const int ntg = (int)specs[s].plan->tgs.size();
         for (int g = 0; g < ntg; ++g) total_tg += (g % n_blocks == block) && specs[s].job.ld > 0;
     }
-    const int64_t target_ctas = (int64_t)ctx->n_sm * 2 * 4;  // ~4 waves of 2 CTAs/SM
+    const int64_t target_ctas = (int64_t)ctx->n_sm * 3 * 6;  // ~6 items per resident CTA (dynamic queue)
     std::vector<ItemDesc> items;
     size_t amp_elems = 0;
     std::vector<size_t> off_amp(ns);
@@ -734,6 +738,7 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
     MB_TRY(ctx->d_jobs.ensure(b_jobs));
     MB_TRY(ctx->d_segs.ensure(b_segs));
     MB_TRY(ctx->d_items.ensure(std::max<size_t>(b_items, 16)));
+    MB_TRY(ctx->d_counter.ensure(16));
     MB_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, hs, b_jobs, cudaMemcpyHostToDevice, ctx->stream));
     MB_CUDA(cudaMemcpyAsync(ctx->d_segs.p, hs + b_jobs, b_segs, cudaMemcpyHostToDevice, ctx->stream));
     if (b_items)
@@ -755,8 +760,10 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
             g_smem_attr_set = true;
         }
         if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-        k_sf_contract<<<(unsigned)items.size(), NTHREADS, SMEM_TOTAL, ctx->stream>>>(ctx->d_items.as<ItemDesc>(),
-                                                                                  ctx->d_segs.as<SegDesc>());
+        MB_CUDA(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
+        const unsigned n_cta = (unsigned)std::min<size_t>(items.size(), (size_t)ctx->n_sm * 3);
+        k_sf_contract<<<n_cta, NTHREADS, SMEM_TOTAL, ctx->stream>>>(ctx->d_items.as<ItemDesc>(), (int)items.size(),
+                                                                   ctx->d_segs.as<SegDesc>(), ctx->d_counter.as<int>());
         MB_CUDA(cudaGetLastError());
         if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
         ++launched;
