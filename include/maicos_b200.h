@@ -22,6 +22,7 @@
 #ifndef MAICOS_B200_H
 #define MAICOS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -61,6 +62,10 @@ int mb200_ctx_stats(mb200_ctx *ctx, int64_t out[8]);
 int mb200_ctx_set_timing(mb200_ctx *ctx, int enable);
 /* Total kernels launched by this context since creation. */
 int64_t mb200_ctx_launch_count(mb200_ctx *ctx);
+/* Page-locked host memory for frame staging (full-rate asynchronous H2D / D2H).  Any host pointer
+ * is accepted by the compute calls; pinned ones avoid the driver's bounce buffer. */
+int mb200_host_alloc(size_t bytes, void **out);
+void mb200_host_free(void *p);
 
 /* ---- path 1: reciprocal-space structure factor -------------------------------- */
 

@@ -32,6 +32,8 @@ SIGNATURES = {
     "mb200_ctx_stats": (ctypes.c_int, [ctypes.c_void_p, c_i64_p]),
     "mb200_ctx_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "mb200_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "mb200_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
+    "mb200_host_free": (None, [ctypes.c_void_p]),
     "mb200_sfactor_maxn": (ctypes.c_int, [c_double_p, ctypes.c_double, c_i32_p]),
     "mb200_structure_factor": (
         ctypes.c_int,
@@ -177,3 +179,41 @@ def ptr(a: np.ndarray | None):
 
 def check(rc: int) -> None:
     _check(rc)
+
+
+class _PinnedBlock:
+    """One page-locked allocation (freed explicitly when its slot grows)."""
+
+    def __init__(self, nbytes: int):
+        p = ctypes.c_void_p()
+        _check(load().mb200_host_alloc(nbytes, ctypes.byref(p)))
+        self.ptr, self.nbytes = p, nbytes
+        self.buf = (ctypes.c_char * nbytes).from_address(p.value)
+
+    def free(self):
+        if self.ptr:
+            load().mb200_host_free(self.ptr)
+            self.ptr = None
+
+
+_pinned_slots: dict[str, _PinnedBlock] = {}
+
+
+def pinned_empty(shape, dtype, slot: str = "default") -> np.ndarray:
+    """Page-locked staging array backed by the grow-only block of ``slot``.
+
+    A slot's previous array is invalidated by the next call with the same slot (staging buffers are
+    reused batch after batch).  Without a CUDA device (host-logic tests) an ordinary array is
+    returned; it is only a buffer, never a compute fallback.
+    """
+    dtype = np.dtype(dtype)
+    count = int(np.prod(tuple(int(x) for x in shape), dtype=np.int64))
+    nbytes = max(count * dtype.itemsize, 1)
+    if device_count() <= 0:
+        return np.empty(shape, dtype=dtype)
+    block = _pinned_slots.get(slot)
+    if block is None or block.nbytes < nbytes:
+        if block is not None:
+            block.free()
+        block = _pinned_slots[slot] = _PinnedBlock(nbytes + nbytes // 4)
+    return np.frombuffer(block.buf, dtype=dtype, count=count).reshape(shape)

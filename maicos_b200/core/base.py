@@ -1,0 +1,552 @@
+"""Frame loop, running statistics and profile base of the drop-in analysis classes.
+
+Keeps the protocol of ``maicos.core.base`` (``/root/reference/src/maicos/core/base.py``):
+
+* ``AnalysisBase(atomgroup, unwrap, pack, refgroup, jitter, concfreq, wrap_compound)``,
+  ``.run(start, stop, step, frames, verbose, progressbar_kwargs) -> self`` (``base.py:517-536``),
+  hooks ``_prepare / _single_frame / _conclude / save``, attributes ``results, _obs, sums, means,
+  sems, n_frames, frames, times, timeseries, corrtime, _index, _frame_index`` (``base.py:138-171``),
+  the per-frame order *unwrap -> refgroup centring -> wrap -> jitter -> _single_frame -> statistics*
+  (``base.py:417-499``), ``concfreq`` (``496-499``) and ``savetxt`` (``538-599``);
+* ``ProfileBase`` (``base.py:722-857``): weighted + count histogram per frame, normalisation
+  ``none / volume / number``.
+
+What is different, by design: the loop *stages* frames and hands a whole batch to one C-ABI call
+(``_stage_frame`` / ``_compute_staged``), so the GPU sees hundreds of frames per launch sequence;
+the per-frame observables come back as small arrays and enter the statistics in frame order with
+the reference's own recurrences (``lib/math.py:325-459``), so ``means / sems / sums`` are what a
+serial run produces.  ``_single_frame()`` stays callable on its own (the reference's tests call
+it directly) and is then a batch of one.  With ``maicos_b200.parallel`` initialised, frames are
+sharded over ranks and merged by one allreduce at the end.
+"""
+
+from __future__ import annotations
+
+import logging
+import warnings
+from collections.abc import Callable
+from datetime import datetime
+
+import numpy as np
+
+from .. import __version__, parallel
+from ..lib.math import center_cluster, new_mean, new_variance
+from ..lib.util import atomgroup_header, correlation_analysis, get_center, get_cli_input, get_module_input_str
+
+_COMPATIBLE = (np.ndarray, float, int, list, np.float32, np.float64, np.int32, np.int64)
+_WRAP_COMPOUNDS = ["atoms", "group", "residues", "segments", "molecules", "fragments"]
+
+
+class Results(dict):
+    """Dictionary with attribute access (the ``MDAnalysis.analysis.base.Results`` behaviour used here)."""
+
+    def __getattr__(self, key):
+        try:
+            return self[key]
+        except KeyError as err:
+            raise AttributeError(f"'Results' object has no attribute '{key}'") from err
+
+    def __setattr__(self, key, value):
+        self[key] = value
+
+    def __delattr__(self, key):
+        try:
+            del self[key]
+        except KeyError as err:
+            raise AttributeError(f"'Results' object has no attribute '{key}'") from err
+
+    def copy(self):
+        return Results(self)
+
+
+class _Runner:
+    """Shared ``run`` machinery of :class:`AnalysisBase` and :class:`AnalysisCollection`."""
+
+    def _run(self, analysis_instances, start=None, stop=None, step=None, frames=None, verbose=None,
+             progressbar_kwargs=None):
+        self._run_locals = locals()
+        logging.getLogger(__name__).setLevel(logging.INFO if verbose else logging.WARNING)
+        if frames is not None and not all(opt is None for opt in [start, stop, step]):
+            raise ValueError("start/stop/step cannot be combined with frames")
+        for a in analysis_instances:
+            a._run_locals = self._run_locals
+            a._setup_frames(a._trajectory, start=start, stop=stop, step=step, frames=frames)
+        for a in analysis_instances:
+            a._call_prepare()
+
+        first = analysis_instances[0]
+        local = first._local_frame_slots()
+        trajectory = first._trajectory
+        for slot in local:
+            ts = trajectory[int(first.frames_selected[slot])]
+            ts_original = ts.copy() if len(analysis_instances) > 1 else None
+            for a in analysis_instances:
+                if ts_original is not None:
+                    # every analysis starts from the untouched frame
+                    ts.positions[...] = ts_original.positions
+                a._enqueue_frame(ts, int(slot))
+        for a in analysis_instances:
+            a._flush_staged()
+            a._merge_ranks()
+        for a in analysis_instances:
+            a._call_conclude()
+        return self
+
+
+class AnalysisBase(_Runner):
+    """Base class of multi-frame analyses (protocol of ``maicos.core.AnalysisBase``).
+
+    Parameters
+    ----------
+    atomgroup : AtomGroup
+        atoms to analyse (MDAnalysis AtomGroup or the in-memory shim).
+    unwrap : bool
+        make compounds whole before the analysis (``atoms.unwrap(compound=wrap_compound)``).
+    pack : bool
+        wrap compounds into the primary cell.
+    refgroup : AtomGroup or None
+        centre the cell on this group's (periodic) centre of mass every frame.
+    jitter : float
+        magnitude of a uniform random displacement added to every coordinate.
+    concfreq : int
+        call ``_conclude`` (and ``save``) every ``concfreq`` frames; 0 = only at the end.
+    wrap_compound : str
+        compound kept whole when wrapping.
+    """
+
+    #: frames staged per device call by classes that implement ``_stage_frame``/``_compute_staged``
+    _batch_size = 1
+    #: True when ``pack`` with ``wrap_compound="atoms"`` is applied by the kernel instead of the host
+    _device_pack = False
+
+    def __init__(self, atomgroup, unwrap: bool, pack: bool, refgroup, jitter: float, concfreq: int,
+                 wrap_compound: str) -> None:
+        self.atomgroup = atomgroup
+        if self.atomgroup.n_atoms == 0:
+            raise ValueError("The provided `atomgroup` does not contain any atoms.")
+        self._universe = atomgroup.universe
+        self._trajectory = self._universe.trajectory
+        self.refgroup = refgroup
+        self.unwrap = unwrap
+        self.pack = pack
+        self.jitter = jitter
+        self.concfreq = concfreq
+        if wrap_compound not in _WRAP_COMPOUNDS:
+            raise ValueError(
+                "Unrecognized `wrap_compound` definition "
+                f"{wrap_compound}: \nPlease use "
+                "one of 'atoms', 'group', 'residues', "
+                "'segments', 'molecules', or 'fragments'."
+            )
+        self.wrap_compound = wrap_compound
+        if self.unwrap and self._universe.dimensions is None:
+            raise ValueError("Universe does not have `dimensions` and can't be unwrapped!")
+        if self.pack and self._universe.dimensions is None:
+            raise ValueError("Universe does not have `dimensions` and can't be packed!")
+        if self.unwrap and self.wrap_compound == "atoms":
+            logging.warning(
+                "Unwrapping in combination with the `wrap_compound='atoms` is superfluous. "
+                "`unwrap` will be set to `False`."
+            )
+            self.unwrap = False
+        if self.refgroup is not None:
+            if self.refgroup.n_atoms == 0:
+                raise ValueError("The provided `refgroup` does not contain any atoms.")
+            if not self.pack:
+                raise ValueError(
+                    "Disabling `pack` with a `refgroup` is not allowed. Shifting "
+                    "atoms probably outside of the primary cell withput packing them "
+                    "back may lead to sever problems during the analysis!"
+                )
+        self.module_has_save = callable(getattr(self.__class__, "save", None))
+        self.results = Results()
+        self._obs = Results()
+        self._staged: list = []
+
+    # ---- cell ------------------------------------------------------------------------------
+    @property
+    def box_lengths(self) -> np.ndarray:
+        """Lengths of the simulation cell vectors (float64)."""
+        return self._universe.dimensions[:3].astype(np.float64)
+
+    @property
+    def box_center(self) -> np.ndarray:
+        """Centre of the simulation cell."""
+        return self.box_lengths / 2
+
+    # ---- frame selection -------------------------------------------------------------------
+    def _setup_frames(self, trajectory, start=None, stop=None, step=None, frames=None) -> None:
+        n_total = len(trajectory)
+        if frames is not None:
+            sel = np.asarray(frames)
+            if sel.dtype == bool:
+                sel = np.nonzero(sel)[0]
+            sel = np.asarray(sel, dtype=np.int64)
+        else:
+            sel = np.arange(n_total, dtype=np.int64)[slice(start, stop, step)]
+        self.start, self.stop, self.step = start, stop, step
+        self.frames_selected = sel
+        self.n_frames = len(sel)
+        self.frames = np.zeros(self.n_frames, dtype=int)
+        self.times = np.zeros(self.n_frames)
+        self._sliced_trajectory = trajectory[sel]
+
+    def _local_frame_slots(self) -> np.ndarray:
+        """Slots (positions in the selected-frame list) this rank analyses."""
+        slots = np.arange(self.n_frames)
+        if parallel.frame_sharded():
+            if self.n_frames < parallel.world():
+                raise ValueError(
+                    f"{self.n_frames} frames cannot be sharded over {parallel.world()} ranks; "
+                    "use parallel.init(mode='qblocks') for single huge frames"
+                )
+            slots = slots[parallel.rank()::parallel.world()]
+        return slots
+
+    # ---- hooks ---------------------------------------------------------------------------------
+    def _prepare(self) -> None:
+        """Set things up before the frame loop."""
+
+    def _single_frame(self):
+        """Analyse the current frame: fill ``self._obs`` and return the correlation scalar."""
+        raise NotImplementedError("Only implemented in child classes")
+
+    def _single_frame_from_batch(self):
+        """``_single_frame`` of the batched classes: a batch of one frame through the device call."""
+        (obs, value), = self._compute_staged([self._stage_frame()])
+        self._obs.update(obs)
+        return value
+
+    _single_frame_from_batch._from_batch = True
+
+    def _stage_frame(self):
+        """Capture what the device needs from the current (already transformed) frame."""
+        return None
+
+    def _compute_staged(self, staged: list) -> list:
+        """Turn staged frames into ``[(obs dict, correlation scalar), ...]`` with one device call."""
+        raise NotImplementedError
+
+    def _conclude(self) -> None:
+        """Finalise ``results`` from ``sums / means / sems``."""
+
+    # ---- driver --------------------------------------------------------------------------------
+    def _call_prepare(self) -> None:
+        if self.refgroup is not None:
+            if not hasattr(self.refgroup, "masses") or np.sum(self.refgroup.masses) == 0:
+                logging.warning("No masses available in refgroup, falling back to center of geometry")
+                self.ref_weights = np.ones(self.refgroup.n_atoms)
+            else:
+                self.ref_weights = self.refgroup.masses
+        self._prepare()
+        if self.refgroup is not None:
+            logging.info(
+                f"Coordinates are relative to the center of mass of reference atomgroup "
+                f"{atomgroup_header(self.refgroup)}."
+            )
+        else:
+            logging.info("Coordinates are relative to the center of the simulation box.")
+        logging.info(f"Considered atomgroup {atomgroup_header(self.atomgroup)}.")
+        if hasattr(self, "n_bins"):
+            logging.info(f"Using {self.n_bins} bins.")
+        self.timeseries = np.zeros(self.n_frames)
+        self._n_local = 0
+        self._staged = []
+        for name in ("sums", "means", "sems"):
+            if hasattr(self, name):
+                delattr(self, name)
+        logging.info(f"Analysing {self.n_frames} trajectory frames.")
+        logging.debug(f"Module input: {get_module_input_str(self)}")
+
+    def _transform_frame(self, ts) -> None:
+        """unwrap -> refgroup centring -> wrap -> jitter, in the reference's order (base.py:436-451)."""
+        if self.unwrap:
+            self._universe.atoms.unwrap(compound=self.wrap_compound)
+        if self.refgroup is not None:
+            com_refgroup = center_cluster(self.refgroup, self.ref_weights)
+            self._universe.atoms.translate(self.box_center - com_refgroup)
+        if self.pack and self._universe.dimensions is not None and not (
+            self._device_pack and self.wrap_compound == "atoms"
+        ):
+            self._universe.atoms.wrap(compound=self.wrap_compound)
+        if self.jitter != 0.0:
+            ts.positions += np.random.random(size=(len(ts.positions), 3)) * self.jitter
+
+    def _begin_frame(self, ts, slot: int) -> None:
+        self._frame_index = slot
+        self._ts = ts
+        self.frames[slot] = ts.frame
+        self.times[slot] = ts.time
+        self._transform_frame(ts)
+
+    def _enqueue_frame(self, ts, slot: int) -> None:
+        self._begin_frame(ts, slot)
+        # batched unless a subclass replaced `_single_frame` with its own per-frame code
+        if getattr(type(self)._single_frame, "_from_batch", False):
+            self._staged.append((slot, self._stage_frame()))
+            if len(self._staged) >= max(1, self._batch_size):
+                self._flush_staged()
+        else:
+            self._obs = Results()
+            value = self._single_frame()
+            self._accumulate(slot, value)
+
+    def _flush_staged(self) -> None:
+        if not self._staged:
+            return
+        staged, self._staged = self._staged, []
+        out = self._compute_staged([s for _, s in staged])
+        for (slot, _), (obs, value) in zip(staged, out):
+            self._frame_index = slot
+            self._obs = Results(obs)
+            self._accumulate(slot, value)
+
+    def _call_single_frame(self, ts, current_frame_index) -> None:
+        """Serial entry point with the reference's signature (one frame, statistics updated)."""
+        self._begin_frame(ts, current_frame_index)
+        self._obs = Results()
+        value = self._single_frame()
+        self._accumulate(current_frame_index, value)
+
+    def _accumulate(self, slot: int, value) -> None:
+        """Running mean / standard error / sum of every observable (base.py:453-499)."""
+        self.timeseries[slot] = np.nan if value is None else value
+        self._n_local += 1
+        self._index = n = self._n_local
+        if n == 1 or not hasattr(self, "means"):
+            for key in self._obs:
+                if type(self._obs[key]) is list:
+                    self._obs[key] = np.array(self._obs[key])
+                if not isinstance(self._obs[key], _COMPATIBLE):
+                    raise TypeError(f"Obervable {key} has uncompatible type.")
+            self.sums = self._obs.copy()
+            self.means = self._obs.copy()
+            self.sems = Results({key: np.zeros(np.shape(self._obs[key])) for key in self._obs})
+        else:
+            for key in self._obs:
+                x = self._obs[key]
+                if type(x) is list:
+                    x = self._obs[key] = np.array(x)
+                old_mean = self.means[key]
+                old_var = self.sems[key] ** 2 * (n - 1)
+                self.means[key] = new_mean(old_mean, x, n)
+                self.sems[key] = np.sqrt(new_variance(old_var, old_mean, self.means[key], x, n) / n)
+                self.sums[key] = self.sums[key] + x
+        if self.concfreq and n % self.concfreq == 0 and slot > 0 and not parallel.frame_sharded():
+            self._conclude()
+            if self.module_has_save:
+                self.save()
+
+    def _merge_ranks(self) -> None:
+        """Frame-sharded runs: merge the per-rank statistics with one allreduce."""
+        if not parallel.frame_sharded():
+            return
+        mine = np.zeros(self.n_frames, dtype=bool)
+        mine[self._local_frame_slots()] = True
+        dtypes = {k: np.asarray(v).dtype for k, v in self.sums.items()}
+        extra = {
+            "timeseries": np.where(mine, self.timeseries, 0.0),
+            "frames": np.where(mine, self.frames, 0).astype(np.float64),
+            "times": np.where(mine, self.times, 0.0),
+        }
+        n, means, sems, sums, extra = parallel.merge_welford(self._n_local, self.means, self.sems, self.sums, extra)
+        for k in sums:  # integer observables (bin counts) stay integers: float64 holds them exactly
+            if np.issubdtype(dtypes[k], np.integer):
+                sums[k] = np.rint(sums[k]).astype(dtypes[k])
+        self.means, self.sems, self.sums = Results(means), Results(sems), Results(sums)
+        self.timeseries = extra["timeseries"]
+        self.frames = np.rint(extra["frames"]).astype(int)
+        self.times = extra["times"]
+        self._index = n
+
+    def _call_conclude(self) -> None:
+        with warnings.catch_warnings():
+            if parallel.rank() != 0:
+                warnings.simplefilter("ignore")
+            self.corrtime = correlation_analysis(self.timeseries)
+        self._conclude()
+        if self.concfreq and self.module_has_save and parallel.rank() == 0:
+            self.save()
+
+    def run(self, start=None, stop=None, step=None, frames=None, verbose=None, progressbar_kwargs=None):
+        """Iterate over the trajectory (same arguments as ``maicos.core.AnalysisBase.run``)."""
+        return _Runner._run(self, analysis_instances=(self,), start=start, stop=stop, step=step, frames=frames,
+                            verbose=verbose, progressbar_kwargs=progressbar_kwargs)
+
+    # ---- output --------------------------------------------------------------------------------
+    def savetxt(self, fname: str, X: np.ndarray, columns: list[str] | None = None) -> None:
+        """``numpy.savetxt`` with the self-describing header of MAICoS output files."""
+        fname = str(fname)
+        now = datetime.now().strftime("%a, %b %d %Y at %H:%M:%S ")
+        name = self.__class__.__name__
+        messages = []
+        for cls in self.__class__.mro()[-3::-1]:
+            if hasattr(cls, "OUTPUT") and cls.OUTPUT not in messages:
+                messages.append(cls.OUTPUT)
+        groups = f"  (grp) {atomgroup_header(self.atomgroup)}\n"
+        if getattr(self, "refgroup", None) is not None:
+            groups += f"  (ref) {atomgroup_header(self.refgroup)}\n"
+        header = (
+            f"This file was generated by {name} on {now}\n\n"
+            f"{name} is part of MAICoS v{__version__}\n\n"
+            f"Command line:    {get_cli_input()}\n"
+            f"Module input:    {get_module_input_str(self)}\n\n"
+            f"Statistics over {self._index} frames\n\n"
+            f"Considered atomgroups:\n"
+            f"{groups}\n"
+            + "\n".join(messages)
+            + "\n\n"
+        )
+        if columns is not None:
+            header += "|".join([f"{c:^23}" for c in columns])[3:]
+        if not fname.endswith(".dat"):
+            fname += ".dat"
+        np.savetxt(fname, X, header=header, fmt="% .14e ", encoding="utf8")
+
+
+class AnalysisCollection(_Runner):
+    """Run several analyses over the same trajectory in one loop (``base.py:602-718``).
+
+    Every instance sees the original, untransformed frame.
+    """
+
+    def __init__(self, *analysis_instances: AnalysisBase) -> None:
+        for a in analysis_instances:
+            if a._trajectory is not analysis_instances[0]._trajectory:
+                raise ValueError("`analysis_instances` do not have the same trajectory.")
+            if not isinstance(a, AnalysisBase):
+                raise TypeError(f"Analysis object {a} is not a child of `AnalysisBase`.")
+        self._analysis_instances = analysis_instances
+
+    def run(self, start=None, stop=None, step=None, frames=None, verbose=None, progressbar_kwargs=None):
+        return _Runner._run(self, analysis_instances=self._analysis_instances, start=start, stop=stop, step=step,
+                            frames=frames, verbose=verbose, progressbar_kwargs=progressbar_kwargs)
+
+    def save(self) -> None:
+        for a in self._analysis_instances:
+            if not a.module_has_save:
+                warnings.warn(f"`{a}` has no save() method. Analysis results of this instance can not be written.", stacklevel=2)
+            else:
+                a.save()
+
+
+class ProfileBase:
+    """Weighted profile + bin counts per frame (``base.py:722-857``).
+
+    The two numpy histogram passes of the reference (``base.py:815-818``) are one fused CUDA
+    pass here (``mb200_profile_hist``), batched over the staged frames.
+    """
+
+    #: set by modules whose weights depend on topology only (masses, charges, counts)
+    _static_weights = False
+
+    def __init__(self, atomgroup, grouping: str, bin_method: str, output: str, weighting_function: Callable,
+                 weighting_function_kwargs: None | dict, normalization: str) -> None:
+        self.atomgroup = atomgroup
+        self.grouping = grouping.lower()
+        self.bin_method = bin_method.lower()
+        self.output = output
+        self.normalization = normalization.lower()
+        kwargs = {} if weighting_function_kwargs is None else weighting_function_kwargs
+        self.weighting_function = lambda ag: weighting_function(ag, grouping, **kwargs)
+        if not hasattr(self, "results"):
+            self.results = Results()
+        if not hasattr(self, "_obs"):
+            self._obs = Results()
+
+    def _prepare(self):
+        normalizations = ["none", "volume", "number"]
+        if self.normalization not in normalizations:
+            raise ValueError(
+                f"Normalization '{self.normalization}' not supported. Use {', '.join(normalizations)}."
+            )
+        groupings = ["atoms", "segments", "residues", "molecules", "fragments"]
+        if self.grouping not in groupings:
+            raise ValueError(
+                f"'{self.grouping}' is not a valid option for grouping. Use {', '.join(groupings)}."
+            )
+        logging.info(f"Atoms grouped by {self.grouping}.")
+        if not hasattr(self, "unwrap"):
+            self.unwrap = True
+        self._cached_weights = None
+
+    # geometry classes provide these two
+    def _hist_geometry(self) -> dict:
+        """``dict(geometry, dim, edges, center, zrange)`` of the current frame for the kernel."""
+        raise NotImplementedError("Only implemented in child classes.")
+
+    def _compute_histogram(self, positions: np.ndarray, weights: np.ndarray | None = None) -> np.ndarray:
+        """Histogram of ``positions`` in the current frame's bins (CUDA), ``weights=None`` -> counts."""
+        from ..lib._hist import profile_hist
+
+        g = self._hist_geometry()
+        pos = np.ascontiguousarray(positions)
+        if pos.dtype not in (np.float32, np.float64):
+            pos = pos.astype(np.float64)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        hw, hc = profile_hist(g["geometry"], pos[None], g["dim"], None if w is None else w[None],
+                              g["edges"][None], None if g["center"] is None else g["center"][None],
+                              None if g["zrange"] is None else g["zrange"][None])
+        if weights is None:
+            return hc[0] if g["geometry"] != 1 else hc[0].astype(float)
+        return hw[0]
+
+    def _profile_positions(self) -> np.ndarray:
+        if self.grouping == "atoms":
+            return self.atomgroup.positions
+        return get_center(self.atomgroup, bin_method=self.bin_method, compound=self.grouping)
+
+    def _profile_weights(self) -> np.ndarray:
+        if self._static_weights:
+            if self._cached_weights is None:
+                self._cached_weights = np.ascontiguousarray(self.weighting_function(self.atomgroup), dtype=np.float64)
+            return self._cached_weights
+        return np.ascontiguousarray(self.weighting_function(self.atomgroup), dtype=np.float64)
+
+    def _stage_profile(self) -> dict:
+        """Positions, weights and bin geometry of the current frame (after the geometry base ran)."""
+        st = dict(self._hist_geometry())
+        st["positions"] = np.ascontiguousarray(self._profile_positions())
+        st["weights"] = self._profile_weights()
+        st["obs"] = dict(self._obs)
+        return st
+
+    def _compute_profiles(self, staged: list) -> list:
+        from ..lib._hist import profile_hist
+
+        g0 = staged[0]
+        pos = np.stack([s["positions"] for s in staged])
+        if self._static_weights:
+            w = g0["weights"][None]
+        else:
+            w = np.stack([s["weights"] for s in staged])
+        edges = np.stack([s["edges"] for s in staged])
+        center = None if g0["center"] is None else np.stack([s["center"] for s in staged])
+        zrange = None if g0["zrange"] is None else np.stack([s["zrange"] for s in staged])
+        hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], w, edges, center, zrange)
+        out = []
+        for f, s in enumerate(staged):
+            obs = s["obs"]
+            profile = hw[f]
+            obs["bincount"] = hc[f].astype(float) if g0["geometry"] == 1 else hc[f]
+            if self.normalization == "volume":
+                profile = profile / obs["bin_volume"]
+            obs["profile"] = profile
+            out.append(obs)
+        return out
+
+    def _conclude(self) -> None:
+        if self.normalization == "number":
+            with np.errstate(divide="ignore", invalid="ignore"):
+                self.results.profile = self.sums.profile / self.sums.bincount
+        else:
+            self.results.profile = self.means.profile
+        self.results.dprofile = self.sems.profile
+
+    def save(self) -> None:
+        """Write ``positions, profile, error`` columns to ``self.output``."""
+        AnalysisBase.savetxt(
+            self, self.output,
+            np.vstack((self.results.bin_pos, self.results.profile, self.results.dprofile)).T,
+            columns=["positions [Å]", "profile", "error"],
+        )

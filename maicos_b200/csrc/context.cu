@@ -80,3 +80,19 @@ extern "C" int mb200_ctx_set_timing(mb200_ctx *ctx, int enable) {
 }
 
 extern "C" int64_t mb200_ctx_launch_count(mb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int mb200_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(MB200_EINVAL, "null output pointer");
+    *out = nullptr;
+    if (mb200_device_count() <= 0) return fail(MB200_ENODEVICE, "no CUDA device visible: cannot pin host memory");
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        *out = nullptr;
+        return fail(MB200_ENOMEM, "cudaMallocHost(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return MB200_OK;
+}
+
+extern "C" void mb200_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}

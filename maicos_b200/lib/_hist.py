@@ -1,0 +1,56 @@
+"""Host wrapper of ``mb200_profile_hist``: fused weighted + count slab / shell histograms.
+
+Replaces the two ``np.histogram`` / ``np.histogram2d`` passes behind
+``ProfileBase._single_frame`` (``/root/reference/src/maicos/core/base.py:815-818``;
+``core/planar.py:235-243``, ``core/cylinder.py:229-243``, ``core/sphere.py:215-223``) for a batch
+of frames.  Bin semantics are numpy's (values outside ``[edges[0], edges[-1]]`` dropped, right edge
+inclusive, ``edges[i] <= x < edges[i+1]``), counts are exact.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _cabi
+
+PLANAR, CYLINDER, SPHERE = 0, 1, 2
+
+
+def profile_hist(geometry: int, positions: np.ndarray, dim: int, weights: np.ndarray | None, edges: np.ndarray,
+                 center: np.ndarray | None = None, zrange: np.ndarray | None = None, device: int | None = None):
+    """Histogram ``positions [F, n, 3]`` (float32 or float64) into ``edges [F, n_bins + 1]``.
+
+    ``weights``: ``None`` (counts only), ``[1, n]`` (same for all frames) or ``[F, n]``.
+    Returns ``(hist_w float64 [F, n_bins] or None, hist_c int64 [F, n_bins])``.
+    """
+    positions = np.ascontiguousarray(positions)
+    if positions.ndim != 3 or positions.shape[2] != 3:
+        raise ValueError("positions must have shape (n_frames, n, 3)")
+    if positions.dtype not in (np.float32, np.float64):
+        raise ValueError("positions must be float32 or float64")
+    F, n = positions.shape[0], positions.shape[1]
+    edges = np.ascontiguousarray(edges, dtype=np.float64)
+    if edges.shape[0] != F:
+        raise ValueError("edges must have one row per frame")
+    n_bins = edges.shape[1] - 1
+    per_frame = 0
+    if weights is not None:
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        if weights.shape not in ((1, n), (F, n)):
+            raise ValueError(f"weights must have shape (1, {n}) or ({F}, {n})")
+        per_frame = int(weights.shape[0] == F and F > 1)
+    if center is not None:
+        center = np.ascontiguousarray(center, dtype=np.float64)
+    if zrange is not None:
+        zrange = np.ascontiguousarray(zrange, dtype=np.float64)
+    hist_c = np.zeros((F, n_bins), dtype=np.int64)
+    hist_w = np.zeros((F, n_bins), dtype=np.float64) if weights is not None else None
+    ctx = _cabi.context(device)
+    _cabi.check(
+        _cabi.load().mb200_profile_hist(
+            ctx.handle, int(geometry), _cabi.ptr(positions), int(positions.dtype == np.float32), 0, F, n, int(dim),
+            _cabi.ptr(weights), per_frame, 0, _cabi.ptr(edges), n_bins, _cabi.ptr(center), _cabi.ptr(zrange),
+            _cabi.ptr(hist_w), _cabi.ptr(hist_c),
+        )
+    )
+    return hist_w, hist_c

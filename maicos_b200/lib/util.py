@@ -1,0 +1,127 @@
+"""Small host utilities next to the hot path.
+
+Counterparts in the reference (``/root/reference/src/maicos/lib/util.py``): ``get_center``
+(642-680), ``unit_vectors_planar`` (684-706), ``correlation_analysis`` (309-355), the output
+header helpers ``get_cli_input`` / ``atomgroup_header`` / ``get_module_input_str`` (391-430,
+828-869).  The docstring templating and banner plumbing of the reference are out of scope.
+"""
+
+from __future__ import annotations
+
+import inspect
+import logging
+import sys
+import warnings
+from pathlib import Path
+
+import numpy as np
+
+from .math import correlation_time
+
+
+def get_center(atomgroup, bin_method: str, compound: str) -> np.ndarray:
+    """Per-compound centre: ``cog`` (geometry), ``com`` (mass) or ``coc`` (absolute charge)."""
+    if bin_method == "cog":
+        weights = None
+    elif bin_method == "com":
+        weights = atomgroup.masses
+    elif bin_method == "coc":
+        weights = np.abs(atomgroup.charges)
+    else:
+        raise ValueError(f"'{bin_method}' is an unknown binning method. Use 'cog', 'com' or 'coc'.")
+    return atomgroup.center(weights=weights, compound=compound)
+
+
+def unit_vectors_planar(atomgroup, grouping: str, pdim: int) -> np.ndarray:  # noqa: ARG001
+    """Cartesian unit vector along ``pdim``."""
+    e = np.zeros(3)
+    e[pdim] = 1.0
+    return e
+
+
+def unit_vectors_cylinder(atomgroup, grouping: str, bin_method: str, dim: int, pdim: str) -> np.ndarray:
+    """Cartesian unit vectors of a cylinder frame with axis ``dim``: ``pdim`` = ``"z"`` or ``"r"``."""
+    if pdim == "z":
+        return unit_vectors_planar(atomgroup, grouping, dim)
+    if pdim != "r":
+        raise ValueError(f"'{pdim}' is an unknown direction for the projection. Use 'r' or 'z'.")
+    rel = get_center(atomgroup=atomgroup, bin_method=bin_method, compound=grouping)
+    rel -= atomgroup.universe.dimensions[:3] / 2
+    rel[:, dim] = 0  # the radial direction has no axial component
+    rel /= np.linalg.norm(rel, axis=1)[:, np.newaxis]
+    return rel
+
+
+def unit_vectors_sphere(atomgroup, grouping: str, bin_method: str) -> np.ndarray:
+    """Radial Cartesian unit vectors about the box centre, one per compound."""
+    rel = get_center(atomgroup=atomgroup, bin_method=bin_method, compound=grouping)
+    rel -= atomgroup.universe.dimensions[:3] / 2
+    rel /= np.linalg.norm(rel, axis=1)[:, np.newaxis]
+    return rel
+
+
+def correlation_analysis(timeseries: np.ndarray) -> float:
+    """Correlation time of the per-frame scalar; warns when frames are visibly correlated."""
+    if np.any(np.isnan(timeseries)):
+        return -1
+    if len(timeseries) <= 4:
+        warnings.warn(
+            "Your trajectory is too short to estimate a correlation time. Use the "
+            "calculated error estimates with caution.",
+            stacklevel=2,
+        )
+        return -1
+    corrtime = correlation_time(timeseries)
+    if corrtime == -1:
+        warnings.warn(
+            "Your trajectory does not provide sufficient statistics to estimate a "
+            "correlation time. Use the calculated error estimates with caution.",
+            stacklevel=2,
+        )
+    if corrtime > 0.5:
+        warnings.warn(
+            "Your data seems to be correlated with a correlation time which is "
+            f"{corrtime + 1:.2f} times larger than your step size. Consider increasing "
+            f"your step size by a factor of {int(np.ceil(2 * corrtime + 1)):d} to get "
+            "a reasonable error estimate.",
+            stacklevel=2,
+        )
+    return corrtime
+
+
+def get_cli_input() -> str:
+    """The command line, with arguments containing blanks re-quoted."""
+    args = [f'"{a}"' if " " in a else a for a in sys.argv[1:]]
+    return "{} {}".format(Path(sys.argv[0]).name, " ".join(args))
+
+
+def atomgroup_header(ag) -> str:
+    """``"<type> <count> & ..."`` summary of an atom group for output headers."""
+    if not hasattr(ag, "types"):
+        logging.warning("AtomGroup does not contain atom types. Not writing AtomGroup information to output.")
+        return f"{len(ag.atoms)} unkown particles"
+    names, counts = np.unique(ag.types, return_counts=True)
+    return " & ".join(f"{n} {c}" for n, c in zip(names, counts))
+
+
+def get_module_input_str(obj) -> str:
+    """``Module(arg=..., ...).run(...)`` string of the call that produced an output file."""
+    name = obj.__class__.__name__
+    if not (hasattr(obj, "_locals") and hasattr(obj, "_run_locals")):
+        return f"{name}(*args).run(*args)"
+
+    def fmt(param, value):
+        if type(value) is str:
+            return f"{param}='{value}'"
+        if param == "atomgroup" or (param == "refgroup" and value is not None):
+            return f"{param}=<AtomGroup>"
+        return f"{param}={value}"
+
+    init_args = [p for p in inspect.getfullargspec(obj.__class__).args if p != "self"]
+    run_args = [p for p in inspect.getfullargspec(obj.run).args if p != "self"]
+    init_sig = ", ".join(fmt(p, obj._locals[p]) for p in init_args)
+    run_sig = ", ".join(
+        f"{p}='{obj._run_locals[p]}'" if type(obj._run_locals[p]) is str else f"{p}={obj._run_locals[p]}"
+        for p in run_args
+    )
+    return f"{name}({init_sig}).run({run_sig})"

@@ -1,0 +1,103 @@
+"""Structure factor of the dipolar orientation field: ``DiporderStructureFactor``.
+
+Drop-in for ``maicos.DiporderStructureFactor``
+(``/root/reference/src/maicos/modules/diporderstructurefactor.py``): per frame, the centres of the
+compounds carry the three Cartesian components of their unit dipole as weights; the structure
+factor of each component is binned by ``|q|`` and averaged *per frame* over the q-vectors of a bin,
+the three components are summed and divided by the number of compounds (93-155).  The reference
+calls the kernel three times on identical positions; ``mb200_dipsf_frames`` shares the y / z phase
+tables between the three weight sets.
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from .. import _cabi, parallel
+from ..core.base import AnalysisBase
+from ..lib.util import get_center
+
+
+class DiporderStructureFactor(AnalysisBase):
+    r"""Structure factor :math:`S(q)` of :math:`\hat\mu`-weighted compound centres.
+
+    Parameters are those of the reference: ``atomgroup, bin_method="com", grouping="molecules",
+    refgroup=None, unwrap=True, pack=True, jitter=0.0, concfreq=0, qmin=0, qmax=6, dq=0.01,
+    output="sq.dat"``.  Results: ``results.scattering_vectors``, ``results.structure_factors``.
+    """
+
+    _batch_size = 16
+
+    def __init__(self, atomgroup, bin_method: str = "com", grouping: str = "molecules", refgroup=None,
+                 unwrap: bool = True, pack: bool = True, jitter: float = 0.0, concfreq: int = 0, qmin: float = 0,
+                 qmax: float = 6, dq: float = 0.01, output: str = "sq.dat") -> None:
+        self._locals = locals()
+        super().__init__(atomgroup, unwrap=unwrap, pack=pack, refgroup=refgroup, jitter=jitter,
+                         wrap_compound=grouping, concfreq=concfreq)
+        self.bin_method = str(bin_method).lower()
+        self.qmin = qmin
+        self.qmax = qmax
+        self.dq = dq
+        self.output = output
+
+    def _prepare(self) -> None:
+        logging.info("Analysis of the structure factor of dipoles.")
+        self.n_bins = int(np.ceil((self.qmax - self.qmin) / self.dq))
+
+    def _stage_frame(self):
+        box = np.double(np.array(self._ts.dimensions[:3], dtype=np.float32))
+        positions = np.ascontiguousarray(
+            get_center(atomgroup=self.atomgroup, bin_method=self.bin_method, compound=self.wrap_compound),
+            dtype=np.float64,
+        )
+        # diporder_weights(order_parameter="cos_theta") with the unit vector e_pdim is the pdim-th
+        # component of mu / |mu| (weights.py:165-169); the dipoles are computed once, not three times
+        dipoles = self.atomgroup.dipole_vector(compound=self.wrap_compound)
+        unit = dipoles / np.linalg.norm(dipoles, axis=1)[:, np.newaxis]
+        return positions, np.ascontiguousarray(unit.T, dtype=np.float64), box
+
+    def _compute_staged(self, staged: list) -> list:
+        F = len(staged)
+        n = staged[0][0].shape[0]
+        pos = np.stack([s[0] for s in staged])
+        w = np.stack([s[1] for s in staged])
+        boxes = np.stack([s[2] for s in staged])
+        sb = np.zeros((F, 3, self.n_bins))
+        cb = np.zeros((F, 3, self.n_bins), dtype=np.int64)
+        block, n_blocks = parallel.q_block()
+        ctx = _cabi.context()
+        _cabi.check(
+            _cabi.load().mb200_dipsf_frames(
+                ctx.handle, _cabi.ptr(pos), _cabi.ptr(w), F, n, _cabi.ptr(boxes), float(self.qmin), float(self.qmax),
+                self.n_bins, block, n_blocks, _cabi.ptr(sb), _cabi.ptr(cb),
+            )
+        )
+        if parallel.q_sharded():
+            packed = np.concatenate([sb.reshape(-1), cb.reshape(-1).astype(np.float64)])
+            parallel.allreduce_sum(packed)
+            sb = packed[:sb.size].reshape(sb.shape)
+            cb = np.rint(packed[sb.size:]).astype(np.int64).reshape(sb.shape)
+        out = []
+        for f in range(F):
+            total = np.zeros(self.n_bins)
+            for pdim in range(3):
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    total += np.nan_to_num(sb[f, pdim] / cb[f, pdim])
+            total /= n
+            out.append(({"structure_factors": total}, total[-1]))
+        return out
+
+    _single_frame = AnalysisBase._single_frame_from_batch
+
+    def _conclude(self) -> None:
+        q = np.arange(self.qmin, self.qmax, self.dq) + 0.5 * self.dq
+        keep = np.where(self.means.structure_factors != 0)[0]
+        self.results.scattering_vectors = q[keep]
+        self.results.structure_factors = self.means.structure_factors[keep]
+
+    def save(self) -> None:
+        """Write q and S(q) to ``self.output``."""
+        self.savetxt(self.output, np.vstack([self.results.scattering_vectors, self.results.structure_factors]).T,
+                     columns=["q (1/Å)", "S(q) (arb. units)"])

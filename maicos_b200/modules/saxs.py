@@ -1,0 +1,212 @@
+"""Small-angle X-ray scattering: ``Saxs`` with the reference's API on the CUDA structure-factor path.
+
+Drop-in for ``maicos.Saxs`` (``/root/reference/src/maicos/modules/saxs.py``): same constructor
+(99-114), ``results`` layout (``scattering_vectors, structure_factors, scattering_intensities,
+dstructure_factors, dscattering_intensities`` and ``miller_indices`` for ``bin_spectrum=False``;
+292-300) and output file (303-350).  The reference's semantics are kept, quirks included:
+one structure factor *per element group* weighted by ``f_element(q)^2`` (no cross terms, 158-164,
+207-210), ``bincount`` taken from the last group (233), errors not divided by the bin count
+(252-253).
+
+The frame body (175-241) -- wrap to ``[-L/2, L/2]``, S(q) on the reciprocal lattice, form factors,
+three ``|q|`` histograms -- is one fused device call per batch of frames: ``mb200_saxs_frames``.
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from .. import _cabi, parallel
+from ..core.base import AnalysisBase
+from ..lib import tables
+from ..lib.math import atomic_form_factor, structure_factor
+
+
+class Saxs(AnalysisBase):
+    r"""Small angle X-ray scattering intensities :math:`I(q) = \sum_e f_e(q)^2 S_e(q)`.
+
+    Parameters
+    ----------
+    atomgroup : AtomGroup
+        atoms to analyse; needs ``elements``.
+    unwrap, pack, refgroup, jitter, concfreq
+        see :class:`maicos_b200.core.AnalysisBase`.
+    bin_spectrum : bool
+        bin by :math:`|q|` (default) or keep every Miller vector (needs a constant box).
+    qmin, qmax, dq : float
+        range and bin width of :math:`|q|` in 1/Å.
+    thetamin, thetamax : float
+        accepted angle between :math:`q` and the z axis in degrees.
+    output : str
+        output file name.
+
+    Attributes
+    ----------
+    results.scattering_vectors, results.structure_factors, results.scattering_intensities,
+    results.dstructure_factors, results.dscattering_intensities, results.miller_indices
+    """
+
+    _batch_size = 32
+    _device_pack = True
+
+    def __init__(self, atomgroup, unwrap: bool = False, pack: bool = True, refgroup=None, jitter: float = 0.0,
+                 concfreq: int = 0, bin_spectrum: bool = True, qmin: float = 0, qmax: float = 6, dq: float = 0.1,
+                 thetamin: float = 0, thetamax: float = 180, output: str = "sq.dat") -> None:
+        self._locals = locals()
+        super().__init__(atomgroup, unwrap=unwrap, pack=pack, refgroup=refgroup, jitter=jitter, concfreq=concfreq,
+                         wrap_compound="atoms")
+        self.bin_spectrum = bin_spectrum
+        self.qmin = qmin
+        self.qmax = qmax
+        self.dq = dq
+        self.thetamin = thetamin
+        self.thetamax = thetamax
+        self.output = output
+
+    def _prepare(self) -> None:
+        logging.info("Analysis of small angle X-ray scattering intensities (SAXS).")
+        self.thetamin = min(self.thetamin, self.thetamax)
+        self.thetamax = max(self.thetamin, self.thetamax)
+        if self.thetamin < 0 or self.thetamin > 180:
+            raise ValueError(f"thetamin ({self.thetamin}°) has to between 0 and 180°.")
+        if self.thetamax < 0 or self.thetamax > 180:
+            raise ValueError(f"thetamax ({self.thetamax}°) has to between 0 and 180°.")
+        if self.thetamin > self.thetamax:
+            raise ValueError(f"thetamin ({self.thetamin}°) larger than thetamax ({self.thetamax}°).")
+        self.thetamin *= np.pi / 180
+        self.thetamax *= np.pi / 180
+
+        # one group per element; weights are ones, form factors are applied after the kernel
+        elements = np.asarray(self.atomgroup.elements)
+        self.groups, self.weights, self.elements, self._group_index = [], [], [], []
+        for element in np.unique(elements):
+            idx = np.nonzero(elements == element)[0].astype(np.int32)
+            self._group_index.append(idx)
+            self.groups.append(self.atomgroup[idx])
+            self.weights.append(np.ones(len(idx)))
+            self.elements.append(element)
+        self._group_ptr = np.concatenate([[0], np.cumsum([len(i) for i in self._group_index])]).astype(np.int64)
+        self._group_flat = np.ascontiguousarray(np.concatenate(self._group_index), dtype=np.int32)
+        self._cm = np.ascontiguousarray(np.stack([tables.cm_packed(str(el)) for el in self.elements]))
+
+        if self.bin_spectrum:
+            self.n_bins = int(np.ceil((self.qmax - self.qmin) / self.dq))
+        else:
+            self.box = np.asarray(self._universe.dimensions[:3])
+            self.scattering_vector_factors = 2 * np.pi / self.box
+            self.max_n = np.ceil(self.qmax / self.scattering_vector_factors).astype(int)
+
+    # ---- frame body ------------------------------------------------------------------------
+    def _stage_frame(self):
+        box = np.array(self._ts.dimensions[:3], dtype=np.float32)
+        if not self.bin_spectrum and not np.all(box == self.box):
+            raise ValueError(
+                f"Dimensions in frame {self._frame_index} are different from "
+                "initial dimenions. Can not use `bin_spectrum=False`."
+            )
+        return np.ascontiguousarray(self.atomgroup.positions, dtype=np.float32), box
+
+    def _device_packs(self) -> bool:
+        return bool(self.pack and self._universe.dimensions is not None)
+
+    def _compute_staged(self, staged: list) -> list:
+        if not self.bin_spectrum:
+            return [self._unbinned_frame(pos, box) for pos, box in staged]
+        F, n, G = len(staged), self.atomgroup.n_atoms, len(self.groups)
+        pos = _cabi.pinned_empty((F, n, 3), np.float32, slot="saxs_pos")
+        boxes = np.empty((F, 3), dtype=np.float32)
+        for f, (p, b) in enumerate(staged):
+            pos[f] = p
+            boxes[f] = b
+        s = np.zeros((F, G, self.n_bins))
+        i = np.zeros((F, G, self.n_bins))
+        c = np.zeros((F, G, self.n_bins), dtype=np.int64)
+        block, n_blocks = parallel.q_block()
+        ctx = _cabi.context()
+        _cabi.check(
+            _cabi.load().mb200_saxs_frames(
+                ctx.handle, _cabi.ptr(pos), 0, F, n, _cabi.ptr(boxes), _cabi.ptr(self._group_flat),
+                _cabi.ptr(self._group_ptr), G, _cabi.ptr(self._cm), float(self.qmin), float(self.qmax),
+                float(self.thetamin), float(self.thetamax), self.n_bins, int(self._device_packs()), block, n_blocks,
+                _cabi.ptr(s), _cabi.ptr(i), _cabi.ptr(c),
+            )
+        )
+        if parallel.q_sharded():
+            packed = np.concatenate([s.reshape(-1), i.reshape(-1), c.reshape(-1).astype(np.float64)])
+            parallel.allreduce_sum(packed)
+            m = s.size
+            s = packed[:m].reshape(s.shape)
+            i = packed[m:2 * m].reshape(s.shape)
+            c = np.rint(packed[2 * m:]).astype(np.int64).reshape(s.shape)
+        out = []
+        for f in range(F):
+            obs = {
+                "structure_factors": s[f].sum(axis=0) if G > 1 else s[f, 0].copy(),
+                "scattering_intensities": i[f].sum(axis=0) if G > 1 else i[f, 0].copy(),
+                "bincount": c[f, G - 1].copy(),
+            }
+            out.append((obs, s[f, G - 1, -1]))
+        return out
+
+    def _unbinned_frame(self, positions: np.ndarray, box: np.ndarray):
+        """``bin_spectrum=False``: raw cubes summed over element groups (saxs.py:188-189, 238-239)."""
+        if self._device_packs():
+            positions = positions - np.floor(positions / box) * box
+        sf = np.zeros(self.max_n)
+        si = np.zeros(self.max_n)
+        s_last = None
+        for idx, element in zip(self._group_index, self.elements):
+            p = positions[idx]
+            p = p - box * np.round(p / box)
+            q, s_last = structure_factor(np.double(p), np.double(box), self.qmin, self.qmax, self.thetamin,
+                                         self.thetamax, np.ones(len(idx)))
+            sf += s_last
+            si += atomic_form_factor(q, str(element)) ** 2 * s_last
+        return {"structure_factors": sf, "scattering_intensities": si}, s_last.flatten()[-1]
+
+    _single_frame = AnalysisBase._single_frame_from_batch
+
+    def _conclude(self) -> None:
+        if self.bin_spectrum:
+            q = np.arange(self.qmin, self.qmax, self.dq) + 0.5 * self.dq
+            with np.errstate(divide="ignore", invalid="ignore"):
+                sf = self.sums.structure_factors / self.sums.bincount
+                si = self.sums.scattering_intensities / self.sums.bincount
+            dsf = self.sems.structure_factors
+            dsi = self.sems.scattering_intensities
+        else:
+            miller = np.array(list(np.ndindex(tuple(self.max_n))))
+            q = np.linalg.norm(miller * self.scattering_vector_factors[np.newaxis, :], axis=1)
+            order = np.argsort(q)
+            q, miller = q[order], miller[order]
+            sf = self.means.structure_factors.flatten()[order]
+            si = self.means.scattering_intensities.flatten()[order]
+        keep = np.invert(np.isnan(sf))
+        n = self.atomgroup.n_atoms
+        self.results.scattering_vectors = q[keep]
+        self.results.structure_factors = sf[keep] / n
+        self.results.scattering_intensities = si[keep] / n
+        if self.bin_spectrum:
+            self.results.dstructure_factors = dsf[keep] / n
+            self.results.dscattering_intensities = dsi[keep] / n
+        else:
+            self.results.miller_indices = miller[keep]
+
+    def save(self) -> None:
+        """Write q, S(q), I(q) (and errors or Miller indices) to ``self.output``."""
+        r = self.results
+        if self.bin_spectrum:
+            self.savetxt(
+                self.output,
+                np.vstack([r.scattering_vectors, r.structure_factors, r.scattering_intensities,
+                           r.dstructure_factors, r.dscattering_intensities]).T,
+                columns=["q (1/Å)", "S(q) (arb. units)", "I(q) (arb. units)", "ΔS(q)", "ΔI(q)"],
+            )
+        else:
+            out = np.hstack([r.scattering_vectors[:, np.newaxis], r.miller_indices,
+                             r.structure_factors[:, np.newaxis], r.scattering_intensities[:, np.newaxis]])
+            boxinfo = "box_x = {:.3f} Å, box_y = {:.3f} Å, box_z = {:.3f} Å\n".format(*self.box)
+            self.savetxt(self.output, out, columns=[boxinfo, "q (1/Å)", "q_i", "q_j", "q_k", "S(q) (arb. units)",
+                                                   "I(q) (arb. units)"])

@@ -1,0 +1,31 @@
+"""Worker of tests/test_distributed_cpu.py: frame-sharded toy analysis under torchrun + gloo."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+
+from maicos_b200 import parallel  # noqa: E402
+from test_host_logic import Series, small_universe  # noqa: E402
+
+
+def main(out):
+    parallel.init(mode="frames", backend="gloo")
+    u = small_universe(n_frames=23)
+    ana = Series(u.atoms).run(start=1, step=2)
+    # q-block style reduction of a per-frame partial sum
+    buf = np.full(7, float(parallel.rank() + 1))
+    parallel.allreduce_sum(buf)
+    if parallel.rank() == 0:
+        np.savez(out, mean=ana.means.observable, sem=ana.sems.observable, total=ana.sums.observable,
+                 vec_mean=ana.means.vec, vec_sem=ana.sems.vec, count=ana.sums.count, frames=ana.frames,
+                 times=ana.times, timeseries=ana.timeseries, index=ana._index, result=ana.results.mean,
+                 corrtime=ana.corrtime, buf=buf, world=parallel.world())
+    parallel.barrier()
+    parallel.shutdown()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

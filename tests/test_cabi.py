@@ -1,0 +1,74 @@
+"""The C-ABI library: loads, exports every symbol the header declares, fails loudly without a GPU."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from maicos_b200 import _cabi
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def header_symbols():
+    text = (ROOT / "include" / "maicos_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exists_and_loads():
+    assert _cabi.library_path().exists(), "build it: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = _cabi.load()
+    assert lib.mb200_abi_version() >= 1
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = ctypes.CDLL(str(_cabi.library_path()))
+    names = header_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/maicos_b200.h but not exported"
+        assert name in _cabi.SIGNATURES, f"{name} has no ctypes signature in maicos_b200/_cabi.py"
+    assert sorted(_cabi.SIGNATURES) == names
+
+
+def test_maxn_host_helper():
+    """mb200_sfactor_maxn is pure host code: _cmath.pyx:93-96 including the float32 cast."""
+    from maicos_b200.lib.math import sfactor_maxn
+    from oracle import kernel
+
+    rng = np.random.default_rng(5)
+    for _ in range(500):
+        dims = rng.uniform(5, 400, 3)
+        qmax = rng.uniform(0.05, 6)
+        assert tuple(sfactor_maxn(dims, qmax)) == tuple(kernel.port_maxn(dims, qmax))
+
+
+def test_no_cpu_fallback_without_device():
+    """No GPU -> every compute entry point raises; there is nothing to fall back to."""
+    if _cabi.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    from maicos_b200.lib.math import structure_factor
+    from maicos_b200.lib._hist import profile_hist
+
+    with pytest.raises(_cabi.MB200Error, match="no CUDA device"):
+        structure_factor(np.zeros((4, 3)), np.array([10.0, 10, 10]), 0, 2, 0, np.pi, np.ones(4))
+    with pytest.raises(_cabi.MB200Error, match="no CUDA device"):
+        profile_hist(0, np.zeros((1, 4, 3), np.float32), 2, None, np.linspace(0, 1, 5)[None])
+    # NULL context is rejected by the library itself as well
+    rc = _cabi.load().mb200_ctx_synchronize(None)
+    assert rc == -2 and b"no CUDA context" in _cabi.load().mb200_last_error()
+
+
+def test_reference_error_conventions():
+    """Probed on the compiled reference: dtype mismatch -> ValueError, bad shapes -> AssertionError."""
+    from maicos_b200.lib.math import compute_structure_factor, structure_factor
+
+    assert compute_structure_factor is structure_factor  # CHANGELOG.rst:38-40
+    with pytest.raises(ValueError, match="Buffer dtype mismatch, expected 'double' but got 'float'"):
+        structure_factor(np.zeros((4, 3), np.float32), np.array([10.0, 10, 10]), 0, 2, 0, np.pi, np.ones(4))
+    with pytest.raises(AssertionError):
+        structure_factor(np.zeros((4, 2)), np.array([10.0, 10, 10]), 0, 2, 0, np.pi, np.ones(4))
+    with pytest.raises(AssertionError):
+        structure_factor(np.zeros((4, 3)), np.array([10.0, 10, 10]), 0, 2, 0, np.pi, np.ones(5))

@@ -1,0 +1,230 @@
+"""Parity of the CUDA slab / shell histograms (path 2) against numpy: counts bit-exact."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+import maicos_b200 as mb
+from maicos_b200.core import ProfileCylinderBase, ProfilePlanarBase, ProfileSphereBase
+from maicos_b200.lib._hist import profile_hist
+from maicos_b200.lib.weights import density_weights
+from maicos_b200.mdshim import MemoryTrajectory, Universe
+from oracle import restatement
+
+pytestmark = pytest.mark.gpu
+WTOL = 1e-12  # weighted sums: float64 atomics in arbitrary order
+
+
+def frames(F, n, lo, hi, dtype, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(lo, hi, (F, n, 3)).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n_bins", [1, 7, 2153, 5000])
+def test_planar_vs_numpy(dtype, n_bins):
+    F, n = 3, 50_000
+    pos = frames(F, n, -5, 220, dtype)
+    pos[0, :50, 2] = 0.0
+    pos[0, 50:100, 2] = dtype(215.3)  # exactly on the inclusive right edge of frame 0
+    w = np.random.default_rng(1).uniform(-1, 16, (F, n))
+    edges = np.stack([np.linspace(np.float64(0), np.float64(215.3) * (1 + 1e-3 * f), n_bins + 1) for f in range(F)])
+    pos[1, :n_bins + 1, 2] = edges[1].astype(dtype)  # values sitting on bin edges
+    for weights in (None, w[:1], w):
+        hw, hc = profile_hist(0, pos, 2, weights, edges)
+        for f in range(F):
+            wf = None if weights is None else weights[min(f, len(weights) - 1)]
+            assert_array_equal(hc[f], restatement.hist_planar(pos[f], None, 2, n_bins, edges[f, 0], edges[f, -1]))
+            if weights is not None:
+                ref = restatement.hist_planar(pos[f], wf, 2, n_bins, edges[f, 0], edges[f, -1])
+                assert_allclose(hw[f], ref, rtol=WTOL, atol=WTOL * np.abs(wf).sum())
+
+
+@pytest.mark.parametrize("dim", [0, 1, 2])
+def test_cylinder_and_sphere_vs_numpy(dim):
+    F, n, nb = 2, 40_000, 333
+    L = np.array([60.0, 70.0, 80.0])
+    pos = frames(F, n, -3, 83, np.float32, seed=dim)
+    w = np.random.default_rng(2).normal(size=(F, n))
+    center = np.tile(L / 2, (F, 1))
+    zr = np.array([[5.0, 55.0], [0.0, 60.0]])
+    er = np.stack([np.linspace(np.float64(0.5), np.float64(29.0 + f), nb + 1) for f in range(F)])
+    hw, hc = profile_hist(1, pos, dim, w, er, center, zr)
+    for f in range(F):
+        p = pos[f]
+        rc = restatement.hist_cylinder(p, None, dim, nb, er[f, 0], er[f, -1], zr[f, 0], zr[f, 1], center[f])
+        rw = restatement.hist_cylinder(p, w[f], dim, nb, er[f, 0], er[f, -1], zr[f, 0], zr[f, 1], center[f])
+        assert_array_equal(hc[f], rc.astype(np.int64))
+        assert_allclose(hw[f], rw, rtol=WTOL, atol=WTOL * np.abs(w[f]).sum())
+    hw, hc = profile_hist(2, pos, 0, w, er, center, None)
+    for f in range(F):
+        assert_array_equal(hc[f], restatement.hist_sphere(pos[f], None, nb, er[f, 0], er[f, -1], center[f]))
+        assert_allclose(hw[f], restatement.hist_sphere(pos[f], w[f], nb, er[f, 0], er[f, -1], center[f]),
+                        rtol=WTOL, atol=WTOL * np.abs(w[f]).sum())
+
+
+def test_empty_and_ragged_inputs():
+    e = np.linspace(0.0, 1.0, 11)[None]
+    hw, hc = profile_hist(0, np.zeros((1, 0, 3), np.float32), 2, np.zeros((1, 0)), e)
+    assert not hc.any() and not hw.any()
+    pos = np.full((1, 5, 3), np.nan, np.float32)  # NaNs are dropped like numpy's range test does
+    pos[0, 0] = 0.55
+    hw, hc = profile_hist(0, pos, 2, None, e)
+    assert hc.sum() == 1 and hc[0, 5] == 1 and hw is None
+
+
+def test_full_size_properties():
+    """Config-4 size (1M atoms, 2154 bins): counts sum to the in-range atoms, linear in the weights."""
+    n, nb = 1_000_000, 2154
+    pos = frames(2, n, -1.0, 216.0, np.float32, seed=9)
+    w = np.random.default_rng(3).uniform(1, 16, (1, n))
+    e = np.tile(np.linspace(np.float64(0), np.float64(215.37), nb + 1), (2, 1))
+    hw, hc = profile_hist(0, pos, 2, w, e)
+    for f in range(2):
+        z = pos[f, :, 2].astype(np.float64)
+        inside = (z >= 0) & (z <= 215.37)
+        assert hc[f].sum() == inside.sum()
+        assert_allclose(hw[f].sum(), w[0][inside].sum(), rtol=1e-12)
+        assert_array_equal(hc[f], np.histogram(z, nb, (0, 215.37))[0])
+    hw2, _ = profile_hist(0, pos, 2, 3.0 * w, e)
+    assert_allclose(hw2, 3.0 * hw, rtol=1e-12)
+
+
+def uniform_universe(n_atoms=125, n_frames=400, seed=1634123):
+    """tests/core/test_planar.py:357-393 (fewer frames)."""
+    coords = np.random.default_rng(seed).random((n_frames, n_atoms, 3)).astype(np.float32)
+    return Universe(n_atoms, MemoryTrajectory(coords, np.array([2, 2, 2, 90, 90, 90], np.float32)),
+                    masses=np.ones(n_atoms), charges=np.ones(n_atoms), resindices=np.arange(n_atoms),
+                    segindices=np.arange(n_atoms))
+
+
+def number_weights(ag, grouping, scale=1):
+    return scale * density_weights(ag, grouping, dens="number")
+
+
+PLANAR = dict(weighting_function=number_weights, weighting_function_kwargs=None, normalization="number", dim=2,
+              zmin=None, zmax=None, bin_width=0.1, refgroup=None, sym=False, sym_odd=False, grouping="atoms",
+              unwrap=False, pack=True, bin_method="com", concfreq=0, output="profile.dat", jitter=False)
+
+
+@pytest.mark.parametrize("normalization", ["volume", "number", "None"])
+def test_planar_profile_known_answers(normalization):
+    """tests/core/test_planar.py:451-473."""
+    u = uniform_universe()
+    p = ProfilePlanarBase(atomgroup=u.atoms, **{**PLANAR, "normalization": normalization}).run()
+    vals = {"volume": 125 / (8 / 2), "number": 1, "None": 125 * p.n_bins / 2 / 100}[normalization]
+    desired = np.zeros(p.n_bins)
+    desired[:10] = vals
+    if normalization == "number":
+        desired[10:] = np.nan
+    assert_allclose(p.results.profile.flatten(), desired, rtol=3e-2)
+    assert p.results.profile.dtype == np.float64
+
+
+def test_compute_histogram_hooks():
+    """tests/core/test_planar.py:509-528, test_cylinder.py:529-547, test_sphere.py:531-549."""
+    u = uniform_universe(n_frames=2)
+    p = ProfilePlanarBase(atomgroup=u.atoms, **PLANAR)
+    p._setup_frames(u.trajectory)
+    p._prepare()
+    pts = np.linspace(3 * [p.zmin], 3 * [p.zmax], p.n_bins)
+    assert_array_equal(p._compute_histogram(pts, weights=None), 1)
+    assert_array_equal(p._compute_histogram(pts, weights=5 * np.ones(p.n_bins)), 5)
+    common = {k: v for k, v in PLANAR.items() if k not in ("sym", "sym_odd", "dim", "zmin", "zmax")}
+    c = ProfileCylinderBase(atomgroup=u.atoms, dim=2, zmin=None, zmax=None, rmin=0, rmax=None, **common)
+    c._setup_frames(u.trajectory)
+    c._prepare()
+    r = (np.arange(c.n_bins) + 0.5) * c.rmax / c.n_bins
+    pts = np.stack([1.0 + r, np.ones_like(r), np.ones_like(r)], 1)
+    assert_array_equal(c._compute_histogram(pts, weights=None), 1)
+    s = ProfileSphereBase(atomgroup=u.atoms, rmin=0, rmax=None, **common)
+    s._setup_frames(u.trajectory)
+    s._prepare()
+    assert_array_equal(s._compute_histogram(pts, weights=5 * np.ones(len(pts))), 5)
+
+
+def test_correlation_bin_and_single_frame():
+    """tests/core/test_planar.py:536-545."""
+    u = uniform_universe(n_frames=3)
+    for n_bins in (1, 2, 3):
+        p = ProfilePlanarBase(atomgroup=u.atoms, **{**PLANAR, "bin_width": 2 / n_bins}).run(stop=1)
+        assert p._single_frame() == p._obs.profile[n_bins // 2]
+
+
+def slab_universe(n_frames=5):
+    fr, topo = mb.synthetic.confined_slab_frames(3000, 800, 42.0, 40.0, 70.0, 36.0, 20261021, n_frames=n_frames)
+    traj = MemoryTrajectory(fr, np.array([42.0, 40.0, 70.0, 90, 90, 90], np.float32))
+    return Universe(fr.shape[1], traj, **topo)
+
+
+def _restated_profile(u, ag, hist_fn, weights_fn, positions_fn, normalization, geometry_fn, n_frames):
+    stats = restatement.RunningStats()
+    for f in range(n_frames):
+        u.trajectory[f]
+        obs = geometry_fn()
+        obs.update(restatement.profile_single_frame(hist_fn, positions_fn(), weights_fn(), normalization,
+                                                    obs["bin_volume"]))
+        stats.update(obs)
+    return stats
+
+
+def test_density_planar_class_vs_restatement():
+    u = slab_universe()
+    water = u.select_atoms("element O H")
+    ana = mb.DensityPlanar(water, dens="mass", bin_width=0.1, unwrap=False, pack=False).run()
+    nb = ana.n_bins
+    assert nb == 700
+
+    def geom():
+        return restatement.planar_geometry(np.double(u.dimensions[:3]), 2, nb)[2]
+
+    st = _restated_profile(u, water, lambda p, w: restatement.hist_planar(p, w, 2, nb, 0.0, np.float64(70.0)),
+                           lambda: water.masses, lambda: water.positions, "volume", geom, 5)
+    assert_array_equal(ana.sums.bincount, st.sums["bincount"])
+    assert_allclose(ana.results.profile, st.means["profile"], rtol=1e-12, atol=1e-15)
+    assert_allclose(ana.results.dprofile, st.sems["profile"], rtol=1e-9, atol=1e-15)
+    assert_allclose(ana.results.bin_pos, st.means["bin_pos"] - 35.0)
+
+
+def test_diporder_planar_and_collection_vs_restatement():
+    u = slab_universe(n_frames=4)
+    water = u.select_atoms("element O H")
+    dens = mb.DensityPlanar(water, dens="charge", bin_width=0.5, unwrap=False, pack=False, grouping="residues")
+    dip = mb.DiporderPlanar(water, bin_width=0.5, unwrap=False, pack=False, order_parameter="cos_theta")
+    mb.AnalysisCollection(dens, dip).run()
+    nb = dip.n_bins
+
+    def geom():
+        return restatement.planar_geometry(np.double(u.dimensions[:3]), 2, nb)[2]
+
+    def w_cos():
+        mu = water.dipole_vector(compound="residues")
+        return (mu / np.linalg.norm(mu, axis=1)[:, None])[:, 2]
+
+    st = _restated_profile(u, water, lambda p, w: restatement.hist_planar(p, w, 2, nb, 0.0, np.float64(70.0)),
+                           w_cos, lambda: water.center(water.masses, compound="residues"), "number", geom, 4)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ref = st.sums["profile"] / st.sums["bincount"]
+    assert_array_equal(dip.sums.bincount, st.sums["bincount"])
+    assert_allclose(dip.results.profile, ref, rtol=1e-10, atol=1e-14, equal_nan=True)
+    solo = mb.DensityPlanar(water, dens="charge", bin_width=0.5, unwrap=False, pack=False, grouping="residues").run()
+    assert_allclose(dens.results.profile, solo.results.profile, rtol=1e-12, atol=1e-15)
+
+
+def test_density_cylinder_and_sphere_classes():
+    u = slab_universe(n_frames=3)
+    water = u.select_atoms("element O H")
+    cyl = mb.DensityCylinder(water, dens="number", bin_width=0.5, unwrap=False, pack=False).run()
+    sph = mb.DensitySphere(water, dens="mass", bin_width=0.5, unwrap=False, pack=False).run()
+    center = np.array([21.0, 20.0, 35.0])
+    st_c, st_s = restatement.RunningStats(), restatement.RunningStats()
+    for f in range(3):
+        u.trajectory[f]
+        p = water.positions
+        st_c.update({"c": restatement.hist_cylinder(p, None, 2, cyl.n_bins, 0.0, 20.0, 0.0, 70.0, center)})
+        st_s.update({"c": restatement.hist_sphere(p, None, sph.n_bins, 0.0, 20.0, center)})
+    assert cyl.rmax == 20.0 and sph.rmax == 20.0
+    assert_array_equal(cyl.sums.bincount, st_c.sums["c"])
+    assert_array_equal(sph.sums.bincount, st_s.sums["c"])
+    edges = np.linspace(0.0, 20.0, cyl.n_bins + 1)
+    vol = np.pi * np.diff(edges**2) * 70.0
+    assert_allclose(cyl.results.profile, st_c.means["c"] / vol, rtol=1e-12)
