@@ -23,6 +23,7 @@ sharded over ranks and merged by one allreduce at the end.
 from __future__ import annotations
 
 import logging
+import time
 import warnings
 from collections.abc import Callable
 from datetime import datetime
@@ -57,6 +58,21 @@ class Results(dict):
 
     def copy(self):
         return Results(self)
+
+
+def positions_into(atomgroup, out: np.ndarray) -> np.ndarray:
+    """Copy the current positions of ``atomgroup`` into ``out`` (one pass, no temporary)."""
+    try:
+        src = atomgroup.universe.trajectory.ts.positions
+        idx = atomgroup.indices
+        if len(idx) == len(src) and (len(idx) == 0 or (idx[0] == 0 and idx[-1] == len(src) - 1 and
+                                                      getattr(atomgroup, "_all", False))):
+            np.copyto(out, src)
+        else:
+            np.take(src, idx, axis=0, out=out)
+    except (AttributeError, TypeError, ValueError):
+        out[...] = atomgroup.positions
+    return out
 
 
 class _Runner:
@@ -162,6 +178,10 @@ class AnalysisBase(_Runner):
         self.results = Results()
         self._obs = Results()
         self._staged: list = []
+        self._pool = None
+        self._inflight = None
+        self._stage_parity = 0
+        self.timings = {"stage_s": 0.0, "wait_device_s": 0.0, "device_call_s": 0.0}
 
     # ---- cell ------------------------------------------------------------------------------
     @property
@@ -223,6 +243,18 @@ class AnalysisBase(_Runner):
         """Capture what the device needs from the current (already transformed) frame."""
         return None
 
+    def _staging_rows(self, shape, dtype, tag: str) -> tuple[np.ndarray, int]:
+        """``(pinned batch buffer [batch, *shape], row)`` for the frame being staged.
+
+        Two buffers alternate per batch: one is read by the in-flight device call while the host
+        fills the other, so frames go trajectory -> pinned memory -> HBM with one host copy.
+        """
+        from .. import _cabi
+
+        rows = max(1, self._batch_size)
+        buf = _cabi.pinned_empty((rows, *shape), dtype, slot=f"{type(self).__name__}:{tag}:{self._stage_parity}")
+        return buf, len(self._staged) % rows
+
     def _compute_staged(self, staged: list) -> list:
         """Turn staged frames into ``[(obs dict, correlation scalar), ...]`` with one device call."""
         raise NotImplementedError
@@ -252,6 +284,9 @@ class AnalysisBase(_Runner):
         self.timeseries = np.zeros(self.n_frames)
         self._n_local = 0
         self._staged = []
+        self._inflight = None
+        #: host-side time split of the last run: staging, waiting for the device, inside the C-ABI call
+        self.timings = {"stage_s": 0.0, "wait_device_s": 0.0, "device_call_s": 0.0}
         for name in ("sums", "means", "sems"):
             if hasattr(self, name):
                 delattr(self, name)
@@ -283,50 +318,81 @@ class AnalysisBase(_Runner):
         self._begin_frame(ts, slot)
         # batched unless a subclass replaced `_single_frame` with its own per-frame code
         if getattr(type(self)._single_frame, "_from_batch", False):
+            t0 = time.perf_counter()
             self._staged.append((slot, self._stage_frame()))
+            self.timings["stage_s"] += time.perf_counter() - t0
             if len(self._staged) >= max(1, self._batch_size):
-                self._flush_staged()
+                self._flush_staged(wait=False)
         else:
             self._obs = Results()
             value = self._single_frame()
-            self._accumulate(slot, value)
+            self._accumulate(slot, value, self._obs)
 
-    def _flush_staged(self) -> None:
-        if not self._staged:
-            return
-        staged, self._staged = self._staged, []
+    def _flush_staged(self, wait: bool = True) -> None:
+        """Hand the staged frames to the device.
+
+        The device call runs on a worker thread (the C ABI releases the GIL) so that the host can
+        stage the next batch meanwhile; at most one batch is in flight, batches complete in order
+        and the statistics are updated by the worker in frame order.
+        """
+        if self._staged:
+            staged, self._staged = self._staged, []
+            self._drain()
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mb200-batch")
+            self._inflight = self._pool.submit(self._process_batch, staged)
+            self._stage_parity ^= 1  # the next batch is staged into the other pinned buffer
+        if wait:
+            self._drain()
+
+    def _drain(self) -> None:
+        fut, self._inflight = self._inflight, None
+        if fut is not None:
+            t0 = time.perf_counter()
+            last = fut.result()  # re-raises worker exceptions
+            self.timings["wait_device_s"] += time.perf_counter() - t0
+            if last is not None:
+                self._frame_index, self._obs = last
+
+    def _process_batch(self, staged: list):
+        t0 = time.perf_counter()
         out = self._compute_staged([s for _, s in staged])
+        self.timings["device_call_s"] += time.perf_counter() - t0
+        last = None
         for (slot, _), (obs, value) in zip(staged, out):
-            self._frame_index = slot
-            self._obs = Results(obs)
-            self._accumulate(slot, value)
+            obs = Results(obs)
+            self._accumulate(slot, value, obs)
+            last = (slot, obs)
+        return last
 
     def _call_single_frame(self, ts, current_frame_index) -> None:
         """Serial entry point with the reference's signature (one frame, statistics updated)."""
         self._begin_frame(ts, current_frame_index)
         self._obs = Results()
         value = self._single_frame()
-        self._accumulate(current_frame_index, value)
+        self._accumulate(current_frame_index, value, self._obs)
 
-    def _accumulate(self, slot: int, value) -> None:
+    def _accumulate(self, slot: int, value, obs) -> None:
         """Running mean / standard error / sum of every observable (base.py:453-499)."""
         self.timeseries[slot] = np.nan if value is None else value
         self._n_local += 1
         self._index = n = self._n_local
         if n == 1 or not hasattr(self, "means"):
-            for key in self._obs:
-                if type(self._obs[key]) is list:
-                    self._obs[key] = np.array(self._obs[key])
-                if not isinstance(self._obs[key], _COMPATIBLE):
+            for key in obs:
+                if type(obs[key]) is list:
+                    obs[key] = np.array(obs[key])
+                if not isinstance(obs[key], _COMPATIBLE):
                     raise TypeError(f"Obervable {key} has uncompatible type.")
-            self.sums = self._obs.copy()
-            self.means = self._obs.copy()
-            self.sems = Results({key: np.zeros(np.shape(self._obs[key])) for key in self._obs})
+            self.sums = obs.copy()
+            self.means = obs.copy()
+            self.sems = Results({key: np.zeros(np.shape(obs[key])) for key in obs})
         else:
-            for key in self._obs:
-                x = self._obs[key]
+            for key in obs:
+                x = obs[key]
                 if type(x) is list:
-                    x = self._obs[key] = np.array(x)
+                    x = obs[key] = np.array(x)
                 old_mean = self.means[key]
                 old_var = self.sems[key] ** 2 * (n - 1)
                 self.means[key] = new_mean(old_mean, x, n)

@@ -19,7 +19,7 @@ import logging
 import numpy as np
 
 from .. import _cabi, parallel
-from ..core.base import AnalysisBase
+from ..core.base import AnalysisBase, positions_into
 from ..lib import tables
 from ..lib.math import atomic_form_factor, structure_factor
 
@@ -79,10 +79,11 @@ class Saxs(AnalysisBase):
         self.thetamax *= np.pi / 180
 
         # one group per element; weights are ones, form factors are applied after the kernel
-        elements = np.asarray(self.atomgroup.elements)
+        elements = np.asarray(self.atomgroup.elements).astype(str)  # fixed-width strings sort fast
+        unique, inverse = np.unique(elements, return_inverse=True)
         self.groups, self.weights, self.elements, self._group_index = [], [], [], []
-        for element in np.unique(elements):
-            idx = np.nonzero(elements == element)[0].astype(np.int32)
+        for g, element in enumerate(unique):
+            idx = np.flatnonzero(inverse == g).astype(np.int32)
             self._group_index.append(idx)
             self.groups.append(self.atomgroup[idx])
             self.weights.append(np.ones(len(idx)))
@@ -106,20 +107,22 @@ class Saxs(AnalysisBase):
                 f"Dimensions in frame {self._frame_index} are different from "
                 "initial dimenions. Can not use `bin_spectrum=False`."
             )
-        return np.ascontiguousarray(self.atomgroup.positions, dtype=np.float32), box
+        buf, row = self._staging_rows((self.atomgroup.n_atoms, 3), np.float32, "pos")
+        positions_into(self.atomgroup, buf[row])
+        return buf, row, box
 
     def _device_packs(self) -> bool:
         return bool(self.pack and self._universe.dimensions is not None)
 
     def _compute_staged(self, staged: list) -> list:
         if not self.bin_spectrum:
-            return [self._unbinned_frame(pos, box) for pos, box in staged]
+            return [self._unbinned_frame(buf[row].copy(), box) for buf, row, box in staged]
         F, n, G = len(staged), self.atomgroup.n_atoms, len(self.groups)
-        pos = _cabi.pinned_empty((F, n, 3), np.float32, slot="saxs_pos")
-        boxes = np.empty((F, 3), dtype=np.float32)
-        for f, (p, b) in enumerate(staged):
-            pos[f] = p
-            boxes[f] = b
+        pos = staged[0][0]
+        base = pos.ctypes.data
+        if any(st[0].ctypes.data != base or st[1] != f for f, st in enumerate(staged)):
+            pos = np.stack([buf[row] for buf, row, _ in staged])  # not one contiguous staging run
+        boxes = np.stack([st[2] for st in staged]).astype(np.float32)
         s = np.zeros((F, G, self.n_bins))
         i = np.zeros((F, G, self.n_bins))
         c = np.zeros((F, G, self.n_bins), dtype=np.int64)
