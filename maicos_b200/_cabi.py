@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libmaicos_b200.so"
+_LIB_PATH = Path(os.environ.get("MAICOS_B200_LIB") or Path(__file__).resolve().parent / "_lib" / "libmaicos_b200.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_float_p = ctypes.POINTER(ctypes.c_float)

@@ -39,18 +39,25 @@ namespace mb200 {
 constexpr int KT = 8;          // atoms per pipeline stage (two DMMA k-steps of 4)
 constexpr int WPC = 4;         // warps per CTA
 constexpr int NTHREADS = WPC * 32;
-constexpr int NSTAGE = 4;      // cp.async ring depth
+#ifndef MB_NSTAGE
+#define MB_NSTAGE 5
+#endif
+#ifndef MB_LOOKAHEAD
+#define MB_LOOKAHEAD (MB_NSTAGE - 2)
+#endif
+constexpr int NSTAGE = MB_NSTAGE;        // staging ring depth
+constexpr int LOOKAHEAD = MB_LOOKAHEAD;  // stages in flight ahead of the one being consumed
 constexpr int MAXX = 4;        // distinct (h,k) quads (4h x 8k = 32 rows) a CTA may stage
 constexpr int MAXY = 4;        // distinct l-pairs (16 l) a CTA may stage
 constexpr int QH = 4, QK = 8;  // quad shape
 constexpr int NL = 16;         // l extent of a warp tile
-constexpr int RAWROW = 9;      // double2 per staged table row: 8 atoms + 1 pad (bank spread)
+constexpr int RAWROW = 8;      // double2 per staged table row: 8 atoms; odd rows are rotated by one atom (bank spread)
 constexpr int XY_ROWS = MAXX * (QH + QK);  // 48
 constexpr int Z_ROWS = MAXY * NL;          // 64
 constexpr int ST_ROWS = XY_ROWS + Z_ROWS;  // 112 rows per stage
 constexpr int SMEM_STAGE = ST_ROWS * RAWROW * 16;       // 16128
-constexpr int SMEM_PTR = ST_ROWS * 8;                   // 896
-constexpr int SMEM_TOTAL = NSTAGE * SMEM_STAGE + SMEM_PTR + 16;
+constexpr int SMEM_BAR = 2 * NSTAGE * 8;                // full + empty mbarriers
+constexpr int SMEM_TOTAL = NSTAGE * SMEM_STAGE + SMEM_BAR + 16;
 
 struct __align__(16) TileGroupDesc {
     int16_t xh0[MAXX];
@@ -72,6 +79,8 @@ struct SegDesc {
     const int32_t *bin_start;      // [n_bins+1] entry ranges per |q| bin (entries sorted by bin)
     const double *ff2;             // [n_valid] squared form factor per entry (may be null)
     int32_t ld, n_split, n_wt, n_valid;
+    int32_t rows[3];               // table rows per axis (block stride = rows * 8 double2)
+    int32_t pad_;
 };
 
 struct ItemDesc {
@@ -111,6 +120,13 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// Table layout: [atom block of 8][row][8 atoms] double2, atoms of odd rows rotated by one position.
+// One pipeline stage of the contraction (8 atoms) is then a handful of contiguous 512 B .. 2 KB
+// pieces (4 Ex rows, 8 Ey rows, 16 Ez rows) that land in shared memory bank-conflict free.
+__host__ __device__ __forceinline__ size_t tab_index(int atom, int row, int rows) {
+    return ((size_t)(atom >> 3) * rows + row) * 8 + (((atom & 7) + (row & 1)) & 7);
+}
+
 // ------------------------------------------------------------------------------------------
 // k_sf_tables: phase tables
 //   grid = (ceil(ld/128), 3, n_jobs); thread = one atom on one axis.
@@ -124,7 +140,7 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
     if (j >= jb.ld) return;
     const int rows = jb.rows[axis];
     if (j >= jb.n) {  // zero padding up to the leading dimension
-        for (int r = 0; r < rows; ++r) tab[(size_t)r * jb.ld + j] = make_double2(0.0, 0.0);
+        for (int r = 0; r < rows; ++r) tab[tab_index(j, r, rows)] = make_double2(0.0, 0.0);
         return;
     }
     const int64_t a = jb.index ? (int64_t)jb.index[j] : (int64_t)j;
@@ -154,7 +170,7 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
             t -= rint(t);
             sincospi(2.0 * t, &ci, &cr);
         }
-        tab[(size_t)r * jb.ld + j] = make_double2(w * cr, w * ci);
+        tab[tab_index(j, r, rows)] = make_double2(w * cr, w * ci);
         const double nr = cr * c1 - ci * s1;
         const double ni = cr * s1 + ci * c1;
         cr = nr;
@@ -165,69 +181,187 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
 // ------------------------------------------------------------------------------------------
 // k_sf_contract: the DMMA contraction (persistent CTAs, dynamic item queue)
 //
-//   per stage (8 atoms) a CTA stages, with cp.async, the table rows its warps need:
-//     Ex rows h0..h0+3 and Ey rows k0..k0+7 of each of its (h,k) quads, Ez rows l0..l0+15 of
-//     each of its l-pairs; [row][8 atoms + pad] double2, NSTAGE-deep ring, one barrier per stage.
+//   per stage (8 atoms) a CTA stages the table rows its warps need -- Ex rows h0..h0+3 and Ey rows
+//   k0..k0+7 of each of its (h,k) quads, Ez rows l0..l0+15 of each of its l-pairs -- as
+//   [row][8 atoms + pad] double2 in an NSTAGE-deep ring.  Thread r owns row r: one 128-byte
+//   cp.async.bulk (SASS UBLKCP) per stage, completion counted on the slot's "full" mbarrier; a slot
+//   is refilled after every warp has arrived on its "empty" mbarrier.  No block-wide barrier in the
+//   atom loop: warps drift up to NSTAGE-1 stages apart.
 //   every warp owns a 32 (hk) x 16 (l) tile: 4 x 2 DMMA tiles x 3 planes of accumulators.
 //   A fragments P = Ex*Ey (and Pr+Pi) are formed in registers from the staged rows, B fragments
-//   are the staged Ez rows (and Zr+Zi); k index of the MMA = atom.
+//   are the staged Ez rows (and Zr+Zi); k index of the MMA = atom.  Warp tiles that lie fully
+//   inside the q-sphere take an unpredicated instruction stream.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+        if (spin > (1u << 26)) __trap();  // a lost completion must fail the launch, never hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// MMAs of one 8-atom stage for one warp tile.  FULL: every 8x8 tile valid -> no predication.
+// Fragment positions: lane (g, tig) needs atoms 2*tig and 2*tig+1 of its rows; in a row of parity p
+// they sit at positions (2*tig + p) & 7 and (2*tig + 1 + p) & 7 (rotation of odd rows).
+struct FragOff {
+    int ex[2][2];  // [row parity][atom]  (row = h0 + mt, parity = mt & 1; row base added per mt)
+    int ey[2];     // Ey row k0 + g
+    int ez[2];     // Ez row l0 + g (second n-tile: + 8 rows, same parity)
+};
+
+template <bool FULL>
+__device__ __forceinline__ void contract_stage(double (&acc)[4][2][3][2], const double2 *__restrict__ st,
+                                               const FragOff &fo, unsigned wmask) {
+    double br[2][2], bi[2][2], bs[2][2];  // [nt][kstep]
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+        const double2 z0 = st[fo.ez[0] + nt * 8 * RAWROW], z1 = st[fo.ez[1] + nt * 8 * RAWROW];
+        br[nt][0] = z0.x; bi[nt][0] = z0.y; bs[nt][0] = z0.x + z0.y;
+        br[nt][1] = z1.x; bi[nt][1] = z1.y; bs[nt][1] = z1.x + z1.y;
+    }
+    const double2 y0 = st[fo.ey[0]], y1 = st[fo.ey[1]];
+    double2 xn0 = st[fo.ex[0][0]], xn1 = st[fo.ex[0][1]];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const double2 x0 = xn0, x1 = xn1;
+        if (mt < 3) {  // prefetch the next Ex row while this row's DMMAs issue
+            xn0 = st[fo.ex[(mt + 1) & 1][0] + (mt + 1) * RAWROW];
+            xn1 = st[fo.ex[(mt + 1) & 1][1] + (mt + 1) * RAWROW];
+        }
+        if (FULL || ((wmask >> (2 * mt)) & 3u)) {
+            const double pr0 = x0.x * y0.x - x0.y * y0.y, pi0 = x0.x * y0.y + x0.y * y0.x;
+            const double pr1 = x1.x * y1.x - x1.y * y1.y, pi1 = x1.x * y1.y + x1.y * y1.x;
+            const double ps0 = pr0 + pi0, ps1 = pr1 + pi1;
+            const bool v0 = FULL || ((wmask >> (2 * mt)) & 1u), v1 = FULL || ((wmask >> (2 * mt + 1)) & 1u);
+            if (v0) {
+                dmma(acc[mt][0][0][0], acc[mt][0][0][1], pr0, br[0][0]);
+                dmma(acc[mt][0][1][0], acc[mt][0][1][1], pi0, bi[0][0]);
+                dmma(acc[mt][0][2][0], acc[mt][0][2][1], ps0, bs[0][0]);
+            }
+            if (v1) {
+                dmma(acc[mt][1][0][0], acc[mt][1][0][1], pr0, br[1][0]);
+                dmma(acc[mt][1][1][0], acc[mt][1][1][1], pi0, bi[1][0]);
+                dmma(acc[mt][1][2][0], acc[mt][1][2][1], ps0, bs[1][0]);
+            }
+            if (v0) {
+                dmma(acc[mt][0][0][0], acc[mt][0][0][1], pr1, br[0][1]);
+                dmma(acc[mt][0][1][0], acc[mt][0][1][1], pi1, bi[0][1]);
+                dmma(acc[mt][0][2][0], acc[mt][0][2][1], ps1, bs[0][1]);
+            }
+            if (v1) {
+                dmma(acc[mt][1][0][0], acc[mt][1][0][1], pr1, br[1][1]);
+                dmma(acc[mt][1][1][0], acc[mt][1][1][1], pi1, bi[1][1]);
+                dmma(acc[mt][1][2][0], acc[mt][1][2][1], ps1, bs[1][1]);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 3)
 k_sf_contract(const ItemDesc *__restrict__ items, int n_items, const SegDesc *__restrict__ segs,
               int *__restrict__ counter) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2 *raw = reinterpret_cast<double2 *>(smem);  // [NSTAGE][ST_ROWS][RAWROW]
-    const double2 **rowptr = reinterpret_cast<const double2 **>(smem + NSTAGE * SMEM_STAGE);  // [ST_ROWS]
-    int *s_item = reinterpret_cast<int *>(smem + NSTAGE * SMEM_STAGE + SMEM_PTR);
+    unsigned long long *full_bar = reinterpret_cast<unsigned long long *>(smem + NSTAGE * SMEM_STAGE);  // [NSTAGE]
+    unsigned long long *empty_bar = full_bar + NSTAGE;                                                  // [NSTAGE]
+    int *s_item = reinterpret_cast<int *>(empty_bar + NSTAGE);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tig = lane & 3;
 
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(full_bar + s, 1);     // one arrive.expect_tx per fill
+            mbar_init(empty_bar + s, WPC);  // one arrive per warp per drain
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    unsigned gstage = 0;  // stages issued / consumed by this CTA so far (uniform over threads)
+
     for (;;) {
         if (tid == 0) *s_item = atomicAdd(counter, 1);
-        __syncthreads();
+        __syncthreads();  // also: every warp is done with the previous item
         const int item = *s_item;
         if (item >= n_items) break;
 
         const ItemDesc it = items[item];
         const SegDesc &sg = segs[it.seg];
         const TileGroupDesc *tg = sg.tgs + it.tg;
-        const int ld = sg.ld;
         const int n_x = tg->n_x, n_y = tg->n_y;
 
-        // source row pointers (at atom j0) of every staged row: x-slot rows (4 Ex + 8 Ey), then Ez rows
+        // staged pieces of one 8-atom block: per (h,k) quad 4 Ex rows (512 B) + 8 Ey rows (1 KB), per l-pair
+        // 16 Ez rows (2 KB); thread c < n_copy owns piece c.  Stage layout: [x-slot][4 Ex + 8 Ey][8], [y-slot][16][8].
         const int n_xy = n_x * (QH + QK);
         const int n_rows = n_xy + n_y * NL;
-        for (int r = tid; r < n_rows; r += NTHREADS) {
-            const double2 *p;
-            if (r < n_xy) {
-                const int xs = r / (QH + QK), q = r % (QH + QK);
-                p = (q < QH) ? sg.ex + (size_t)(tg->xh0[xs] + q) * ld
-                             : sg.ey + (size_t)(tg->xk0[xs] + (q - QH)) * ld;
+        const int n_copy = 2 * n_x + n_y;
+        const double2 *my_src = nullptr;
+        unsigned my_bytes = 0, my_dst = 0;
+        size_t my_stride = 0;  // double2 per atom block
+        if (tid < n_copy) {
+            const size_t blk0 = (size_t)(it.j0 >> 3);
+            if (tid < 2 * n_x) {
+                const int xs = tid >> 1;
+                if ((tid & 1) == 0) {
+                    my_stride = (size_t)sg.rows[0] * 8;
+                    my_src = sg.ex + blk0 * my_stride + (size_t)tg->xh0[xs] * 8;
+                    my_bytes = QH * 128u;
+                    my_dst = (unsigned)(xs * (QH + QK)) * RAWROW;
+                } else {
+                    my_stride = (size_t)sg.rows[1] * 8;
+                    my_src = sg.ey + blk0 * my_stride + (size_t)tg->xk0[xs] * 8;
+                    my_bytes = QK * 128u;
+                    my_dst = (unsigned)(xs * (QH + QK) + QH) * RAWROW;
+                }
             } else {
-                const int rz = r - n_xy;
-                p = sg.ez + (size_t)(tg->yl0[rz / NL] + (rz % NL)) * ld;
+                const int ys = tid - 2 * n_x;
+                my_stride = (size_t)sg.rows[2] * 8;
+                my_src = sg.ez + blk0 * my_stride + (size_t)tg->yl0[ys] * 8;
+                my_bytes = NL * 128u;
+                my_dst = (unsigned)(n_xy + ys * NL) * RAWROW;
             }
-            rowptr[r] = p + it.j0;
         }
         const bool active = warp < tg->n_warp;
         const int wx = active ? tg->wx[warp] : 0, wy = active ? tg->wy[warp] : 0;
         const unsigned wmask = active ? tg->wmask[warp] : 0u;
-        __syncthreads();
+        __syncthreads();  // s_item may be rewritten only after everybody has read it
 
         const int n_stage = (it.j1 - it.j0) / KT;
-        const int n_chunk = n_rows * KT;
+        const unsigned stage_bytes = (unsigned)n_rows * KT * 16u;
 
-        auto issue = [&](int t) {  // cp.async stage t -> ring slot t % NSTAGE
+        auto issue = [&](int t) {  // fill ring slot of stage t (thread r: row r)
             if (t < n_stage) {
-                double2 *dst = raw + (t % NSTAGE) * (ST_ROWS * RAWROW);
-                const int off = t * KT;
-                for (int q = tid; q < n_chunk; q += NTHREADS) {
-                    const int r = q >> 3, c = q & 7;
-                    cp_async16(dst + r * RAWROW + c, rowptr[r] + off + c);
+                const unsigned gs = gstage + (unsigned)t;
+                const unsigned slot = gs % NSTAGE, use = gs / NSTAGE;
+                if (tid < n_copy) {
+                    if (use > 0) mbar_wait(empty_bar + slot, (use - 1) & 1u);  // all warps drained the previous use
+                    if (tid == 0) mbar_arrive_expect_tx(full_bar + slot, stage_bytes);
+                    bulk_g2s(raw + slot * (ST_ROWS * RAWROW) + my_dst, my_src + (size_t)t * my_stride, my_bytes,
+                             full_bar + slot);
                 }
             }
-            cp_async_commit();
         };
 
         // accumulators: [mt][nt] x planes (T1,T2,T3) x {c0,c1}
@@ -239,67 +373,35 @@ k_sf_contract(const ItemDesc *__restrict__ items, int n_items, const SegDesc *__
 #pragma unroll
                 for (int p = 0; p < 3; ++p) acc[mt][nt][p][0] = acc[mt][nt][p][1] = 0.0;
 
-        issue(0);
-        issue(1);
-        issue(2);
+#pragma unroll
+        for (int s = 0; s < LOOKAHEAD; ++s) issue(s);
         // per-thread fragment offsets inside a stage (double2 units)
-        const int off_ex = (wx * (QH + QK)) * RAWROW + 2 * tig;
-        const int off_ey = (wx * (QH + QK) + QH + g) * RAWROW + 2 * tig;
-        const int off_ez = (n_xy + wy * NL + g) * RAWROW + 2 * tig;
+        FragOff fo;
+        {
+            const int pg = g & 1;  // parity of rows k0 + g and l0 (+8) + g; h0 + mt has parity mt & 1
+            const int bx = (wx * (QH + QK)) * RAWROW, by = (wx * (QH + QK) + QH + g) * RAWROW,
+                      bz = (n_xy + wy * NL + g) * RAWROW;
+            fo.ex[0][0] = bx + 2 * tig;               fo.ex[0][1] = bx + 2 * tig + 1;
+            fo.ex[1][0] = bx + ((2 * tig + 1) & 7);   fo.ex[1][1] = bx + ((2 * tig + 2) & 7);
+            fo.ey[0] = by + ((2 * tig + pg) & 7);     fo.ey[1] = by + ((2 * tig + 1 + pg) & 7);
+            fo.ez[0] = bz + ((2 * tig + pg) & 7);     fo.ez[1] = bz + ((2 * tig + 1 + pg) & 7);
+        }
 
         for (int t = 0; t < n_stage; ++t) {
-            cp_async_wait<NSTAGE - 2>();
-            __syncthreads();  // stage t visible to all; every warp is done with stage t-1
-            issue(t + NSTAGE - 1);
-
-            if (wmask) {
-                const double2 *st = raw + (t % NSTAGE) * (ST_ROWS * RAWROW);
-                double br[2][2], bi[2][2], bs[2][2];  // [nt][kstep]
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    const double2 z0 = st[off_ez + nt * 8 * RAWROW], z1 = st[off_ez + nt * 8 * RAWROW + 1];
-                    br[nt][0] = z0.x; bi[nt][0] = z0.y; bs[nt][0] = z0.x + z0.y;
-                    br[nt][1] = z1.x; bi[nt][1] = z1.y; bs[nt][1] = z1.x + z1.y;
-                }
-                const double2 y0 = st[off_ey], y1 = st[off_ey + 1];
-                double2 xn0 = st[off_ex], xn1 = st[off_ex + 1];
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
-                    const double2 x0 = xn0, x1 = xn1;
-                    if (mt < 3) {  // prefetch the next Ex row while this row's DMMAs issue
-                        xn0 = st[off_ex + (mt + 1) * RAWROW];
-                        xn1 = st[off_ex + (mt + 1) * RAWROW + 1];
-                    }
-                    if ((wmask >> (2 * mt)) & 3u) {
-                        const double pr0 = x0.x * y0.x - x0.y * y0.y, pi0 = x0.x * y0.y + x0.y * y0.x;
-                        const double pr1 = x1.x * y1.x - x1.y * y1.y, pi1 = x1.x * y1.y + x1.y * y1.x;
-                        const double ps0 = pr0 + pi0, ps1 = pr1 + pi1;
-                        const bool v0 = (wmask >> (2 * mt)) & 1u, v1 = (wmask >> (2 * mt + 1)) & 1u;
-                        if (v0) {
-                            dmma(acc[mt][0][0][0], acc[mt][0][0][1], pr0, br[0][0]);
-                            dmma(acc[mt][0][1][0], acc[mt][0][1][1], pi0, bi[0][0]);
-                            dmma(acc[mt][0][2][0], acc[mt][0][2][1], ps0, bs[0][0]);
-                        }
-                        if (v1) {
-                            dmma(acc[mt][1][0][0], acc[mt][1][0][1], pr0, br[1][0]);
-                            dmma(acc[mt][1][1][0], acc[mt][1][1][1], pi0, bi[1][0]);
-                            dmma(acc[mt][1][2][0], acc[mt][1][2][1], ps0, bs[1][0]);
-                        }
-                        if (v0) {
-                            dmma(acc[mt][0][0][0], acc[mt][0][0][1], pr1, br[0][1]);
-                            dmma(acc[mt][0][1][0], acc[mt][0][1][1], pi1, bi[0][1]);
-                            dmma(acc[mt][0][2][0], acc[mt][0][2][1], ps1, bs[0][1]);
-                        }
-                        if (v1) {
-                            dmma(acc[mt][1][0][0], acc[mt][1][0][1], pr1, br[1][1]);
-                            dmma(acc[mt][1][1][0], acc[mt][1][1][1], pi1, bi[1][1]);
-                            dmma(acc[mt][1][2][0], acc[mt][1][2][1], ps1, bs[1][1]);
-                        }
-                    }
-                }
+            const unsigned gs = gstage + (unsigned)t;
+            const unsigned slot = gs % NSTAGE;
+            issue(t + LOOKAHEAD);  // LOOKAHEAD < NSTAGE - 1 leaves slack: warps may drift apart without blocking
+            mbar_wait(full_bar + slot, (gs / NSTAGE) & 1u);
+            const double2 *st = raw + slot * (ST_ROWS * RAWROW);
+            if (wmask == 0xFFu) {
+                contract_stage<true>(acc, st, fo, wmask);
+            } else if (wmask) {
+                contract_stage<false>(acc, st, fo, wmask);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + slot);
         }
-        cp_async_wait<0>();
+        gstage += (unsigned)n_stage;
 
         // epilogue: Re = T1 - T2, Im = T3 - T1 - T2 -> amp[split][wt][row][col]
         if (wmask) {
@@ -691,6 +793,7 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
         amp_elems += (size_t)n_split * sp.plan->n_wt * 512;
         SegDesc &sd = segs_host[s];
         sd.ld = ld; sd.n_split = n_split; sd.n_wt = sp.plan->n_wt; sd.n_valid = (int32_t)sp.plan->cell.size();
+        for (int a = 0; a < 3; ++a) sd.rows[a] = sp.plan->rows[a];
         sd.tgs = sp.plan->d_tgs.as<TileGroupDesc>();
         sd.ent_amp = sp.plan->d_ent_amp.as<int32_t>();
         sd.bin_start = sp.plan->d_bin_start.as<int32_t>();

@@ -47,7 +47,10 @@ def init(mode: str = "frames", backend: str | None = None) -> None:
         _state["device"] = torch.device("cpu")
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend=backend)
+        if backend == "nccl":
+            dist.init_process_group(backend=backend, device_id=_state["device"])
+        else:
+            dist.init_process_group(backend=backend)
     _state.update(initialised=True, rank=dist.get_rank(), world=dist.get_world_size(), backend=backend)
 
 
