@@ -286,8 +286,45 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl)
+    if world == 1 and not args.no_e2e:
+        line["path2_profile_hist"] = path2_summary(ctx, lib, torch)
     print(json.dumps(line))
     parallel.shutdown()
+
+
+def path2_summary(ctx, lib, torch):
+    """Secondary hot path (slab histogram, BASELINE.json configs[3] size): frames/s and HBM roofline fraction."""
+    from maicos_b200 import _cabi
+
+    n, nb, F, lz = 1_000_000, 2154, 16, 215.37
+    rng = np.random.default_rng(20261021)
+    d_pos = torch.from_numpy(rng.uniform(0, lz, (F, n, 3)).astype(np.float32)).cuda()
+    d_w = torch.from_numpy(rng.uniform(1, 16, n)).cuda()
+    edges = np.tile(np.linspace(np.float64(0), np.float64(lz), nb + 1), (F, 1))
+    hw = np.zeros((F, nb)); hc = np.zeros((F, nb), dtype=np.int64)
+    stream = torch.cuda.ExternalStream(int(lib.mb200_ctx_stream(ctx.handle)))
+    torch.cuda.synchronize()
+
+    def call():
+        _cabi.check(lib.mb200_profile_hist(ctx.handle, 0, d_pos.data_ptr(), 1, 1, F, n, 2, d_w.data_ptr(), 0, 1,
+                                           _cabi.ptr(edges), nb, None, None, _cabi.ptr(hw), _cabi.ptr(hc)))
+    for _ in range(3):
+        call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(10):
+        call()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 10 * 1e-3
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    peak = peaks.get("hbm_gbs", 6650.0)
+    gbs = 12.0 * n * F / sec / 1e9
+    return {"workload": f"weighted + count slab histogram, {n} atoms x {F} frames resident, {nb} bins",
+            "frames_per_s": F / sec, "atoms_per_s": n * F / sec,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic_bytes_per_atom_frame": 12,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}}
 
 
 def cpu_baseline(wl):
