@@ -124,15 +124,47 @@ int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int positions_on_d
 /* Fused DiporderStructureFactor frame body (replaces
  * src/maicos/modules/diporderstructurefactor.py:105-150): three weight sets on identical
  * positions share one set of phase tables; per frame and component S is binned by |q|.
- *   positions : host float64 [n_frames][n][3] (compound centres)
- *   weights   : host float64 [n_frames][3][n]
+ *   positions : float64 [n_frames][n][3] (compound centres), host or device (inputs_on_device,
+ *               e.g. the output of mb200_compound_prologue)
+ *   weights   : float64 [n_frames][3][n], same residence as positions
  *   boxes     : host float64 [n_frames][3]
  * outputs (host): s_binned float64 [n_frames][3][n_bins] (sum of S per bin),
  *                 bincount int64 [n_frames][3][n_bins] (entries with S != 0).  */
 int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const double *weights,
-                       int64_t n_frames, int64_t n, const double *boxes, double qmin,
-                       double qmax, int32_t n_bins, int32_t block, int32_t n_blocks,
+                       int inputs_on_device, int64_t n_frames, int64_t n, const double *boxes,
+                       double qmin, double qmax, int32_t n_bins, int32_t block, int32_t n_blocks,
                        double *s_binned, int64_t *bincount);
+
+/* ---- per-frame compound prologue ------------------------------------ */
+
+/* Plain device buffers for intermediate results that stay on the GPU between two entry points. */
+int mb200_dev_alloc(mb200_ctx *ctx, size_t bytes, void **out);
+int mb200_dev_free(mb200_ctx *ctx, void *p);
+int mb200_dev_read(mb200_ctx *ctx, const void *dev, void *host, size_t bytes);
+
+/* Compound centres and dipole-derived weights from raw atom coordinates, for compounds that are
+ * contiguous runs of atoms.  Replaces the per-frame host calls
+ *   atoms.unwrap / atoms.wrap(compound)        src/maicos/core/base.py:438-448
+ *   get_center(ag, bin_method, compound)       src/maicos/lib/util.py:642-680
+ *   diporder_weights(ag, compound, ...)        src/maicos/lib/weights.py:131-178
+ *   positions      : float32 [n_frames][n_atoms][3] (host, or device if positions_on_device)
+ *   boxes          : host float32 [n_frames][3]
+ *   compound_ptr   : host int64 [n_c+1], atoms of compound c are compound_ptr[c] .. compound_ptr[c+1]-1
+ *   center_weights : host float64 [n_atoms] (masses for "com", |charges| for "coc") or NULL ("cog")
+ *   masses, charges: host float64 [n_atoms]; masses also give the wrap reference point (NULL: geometry)
+ *   make_whole     : minimum image about the first atom of each compound (float32)
+ *   wrap_center    : shift every compound so that its centre of mass lies in the cell
+ *   weight_mode    : 0 none, 1 mu.e_pdim (P0), 2 cos_theta = mu.e_pdim/|mu|, 3 cos_theta^2,
+ *                    4 all three components of mu/|mu| laid out [n_frames][3][n_c]
+ * outputs (DEVICE): centers_dev float64 [n_frames][n_c][3], weights_dev float64 [n_frames][n_c]
+ *                   (or [n_frames][3][n_c] for mode 4); feed them to mb200_profile_hist /
+ *                   mb200_dipsf_frames with their *_on_device flags. */
+int mb200_compound_prologue(mb200_ctx *ctx, const float *positions, int positions_on_device,
+                            int64_t n_frames, int64_t n_atoms, const float *boxes,
+                            const int64_t *compound_ptr, int64_t n_c, const double *center_weights,
+                            const double *masses, const double *charges, int make_whole,
+                            int wrap_center, int weight_mode, int pdim, double *centers_dev,
+                            double *weights_dev);
 
 /* ---- path 2: weighted slab / shell histograms --------------------------------- */
 

@@ -54,9 +54,18 @@ SIGNATURES = {
          ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_int, ctypes.c_int32, ctypes.c_int32,
          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
     ),
+    "mb200_dev_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
+    "mb200_dev_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "mb200_dev_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "mb200_compound_prologue": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p],
+    ),
     "mb200_dipsf_frames": (
         ctypes.c_int,
-        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
          ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
          ctypes.c_void_p],
     ),
@@ -197,6 +206,19 @@ class _PinnedBlock:
 
 
 _pinned_slots: dict[str, _PinnedBlock] = {}
+_pinned_free: list[_PinnedBlock] = []      # released blocks kept for the next run (cudaMallocHost is slow)
+_PINNED_POOL_BYTES = 2 << 30
+
+
+def _pinned_acquire(nbytes: int) -> _PinnedBlock:
+    best = None
+    for blk in _pinned_free:
+        if blk.nbytes >= nbytes and (best is None or blk.nbytes < best.nbytes):
+            best = blk
+    if best is not None and best.nbytes <= 4 * nbytes + (1 << 20):
+        _pinned_free.remove(best)
+        return best
+    return _PinnedBlock(nbytes + nbytes // 4)
 
 
 def pinned_empty(shape, dtype, slot: str = "default") -> np.ndarray:
@@ -214,6 +236,49 @@ def pinned_empty(shape, dtype, slot: str = "default") -> np.ndarray:
     block = _pinned_slots.get(slot)
     if block is None or block.nbytes < nbytes:
         if block is not None:
-            block.free()
-        block = _pinned_slots[slot] = _PinnedBlock(nbytes + nbytes // 4)
+            _pinned_release_block(block)
+        block = _pinned_slots[slot] = _pinned_acquire(nbytes)
     return np.frombuffer(block.buf, dtype=dtype, count=count).reshape(shape)
+
+
+def _pinned_release_block(block: _PinnedBlock) -> None:
+    if sum(b.nbytes for b in _pinned_free) + block.nbytes <= _PINNED_POOL_BYTES:
+        _pinned_free.append(block)
+    else:
+        block.free()
+
+
+def release_pinned(prefix: str) -> None:
+    """Return the staging blocks whose slot name starts with ``prefix`` to the pool (end of a run)."""
+    for name in [k for k in _pinned_slots if k.startswith(prefix)]:
+        _pinned_release_block(_pinned_slots.pop(name))
+
+
+class DeviceBuffer:
+    """Grow-only device allocation owned by the host layer (intermediates that stay on the GPU)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx, self.ptr, self.nbytes = ctx, ctypes.c_void_p(), 0
+
+    def ensure(self, nbytes: int) -> int:
+        if nbytes > self.nbytes:
+            self.free()
+            _check(load().mb200_dev_alloc(self.ctx.handle, int(nbytes + nbytes // 8), ctypes.byref(self.ptr)))
+            self.nbytes = int(nbytes + nbytes // 8)
+        return self.ptr.value
+
+    def read(self, shape, dtype=np.float64) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        _check(load().mb200_dev_read(self.ctx.handle, self.ptr, ptr(out), out.nbytes))
+        return out
+
+    def free(self) -> None:
+        if self.ptr:
+            _check(load().mb200_dev_free(self.ctx.handle, self.ptr))
+        self.ptr, self.nbytes = ctypes.c_void_p(), 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

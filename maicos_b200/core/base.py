@@ -75,6 +75,88 @@ def positions_into(atomgroup, out: np.ndarray) -> np.ndarray:
     return out
 
 
+_COMPOUND_ATTR = {"residues": "resindices", "molecules": "molnums", "segments": "segindices",
+                  "fragments": "fragindices"}
+
+
+def compound_runs(atomgroup, compound: str):
+    """``compound_ptr`` (int64 ``[n_c + 1]``) when the device prologue can own the compounds, else ``None``.
+
+    Requirements: the in-memory shim (its wrap / unwrap semantics are what ``mb200_compound_prologue``
+    restates bit for bit -- with a real MDAnalysis universe the host path keeps MDAnalysis' own),
+    compounds are contiguous runs of the atom group in ascending id order (the order
+    ``AtomGroup.center(compound=...)`` returns), complete with respect to the universe, at most 64 atoms.
+    """
+    from ..mdshim import Universe as ShimUniverse
+
+    if compound not in _COMPOUND_ATTR or not isinstance(atomgroup.universe, ShimUniverse):
+        return None
+    ids = np.asarray(getattr(atomgroup, _COMPOUND_ATTR[compound]))
+    if len(ids) == 0:
+        return None
+    starts = np.concatenate([[0], np.flatnonzero(np.diff(ids)) + 1])
+    run_ids = ids[starts]
+    if np.any(np.diff(run_ids) <= 0):
+        return None
+    ptr = np.concatenate([starts, [len(ids)]]).astype(np.int64)
+    if np.max(np.diff(ptr)) > 64:
+        return None
+    all_ids = np.asarray(getattr(atomgroup.universe.atoms, _COMPOUND_ATTR[compound]))
+    if np.count_nonzero(np.isin(all_ids, run_ids)) != len(ids):
+        return None
+    return ptr
+
+
+def center_weights_for(atomgroup, bin_method: str):
+    """Per-atom weights of ``get_center`` (``lib/util.py:668-679``): masses, |charges| or None."""
+    if bin_method == "cog":
+        return None
+    if bin_method == "com":
+        return np.ascontiguousarray(atomgroup.masses, dtype=np.float64)
+    if bin_method == "coc":
+        return np.ascontiguousarray(np.abs(atomgroup.charges), dtype=np.float64)
+    raise ValueError(f"'{bin_method}' is an unknown binning method. Use 'cog', 'com' or 'coc'.")
+
+
+class CompoundPrologue:
+    """Device-side unwrap / wrap / centre / dipole weights of an atom group's compounds."""
+
+    def __init__(self, atomgroup, compound: str, bin_method: str, make_whole: bool, wrap_center: bool,
+                 weight_mode: int = 0, pdim: int = 0):
+        from .. import _cabi
+
+        self.ptr = compound_runs(atomgroup, compound)
+        if self.ptr is None:
+            raise ValueError("compounds are not eligible for the device prologue")
+        self.n_atoms, self.n_c = atomgroup.n_atoms, len(self.ptr) - 1
+        self.cw = center_weights_for(atomgroup, bin_method)
+        has = atomgroup.universe._attrs
+        self.masses = np.ascontiguousarray(atomgroup.masses, dtype=np.float64) if "masses" in has else None
+        self.charges = np.ascontiguousarray(atomgroup.charges, dtype=np.float64) if "charges" in has else None
+        if weight_mode and (self.masses is None or self.charges is None):
+            raise ValueError("dipole weights need masses and charges")
+        self.make_whole, self.wrap_center = bool(make_whole), bool(wrap_center)
+        self.weight_mode, self.pdim = int(weight_mode), int(pdim)
+        self.ctx = _cabi.context()
+        self.centers = _cabi.DeviceBuffer(self.ctx)
+        self.weights = _cabi.DeviceBuffer(self.ctx)
+
+    def run(self, positions: np.ndarray, boxes: np.ndarray):
+        """positions float32 [F, n_atoms, 3] (pinned), boxes float32 [F, 3] -> device pointers (centres, weights)."""
+        from .. import _cabi
+
+        F = positions.shape[0]
+        c_ptr = self.centers.ensure(F * self.n_c * 24)
+        n_w = {0: 0, 1: 1, 2: 1, 3: 1, 4: 3}[self.weight_mode]
+        w_ptr = self.weights.ensure(F * self.n_c * 8 * n_w) if n_w else None
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+        _cabi.check(_cabi.load().mb200_compound_prologue(
+            self.ctx.handle, _cabi.ptr(positions), 0, F, self.n_atoms, _cabi.ptr(boxes), _cabi.ptr(self.ptr), self.n_c,
+            _cabi.ptr(self.cw), _cabi.ptr(self.masses), _cabi.ptr(self.charges), int(self.make_whole),
+            int(self.wrap_center), self.weight_mode, self.pdim, c_ptr, w_ptr))
+        return c_ptr, w_ptr
+
+
 class _Runner:
     """Shared ``run`` machinery of :class:`AnalysisBase` and :class:`AnalysisCollection`."""
 
@@ -243,6 +325,9 @@ class AnalysisBase(_Runner):
         """Capture what the device needs from the current (already transformed) frame."""
         return None
 
+    def _slot_prefix(self) -> str:
+        return f"{type(self).__name__}@{id(self):x}:"
+
     def _staging_rows(self, shape, dtype, tag: str) -> tuple[np.ndarray, int]:
         """``(pinned batch buffer [batch, *shape], row)`` for the frame being staged.
 
@@ -252,7 +337,7 @@ class AnalysisBase(_Runner):
         from .. import _cabi
 
         rows = max(1, self._batch_size)
-        buf = _cabi.pinned_empty((rows, *shape), dtype, slot=f"{type(self).__name__}:{tag}:{self._stage_parity}")
+        buf = _cabi.pinned_empty((rows, *shape), dtype, slot=f"{self._slot_prefix()}{tag}:{self._stage_parity}")
         return buf, len(self._staged) % rows
 
     def _compute_staged(self, staged: list) -> list:
@@ -271,14 +356,15 @@ class AnalysisBase(_Runner):
             else:
                 self.ref_weights = self.refgroup.masses
         self._prepare()
-        if self.refgroup is not None:
-            logging.info(
-                f"Coordinates are relative to the center of mass of reference atomgroup "
-                f"{atomgroup_header(self.refgroup)}."
-            )
-        else:
-            logging.info("Coordinates are relative to the center of the simulation box.")
-        logging.info(f"Considered atomgroup {atomgroup_header(self.atomgroup)}.")
+        if logging.getLogger().isEnabledFor(logging.INFO):  # the headers scan every atom: only when shown
+            if self.refgroup is not None:
+                logging.info(
+                    f"Coordinates are relative to the center of mass of reference atomgroup "
+                    f"{atomgroup_header(self.refgroup)}."
+                )
+            else:
+                logging.info("Coordinates are relative to the center of the simulation box.")
+            logging.info(f"Considered atomgroup {atomgroup_header(self.atomgroup)}.")
         if hasattr(self, "n_bins"):
             logging.info(f"Using {self.n_bins} bins.")
         self.timeseries = np.zeros(self.n_frames)
@@ -295,12 +381,13 @@ class AnalysisBase(_Runner):
 
     def _transform_frame(self, ts) -> None:
         """unwrap -> refgroup centring -> wrap -> jitter, in the reference's order (base.py:436-451)."""
-        if self.unwrap:
+        device_compounds = getattr(self, "_prologue", None) is not None
+        if self.unwrap and not device_compounds:
             self._universe.atoms.unwrap(compound=self.wrap_compound)
         if self.refgroup is not None:
             com_refgroup = center_cluster(self.refgroup, self.ref_weights)
             self._universe.atoms.translate(self.box_center - com_refgroup)
-        if self.pack and self._universe.dimensions is not None and not (
+        if self.pack and self._universe.dimensions is not None and not device_compounds and not (
             self._device_pack and self.wrap_compound == "atoms"
         ):
             self._universe.atoms.wrap(compound=self.wrap_compound)
@@ -433,6 +520,9 @@ class AnalysisBase(_Runner):
         self._conclude()
         if self.concfreq and self.module_has_save and parallel.rank() == 0:
             self.save()
+        from .. import _cabi
+
+        _cabi.release_pinned(self._slot_prefix())  # staging buffers live for one run
 
     def run(self, start=None, stop=None, step=None, frames=None, verbose=None, progressbar_kwargs=None):
         """Iterate over the trajectory (same arguments as ``maicos.core.AnalysisBase.run``)."""
@@ -535,6 +625,22 @@ class ProfileBase:
         if not hasattr(self, "unwrap"):
             self.unwrap = True
         self._cached_weights = None
+        # frames per device call: bounded by ~64 MB of staged positions per batch
+        n_pos = self.atomgroup.n_atoms
+        self._batch_size = int(max(1, min(64, (64 << 20) // max(1, n_pos * 12))))
+        # compounds: unwrap / wrap / centres / dipole weights on the device when they are eligible
+        self._prologue = None
+        mode = getattr(self, "_device_weight_mode", None)
+        if (self.grouping != "atoms" and getattr(self, "refgroup", None) is None and not getattr(self, "jitter", 0.0)
+                and (self._static_weights or mode is not None) and compound_runs(self.atomgroup, self.grouping) is not None):
+            wm, pdim = mode if mode is not None else (0, 0)
+            try:
+                self._prologue = CompoundPrologue(
+                    self.atomgroup, self.grouping, self.bin_method, make_whole=bool(getattr(self, "unwrap", False)),
+                    wrap_center=bool(getattr(self, "unwrap", False) or getattr(self, "pack", False)),
+                    weight_mode=wm, pdim=pdim)
+            except ValueError:
+                self._prologue = None
 
     # geometry classes provide these two
     def _hist_geometry(self) -> dict:
@@ -570,26 +676,66 @@ class ProfileBase:
         return np.ascontiguousarray(self.weighting_function(self.atomgroup), dtype=np.float64)
 
     def _stage_profile(self) -> dict:
-        """Positions, weights and bin geometry of the current frame (after the geometry base ran)."""
+        """Positions, weights and bin geometry of the current frame (after the geometry base ran).
+
+        Positions (and per-frame weights) go straight into the pinned batch buffer of the frame's row.
+        """
         st = dict(self._hist_geometry())
-        st["positions"] = np.ascontiguousarray(self._profile_positions())
-        st["weights"] = self._profile_weights()
+        if self._prologue is not None:  # raw atoms; centres and weights are formed on the device
+            buf, row = self._staging_rows((self.atomgroup.n_atoms, 3), np.float32, "pos")
+            positions_into(self.atomgroup, buf[row])
+            st["positions"] = (buf, row)
+            st["box"] = np.array(self._universe.dimensions[:3], dtype=np.float32)
+            st["weights"] = self._profile_weights() if self._static_weights else None
+            st["obs"] = dict(self._obs)
+            return st
+        if self.grouping == "atoms":
+            buf, row = self._staging_rows((self.atomgroup.n_atoms, 3), np.float32, "pos")
+            positions_into(self.atomgroup, buf[row])
+        else:
+            centres = get_center(self.atomgroup, bin_method=self.bin_method, compound=self.grouping)
+            buf, row = self._staging_rows(centres.shape, np.float64, "pos")
+            buf[row] = centres
+        st["positions"] = (buf, row)
+        if self._static_weights:
+            st["weights"] = self._profile_weights()
+        else:
+            w = self._profile_weights()
+            wbuf, wrow = self._staging_rows(w.shape, np.float64, "w")
+            wbuf[wrow] = w
+            st["weights"] = (wbuf, wrow)
         st["obs"] = dict(self._obs)
         return st
+
+    @staticmethod
+    def _gather_rows(rows: list) -> np.ndarray:
+        """``[F, ...]`` view of consecutively staged rows (copy only when they are not one run)."""
+        buf = rows[0][0]
+        base = buf.ctypes.data
+        if all(r[0].ctypes.data == base and r[1] == rows[0][1] + i for i, r in enumerate(rows)):
+            return buf[rows[0][1]:rows[0][1] + len(rows)]
+        return np.stack([b[r] for b, r in rows])
 
     def _compute_profiles(self, staged: list) -> list:
         from ..lib._hist import profile_hist
 
         g0 = staged[0]
-        pos = np.stack([s["positions"] for s in staged])
-        if self._static_weights:
-            w = g0["weights"][None]
-        else:
-            w = np.stack([s["weights"] for s in staged])
+        pos = self._gather_rows([s["positions"] for s in staged])
         edges = np.stack([s["edges"] for s in staged])
         center = None if g0["center"] is None else np.stack([s["center"] for s in staged])
         zrange = None if g0["zrange"] is None else np.stack([s["zrange"] for s in staged])
-        hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], w, edges, center, zrange)
+        if self._prologue is not None:
+            c_ptr, w_ptr = self._prologue.run(pos, np.stack([s["box"] for s in staged]))
+            dev_w = (w_ptr, True) if w_ptr else None
+            w = g0["weights"][None] if (self._static_weights and not w_ptr) else None
+            hw, hc = profile_hist(g0["geometry"], None, g0["dim"], w, edges, center, zrange,
+                                  device_positions=(c_ptr, len(staged), self._prologue.n_c), device_weights=dev_w)
+        else:
+            if self._static_weights:
+                w = g0["weights"][None]
+            else:
+                w = self._gather_rows([s["weights"] for s in staged])
+            hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], w, edges, center, zrange)
         out = []
         for f, s in enumerate(staged):
             obs = s["obs"]

@@ -109,7 +109,7 @@ struct mb200_ctx {
     mb200::DevBuf d_pos, d_w, d_idx, d_tables, d_amp, d_sval, d_jobs, d_segs, d_items, d_out, d_ff2, d_counter;
     mb200::PinBuf h_stage, h_out;
     // histogram workspaces
-    mb200::DevBuf d_hpos, d_hw, d_hw2, d_hedges, d_hpar, d_hout;
+    mb200::DevBuf d_hpos, d_hw, d_hw2, d_hedges, d_hpar, d_hout, d_ctopo;
     std::list<std::shared_ptr<mb200::SfPlan>> plans;  // small LRU cache keyed by box + q window
     ~mb200_ctx();
 };

@@ -13,7 +13,7 @@ mb200_ctx::~mb200_ctx() {
     if (stream) cudaStreamDestroy(stream);
 }
 
-extern "C" int mb200_abi_version(void) { return 1; }
+extern "C" int mb200_abi_version(void) { return 2; }
 
 extern "C" const char *mb200_last_error(void) { return g_last_error.c_str(); }
 

@@ -1,0 +1,215 @@
+// Per-frame compound prologue of libmaicos_b200 (sm_100a): centres and dipole-derived weights of
+// residues / molecules straight from the float32 atom coordinates of a batch of frames.
+//
+// Replaces, for compounds that are contiguous runs of atoms, the host calls the reference makes every
+// frame before the two hot kernels:
+//   atoms.unwrap(compound) / atoms.wrap(compound)   core/base.py:438-448   (MDAnalysis)
+//   get_center(ag, bin_method, compound)            lib/util.py:642-680    -> ag.center(weights, compound)
+//   diporder_weights(ag, compound, order_parameter) lib/weights.py:131-178 -> ag.dipole_vector(compound)
+// The arithmetic restates maicos_b200/mdshim/universe.py operation by operation (float32 minimum
+// image about the first atom of a compound, float64 sequential sums in atom order, centre-of-mass
+// wrap), so the device prologue and the host prologue agree bit for bit; one thread owns one compound.
+#include "common.cuh"
+
+namespace mb200 {
+
+struct CompoundParams {
+    const float *pos;        // [F][n_atoms][3]
+    const float *boxes;      // [F][3]
+    const long long *ptr;    // [n_c + 1]
+    const double *cw;        // [n_atoms] centre weights (masses, |charges|) or null (geometry)
+    const double *mass;      // [n_atoms] masses for the wrap / dipole reference point, or null
+    const double *charge;    // [n_atoms] or null
+    double *centers;         // [F][n_c][3]
+    double *weights;         // [F][n_c] or [F][3][n_c] or null
+    long long n_atoms, n_c;
+    int make_whole, wrap_center, weight_mode, pdim;
+};
+
+constexpr int MAX_COMPOUND_ATOMS = 64;  // larger compounds take the host path
+
+__global__ void __launch_bounds__(128) k_compound(CompoundParams p) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long f = blockIdx.y;
+    if (c >= p.n_c) return;
+    const long long a0 = p.ptr[c], a1 = p.ptr[c + 1];
+    const int m = (int)(a1 - a0);
+    const float *q = p.pos + ((size_t)f * p.n_atoms + a0) * 3;
+    const float bx = p.boxes[f * 3], by = p.boxes[f * 3 + 1], bz = p.boxes[f * 3 + 2];
+
+    // pass 1: make whole (float32, about the first atom) and the mass-weighted centre for wrapping
+    float ax = q[0], ay = q[1], az = q[2];
+    auto whole = [&](int i, float &x, float &y, float &z) {
+        x = q[i * 3]; y = q[i * 3 + 1]; z = q[i * 3 + 2];
+        if (p.make_whole) {
+            float dx = __fsub_rn(x, ax), dy = __fsub_rn(y, ay), dz = __fsub_rn(z, az);
+            dx = __fsub_rn(dx, __fmul_rn(bx, rintf(__fdiv_rn(dx, bx))));
+            dy = __fsub_rn(dy, __fmul_rn(by, rintf(__fdiv_rn(dy, by))));
+            dz = __fsub_rn(dz, __fmul_rn(bz, rintf(__fdiv_rn(dz, bz))));
+            x = __fadd_rn(ax, dx); y = __fadd_rn(ay, dy); z = __fadd_rn(az, dz);
+        }
+    };
+    float sx = 0.f, sy = 0.f, sz = 0.f;  // float32 shift of the whole compound into the cell
+    if (p.wrap_center) {
+        double nx = 0, ny = 0, nz = 0, ws = 0;
+        for (int i = 0; i < m; ++i) {
+            float x, y, z;
+            whole(i, x, y, z);
+            const double w = p.mass ? p.mass[a0 + i] : 1.0;
+            nx = __dadd_rn(nx, __dmul_rn(w, (double)x));
+            ny = __dadd_rn(ny, __dmul_rn(w, (double)y));
+            nz = __dadd_rn(nz, __dmul_rn(w, (double)z));
+            ws = __dadd_rn(ws, w);
+        }
+        const double cx = __ddiv_rn(nx, ws), cy = __ddiv_rn(ny, ws), cz = __ddiv_rn(nz, ws);
+        sx = (float)__dmul_rn(-floor(__ddiv_rn(cx, (double)bx)), (double)bx);
+        sy = (float)__dmul_rn(-floor(__ddiv_rn(cy, (double)by)), (double)by);
+        sz = (float)__dmul_rn(-floor(__ddiv_rn(cz, (double)bz)), (double)bz);
+    }
+    // pass 2: requested centre (weights cw) and the centre of mass (dipole reference), float64 sums in atom order
+    double nx = 0, ny = 0, nz = 0, ws = 0, mx = 0, my = 0, mz = 0, ms = 0;
+    for (int i = 0; i < m; ++i) {
+        float x, y, z;
+        whole(i, x, y, z);
+        x = __fadd_rn(x, sx); y = __fadd_rn(y, sy); z = __fadd_rn(z, sz);
+        const double w = p.cw ? p.cw[a0 + i] : 1.0;
+        nx = __dadd_rn(nx, __dmul_rn(w, (double)x));
+        ny = __dadd_rn(ny, __dmul_rn(w, (double)y));
+        nz = __dadd_rn(nz, __dmul_rn(w, (double)z));
+        ws = __dadd_rn(ws, w);
+        if (p.weight_mode) {
+            const double mw = p.mass[a0 + i];
+            mx = __dadd_rn(mx, __dmul_rn(mw, (double)x));
+            my = __dadd_rn(my, __dmul_rn(mw, (double)y));
+            mz = __dadd_rn(mz, __dmul_rn(mw, (double)z));
+            ms = __dadd_rn(ms, mw);
+        }
+    }
+    double *out = p.centers + ((size_t)f * p.n_c + c) * 3;
+    out[0] = __ddiv_rn(nx, ws); out[1] = __ddiv_rn(ny, ws); out[2] = __ddiv_rn(nz, ws);
+    if (!p.weight_mode) return;
+
+    // dipole about the centre of mass: sum_i q_i (r_i - R_com)
+    const double rx = __ddiv_rn(mx, ms), ry = __ddiv_rn(my, ms), rz = __ddiv_rn(mz, ms);
+    double dx = 0, dy = 0, dz = 0;
+    for (int i = 0; i < m; ++i) {
+        float x, y, z;
+        whole(i, x, y, z);
+        x = __fadd_rn(x, sx); y = __fadd_rn(y, sy); z = __fadd_rn(z, sz);
+        const double qi = p.charge[a0 + i];
+        dx = __dadd_rn(dx, __dmul_rn(qi, __dsub_rn((double)x, rx)));
+        dy = __dadd_rn(dy, __dmul_rn(qi, __dsub_rn((double)y, ry)));
+        dz = __dadd_rn(dz, __dmul_rn(qi, __dsub_rn((double)z, rz)));
+    }
+    const double mu[3] = {dx, dy, dz};
+    if (p.weight_mode == 1) {  // P0: mu . e
+        p.weights[(size_t)f * p.n_c + c] = mu[p.pdim];
+        return;
+    }
+    const double norm = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    if (p.weight_mode == 4) {  // the three components of mu / |mu|: [F][3][n_c]
+        for (int d = 0; d < 3; ++d) p.weights[((size_t)f * 3 + d) * p.n_c + c] = __ddiv_rn(mu[d], norm);
+        return;
+    }
+    const double cs = __ddiv_rn(mu[p.pdim], norm);
+    p.weights[(size_t)f * p.n_c + c] = p.weight_mode == 3 ? __dmul_rn(cs, cs) : cs;
+}
+
+}  // namespace mb200
+
+using namespace mb200;
+
+extern "C" int mb200_dev_alloc(mb200_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    if (!out) return fail(MB200_EINVAL, "null output pointer");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    *out = nullptr;
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        *out = nullptr;
+        return fail(MB200_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return MB200_OK;
+}
+
+extern "C" int mb200_dev_free(mb200_ctx *ctx, void *p) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (p) MB_CUDA(cudaFree(p));
+    return MB200_OK;
+}
+
+extern "C" int mb200_dev_read(mb200_ctx *ctx, const void *dev, void *host, size_t bytes) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    MB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MB200_OK;
+}
+
+extern "C" int mb200_compound_prologue(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                                       int64_t n_atoms, const float *boxes, const int64_t *compound_ptr, int64_t n_c,
+                                       const double *center_weights, const double *masses, const double *charges,
+                                       int make_whole, int wrap_center, int weight_mode, int pdim,
+                                       double *centers_dev, double *weights_dev) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    if (n_frames < 0 || n_atoms < 0 || n_c < 0 || !boxes || !compound_ptr || !centers_dev || (n_atoms && !positions) ||
+        weight_mode < 0 || weight_mode > 4 || pdim < 0 || pdim > 2)
+        return fail(MB200_EINVAL, "invalid argument to mb200_compound_prologue");
+    if (weight_mode && (!masses || !charges || !weights_dev))
+        return fail(MB200_EINVAL, "dipole weights need masses, charges and an output buffer");
+    if (n_frames == 0 || n_c == 0) return MB200_OK;
+    if (n_frames > 65535) return fail(MB200_EINVAL, "at most 65535 frames per call");
+    if (compound_ptr[0] != 0 || compound_ptr[n_c] != n_atoms) return fail(MB200_EINVAL, "compound_ptr must cover all atoms");
+    for (int64_t c = 0; c < n_c; ++c) {
+        const int64_t m = compound_ptr[c + 1] - compound_ptr[c];
+        if (m <= 0 || m > MAX_COMPOUND_ATOMS)
+            return fail(MB200_EINVAL, "compound %lld has %lld atoms (supported: 1..%d)", (long long)c, (long long)m,
+                        MAX_COMPOUND_ATOMS);
+    }
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const size_t F = (size_t)n_frames, N = (size_t)n_atoms, NC = (size_t)n_c;
+    CompoundParams p;
+    std::memset(&p, 0, sizeof(p));
+    if (positions_on_device) {
+        p.pos = positions;
+    } else {
+        MB_TRY(ctx->d_hpos.ensure(F * N * 12));
+        MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * 12, cudaMemcpyHostToDevice, ctx->stream));
+        p.pos = ctx->d_hpos.as<float>();
+    }
+    // topology side: ptr | cw | mass | charge | boxes
+    const size_t b_ptr = (NC + 1) * 8, b_at = N * 8;
+    MB_TRY(ctx->d_ctopo.ensure(b_ptr + 3 * b_at + F * 12 + 64));
+    char *base = ctx->d_ctopo.as<char>();
+    MB_CUDA(cudaMemcpyAsync(base, compound_ptr, b_ptr, cudaMemcpyHostToDevice, ctx->stream));
+    p.ptr = reinterpret_cast<const long long *>(base);
+    size_t off = b_ptr;
+    if (center_weights) {
+        MB_CUDA(cudaMemcpyAsync(base + off, center_weights, b_at, cudaMemcpyHostToDevice, ctx->stream));
+        p.cw = reinterpret_cast<const double *>(base + off);
+    }
+    off += b_at;
+    if (masses) {
+        MB_CUDA(cudaMemcpyAsync(base + off, masses, b_at, cudaMemcpyHostToDevice, ctx->stream));
+        p.mass = reinterpret_cast<const double *>(base + off);
+    }
+    off += b_at;
+    if (charges) {
+        MB_CUDA(cudaMemcpyAsync(base + off, charges, b_at, cudaMemcpyHostToDevice, ctx->stream));
+        p.charge = reinterpret_cast<const double *>(base + off);
+    }
+    off += b_at;
+    MB_CUDA(cudaMemcpyAsync(base + off, boxes, F * 12, cudaMemcpyHostToDevice, ctx->stream));
+    p.boxes = reinterpret_cast<const float *>(base + off);
+    p.centers = centers_dev; p.weights = weights_dev;
+    p.n_atoms = n_atoms; p.n_c = n_c;
+    p.make_whole = make_whole; p.wrap_center = wrap_center; p.weight_mode = weight_mode; p.pdim = pdim;
+    dim3 grid((unsigned)((NC + 127) / 128), (unsigned)F);
+    k_compound<<<grid, 128, 0, ctx->stream>>>(p);
+    MB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));  // host topology arrays may be reused by the caller
+    return MB200_OK;
+}

@@ -1062,8 +1062,8 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
     return MB200_OK;
 }
 
-extern "C" int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const double *weights, int64_t n_frames,
-                                  int64_t n, const double *boxes, double qmin, double qmax, int32_t n_bins,
+extern "C" int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const double *weights, int inputs_on_device,
+                                  int64_t n_frames, int64_t n, const double *boxes, double qmin, double qmax, int32_t n_bins,
                                   int32_t block, int32_t n_blocks, double *s_binned, int64_t *bincount) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
     if (n_frames < 0 || n < 0 || n_bins <= 0 || !boxes || !s_binned || !bincount || (n && (!positions || !weights)))
@@ -1086,9 +1086,16 @@ extern "C" int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const
             if (++chunk >= 64) break;
         }
         // inputs: positions [chunk][n][3], weights [chunk][3][n]
-        MB_TRY(ctx->d_pos.ensure(std::max<size_t>(chunk * nn, 1) * 48));
-        double *dp = ctx->d_pos.as<double>(), *dw = dp + chunk * nn * 3;
-        if (nn) {
+        double *dp, *dw;
+        if (inputs_on_device) {
+            dp = const_cast<double *>(positions) + done * nn * 3;
+            dw = const_cast<double *>(weights) + done * nn * 3;
+        } else {
+            MB_TRY(ctx->d_pos.ensure(std::max<size_t>(chunk * nn, 1) * 48));
+            dp = ctx->d_pos.as<double>();
+            dw = dp + chunk * nn * 3;
+        }
+        if (nn && !inputs_on_device) {
             MB_CUDA(cudaMemcpyAsync(dp, positions + done * nn * 3, chunk * nn * 24, cudaMemcpyHostToDevice, ctx->stream));
             MB_CUDA(cudaMemcpyAsync(dw, weights + done * nn * 3, chunk * nn * 24, cudaMemcpyHostToDevice, ctx->stream));
         }

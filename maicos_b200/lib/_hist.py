@@ -16,29 +16,41 @@ from .. import _cabi
 PLANAR, CYLINDER, SPHERE = 0, 1, 2
 
 
-def profile_hist(geometry: int, positions: np.ndarray, dim: int, weights: np.ndarray | None, edges: np.ndarray,
-                 center: np.ndarray | None = None, zrange: np.ndarray | None = None, device: int | None = None):
+def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights: np.ndarray | None, edges: np.ndarray,
+                 center: np.ndarray | None = None, zrange: np.ndarray | None = None, device: int | None = None,
+                 device_positions: tuple | None = None, device_weights: tuple | None = None):
     """Histogram ``positions [F, n, 3]`` (float32 or float64) into ``edges [F, n_bins + 1]``.
 
     ``weights``: ``None`` (counts only), ``[1, n]`` (same for all frames) or ``[F, n]``.
+    ``device_positions = (pointer, F, n)``: float64 ``[F, n, 3]`` already in HBM (output of the
+    compound prologue); ``device_weights = (pointer, per_frame)`` likewise.
     Returns ``(hist_w float64 [F, n_bins] or None, hist_c int64 [F, n_bins])``.
     """
-    positions = np.ascontiguousarray(positions)
-    if positions.ndim != 3 or positions.shape[2] != 3:
-        raise ValueError("positions must have shape (n_frames, n, 3)")
-    if positions.dtype not in (np.float32, np.float64):
-        raise ValueError("positions must be float32 or float64")
-    F, n = positions.shape[0], positions.shape[1]
+    if device_positions is not None:
+        pos_ptr, F, n = device_positions
+        pos_is_f32, pos_on_dev = 0, 1
+    else:
+        positions = np.ascontiguousarray(positions)
+        if positions.ndim != 3 or positions.shape[2] != 3:
+            raise ValueError("positions must have shape (n_frames, n, 3)")
+        if positions.dtype not in (np.float32, np.float64):
+            raise ValueError("positions must be float32 or float64")
+        F, n = positions.shape[0], positions.shape[1]
+        pos_ptr, pos_is_f32, pos_on_dev = _cabi.ptr(positions), int(positions.dtype == np.float32), 0
     edges = np.ascontiguousarray(edges, dtype=np.float64)
     if edges.shape[0] != F:
         raise ValueError("edges must have one row per frame")
     n_bins = edges.shape[1] - 1
-    per_frame = 0
-    if weights is not None:
+    per_frame, w_ptr, w_on_dev = 0, None, 0
+    if device_weights is not None:
+        w_ptr, per_frame, w_on_dev = device_weights[0], int(bool(device_weights[1]) and F > 1), 1
+        weights = True  # weighted histogram requested
+    elif weights is not None:
         weights = np.ascontiguousarray(weights, dtype=np.float64)
         if weights.shape not in ((1, n), (F, n)):
             raise ValueError(f"weights must have shape (1, {n}) or ({F}, {n})")
         per_frame = int(weights.shape[0] == F and F > 1)
+        w_ptr = _cabi.ptr(weights)
     if center is not None:
         center = np.ascontiguousarray(center, dtype=np.float64)
     if zrange is not None:
@@ -48,8 +60,8 @@ def profile_hist(geometry: int, positions: np.ndarray, dim: int, weights: np.nda
     ctx = _cabi.context(device)
     _cabi.check(
         _cabi.load().mb200_profile_hist(
-            ctx.handle, int(geometry), _cabi.ptr(positions), int(positions.dtype == np.float32), 0, F, n, int(dim),
-            _cabi.ptr(weights), per_frame, 0, _cabi.ptr(edges), n_bins, _cabi.ptr(center), _cabi.ptr(zrange),
+            ctx.handle, int(geometry), pos_ptr, pos_is_f32, pos_on_dev, F, n, int(dim),
+            w_ptr, per_frame, w_on_dev, _cabi.ptr(edges), n_bins, _cabi.ptr(center), _cabi.ptr(zrange),
             _cabi.ptr(hist_w), _cabi.ptr(hist_c),
         )
     )

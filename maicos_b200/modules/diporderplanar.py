@@ -30,6 +30,10 @@ class DiporderPlanar(ProfilePlanarBase):
         int = 2, order_parameter: str = "P0", jitter: float = 0.0
     ) -> None:
         self._locals = locals()
+        #: (mode, pdim) of mb200_compound_prologue: the projection needs no host data
+        self._device_weight_mode = ({"P0": 1, "cos_theta": 2, "cos_2_theta": 3}.get(order_parameter), pdim)
+        if self._device_weight_mode[0] is None:
+            self._device_weight_mode = None
 
         def get_unit_vectors(atomgroup, grouping: str):
             return unit_vectors_planar(atomgroup=atomgroup, grouping=grouping, pdim=pdim)

@@ -16,7 +16,7 @@ import logging
 import numpy as np
 
 from .. import _cabi, parallel
-from ..core.base import AnalysisBase
+from ..core.base import AnalysisBase, CompoundPrologue, compound_runs, positions_into
 from ..lib.util import get_center
 
 
@@ -45,9 +45,24 @@ class DiporderStructureFactor(AnalysisBase):
     def _prepare(self) -> None:
         logging.info("Analysis of the structure factor of dipoles.")
         self.n_bins = int(np.ceil((self.qmax - self.qmin) / self.dq))
+        # centres and unit dipoles on the device when the compounds are eligible (contiguous, complete)
+        self._prologue = None
+        if (self.refgroup is None and not self.jitter and self.wrap_compound != "atoms"
+                and compound_runs(self.atomgroup, self.wrap_compound) is not None):
+            try:
+                self._prologue = CompoundPrologue(self.atomgroup, self.wrap_compound, self.bin_method,
+                                                  make_whole=self.unwrap, wrap_center=self.unwrap or self.pack,
+                                                  weight_mode=4)
+            except ValueError:
+                self._prologue = None
+        self._batch_size = int(max(1, min(type(self)._batch_size, (128 << 20) // max(1, self.atomgroup.n_atoms * 12))))
 
     def _stage_frame(self):
         box = np.double(np.array(self._ts.dimensions[:3], dtype=np.float32))
+        if self._prologue is not None:
+            buf, row = self._staging_rows((self.atomgroup.n_atoms, 3), np.float32, "pos")
+            positions_into(self.atomgroup, buf[row])
+            return buf, row, box
         positions = np.ascontiguousarray(
             get_center(atomgroup=self.atomgroup, bin_method=self.bin_method, compound=self.wrap_compound),
             dtype=np.float64,
@@ -60,17 +75,28 @@ class DiporderStructureFactor(AnalysisBase):
 
     def _compute_staged(self, staged: list) -> list:
         F = len(staged)
-        n = staged[0][0].shape[0]
-        pos = np.stack([s[0] for s in staged])
-        w = np.stack([s[1] for s in staged])
         boxes = np.stack([s[2] for s in staged])
+        on_device = 0
+        if self._prologue is not None:
+            base = staged[0][0].ctypes.data
+            if all(st[0].ctypes.data == base and st[1] == staged[0][1] + f for f, st in enumerate(staged)):
+                raw = staged[0][0][staged[0][1]:staged[0][1] + F]
+            else:
+                raw = np.stack([buf[row] for buf, row, _ in staged])
+            pos, w = self._prologue.run(raw, boxes.astype(np.float32))
+            n, on_device = self._prologue.n_c, 1
+        else:
+            n = staged[0][0].shape[0]
+            pos_h = np.stack([s[0] for s in staged])  # keep the arrays alive across the call
+            w_h = np.stack([s[1] for s in staged])
+            pos, w = _cabi.ptr(pos_h), _cabi.ptr(w_h)
         sb = np.zeros((F, 3, self.n_bins))
         cb = np.zeros((F, 3, self.n_bins), dtype=np.int64)
         block, n_blocks = parallel.q_block()
         ctx = _cabi.context()
         _cabi.check(
             _cabi.load().mb200_dipsf_frames(
-                ctx.handle, _cabi.ptr(pos), _cabi.ptr(w), F, n, _cabi.ptr(boxes), float(self.qmin), float(self.qmax),
+                ctx.handle, pos, w, on_device, F, n, _cabi.ptr(boxes), float(self.qmin), float(self.qmax),
                 self.n_bins, block, n_blocks, _cabi.ptr(sb), _cabi.ptr(cb),
             )
         )

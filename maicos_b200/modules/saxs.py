@@ -92,6 +92,8 @@ class Saxs(AnalysisBase):
         self._group_flat = np.ascontiguousarray(np.concatenate(self._group_index), dtype=np.int32)
         self._cm = np.ascontiguousarray(np.stack([tables.cm_packed(str(el)) for el in self.elements]))
 
+        # frames per device call: bounded by ~128 MB of staged positions (and by the table workspace)
+        self._batch_size = int(max(1, min(type(self)._batch_size, (128 << 20) // max(1, self.atomgroup.n_atoms * 12))))
         if self.bin_spectrum:
             self.n_bins = int(np.ceil((self.qmax - self.qmin) / self.dq))
         else:

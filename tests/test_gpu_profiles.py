@@ -228,3 +228,47 @@ def test_density_cylinder_and_sphere_classes():
     edges = np.linspace(0.0, 20.0, cyl.n_bins + 1)
     vol = np.pi * np.diff(edges**2) * 70.0
     assert_allclose(cyl.results.profile, st_c.means["c"] / vol, rtol=1e-12)
+
+
+def test_device_compound_prologue_equals_host_prologue(monkeypatch):
+    """mb200_compound_prologue (unwrap, wrap, centres, dipole weights) vs the shim's host path: bit for bit."""
+    import maicos_b200.core.base as base
+    import maicos_b200.modules.diporderstructurefactor as dsf
+
+    # molecules scattered over periodic images and broken across the cell faces
+    u = mb.synthetic.spce_universe(1500, 77, n_frames=4)
+    L = u.dimensions[:3]
+    rng = np.random.default_rng(4)
+    for f in range(4):
+        ts = u.trajectory[f]
+        u.trajectory.coordinates[f] = ts.positions + L * rng.integers(-1, 2, ts.positions.shape)
+
+    def run_all():
+        out = {}
+        for op in ("P0", "cos_theta", "cos_2_theta"):
+            a = mb.DiporderPlanar(u.atoms, bin_width=0.7, order_parameter=op, pdim=1).run()
+            out[op] = (a.results.profile.copy(), a.sums.bincount.copy(), a._prologue is not None)
+        a = mb.DensityPlanar(u.atoms, dens="mass", grouping="residues", bin_method="coc", bin_width=0.9).run()
+        out["dens"] = (a.results.profile.copy(), a.sums.bincount.copy(), a._prologue is not None)
+        a = mb.DensitySphere(u.atoms, dens="charge", grouping="molecules", bin_method="cog", bin_width=1.1, unwrap=False).run()
+        out["sph"] = (a.results.profile.copy(), a.sums.bincount.copy(), a._prologue is not None)
+        a = mb.DiporderStructureFactor(u.atoms, qmax=2.0, dq=0.1, grouping="residues").run()
+        out["dsf"] = (a.results.structure_factors.copy(), np.zeros(1), a._prologue is not None)
+        return out
+
+    dev = run_all()
+    assert all(v[2] for v in dev.values()), "device prologue should be active for whole contiguous molecules"
+    monkeypatch.setattr(base, "compound_runs", lambda ag, c: None)
+    monkeypatch.setattr(dsf, "compound_runs", lambda ag, c: None)
+    host = run_all()
+    assert not any(v[2] for v in host.values())
+    for k in dev:
+        assert_array_equal(dev[k][1], host[k][1])
+        assert_allclose(dev[k][0], host[k][0], rtol=1e-12, atol=1e-15, equal_nan=True)
+
+
+def test_device_prologue_not_used_for_partial_compounds():
+    u = slab_universe(n_frames=2)
+    oxy = u.select_atoms("element O")  # one atom of every residue: incomplete compounds
+    a = mb.DensityPlanar(oxy, dens="mass", grouping="residues", bin_width=1.0, unwrap=False, pack=False).run()
+    assert a._prologue is None and a.sums.bincount.sum() > 0

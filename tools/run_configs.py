@@ -54,7 +54,7 @@ L = float(u.dimensions[0])
 for qmax, dq in ((2.0, 0.01), (6.0, 0.01)):
     nq = n_valid_q(L, qmax)
     a = mb.DiporderStructureFactor(u.atoms, qmax=qmax, dq=dq, unwrap=False, pack=False)
-    a.run(stop=1)
+    a.run()
     a, dt = timed(lambda: mb.DiporderStructureFactor(u.atoms, qmax=qmax, dq=dq, unwrap=False, pack=False).run())
     out[f"C3_dipsf_300k_qmax{qmax:g}"] = {
         "frames": a.n_frames, "frames_per_s": a.n_frames / dt, "n_compounds": n_mol, "n_q_valid": nq,
@@ -63,9 +63,9 @@ for qmax, dq in ((2.0, 0.01), (6.0, 0.01)):
 
 # ---- C4 ------------------------------------------------------------------------------------------
 n_c, n_w = 100_000, 300_000
-fr, topo = mb.synthetic.confined_slab_frames(n_w, n_c, 215.0, 215.0, 215.4, 200.0, 20261021, n_frames=6)
+fr, topo = mb.synthetic.confined_slab_frames(n_w, n_c, 215.0, 215.0, 215.4, 200.0, 20261021, n_frames=24)
 u = Universe(fr.shape[1], MemoryTrajectory(fr, np.float32([215.0, 215.0, 215.4, 90, 90, 90])), **topo)
-mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.1, unwrap=False, pack=False).run(stop=2)
+mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.1, unwrap=False, pack=False).run()
 a, dt = timed(lambda: mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.1, unwrap=False, pack=False).run())
 out["C4_densityplanar_1M"] = {"frames": a.n_frames, "frames_per_s": a.n_frames / dt, "n_atoms": int(fr.shape[1]),
                               "n_bins": a.n_bins, "timings": a.timings}
