@@ -159,3 +159,50 @@ def test_running_stats_contract():
     assert_allclose(st.means["o"], x.mean(0))
     assert_allclose(st.sems["o"], x.std(0) / np.sqrt(len(x)))
     assert_allclose(st.sems["c"], x[:, 0].std() / np.sqrt(len(x)))
+
+
+def test_shim_semantics_reproduce_reference_diporder_planar_values(water_gro):
+    """tests/modules/test_diporderplanar.py:41-82: 45 regression numbers produced by MAICoS + MDAnalysis.
+
+    Pins the in-memory shim's unwrap / refgroup centring / compound wrap / centre-of-mass / dipole
+    semantics (MDAnalysis itself is absent) together with the restated planar histogram and its
+    normalisations (core/base.py:436-451, 804-835)."""
+    from conftest import water_universe
+    from maicos_b200.lib.math import center_cluster
+    from reference_values import DIPORDER_PLANAR
+
+    for dim in range(3):
+        u = water_universe(water_gro["positions"], water_gro["dimensions"], water_gro["elements"])
+        ag = u.atoms
+        ag.unwrap(compound="residues")
+        L = u.dimensions[:3].astype(np.float64)
+        ag.translate(L / 2 - center_cluster(ag, ag.masses))
+        ag.wrap(compound="residues")
+        pos = ag.center(ag.masses, compound="residues")
+        mu = ag.dipole_vector(compound="residues")
+        n_bins = int(np.ceil(L[dim] / 5))
+        zmin, zmax, obs = restatement.planar_geometry(L, dim, n_bins)
+        cnt = restatement.hist_planar(pos, None, dim, n_bins, zmin, zmax)
+        cos = mu[:, dim] / np.linalg.norm(mu, axis=1)
+        for op, w in (("P0", mu[:, dim]), ("cos_theta", cos), ("cos_2_theta", cos * cos)):
+            prof = restatement.hist_planar(pos, w, dim, n_bins, zmin, zmax)
+            out = prof / obs["bin_volume"] if op == "P0" else prof / cnt
+            assert_allclose(out, DIPORDER_PLANAR[dim][op], rtol=1e-2)
+
+
+def test_density_cylinder_reference_means(water_gro):
+    """tests/modules/test_densitycylinder.py:38-48 through the restated cylinder histogram."""
+    from conftest import water_universe
+    from maicos_b200.lib.weights import density_weights
+    from reference_values import DENSITY_CYLINDER_MEAN
+
+    u = water_universe(water_gro["positions"], water_gro["dimensions"], water_gro["elements"])
+    u.atoms.wrap(compound="atoms")
+    L = u.dimensions[:3].astype(np.float64)
+    rmax = L[:2].min() / 2
+    nb = int(np.ceil(rmax))
+    vol = np.pi * np.diff(np.linspace(0, rmax, nb + 1) ** 2) * L[2]
+    for dens, mean in DENSITY_CYLINDER_MEAN.items():
+        w = density_weights(u.atoms, "atoms", dens)
+        prof = restatement.hist_cylinder(u.atoms.positions, w, 2, nb, 0.0, rmax, 0.0, L[2], L / 2) / vol
+        assert_allclose(prof.mean(), mean, atol=1e-4, rtol=1e-2)
