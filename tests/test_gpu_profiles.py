@@ -39,9 +39,10 @@ def test_planar_vs_numpy(dtype, n_bins):
                 assert_allclose(hw[f], ref, rtol=WTOL, atol=WTOL * np.abs(wf).sum())
 
 
+@pytest.mark.parametrize("nb", [333, 1500])
 @pytest.mark.parametrize("dim", [0, 1, 2])
-def test_cylinder_and_sphere_vs_numpy(dim):
-    F, n, nb = 2, 40_000, 333
+def test_cylinder_and_sphere_vs_numpy(dim, nb):
+    F, n = 2, 40_000
     L = np.array([60.0, 70.0, 80.0])
     pos = frames(F, n, -3, 83, np.float32, seed=dim)
     w = np.random.default_rng(2).normal(size=(F, n))
@@ -60,6 +61,29 @@ def test_cylinder_and_sphere_vs_numpy(dim):
         assert_array_equal(hc[f], restatement.hist_sphere(pos[f], None, nb, er[f, 0], er[f, -1], center[f]))
         assert_allclose(hw[f], restatement.hist_sphere(pos[f], w[f], nb, er[f, 0], er[f, -1], center[f]),
                         rtol=WTOL, atol=WTOL * np.abs(w[f]).sum())
+
+
+def test_heavy_collisions_unaligned_frames_and_nonfinite_weights():
+    """Half of the atoms in one bin (carry chains of the fixed-point limbs), unaligned frames, inf / nan weights."""
+    F, n, nb = 3, 33_333, 1200  # n * 12 B is not a multiple of 16: frames start unaligned
+    rng = np.random.default_rng(8)
+    pos = rng.uniform(0, 50, (F, n, 3)).astype(np.float32)
+    pos[:, : n // 2, 2] = np.float32(17.31)  # half of the atoms in one bin
+    w = rng.normal(size=(F, n)) * 1e3
+    e = np.tile(np.linspace(np.float64(0), np.float64(50), nb + 1), (F, 1))
+    hw, hc = profile_hist(0, pos, 2, w, e)
+    for f in range(F):
+        assert_array_equal(hc[f], restatement.hist_planar(pos[f], None, 2, nb, 0.0, 50.0))
+        assert_allclose(hw[f], restatement.hist_planar(pos[f], w[f], 2, nb, 0.0, 50.0), rtol=WTOL,
+                        atol=WTOL * np.abs(w[f]).sum())
+    hw2, _ = profile_hist(0, pos, 2, w, e)
+    assert_array_equal(hw2, hw)  # fixed-point sums: bitwise reproducible
+    w[1, 5] = np.inf
+    w[2, 7] = np.nan
+    hw, hc = profile_hist(0, pos, 2, w, e)
+    assert_allclose(hw[0], restatement.hist_planar(pos[0], w[0], 2, nb, 0.0, 50.0), rtol=WTOL, atol=WTOL * np.abs(w[0]).sum())
+    assert np.isinf(hw[1]).sum() == 1 and np.isnan(hw[2]).sum() == 1
+    assert_array_equal(hc[1], restatement.hist_planar(pos[1], None, 2, nb, 0.0, 50.0))
 
 
 def test_empty_and_ragged_inputs():
