@@ -103,6 +103,7 @@ struct mb200_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false;
+    bool sf_attr_set = false, hist_attr_set = false;  // cudaFuncSetAttribute done on this device
     int64_t launches = 0;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // S(q) workspaces

@@ -257,7 +257,6 @@ __global__ void k_hist_merge(HistParams p, int fixed_point, double *__restrict__
 
 using namespace mb200;
 
-static bool g_hist_attr_set = false;
 
 extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *positions, int pos_is_f32,
                                   int positions_on_device, int64_t n_frames, int64_t n, int dim, const double *weights,
@@ -339,10 +338,10 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
     if (N) {
         // enough CTAs to fill the GPU across frames, each streaming >= 16 elements per thread
         const size_t smem = mode == 2 ? 0 : (NB + 1) * 8 + NB * 4 * (mode == 0 ? 4 : 1);
-        if (!g_hist_attr_set) {
+        if (!ctx->hist_attr_set) {  // per device: a process may own several contexts
             MB_CUDA(cudaFuncSetAttribute(k_hist<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             MB_CUDA(cudaFuncSetAttribute(k_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            g_hist_attr_set = true;
+            ctx->hist_attr_set = true;
         }
         long long per_frame = (long long)((N + (size_t)H_THREADS * 16 - 1) / ((size_t)H_THREADS * 16));
         long long want = ((long long)ctx->n_sm * 4 + (long long)F - 1) / (long long)F;

@@ -738,7 +738,6 @@ struct SegSpec {       // one contraction problem (one reference structure_facto
     int ff2_group;      // index into plan ff2, -1 none
 };
 
-static bool g_smem_attr_set = false;
 
 // Runs tables + contraction for all segments; leaves SegDesc array on the device (ctx->d_segs).
 static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t block, int32_t n_blocks,
@@ -858,9 +857,9 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
         ++launched;
     }
     if (!items.empty()) {
-        if (!g_smem_attr_set) {
+        if (!ctx->sf_attr_set) {  // per device: a process may own several contexts
             MB_CUDA(cudaFuncSetAttribute(k_sf_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-            g_smem_attr_set = true;
+            ctx->sf_attr_set = true;
         }
         if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
         MB_CUDA(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
