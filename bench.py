@@ -285,7 +285,21 @@ def main():
         "roofline": roofline,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wl)
+        line["cpu_baseline"], ref_obs, ref_frame = cpu_baseline(wl)
+        # parity next to the throughput: the same frame through the C ABI vs the reference kernel's result
+        s1 = np.zeros((1, G, n_bins)); i1 = np.zeros((1, G, n_bins)); c1 = np.zeros((1, G, n_bins), dtype=np.int64)
+        fr = np.ascontiguousarray(ref_frame[None])
+        _cabi.check(lib.mb200_saxs_frames(ctx.handle, _cabi.ptr(fr), 0, 1, n, _cabi.ptr(boxes[:1].copy()), _cabi.ptr(gflat),
+                                          _cabi.ptr(gptr), G, _cabi.ptr(cm), 0.0, QMAX, 0.0, float(np.pi), n_bins, 1,
+                                          0, 1, _cabi.ptr(s1), _cabi.ptr(i1), _cabi.ptr(c1)))
+        nz = ref_obs["structure_factors"] != 0
+        line["parity"] = {
+            "checked": "frame 0 of the cpu_baseline sample: binned S, I, bincount vs reference Cython kernel + NumPy body",
+            "max_rel_err_S_binned": float(np.max(np.abs(s1[0].sum(0)[nz] / ref_obs["structure_factors"][nz] - 1))),
+            "max_rel_err_I_binned": float(np.max(np.abs(i1[0].sum(0)[nz] / ref_obs["scattering_intensities"][nz] - 1))),
+            "bincount_equal": bool(np.array_equal(c1[0, -1], ref_obs["bincount"])),
+            "tolerance": "rel <= 1e-6 (FP64 mode), counts exact",
+        }
     if world == 1 and not args.no_e2e:
         line["path2_profile_hist"] = path2_summary(ctx, lib, torch)
     print(json.dumps(line))
@@ -340,15 +354,18 @@ def cpu_baseline(wl):
                                   np.pi, n_bins)  # warm the OpenMP pool
     t0 = time.perf_counter()
     done = 0
+    first_obs = None
     while done < 8 and (time.perf_counter() - t0 < 12.0 or done < 2):
         pos = restatement.wrap_atoms_f32(frames[done % 3], box)
-        restatement.saxs_single_frame(pos, box, el, 0.0, QMAX, 0.0, np.pi, n_bins)
+        obs, _ = restatement.saxs_single_frame(pos, box, el, 0.0, QMAX, 0.0, np.pi, n_bins)
+        if first_obs is None:
+            first_obs = obs
         done += 1
     dt = time.perf_counter() - t0
     return {"value": done * wl["atomq_per_frame"] / dt, "unit": "atom*q/s", "cores": kernel.n_threads(),
             "kind": kernel.kind(), "frames_per_s": done / dt,
             "sample": f"{done} full frame(s) of the workload (O + H groups, {wl['atomq_per_frame']:.3e} atom*q each) "
-                      f"through the Cython kernel + NumPy Saxs frame body in {dt:.1f} s"}
+                      f"through the Cython kernel + NumPy Saxs frame body in {dt:.1f} s"}, first_obs, frames[0]
 
 
 if __name__ == "__main__":
