@@ -60,6 +60,12 @@ uint64_t mb200_ctx_stream(mb200_ctx *ctx);
 int mb200_ctx_stats(mb200_ctx *ctx, int64_t out[8]);
 /* Enable (1) / disable (0) CUDA-event timing of the contraction kernel inside calls. */
 int mb200_ctx_set_timing(mb200_ctx *ctx, int enable);
+/* Arithmetic of the fused S(q) calls (mb200_saxs_frames, mb200_dipsf_frames):
+ *   0  FP64 tables + FP64 DMMA accumulation -- the parity mode and the default;
+ *   1  split precision: five int8 digits per component, exact int32 accumulation on the tcgen05
+ *      tensor cores (TMEM), |dA| ~ 2e-8 per 32768 atoms -> ~1e-9 relative on binned S(q).
+ * mb200_structure_factor[_block] (the reference's raw-cube API) always computes in FP64. */
+int mb200_ctx_set_precision(mb200_ctx *ctx, int mode);
 /* Total kernels launched by this context since creation. */
 int64_t mb200_ctx_launch_count(mb200_ctx *ctx);
 /* Page-locked host memory for frame staging (full-rate asynchronous H2D / D2H).  Any host pointer

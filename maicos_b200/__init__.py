@@ -13,4 +13,19 @@ from .core import AnalysisBase, AnalysisCollection  # noqa: E402
 from .modules import *  # noqa: E402,F401,F403
 from .modules import __all__ as _modules_all  # noqa: E402
 
-__all__ = ["AnalysisBase", "AnalysisCollection", "core", "lib", "mdshim", "parallel", "synthetic", *_modules_all]
+
+
+def set_precision(mode: str = "fp64", device: int | None = None) -> None:
+    """Arithmetic of the fused S(q) paths (``Saxs``, ``DiporderStructureFactor``) on this process' GPU.
+
+    ``"fp64"`` -- FP64 phase tables and FP64 DMMA accumulation: the parity mode and the default.
+    ``"i8x5"`` -- split precision on the tcgen05 tensor cores (five int8 digits per component, exact
+    int32 accumulation in TMEM): several times faster, ~1e-9 relative on binned S(q); isolated weak
+    cells of the raw cube can exceed 1e-6, so ``lib.math.structure_factor`` always stays FP64.
+    """
+    from . import _cabi
+
+    _cabi.context(device).set_precision(mode)
+
+
+__all__ = ["AnalysisBase", "set_precision", "AnalysisCollection", "core", "lib", "mdshim", "parallel", "synthetic", *_modules_all]

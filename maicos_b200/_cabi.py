@@ -32,6 +32,7 @@ SIGNATURES = {
     "mb200_ctx_stats": (ctypes.c_int, [ctypes.c_void_p, c_i64_p]),
     "mb200_ctx_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "mb200_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "mb200_ctx_set_precision": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "mb200_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mb200_host_free": (None, [ctypes.c_void_p]),
     "mb200_sfactor_maxn": (ctypes.c_int, [c_double_p, ctypes.c_double, c_i32_p]),
@@ -147,6 +148,10 @@ class Context:
         _check(load().mb200_ctx_stats(self._h, out))
         keys = ["launches", "n_valid_q", "ctas", "dmma_steps", "atom_q", "contract_ns", "k_splits", "warp_tiles"]
         return dict(zip(keys, [int(v) for v in out]))
+
+    def set_precision(self, mode: str) -> None:
+        """``"fp64"`` (parity default) or ``"i8x5"`` (split precision on the tcgen05 tensor cores)."""
+        _check(load().mb200_ctx_set_precision(self._h, {"fp64": 0, "i8x5": 1}[mode]))
 
     def launch_count(self) -> int:
         return int(load().mb200_ctx_launch_count(self._h))

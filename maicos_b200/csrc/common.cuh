@@ -103,11 +103,13 @@ struct mb200_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false;
-    bool sf_attr_set = false, hist_attr_set = false;  // cudaFuncSetAttribute done on this device
+    bool sf_attr_set = false, hist_attr_set = false, tc_attr_set = false;
+    int precision = 0;        // 0: FP64 DMMA (parity default)  1: int8 x 5 split precision on tcgen05
+    bool force_fp64 = false;  // cudaFuncSetAttribute done on this device
     int64_t launches = 0;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // S(q) workspaces
-    mb200::DevBuf d_pos, d_w, d_idx, d_tables, d_amp, d_sval, d_jobs, d_segs, d_items, d_out, d_ff2, d_counter;
+    mb200::DevBuf d_pos, d_w, d_idx, d_tables, d_amp, d_sval, d_jobs, d_segs, d_items, d_out, d_ff2, d_counter, d_bimg, d_tcdesc;
     mb200::PinBuf h_stage, h_out;
     // histogram workspaces
     mb200::DevBuf d_hpos, d_hw, d_hw2, d_hedges, d_hpar, d_hout, d_ctopo;

@@ -81,6 +81,7 @@ struct SegDesc {
     int32_t ld, n_split, n_wt, n_valid;
     int32_t rows[3];               // table rows per axis (block stride = rows * 8 double2)
     int32_t pad_;
+    long long amp_stride;          // double2 per split in `amp`
 };
 
 struct ItemDesc {
@@ -431,7 +432,7 @@ k_sf_contract(const ItemDesc *__restrict__ items, int n_items, const SegDesc *__
 __device__ __forceinline__ double s_of_entry(const SegDesc &sg, int e) {
     const int ai = sg.ent_amp[e];
     double re = 0.0, im = 0.0;
-    const size_t stride = (size_t)sg.n_wt * 512;
+    const size_t stride = (size_t)sg.amp_stride;
     for (int s = 0; s < sg.n_split; ++s) {  // fixed order -> reproducible
         const double2 v = sg.amp[s * stride + ai];
         re += v.x;
@@ -485,6 +486,10 @@ __global__ void __launch_bounds__(128) k_sf_binned(const SegDesc *__restrict__ s
     }
 }
 
+}  // namespace mb200
+#include "sfactor_tc.cuh"
+namespace mb200 {
+
 // ------------------------------------------------------------------------------------------
 // host: q-plan
 // ------------------------------------------------------------------------------------------
@@ -504,8 +509,13 @@ struct SfPlan {
     std::vector<TileGroupDesc> tgs;
     int32_t n_wt = 0;
     int64_t n_mma_tiles = 0;  // valid 8x8 DMMA tiles
+    // tensor-core (split precision) tiling: packed (h,k) rows in tiles of 128, l tiles of <= 48
+    std::vector<uint8_t> tc_rows;       // [tc_n_rt * 128][2]
+    std::vector<int32_t> ent_amp_tc;    // index into [tc_n_rt * tc_n_lt][128][tc_lt]
+    int32_t tc_n_rt = 0, tc_n_lt = 0, tc_lt = 0, tc_n_pairs = 0;
+    bool tc_ok = false;
     // device copies
-    DevBuf d_tgs, d_ent_amp, d_bin_start, d_ff2;
+    DevBuf d_tgs, d_ent_amp, d_bin_start, d_ff2, d_tc_rows, d_ent_amp_tc;
     std::vector<double> ff2_key;  // cm params the cached ff2 was built for
     int32_t ff2_groups = 0;
 };
@@ -655,6 +665,34 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
     } else {
         pl->cell.swap(cell); pl->qrr.swap(qv); pl->ent_amp.swap(amp);
     }
+    // tensor-core tiling: (h,k) pairs with at least one valid l, in (h,k) order, 128 per row tile
+    if (m0 <= 255 && m1 <= 255 && m2 >= 1 && nv > 0) {
+        std::vector<int32_t> pos((size_t)m0 * m1, -1);
+        for (int h = 0; h < m0; ++h)
+            for (int k = 0; k < m1; ++k) {
+                bool any = false;
+                for (int l = 0; l < m2 && !any; ++l) any = qcube[((size_t)h * m1 + k) * m2 + l] != 0.0;
+                if (any) {
+                    pos[(size_t)h * m1 + k] = (int32_t)(pl->tc_rows.size() / 2);
+                    pl->tc_rows.push_back((uint8_t)h);
+                    pl->tc_rows.push_back((uint8_t)k);
+                }
+            }
+        pl->tc_n_pairs = (int32_t)(pl->tc_rows.size() / 2);
+        pl->tc_n_rt = (pl->tc_n_pairs + TC_M - 1) / TC_M;
+        pl->tc_rows.resize((size_t)pl->tc_n_rt * TC_M * 2, 0);
+        pl->tc_n_lt = (m2 + TC_MAX_LT - 1) / TC_MAX_LT;
+        pl->tc_lt = (((m2 + pl->tc_n_lt - 1) / pl->tc_n_lt) + 7) / 8 * 8;
+        pl->ent_amp_tc.resize(nv);
+        for (size_t e = 0; e < nv; ++e) {
+            const int32_t ci = pl->cell[e];
+            const int l = ci % m2, k = (ci / m2) % m1, h = ci / (m2 * m1);
+            const int32_t pp = pos[(size_t)h * m1 + k];
+            const int32_t tile = (pp / TC_M) * pl->tc_n_lt + l / pl->tc_lt;
+            pl->ent_amp_tc[e] = (tile * TC_M + pp % TC_M) * pl->tc_lt + l % pl->tc_lt;
+        }
+        pl->tc_ok = true;
+    }
     out = pl;
     return MB200_OK;
 }
@@ -674,6 +712,13 @@ static int upload_plan(mb200_ctx *ctx, SfPlan &pl) {
         MB_TRY(pl.d_bin_start.ensure(pl.bin_start.size() * 4));
         MB_CUDA(cudaMemcpyAsync(pl.d_bin_start.p, pl.bin_start.data(), pl.bin_start.size() * 4,
                                 cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (pl.tc_ok) {
+        MB_TRY(pl.d_tc_rows.ensure(pl.tc_rows.size()));
+        MB_CUDA(cudaMemcpyAsync(pl.d_tc_rows.p, pl.tc_rows.data(), pl.tc_rows.size(), cudaMemcpyHostToDevice, ctx->stream));
+        MB_TRY(pl.d_ent_amp_tc.ensure(pl.ent_amp_tc.size() * 4));
+        MB_CUDA(cudaMemcpyAsync(pl.d_ent_amp_tc.p, pl.ent_amp_tc.data(), pl.ent_amp_tc.size() * 4, cudaMemcpyHostToDevice,
+                                ctx->stream));
     }
     MB_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors may be read again only after this
     return MB200_OK;
@@ -739,6 +784,164 @@ struct SegSpec {       // one contraction problem (one reference structure_facto
 };
 
 
+
+// Split-precision variant of run_segments: FP64 tables -> int8 Z image -> tcgen05 contraction.
+static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t block, int32_t n_blocks,
+                           std::vector<SegDesc> &segs_host) {
+    const int ns = (int)specs.size();
+    // ---- workspaces: FP64 tables (ld padded to the 16-atom K-step), Z images, partial amplitudes
+    size_t tab_elems = 0, img_bytes = 0, amp_elems = 0;
+    std::vector<size_t> off_x(ns), off_y(ns), off_z(ns), off_img(ns), off_amp(ns);
+    std::vector<int> n_split(ns, 1);
+    std::vector<TcItem> items;
+    int64_t atomq = 0, n_mma = 0;
+    int64_t total_tiles = 0;
+    for (int s = 0; s < ns; ++s) total_tiles += (int64_t)specs[s].plan->tc_n_rt * specs[s].plan->tc_n_lt;
+    for (int s = 0; s < ns; ++s) {
+        SegSpec &sp = specs[s];
+        const SfPlan &pl = *sp.plan;
+        const int ld = (sp.job.n + TC_KA - 1) / TC_KA * TC_KA;
+        sp.job.ld = ld;
+        for (int a = 0; a < 3; ++a) sp.job.rows[a] = pl.rows[a];
+        off_x[s] = tab_elems; tab_elems += (size_t)pl.rows[0] * ld;
+        if (sp.share_yz_with >= 0) {
+            off_y[s] = off_y[sp.share_yz_with]; off_z[s] = off_z[sp.share_yz_with]; off_img[s] = off_img[sp.share_yz_with];
+        } else {
+            off_y[s] = tab_elems; tab_elems += (size_t)pl.rows[1] * ld;
+            off_z[s] = tab_elems; tab_elems += (size_t)pl.rows[2] * ld;
+            off_img[s] = img_bytes;
+            img_bytes += (size_t)pl.tc_n_lt * (ld / TC_KA) * (size_t)(TC_S * 2 * pl.tc_lt * 32);
+        }
+        // atom chunks: at most TC_CHUNK atoms, enough items to fill the SMs a few times over
+        const int64_t tiles = (int64_t)pl.tc_n_rt * pl.tc_n_lt;
+        int ns_s = std::max<int>(1, (ld + TC_CHUNK - 1) / TC_CHUNK);
+        const int64_t want = ((int64_t)ctx->n_sm * 3 + total_tiles - 1) / std::max<int64_t>(total_tiles, 1);
+        ns_s = (int)std::max<int64_t>(ns_s, std::min<int64_t>(want, ld / (64 * TC_KA)));
+        ns_s = std::max(ns_s, 1);
+        const int steps_total = ld / TC_KA;
+        const int steps_per = (steps_total + ns_s - 1) / ns_s;
+        ns_s = steps_per ? (steps_total + steps_per - 1) / steps_per : 1;
+        n_split[s] = std::max(ns_s, 1);
+        off_amp[s] = amp_elems;
+        amp_elems += (size_t)n_split[s] * tiles * TC_M * pl.tc_lt;
+        if (ld == 0) continue;
+        for (int sp_i = 0; sp_i < n_split[s]; ++sp_i) {
+            const int j0 = sp_i * steps_per * TC_KA, j1 = std::min(ld, (sp_i + 1) * steps_per * TC_KA);
+            if (j1 <= j0) continue;
+            for (int rt = 0; rt < pl.tc_n_rt; ++rt)
+                for (int lt = 0; lt < pl.tc_n_lt; ++lt) {
+                    if ((rt * pl.tc_n_lt + lt) % n_blocks != block) continue;
+                    items.push_back({s, rt, lt, j0, j1, sp_i});
+                    n_mma += (int64_t)((j1 - j0) / TC_KA) * 15;
+                }
+        }
+        atomq += (int64_t)sp.job.n * (int64_t)pl.cell.size();
+    }
+    MB_TRY(ctx->d_tables.ensure(std::max<size_t>(tab_elems, 1) * 16));
+    MB_TRY(ctx->d_bimg.ensure(std::max<size_t>(img_bytes, 16)));
+    MB_TRY(ctx->d_amp.ensure(std::max<size_t>(amp_elems, 1) * 16));
+    double2 *tab = ctx->d_tables.as<double2>();
+    // tiles that are not computed here (other q-blocks, empty segments) must read as zero
+    if (n_blocks > 1 || items.empty())
+        MB_CUDA(cudaMemsetAsync(ctx->d_amp.p, 0, std::max<size_t>(amp_elems, 1) * 16, ctx->stream));
+    std::vector<TcSeg> tsegs(ns);
+    std::vector<BimgJob> bjobs;
+    int max_steps = 0, max_nlt = 1;
+    for (int s = 0; s < ns; ++s) {
+        SegSpec &sp = specs[s];
+        const SfPlan &pl = *sp.plan;
+        SegDesc &sd = segs_host[s];
+        sd.ld = sp.job.ld; sd.n_split = n_split[s]; sd.n_wt = pl.n_wt; sd.n_valid = (int32_t)pl.cell.size();
+        sd.amp_stride = (long long)pl.tc_n_rt * pl.tc_n_lt * TC_M * pl.tc_lt;
+        for (int a = 0; a < 3; ++a) sd.rows[a] = pl.rows[a];
+        sd.tgs = nullptr;
+        sd.ent_amp = pl.d_ent_amp_tc.as<int32_t>();
+        sd.bin_start = pl.d_bin_start.as<int32_t>();
+        sd.ff2 = (sp.ff2_group >= 0 && pl.d_ff2.p) ? pl.d_ff2.as<double>() + (size_t)sp.ff2_group * sd.n_valid : nullptr;
+        sd.ex = tab + off_x[s]; sd.ey = tab + off_y[s]; sd.ez = tab + off_z[s];
+        sd.amp = ctx->d_amp.as<double2>() + off_amp[s];
+        sp.job.tab[0] = tab + off_x[s];
+        sp.job.tab[1] = sp.share_yz_with >= 0 ? nullptr : tab + off_y[s];
+        sp.job.tab[2] = sp.share_yz_with >= 0 ? nullptr : tab + off_z[s];
+        if (sp.job.ld == 0 && amp_elems && n_blocks == 1 && !items.empty())
+            MB_CUDA(cudaMemsetAsync(sd.amp, 0, (size_t)sd.n_split * sd.amp_stride * 16, ctx->stream));
+        TcSeg &ts = tsegs[s];
+        ts.ex = sd.ex; ts.ey = sd.ey;
+        ts.bimg = ctx->d_bimg.as<int8_t>() + off_img[s];
+        ts.rows = pl.d_tc_rows.as<uint8_t>();
+        ts.amp = sd.amp;
+        ts.rows0 = pl.rows[0]; ts.rows1 = pl.rows[1]; ts.ld = sp.job.ld;
+        ts.n_rt = pl.tc_n_rt; ts.n_lt = pl.tc_n_lt; ts.lt_size = pl.tc_lt; ts.n_pairs = pl.tc_n_pairs; ts.n_split = n_split[s];
+        if (sp.share_yz_with < 0 && sp.job.ld > 0) {
+            BimgJob bj;
+            bj.ez = sd.ez; bj.bimg = ctx->d_bimg.as<int8_t>() + off_img[s];
+            bj.rows2 = pl.rows[2]; bj.ld = sp.job.ld; bj.maxn2 = pl.maxn[2]; bj.n_lt = pl.tc_n_lt; bj.lt_size = pl.tc_lt;
+            bjobs.push_back(bj);
+            max_steps = std::max(max_steps, sp.job.ld / TC_KA);
+            max_nlt = std::max(max_nlt, pl.tc_n_lt);
+        }
+    }
+    // ---- descriptors to the device through the pinned staging buffer
+    const size_t b_jobs = (size_t)ns * sizeof(TableJob), b_segs = (size_t)ns * sizeof(SegDesc), b_tsegs = (size_t)ns * sizeof(TcSeg),
+                 b_bj = bjobs.size() * sizeof(BimgJob), b_items = items.size() * sizeof(TcItem);
+    MB_TRY(ctx->h_stage.ensure(b_jobs + b_segs + b_tsegs + b_bj + b_items + 64));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    char *hs = ctx->h_stage.as<char>();
+    for (int s = 0; s < ns; ++s) std::memcpy(hs + (size_t)s * sizeof(TableJob), &specs[s].job, sizeof(TableJob));
+    std::memcpy(hs + b_jobs, segs_host.data(), b_segs);
+    std::memcpy(hs + b_jobs + b_segs, tsegs.data(), b_tsegs);
+    if (b_bj) std::memcpy(hs + b_jobs + b_segs + b_tsegs, bjobs.data(), b_bj);
+    if (b_items) std::memcpy(hs + b_jobs + b_segs + b_tsegs + b_bj, items.data(), b_items);
+    MB_TRY(ctx->d_jobs.ensure(b_jobs));
+    MB_TRY(ctx->d_segs.ensure(b_segs));
+    MB_TRY(ctx->d_tcdesc.ensure(b_tsegs + b_bj + 64));
+    MB_TRY(ctx->d_items.ensure(std::max<size_t>(b_items, 16)));
+    MB_TRY(ctx->d_counter.ensure(16));
+    MB_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, hs, b_jobs, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(cudaMemcpyAsync(ctx->d_segs.p, hs + b_jobs, b_segs, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(cudaMemcpyAsync(ctx->d_tcdesc.p, hs + b_jobs + b_segs, b_tsegs + b_bj, cudaMemcpyHostToDevice, ctx->stream));
+    if (b_items)
+        MB_CUDA(cudaMemcpyAsync(ctx->d_items.p, hs + b_jobs + b_segs + b_tsegs + b_bj, b_items, cudaMemcpyHostToDevice, ctx->stream));
+    // ---- launches
+    int max_ld = 0;
+    for (int s = 0; s < ns; ++s) max_ld = std::max(max_ld, specs[s].job.ld);
+    int64_t launched = 0;
+    if (max_ld > 0) {
+        k_sf_tables<<<dim3((max_ld + 127) / 128, 3, ns), 128, 0, ctx->stream>>>(ctx->d_jobs.as<TableJob>());
+        MB_CUDA(cudaGetLastError());
+        ++launched;
+    }
+    if (!bjobs.empty()) {
+        const BimgJob *d_bj = reinterpret_cast<const BimgJob *>(ctx->d_tcdesc.as<char>() + b_tsegs);
+        k_sf_bimage<<<dim3((unsigned)max_steps, (unsigned)max_nlt, (unsigned)bjobs.size()), 256, 0, ctx->stream>>>(d_bj);
+        MB_CUDA(cudaGetLastError());
+        ++launched;
+    }
+    if (!items.empty()) {
+        if (!ctx->tc_attr_set) {
+            MB_CUDA(cudaFuncSetAttribute(k_sf_contract_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+            ctx->tc_attr_set = true;
+        }
+        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        MB_CUDA(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
+        const unsigned n_cta = (unsigned)std::min<size_t>(items.size(), (size_t)ctx->n_sm);
+        k_sf_contract_tc<<<n_cta, TC_THREADS, TC_SMEM, ctx->stream>>>(ctx->d_items.as<TcItem>(), (int)items.size(),
+                                                                     ctx->d_tcdesc.as<TcSeg>(), ctx->d_counter.as<int>());
+        MB_CUDA(cudaGetLastError());
+        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        ++launched;
+    }
+    ctx->launches += launched;
+    ctx->stats[0] = launched;
+    ctx->stats[1] = ns ? (int64_t)specs[0].plan->cell.size() : 0;
+    ctx->stats[2] = (int64_t)items.size();
+    ctx->stats[3] = n_mma;
+    ctx->stats[4] = atomq;
+    ctx->stats[6] = ns ? n_split[0] : 0;
+    ctx->stats[7] = ns ? specs[0].plan->tc_n_rt * specs[0].plan->tc_n_lt : 0;
+    return MB200_OK;
+}
+
 // Runs tables + contraction for all segments; leaves SegDesc array on the device (ctx->d_segs).
 static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t block, int32_t n_blocks,
                         std::vector<SegDesc> &segs_host) {
@@ -746,6 +949,11 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
     segs_host.assign(ns, SegDesc());
     if (ns == 0) return MB200_OK;
     if (n_blocks < 1 || block < 0 || block >= n_blocks) return fail(MB200_EINVAL, "invalid q-block %d of %d", block, n_blocks);
+    if (ctx->precision == 1 && !ctx->force_fp64) {  // split-precision tensor-core mode when every plan can be tiled for it
+        bool ok = true;
+        for (int s = 0; s < ns; ++s) ok = ok && specs[s].plan->tc_ok;
+        if (ok) return run_segments_tc(ctx, specs, block, n_blocks, segs_host);
+    }
 
     // ---- table workspace layout
     size_t tab_elems = 0;
@@ -792,6 +1000,7 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
         amp_elems += (size_t)n_split * sp.plan->n_wt * 512;
         SegDesc &sd = segs_host[s];
         sd.ld = ld; sd.n_split = n_split; sd.n_wt = sp.plan->n_wt; sd.n_valid = (int32_t)sp.plan->cell.size();
+        sd.amp_stride = (long long)sp.plan->n_wt * 512;
         for (int a = 0; a < 3; ++a) sd.rows[a] = sp.plan->rows[a];
         sd.tgs = sp.plan->d_tgs.as<TileGroupDesc>();
         sd.ent_amp = sp.plan->d_ent_amp.as<int32_t>();
@@ -899,6 +1108,13 @@ using namespace mb200;
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
+extern "C" int mb200_ctx_set_precision(mb200_ctx *ctx, int mode) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    if (mode != 0 && mode != 1) return fail(MB200_EINVAL, "precision mode must be 0 (fp64) or 1 (i8x5 split precision)");
+    ctx->precision = mode;
+    return MB200_OK;
+}
+
 extern "C" int mb200_sfactor_maxn(const double dimensions[3], double qmax, int32_t maxn[3]) {
     if (!dimensions || !maxn) return fail(MB200_EINVAL, "null argument");
     sfactor_maxn_host(dimensions, qmax, maxn);
@@ -945,7 +1161,10 @@ extern "C" int mb200_structure_factor_block(mb200_ctx *ctx, const double *positi
     for (int d = 0; d < 3; ++d) { sp.job.box[d] = dimensions[d]; sp.job.boxf[d] = (float)dimensions[d]; }
     sp.job.n = (int32_t)n; sp.job.is_f32 = 0; sp.job.wrap_mode = 0;
     std::vector<SegDesc> segs;
-    MB_TRY(run_segments(ctx, specs, block, n_blocks, segs));
+    ctx->force_fp64 = true;  // the raw-cube API carries arbitrary weights and is the parity reference: FP64 only
+    const int rc_seg = run_segments(ctx, specs, block, n_blocks, segs);
+    ctx->force_fp64 = false;
+    MB_TRY(rc_seg);
 
     MB_TRY(ctx->d_sval.ensure(nv * 8));
     dim3 grid((unsigned)((nv + 255) / 256), 1);

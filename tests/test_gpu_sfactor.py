@@ -239,3 +239,31 @@ def test_dipsf_frames_against_restatement():
     assert_allclose(ana.results.structure_factors, stats.means["structure_factors"][keep], rtol=RTOL)
     q = np.arange(0, 3.0, 0.05) + 0.025
     assert_allclose(ana.results.scattering_vectors, q[keep])
+
+
+def test_split_precision_tensor_core_mode(water_gro, water_frames):
+    """tcgen05 int8 x 5 mode of the fused paths: binned S, I within 1e-7 of the FP64 golden values, counts exact."""
+    try:
+        mb.set_precision("i8x5")
+        u = water_universe(water_frames["positions"], water_frames["dimensions"], water_gro["elements"])
+        saxs = mb.Saxs(u.atoms).run()
+        g = load_golden("saxs_water_trr_default.npz")
+        for k in ("scattering_vectors", "structure_factors", "scattering_intensities", "dstructure_factors"):
+            assert_allclose(saxs.results[k], g[k], rtol=1e-7, atol=1e-12)
+        assert_array_equal(saxs.sums.bincount, g["sum_bincount"])
+        # theta window + qmin, bigger box, three-component DiporderStructureFactor
+        u2 = mb.synthetic.spce_universe(3000, 20261020, n_frames=2)
+        a_tc = mb.Saxs(u2.atoms, qmin=0.3, qmax=3.0, dq=0.05, thetamin=20, thetamax=100).run()
+        d_tc = mb.DiporderStructureFactor(u2.atoms, qmax=3.0, dq=0.05, grouping="residues").run()
+        mb.set_precision("fp64")
+        a_64 = mb.Saxs(u2.atoms, qmin=0.3, qmax=3.0, dq=0.05, thetamin=20, thetamax=100).run()
+        d_64 = mb.DiporderStructureFactor(u2.atoms, qmax=3.0, dq=0.05, grouping="residues").run()
+        assert_array_equal(a_tc.sums.bincount, a_64.sums.bincount)
+        assert_allclose(a_tc.results.scattering_intensities, a_64.results.scattering_intensities, rtol=1e-7)
+        assert_allclose(d_tc.results.structure_factors, d_64.results.structure_factors, rtol=1e-7)
+        # the raw-cube API ignores the mode (always FP64)
+        mb.set_precision("i8x5")
+        pos, box = np.double(water_gro["positions"]), np.double(water_gro["dimensions"][:3])
+        check(pos, box, 0, 2.0, 0, np.pi, np.ones(len(pos)))
+    finally:
+        mb.set_precision("fp64")
