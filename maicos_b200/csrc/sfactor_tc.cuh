@@ -3,14 +3,17 @@
 //
 // Same contraction as k_sf_contract,  A[(h,k), l] = sum_j P_j[(h,k)] * Z_j[l]  (complex), evaluated as a real
 // int8 GEMM per 16 atoms (K' = 32 = 16 atoms x {re, im}):
-//   * every real component x in [-1, 1] is cut into five balanced base-128 digits of X = rint(x * 2^34);
+//   * every real component x in [-1, 1] is cut into five balanced base-256 digits (int8, [-128, 127]) of
+//     X = rint(x * 2^38): one FP64 add with a magic constant leaves X + bias in the low mantissa bits, whose
+//     BYTES xor 0x80 are the digits -- no shifts, no masks;
 //   * the fifteen digit products a_s * b_t with s + t <= 6 are accumulated EXACTLY in int32 TMEM accumulators
 //     grouped by g = s + t (five 128 x NP column blocks, NP = 2 * L_t for re/im of an l tile), issued as
 //     MMAs "slice s of A" x "slices t = 1 .. 6 - s of B stacked along N" (N up to 256);
-//   * A = 4 * sum_g D_g * 128^-g in FP64 when an atom chunk (<= 32768 atoms, no int32 overflow) is flushed.
-//   Measured error (tools/microbench/ozaki_tile.cu, 32768 atoms): |dA| <= 2.1e-8, i.e. ~1e-9 relative on binned
-//   S(q); single weak speckle cells can miss the 1e-6 bar, so this is a separately selected mode
-//   (mb200_ctx_set_precision), the FP64 DMMA kernel stays the parity default.
+//   * A = 16 * sum_g D_g * 256^-g in FP64 when an atom chunk (<= 8192 atoms, no int32 overflow) is flushed.
+//   Error: input quantisation 2^-39 and the dropped products (s + t >= 7, <= 2^-36 each) give |dA| ~ 1e-9 for
+//   1e5 atoms, i.e. ~1e-11 relative on binned S(q).  Single vanishing speckle cells of the raw cube can still
+//   exceed a relative 1e-6, so this is a separately selected mode (mb200_ctx_set_precision); the FP64 DMMA
+//   kernel stays the parity default and the only path of the raw-cube API.
 //
 // CTA = 16 generator warps + 1 control warp, one CTA per SM (512 TMEM columns):
 //   generators : thread (atom a of the K-step, row quad o) walks 4 packed (h,k) rows; P = w Ex[h] Ey[k] is
@@ -31,8 +34,7 @@ constexpr int TC_NSTG = 3;         // A / B stages
 constexpr int TC_GEN_WARPS = 16;
 constexpr int TC_THREADS = (TC_GEN_WARPS + 1) * 32;
 constexpr int TC_MAX_LT = 48;      // l values per tile: 5 * 2 * 48 = 480 TMEM columns
-constexpr int TC_CHUNK = 32768;    // atoms per flush (int32 accumulators cannot overflow)
-constexpr long long TC_OFFS = 64LL * (268435456LL + 2097152LL + 16384LL + 128LL + 1LL);
+constexpr int TC_CHUNK = 8192;     // atoms per flush: 2 * 5 * 128 * 128 * 8192 < 2^31, the int32 accumulators cannot overflow
 
 struct TcItem {
     int32_t seg, rt, lt, j0, j1, split;
@@ -52,34 +54,24 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {  // K-major, no sw
     return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
 }
 
-// five balanced base-128 digits of rint(x * 2^34), most significant first, as bytes
-__device__ __forceinline__ void tc_digits(double x, int sign, unsigned (&d)[TC_S]) {
-    const long long X = __double2ll_rn(x * 17179869184.0);
-    const unsigned long long U = (unsigned long long)(X + TC_OFFS);
-    d[0] = (unsigned)(sign * ((int)(U >> 28) - 64)) & 0xffu;
-#pragma unroll
-    for (int s = 1; s < TC_S; ++s) d[s] = (unsigned)(sign * ((int)((U >> (7 * (4 - s))) & 127ull) - 64)) & 0xffu;
-}
-
-// Generator fast path: rint(x * 2^34) + TC_OFFS falls out of ONE FP64 add with a magic constant (the sum lies in
-// [2^18, 2^19), ulp 2^-34, so the low 36 mantissa bits are the biased fixed-point value), the five 7-bit fields are
-// cut with 32-bit shifts, and the (re, im) digits of a slice are paired and re-centred two bytes at a time.
-#define TC_MAGIC (262144.0 + 4.0 + 17315143744.0 / 17179869184.0)
-__device__ __forceinline__ void tc_fields(double x, unsigned (&u)[TC_S]) {
+// Digits: y = x + TC_MAGIC lies in [2^14, 2^15) (ulp 2^-38), so the low 40 mantissa bits of y are
+// U = rint(x * 2^38) + 128 * (256^4 + 256^3 + 256^2 + 256 + 1); byte i of U xor 0x80 is the balanced digit of
+// weight 256^i.  Returned: lo = digits 5, 4, 3, 2 (bytes 0..3), hi = digit 1 (byte 0), already re-centred.
+#define TC_MAGIC (16384.0 + 551911719040.0 / 274877906944.0)
+__device__ __forceinline__ void tc_digits(double x, unsigned &lo, unsigned &hi) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(x + TC_MAGIC);
-    const unsigned w0 = (unsigned)b, w1 = (unsigned)(b >> 32);
-    u[0] = __funnelshift_r(w0, w1, 28) & 0xffu;  // 0 .. 128
-    u[1] = (w0 >> 21) & 0x7fu;
-    u[2] = (w0 >> 14) & 0x7fu;
-    u[3] = (w0 >> 7) & 0x7fu;
-    u[4] = w0 & 0x7fu;
+    lo = (unsigned)b ^ 0x80808080u;
+    hi = ((unsigned)(b >> 32) ^ 0x80u) & 0xffu;
 }
-__device__ __forceinline__ unsigned tc_pair0(unsigned ur, unsigned ui) {  // top digits: u - 64 in [-64, 64]
-    return ((ur + 192u) & 0xffu) | (((ui + 192u) & 0xffu) << 8);
-}
-__device__ __forceinline__ unsigned tc_pair(unsigned ur, unsigned ui) {   // u - 64 on both bytes at once
-    const unsigned p = ur | (ui << 8);
-    return (p ^ 0x4040u) | ((~p & 0x4040u) << 1);
+// (re, im) digit pair of slice s (1 = most significant) as a 16-bit value, re in the low byte
+__device__ __forceinline__ unsigned tc_pair(int s, unsigned rlo, unsigned rhi, unsigned ilo, unsigned ihi) {
+    switch (s) {
+        case 1: return __byte_perm(rhi, ihi, 0x0040);
+        case 2: return __byte_perm(rlo, ilo, 0x0073);
+        case 3: return __byte_perm(rlo, ilo, 0x0062);
+        case 4: return __byte_perm(rlo, ilo, 0x0051);
+        default: return __byte_perm(rlo, ilo, 0x0040);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -103,16 +95,16 @@ __global__ void __launch_bounds__(256) k_sf_bimage(const BimgJob *__restrict__ j
         const int l = lt * jb.lt_size + li;
         double2 z = make_double2(0.0, 0.0);
         if (l < jb.maxn2) z = jb.ez[tab_index(ks * TC_KA + a, l, jb.rows2)];
-        unsigned dr[TC_S], di[TC_S], dn[TC_S];
-        tc_digits(z.x, 1, dr);
-        tc_digits(z.y, 1, di);
-        tc_digits(z.y, -1, dn);
+        unsigned rlo, rhi, ilo, ihi, nlo, nhi;
+        tc_digits(z.x, rlo, rhi);
+        tc_digits(z.y, ilo, ihi);
+        tc_digits(-z.y, nlo, nhi);
 #pragma unroll
-        for (int t = 0; t < TC_S; ++t) {
-            int8_t *b = out + (size_t)t * np * 32;
+        for (int t = 1; t <= TC_S; ++t) {
+            int8_t *b = out + (size_t)(t - 1) * np * 32;
             // row 2l (real part of A): (Zr, -Zi); row 2l + 1 (imaginary part): (Zi, Zr)
-            *reinterpret_cast<uint16_t *>(b + tc_canon(2 * li, 2 * a)) = (uint16_t)(dr[t] | (dn[t] << 8));
-            *reinterpret_cast<uint16_t *>(b + tc_canon(2 * li + 1, 2 * a)) = (uint16_t)(di[t] | (dr[t] << 8));
+            *reinterpret_cast<uint16_t *>(b + tc_canon(2 * li, 2 * a)) = (uint16_t)tc_pair(t, rlo, rhi, nlo, nhi);
+            *reinterpret_cast<uint16_t *>(b + tc_canon(2 * li + 1, 2 * a)) = (uint16_t)tc_pair(t, ilo, ihi, rlo, rhi);
         }
     }
 }
@@ -190,30 +182,45 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
 #pragma unroll
             for (int r = 0; r < 4; ++r) { hh[r] = s_rows[2 * (4 * o + r)]; kk[r] = s_rows[2 * (4 * o + r) + 1]; }
             const int off0 = tc_canon(4 * o, 2 * a);  // rows 4 o + r: + 16 r bytes (same 8-row core matrix)
+            // seeds of the first row and the k-step factor are prefetched one K-step ahead (L2 latency off the chain)
+            const int row1 = 1 < sg.rows1 ? 1 : 0;
+            const bool v0 = 4 * o < n_valid_rows;
+            double2 nx = make_double2(0.0, 0.0), ny = nx, ny1 = nx;
+            if (n_steps > 0) {
+                const int j = it.j0 + a;
+                ny1 = sg.ey[tab_index(j, row1, sg.rows1)];
+                if (v0) { nx = sg.ex[tab_index(j, hh[0], sg.rows0)]; ny = sg.ey[tab_index(j, kk[0], sg.rows1)]; }
+            }
             for (int t = 0; t < n_steps; ++t) {
                 const int st = t % TC_NSTG;
-                if (t >= TC_NSTG) mbar_wait(s_free + st, (unsigned)((t / TC_NSTG) - 1) & 1u);
                 const int j = it.j0 + t * TC_KA + a;
-                const double2 y1 = sg.ey[tab_index(j, 1 < sg.rows1 ? 1 : 0, sg.rows1)];
+                const double2 y1 = ny1, x0 = nx, y0 = ny;
+                if (t + 1 < n_steps) {
+                    const int jn = j + TC_KA;
+                    ny1 = sg.ey[tab_index(jn, row1, sg.rows1)];
+                    if (v0) { nx = sg.ex[tab_index(jn, hh[0], sg.rows0)]; ny = sg.ey[tab_index(jn, kk[0], sg.rows1)]; }
+                }
+                if (t >= TC_NSTG) mbar_wait(s_free + st, (unsigned)((t / TC_NSTG) - 1) & 1u);
                 int8_t *dstA = sA + st * A_STAGE + off0;
                 double2 p = make_double2(0.0, 0.0);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     unsigned w[TC_S];
                     if (4 * o + r < n_valid_rows) {
-                        if (r > 0 && hh[r] == hh[r - 1] && kk[r] == kk[r - 1] + 1) {  // run of consecutive k
+                        if (r == 0) {
+                            p.x = x0.x * y0.x - x0.y * y0.y; p.y = x0.x * y0.y + x0.y * y0.x;
+                        } else if (hh[r] == hh[r - 1] && kk[r] == kk[r - 1] + 1) {  // run of consecutive k
                             const double nr = p.x * y1.x - p.y * y1.y, ni = p.x * y1.y + p.y * y1.x;
                             p.x = nr; p.y = ni;
-                        } else {  // seed from the FP64 tables (weights are folded into Ex)
+                        } else {  // run break inside the quad: seed from the FP64 tables (weights are folded into Ex)
                             const double2 x = sg.ex[tab_index(j, hh[r], sg.rows0)], y = sg.ey[tab_index(j, kk[r], sg.rows1)];
                             p.x = x.x * y.x - x.y * y.y; p.y = x.x * y.y + x.y * y.x;
                         }
-                        unsigned ur[TC_S], ui[TC_S];
-                        tc_fields(p.x, ur);
-                        tc_fields(p.y, ui);
-                        w[0] = tc_pair0(ur[0], ui[0]);
+                        unsigned rlo, rhi, ilo, ihi;
+                        tc_digits(p.x, rlo, rhi);
+                        tc_digits(p.y, ilo, ihi);
 #pragma unroll
-                        for (int s = 1; s < TC_S; ++s) w[s] = tc_pair(ur[s], ui[s]);
+                        for (int s = 0; s < TC_S; ++s) w[s] = tc_pair(s + 1, rlo, rhi, ilo, ihi);
                     } else {
 #pragma unroll
                         for (int s = 0; s < TC_S; ++s) w[s] = 0u;
@@ -283,7 +290,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                                  : "r"(addr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                    const double scale = ldexp(1.0, 2 - 7 * g);
+                    const double scale = ldexp(1.0, 4 - 8 * g);
 #pragma unroll
                     for (int c = 0; c < 16; ++c) acc[c] += (double)(int32_t)v[c] * scale;
                 }
