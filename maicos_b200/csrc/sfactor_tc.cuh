@@ -167,7 +167,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
         const int item = *s_item;
         if (item >= n_items) break;
         const TcItem it = items[item];
-        const TcSeg &sg = segs[it.seg];
+        const TcSeg sg = segs[it.seg];  // by value: the loops below must not re-read the descriptor from global memory
         const int lt_size = sg.lt_size, np = 2 * lt_size;
         const int n_steps = (it.j1 - it.j0) / TC_KA;
         const uint32_t b_bytes = (uint32_t)(TC_S * np * 32);
@@ -182,23 +182,25 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
 #pragma unroll
             for (int r = 0; r < 4; ++r) { hh[r] = s_rows[2 * (4 * o + r)]; kk[r] = s_rows[2 * (4 * o + r) + 1]; }
             const int off0 = tc_canon(4 * o, 2 * a);  // rows 4 o + r: + 16 r bytes (same 8-row core matrix)
-            // seeds of the first row and the k-step factor are prefetched one K-step ahead (L2 latency off the chain)
+            // seeds of the first row and the k-step factor are prefetched one K-step ahead (L2 latency off the chain);
+            // their table addresses advance by a constant stride per K-step (two 8-atom blocks)
             const int row1 = 1 < sg.rows1 ? 1 : 0;
             const bool v0 = 4 * o < n_valid_rows;
+            const int j_first = it.j0 + a;
+            const double2 *px = sg.ex + tab_index(j_first, v0 ? hh[0] : 0, sg.rows0);
+            const double2 *py = sg.ey + tab_index(j_first, v0 ? kk[0] : 0, sg.rows1);
+            const double2 *py1 = sg.ey + tab_index(j_first, row1, sg.rows1);
+            const size_t sx = (size_t)sg.rows0 * 16, sy = (size_t)sg.rows1 * 16;
             double2 nx = make_double2(0.0, 0.0), ny = nx, ny1 = nx;
-            if (n_steps > 0) {
-                const int j = it.j0 + a;
-                ny1 = sg.ey[tab_index(j, row1, sg.rows1)];
-                if (v0) { nx = sg.ex[tab_index(j, hh[0], sg.rows0)]; ny = sg.ey[tab_index(j, kk[0], sg.rows1)]; }
-            }
+            if (n_steps > 0) { ny1 = *py1; if (v0) { nx = *px; ny = *py; } }
             for (int t = 0; t < n_steps; ++t) {
                 const int st = t % TC_NSTG;
                 const int j = it.j0 + t * TC_KA + a;
                 const double2 y1 = ny1, x0 = nx, y0 = ny;
                 if (t + 1 < n_steps) {
-                    const int jn = j + TC_KA;
-                    ny1 = sg.ey[tab_index(jn, row1, sg.rows1)];
-                    if (v0) { nx = sg.ex[tab_index(jn, hh[0], sg.rows0)]; ny = sg.ey[tab_index(jn, kk[0], sg.rows1)]; }
+                    px += sx; py += sy; py1 += sy;
+                    ny1 = *py1;
+                    if (v0) { nx = *px; ny = *py; }
                 }
                 if (t >= TC_NSTG) mbar_wait(s_free + st, (unsigned)((t / TC_NSTG) - 1) & 1u);
                 int8_t *dstA = sA + st * A_STAGE + off0;
