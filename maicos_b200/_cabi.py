@@ -132,6 +132,9 @@ class Context:
         _check(lib.mb200_ctx_create(int(device), ctypes.byref(handle)))
         self._h = handle
         self.device = int(device)
+        mode = os.environ.get("MAICOS_B200_PRECISION", "")
+        if mode:  # e.g. MAICOS_B200_PRECISION=i8x5 for the CLI; maicos_b200.set_precision() overrides
+            self.set_precision(mode)
 
     @property
     def handle(self):

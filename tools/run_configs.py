@@ -20,7 +20,8 @@ from maicos_b200 import _cabi  # noqa: E402
 from maicos_b200.lib.math import sfactor_maxn  # noqa: E402
 from maicos_b200.mdshim import MemoryTrajectory, Universe  # noqa: E402
 
-out = {}
+import os
+out = {"precision": os.environ.get("MAICOS_B200_PRECISION", "fp64")}
 ctx = _cabi.context()
 
 
