@@ -15,8 +15,9 @@
 //   exceed a relative 1e-6, so this is a separately selected mode (mb200_ctx_set_precision); the FP64 DMMA
 //   kernel stays the parity default and the only path of the raw-cube API.
 //
-// CTA = 16 generator warps + 1 control warp, one CTA per SM (512 TMEM columns):
-//   generators : thread (atom a of the K-step, row quad o) walks 4 packed (h,k) rows; P = w Ex[h] Ey[k] is
+// CTA = 8 generator warps + 1 control warp, one CTA per SM (512 TMEM columns):
+//   generators : thread (atom pair of the K-step, row quad o) walks 4 packed (h,k) rows for two atoms (two
+//                independent dependency chains, 32-bit stores); P = w Ex[h] Ey[k] is
 //                seeded from the FP64 tables at the start of a run of consecutive k and advanced by the
 //                recurrence P *= Ey[1] inside the run; digits are written as (re, im) byte pairs into the
 //                canonical K-major no-swizzle UMMA layout (cute ((8,n),2):((1,SBO),LBO), LBO = 128, SBO = 256);
@@ -30,8 +31,8 @@ namespace mb200 {
 constexpr int TC_M = 128;          // rows ((h,k) pairs) per tile
 constexpr int TC_KA = 16;          // atoms per MMA K-step
 constexpr int TC_S = 5;            // digits per component
-constexpr int TC_NSTG = 3;         // A / B stages
-constexpr int TC_GEN_WARPS = 16;
+constexpr int TC_NSTG = 4;         // A / B stages (power of two: cheap stage / phase arithmetic)
+constexpr int TC_GEN_WARPS = 8;
 constexpr int TC_THREADS = (TC_GEN_WARPS + 1) * 32;
 constexpr int TC_MAX_LT = 48;      // l values per tile: 5 * 2 * 48 = 480 TMEM columns
 constexpr int TC_CHUNK = 8192;     // atoms per flush: 2 * 5 * 128 * 128 * 8192 < 2^31, the int32 accumulators cannot overflow
@@ -175,60 +176,76 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
         __syncthreads();
 
         if (is_gen) {
-            // ---- generators: thread (a, o) -> atom a of the K-step, rows 4 o .. 4 o + 3 ----
-            const int a = tid & 15, o = tid >> 4;
-            const int n_valid_rows = min(TC_M, sg.n_pairs - it.rt * TC_M);
+            // ---- generators: thread (ap, o) -> atoms 2 ap, 2 ap + 1 of the K-step, rows 4 o .. 4 o + 3 ----
+            // (rows beyond the last pair of the tile are (0, 0) padding: computed, never referenced)
+            const int ap = tid & 7, o = tid >> 3;
             int hh[4], kk[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) { hh[r] = s_rows[2 * (4 * o + r)]; kk[r] = s_rows[2 * (4 * o + r) + 1]; }
-            const int off0 = tc_canon(4 * o, 2 * a);  // rows 4 o + r: + 16 r bytes (same 8-row core matrix)
-            // seeds of the first row and the k-step factor are prefetched one K-step ahead (L2 latency off the chain);
-            // their table addresses advance by a constant stride per K-step (two 8-atom blocks)
+            unsigned run = 0;  // bit r: row r continues the run of consecutive k of row r - 1
+#pragma unroll
+            for (int r = 1; r < 4; ++r) run |= (hh[r] == hh[r - 1] && kk[r] == kk[r - 1] + 1) ? (1u << r) : 0u;
+            const int off0 = tc_canon(4 * o, 4 * ap);  // K' = 4 ap .. 4 ap + 3; rows 4 o + r: + 16 r bytes
+            // seeds of row 0 and the k-step factor are prefetched one K-step ahead; their table addresses advance
+            // by a constant stride per K-step (two 8-atom blocks)
             const int row1 = 1 < sg.rows1 ? 1 : 0;
-            const bool v0 = 4 * o < n_valid_rows;
-            const int j_first = it.j0 + a;
-            const double2 *px = sg.ex + tab_index(j_first, v0 ? hh[0] : 0, sg.rows0);
-            const double2 *py = sg.ey + tab_index(j_first, v0 ? kk[0] : 0, sg.rows1);
-            const double2 *py1 = sg.ey + tab_index(j_first, row1, sg.rows1);
+            const double2 *px[2], *py[2], *py1[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int jf = it.j0 + 2 * ap + c;
+                px[c] = sg.ex + tab_index(jf, hh[0], sg.rows0);
+                py[c] = sg.ey + tab_index(jf, kk[0], sg.rows1);
+                py1[c] = sg.ey + tab_index(jf, row1, sg.rows1);
+            }
             const size_t sx = (size_t)sg.rows0 * 16, sy = (size_t)sg.rows1 * 16;
-            double2 nx = make_double2(0.0, 0.0), ny = nx, ny1 = nx;
-            if (n_steps > 0) { ny1 = *py1; if (v0) { nx = *px; ny = *py; } }
+            double2 nx[2], ny[2], ny1[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) { nx[c] = *px[c]; ny[c] = *py[c]; ny1[c] = *py1[c]; }
             for (int t = 0; t < n_steps; ++t) {
-                const int st = t % TC_NSTG;
-                const int j = it.j0 + t * TC_KA + a;
-                const double2 y1 = ny1, x0 = nx, y0 = ny;
+                const int st = t & (TC_NSTG - 1);
+                double2 y1[2], p[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    y1[c] = ny1[c];
+                    p[c].x = nx[c].x * ny[c].x - nx[c].y * ny[c].y;
+                    p[c].y = nx[c].x * ny[c].y + nx[c].y * ny[c].x;
+                }
                 if (t + 1 < n_steps) {
-                    px += sx; py += sy; py1 += sy;
-                    ny1 = *py1;
-                    if (v0) { nx = *px; ny = *py; }
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        px[c] += sx; py[c] += sy; py1[c] += sy;
+                        nx[c] = *px[c]; ny[c] = *py[c]; ny1[c] = *py1[c];
+                    }
                 }
                 if (t >= TC_NSTG) mbar_wait(s_free + st, (unsigned)((t / TC_NSTG) - 1) & 1u);
                 int8_t *dstA = sA + st * A_STAGE + off0;
-                double2 p = make_double2(0.0, 0.0);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    unsigned w[TC_S];
-                    if (4 * o + r < n_valid_rows) {
-                        if (r == 0) {
-                            p.x = x0.x * y0.x - x0.y * y0.y; p.y = x0.x * y0.y + x0.y * y0.x;
-                        } else if (hh[r] == hh[r - 1] && kk[r] == kk[r - 1] + 1) {  // run of consecutive k
-                            const double nr = p.x * y1.x - p.y * y1.y, ni = p.x * y1.y + p.y * y1.x;
-                            p.x = nr; p.y = ni;
-                        } else {  // run break inside the quad: seed from the FP64 tables (weights are folded into Ex)
-                            const double2 x = sg.ex[tab_index(j, hh[r], sg.rows0)], y = sg.ey[tab_index(j, kk[r], sg.rows1)];
-                            p.x = x.x * y.x - x.y * y.y; p.y = x.x * y.y + x.y * y.x;
+                    if (r > 0) {
+                        if (run & (1u << r)) {  // run of consecutive k: one complex multiply per atom
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const double nr = p[c].x * y1[c].x - p[c].y * y1[c].y, ni = p[c].x * y1[c].y + p[c].y * y1[c].x;
+                                p[c].x = nr; p[c].y = ni;
+                            }
+                        } else {  // run break inside the quad: seed from the FP64 tables in place
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const int j = it.j0 + t * TC_KA + 2 * ap + c;
+                                const double2 x = sg.ex[tab_index(j, hh[r], sg.rows0)], y = sg.ey[tab_index(j, kk[r], sg.rows1)];
+                                p[c].x = x.x * y.x - x.y * y.y; p[c].y = x.x * y.y + x.y * y.x;
+                            }
                         }
-                        unsigned rlo, rhi, ilo, ihi;
-                        tc_digits(p.x, rlo, rhi);
-                        tc_digits(p.y, ilo, ihi);
-#pragma unroll
-                        for (int s = 0; s < TC_S; ++s) w[s] = tc_pair(s + 1, rlo, rhi, ilo, ihi);
-                    } else {
-#pragma unroll
-                        for (int s = 0; s < TC_S; ++s) w[s] = 0u;
                     }
+                    unsigned lo[2][2], hi[2][2];  // [atom][re / im]
 #pragma unroll
-                    for (int s = 0; s < TC_S; ++s) *reinterpret_cast<uint16_t *>(dstA + s * TC_M * 32 + 16 * r) = (uint16_t)w[s];
+                    for (int c = 0; c < 2; ++c) { tc_digits(p[c].x, lo[c][0], hi[c][0]); tc_digits(p[c].y, lo[c][1], hi[c][1]); }
+#pragma unroll
+                    for (int s = 0; s < TC_S; ++s) {
+                        const unsigned w0 = tc_pair(s + 1, lo[0][0], hi[0][0], lo[0][1], hi[0][1]);
+                        const unsigned w1 = tc_pair(s + 1, lo[1][0], hi[1][0], lo[1][1], hi[1][1]);
+                        *reinterpret_cast<uint32_t *>(dstA + s * TC_M * 32 + 16 * r) = __byte_perm(w0, w1, 0x5410);
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes -> visible to the tensor core
                 __syncwarp();
