@@ -668,16 +668,23 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
     // tensor-core tiling: (h,k) pairs with at least one valid l, in (h,k) order, 128 per row tile
     if (m0 <= 255 && m1 <= 255 && m2 >= 1 && nv > 0) {
         std::vector<int32_t> pos((size_t)m0 * m1, -1);
-        for (int h = 0; h < m0; ++h)
+        for (int h = 0; h < m0; ++h) {
+            int prev_k = -2;
             for (int k = 0; k < m1; ++k) {
                 bool any = false;
                 for (int l = 0; l < m2 && !any; ++l) any = qcube[((size_t)h * m1 + k) * m2 + l] != 0.0;
-                if (any) {
-                    pos[(size_t)h * m1 + k] = (int32_t)(pl->tc_rows.size() / 2);
-                    pl->tc_rows.push_back((uint8_t)h);
-                    pl->tc_rows.push_back((uint8_t)k);
-                }
+                if (!any) continue;
+                if (k != prev_k + 1)  // a new run of consecutive k starts on a quad boundary (padding rows continue the old run)
+                    while ((pl->tc_rows.size() / 2) % 4) {
+                        pl->tc_rows.push_back(pl->tc_rows[pl->tc_rows.size() - 2]);
+                        pl->tc_rows.push_back((uint8_t)std::min(255, (int)pl->tc_rows[pl->tc_rows.size() - 2] + 1));
+                    }
+                pos[(size_t)h * m1 + k] = (int32_t)(pl->tc_rows.size() / 2);
+                pl->tc_rows.push_back((uint8_t)h);
+                pl->tc_rows.push_back((uint8_t)k);
+                prev_k = k;
             }
+        }
         pl->tc_n_pairs = (int32_t)(pl->tc_rows.size() / 2);
         pl->tc_n_rt = (pl->tc_n_pairs + TC_M - 1) / TC_M;
         pl->tc_rows.resize((size_t)pl->tc_n_rt * TC_M * 2, 0);

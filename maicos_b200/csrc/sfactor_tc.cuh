@@ -177,14 +177,11 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
 
         if (is_gen) {
             // ---- generators: thread (ap, o) -> atoms 2 ap, 2 ap + 1 of the K-step, rows 4 o .. 4 o + 3 ----
-            // (rows beyond the last pair of the tile are (0, 0) padding: computed, never referenced)
+            // The plan pads every run of consecutive k to a multiple of four rows, so a quad is always one run:
+            // row 0 is seeded from the FP64 tables, rows 1..3 follow by P *= Ey[1].  Padding rows are computed
+            // and never referenced.
             const int ap = tid & 7, o = tid >> 3;
-            int hh[4], kk[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) { hh[r] = s_rows[2 * (4 * o + r)]; kk[r] = s_rows[2 * (4 * o + r) + 1]; }
-            unsigned run = 0;  // bit r: row r continues the run of consecutive k of row r - 1
-#pragma unroll
-            for (int r = 1; r < 4; ++r) run |= (hh[r] == hh[r - 1] && kk[r] == kk[r - 1] + 1) ? (1u << r) : 0u;
+            const int h0 = s_rows[2 * (4 * o)], k0 = s_rows[2 * (4 * o) + 1];
             const int off0 = tc_canon(4 * o, 4 * ap);  // K' = 4 ap .. 4 ap + 3; rows 4 o + r: + 16 r bytes
             // seeds of row 0 and the k-step factor are prefetched one K-step ahead; their table addresses advance
             // by a constant stride per K-step (two 8-atom blocks)
@@ -193,8 +190,8 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const int jf = it.j0 + 2 * ap + c;
-                px[c] = sg.ex + tab_index(jf, hh[0], sg.rows0);
-                py[c] = sg.ey + tab_index(jf, kk[0], sg.rows1);
+                px[c] = sg.ex + tab_index(jf, h0, sg.rows0);
+                py[c] = sg.ey + tab_index(jf, k0, sg.rows1);
                 py1[c] = sg.ey + tab_index(jf, row1, sg.rows1);
             }
             const size_t sx = (size_t)sg.rows0 * 16, sy = (size_t)sg.rows1 * 16;
@@ -222,19 +219,10 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     if (r > 0) {
-                        if (run & (1u << r)) {  // run of consecutive k: one complex multiply per atom
 #pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                const double nr = p[c].x * y1[c].x - p[c].y * y1[c].y, ni = p[c].x * y1[c].y + p[c].y * y1[c].x;
-                                p[c].x = nr; p[c].y = ni;
-                            }
-                        } else {  // run break inside the quad: seed from the FP64 tables in place
-#pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                const int j = it.j0 + t * TC_KA + 2 * ap + c;
-                                const double2 x = sg.ex[tab_index(j, hh[r], sg.rows0)], y = sg.ey[tab_index(j, kk[r], sg.rows1)];
-                                p[c].x = x.x * y.x - x.y * y.y; p[c].y = x.x * y.y + x.y * y.x;
-                            }
+                        for (int c = 0; c < 2; ++c) {
+                            const double nr = p[c].x * y1[c].x - p[c].y * y1[c].y, ni = p[c].x * y1[c].y + p[c].y * y1[c].x;
+                            p[c].x = nr; p[c].y = ni;
                         }
                     }
                     unsigned lo[2][2], hi[2][2];  // [atom][re / im]
