@@ -51,9 +51,16 @@ struct TcSeg {
 
 __device__ __host__ __forceinline__ int tc_canon(int row, int k) { return (row >> 3) * 256 + (k >> 4) * 128 + (row & 7) * 16 + (k & 15); }
 
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {  // K-major, no swizzle, LBO = 128 B, SBO = 256 B, version 1
-    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+// K-major, no swizzle, descriptor version 1; LBO = distance of the two 16-byte K chunks, SBO = distance of 8-row groups
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo = 128, uint32_t sbo = 256) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
+
+// A operand (written by the generator warps): the 8 x 16 B core matrices are placed with SBO = 144 and LBO = 2336
+// instead of the dense 256 / 128, which shifts neighbouring row groups by one and the second K chunk by two 16-byte
+// slots: the 32 lanes of a warp store (2 row groups x 2 quads x 2 K chunks x 4 atom pairs) hit 32 distinct banks.
+constexpr int TC_A_SBO = 144, TC_A_LBO = 2336, TC_A_SLICE = 4672;
+__device__ __forceinline__ int tc_canon_a(int row, int k) { return (row >> 3) * TC_A_SBO + (k >> 4) * TC_A_LBO + (row & 7) * 16 + (k & 15); }
 
 // Digits: y = x + TC_MAGIC lies in [2^14, 2^15) (ulp 2^-38), so the low 40 mantissa bits of y are
 // U = rint(x * 2^38) + 128 * (256^4 + 256^3 + 256^2 + 256 + 1); byte i of U xor 0x80 is the balanced digit of
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__restrict__ segs, int *__restrict__ counter) {
     extern __shared__ __align__(16) unsigned char smem[];
     // [TC_NSTG] A stages (5 x 128 x 32 B) | [TC_NSTG] B stages (5 x NP_max x 32 B) | barriers | row table
-    constexpr int A_STAGE = TC_S * TC_M * 32;
+    constexpr int A_STAGE = TC_S * TC_A_SLICE;
     constexpr int B_STAGE = TC_S * 2 * TC_MAX_LT * 32;
     int8_t *sA = reinterpret_cast<int8_t *>(smem);
     int8_t *sB = sA + TC_NSTG * A_STAGE;
@@ -182,7 +189,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
             // and never referenced.
             const int ap = tid & 7, o = tid >> 3;
             const int h0 = s_rows[2 * (4 * o)], k0 = s_rows[2 * (4 * o) + 1];
-            const int off0 = tc_canon(4 * o, 4 * ap);  // K' = 4 ap .. 4 ap + 3; rows 4 o + r: + 16 r bytes
+            const int off0 = tc_canon_a(4 * o, 4 * ap);  // K' = 4 ap .. 4 ap + 3; rows 4 o + r: + 16 r bytes
             // seeds of row 0 and the k-step factor are prefetched one K-step ahead; their table addresses advance
             // by a constant stride per K-step (two 8-atom blocks)
             const int row1 = 1 < sg.rows1 ? 1 : 0;
@@ -232,7 +239,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                     for (int s = 0; s < TC_S; ++s) {
                         const unsigned w0 = tc_pair(s + 1, lo[0][0], hi[0][0], lo[0][1], hi[0][1]);
                         const unsigned w1 = tc_pair(s + 1, lo[1][0], hi[1][0], lo[1][1], hi[1][1]);
-                        *reinterpret_cast<uint32_t *>(dstA + s * TC_M * 32 + 16 * r) = __byte_perm(w0, w1, 0x5410);
+                        *reinterpret_cast<uint32_t *>(dstA + s * TC_A_SLICE + 16 * r) = __byte_perm(w0, w1, 0x5410);
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes -> visible to the tensor core
@@ -262,7 +269,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                 const int per = max(1, 256 / np);  // B slices per MMA (N <= 256)
 #pragma unroll 1
                 for (int s = 1; s <= TC_S; ++s) {
-                    const uint64_t da = tc_desc(a_base + (uint32_t)((s - 1) * TC_M * 32));
+                    const uint64_t da = tc_desc(a_base + (uint32_t)((s - 1) * TC_A_SLICE), TC_A_LBO, TC_A_SBO);
                     for (int t_lo = 1; t_lo <= 6 - s; t_lo += per) {
                         const int t_hi = min(6 - s, t_lo + per - 1);
                         const uint64_t db = tc_desc(b_base + (uint32_t)((t_lo - 1) * np * 32));
@@ -314,6 +321,6 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-constexpr int TC_SMEM = TC_NSTG * (TC_S * TC_M * 32 + TC_S * 2 * TC_MAX_LT * 32) + (3 * TC_NSTG + 1) * 8 + 2 * TC_M + 16 + 1024;
+constexpr int TC_SMEM = TC_NSTG * (TC_S * TC_A_SLICE + TC_S * 2 * TC_MAX_LT * 32) + (3 * TC_NSTG + 1) * 8 + 2 * TC_M + 16 + 1024;
 
 }  // namespace mb200
