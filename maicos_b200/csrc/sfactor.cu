@@ -1355,3 +1355,10 @@ extern "C" int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const
     }
     return MB200_OK;
 }
+
+#ifdef MB200_TC_TRACE
+// Developer build only (make TRACE=1): clock64 stamps written by CTA 0 of the last k_sf_contract_tc launch.
+extern "C" int mb200_debug_tc_trace(unsigned long long *out, int n) {
+    return cudaMemcpyFromSymbol(out, mb200::g_tc_trace, (size_t)std::min(n, 512 * 32) * 8) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -32,8 +32,15 @@ constexpr int TC_M = 128;          // rows ((h,k) pairs) per tile
 constexpr int TC_KA = 16;          // atoms per MMA K-step
 constexpr int TC_S = 5;            // digits per component
 constexpr int TC_NSTG = 4;         // A / B stages (power of two: cheap stage / phase arithmetic)
-constexpr int TC_GEN_WARPS = 8;
-constexpr int TC_THREADS = (TC_GEN_WARPS + 1) * 32;
+#ifndef MB200_TC_GEN_WARPS
+#define MB200_TC_GEN_WARPS 16
+#endif
+constexpr int TC_GEN_WARPS = MB200_TC_GEN_WARPS;
+constexpr int TC_THREADS = (TC_GEN_WARPS + 3) * 32;  // generators + MMA warp + seed loader + B loader
+constexpr int TC_W_MMA = TC_GEN_WARPS, TC_W_SEED = TC_GEN_WARPS + 1, TC_W_BLOAD = TC_GEN_WARPS + 2;
+constexpr int TC_TASKS = 8;                // generator tasks per K-step: 4 row quads x 8 atom pairs (one warp pass) each
+constexpr int TC_SEED_MAX = 8;             // seed ring: at most 8 K-steps in flight ...
+constexpr int TC_SEED_BYTES = 40 * 1024;   // ... within this much shared memory (a stage is <= 67 rows x 256 B)
 constexpr int TC_MAX_LT = 48;      // l values per tile: 5 * 2 * 48 = 480 TMEM columns
 constexpr int TC_CHUNK = 8192;     // atoms per flush: 2 * 5 * 128 * 128 * 8192 < 2^31, the int32 accumulators cannot overflow
 
@@ -120,11 +127,26 @@ __global__ void __launch_bounds__(256) k_sf_bimage(const BimgJob *__restrict__ j
 // ---------------------------------------------------------------------------------------------
 // k_sf_contract_tc
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t da, uint64_t db, int n, uint32_t acc) {
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+#ifdef MB200_TC_TRACE  // developer build: per-step clock64 stamps of CTA 0's first item (tools/tc_trace.py)
+__device__ unsigned long long g_tc_trace[512 * 32];
+#define TC_STAMP(slot) do { if (blockIdx.x == 0 && first_item && t < 512) g_tc_trace[t * 32 + (slot)] = clock64(); } while (0)
+#else
+#define TC_STAMP(slot) do { } while (0)
+#endif
+__device__ __forceinline__ uint32_t tc_idesc(int n) {  // s8 x s8 -> s32, K-major A and B, M = 128
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
                  "l"(da), "l"(db), "r"(idesc), "r"(acc)
                  : "memory");
+}
+// One lane of a converged warp (the compiler knows a single thread runs the guarded code: operands move to
+// uniform registers without a per-value loop).
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_commit(unsigned long long *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -142,14 +164,23 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
     unsigned long long *b_full = a_full + TC_NSTG;                                               // [NSTG] bulk copy -> MMA
     unsigned long long *s_free = b_full + TC_NSTG;                                               // [NSTG] MMA done -> refill
     unsigned long long *acc_done = s_free + TC_NSTG;                                             // [1]
-    uint8_t *s_rows = reinterpret_cast<uint8_t *>(acc_done + 1);                                 // [128][2]
+    unsigned long long *seed_full = acc_done + 1;                                                // [SEED_MAX] loader -> generators
+    unsigned long long *seed_free = seed_full + TC_SEED_MAX;                                     // [SEED_MAX] generators -> loader
+    unsigned long long *init_done = seed_free + TC_SEED_MAX;                                     // [1] K-step 0 issued (+ 7 spare)
+    uint8_t *s_rows = reinterpret_cast<uint8_t *>(init_done + 8);                                     // [128][2]
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_rows + 2 * TC_M);
     int *s_item = reinterpret_cast<int *>(s_tmem + 1);
+    int *s_nseed = s_item + 1;                                                                   // [2] unique h, unique k0
+    int *s_task = s_nseed + 2;                                                                   // [1] generator task counter (+ pad)
+    uint8_t *s_quad = reinterpret_cast<uint8_t *>(s_task + 2);                                  // [32][2] quad -> seed row (x, y)
+    uint16_t *s_seedrow = reinterpret_cast<uint16_t *>(s_quad + 64);                             // [67] table row | axis << 15
+    unsigned char *sSeed = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(s_seedrow + 68) + 127) & ~(uintptr_t)127);                  // [depth][n_seed rows][16 atoms] double2
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool is_gen = warp < TC_GEN_WARPS;
 
-    if (warp == TC_GEN_WARPS) {
+    if (warp == TC_W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -158,13 +189,20 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = *s_tmem;
     bool bars_live = false;
+#ifdef MB200_TC_TRACE
+    bool first_item = true;
+#endif
 
     for (;;) {
         if (tid == 0) {
             *s_item = atomicAdd(counter, 1);
-            for (int s = 0; s < 3 * TC_NSTG + 1; ++s) {  // re-arm: every item starts at phase 0
+            *s_task = 0;
+            for (int s = 0; s < 3 * TC_NSTG + 1 + 2 * TC_SEED_MAX + 8; ++s) {  // re-arm: every item starts at phase 0
                 if (bars_live) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(a_full + s)) : "memory");
-                const unsigned count = s < TC_NSTG ? TC_GEN_WARPS : 1u;
+                // a_full: one arrive per generator task; b_full / s_free / acc_done: 1; seed_full: one cp.async arrive per
+                // loader lane; seed_free: one arrive per generator task
+                const unsigned count = s < TC_NSTG ? TC_TASKS : s < 3 * TC_NSTG + 1 ? 1u : s < 3 * TC_NSTG + 1 + TC_SEED_MAX ? 32u :
+                                       s < 3 * TC_NSTG + 1 + 2 * TC_SEED_MAX ? TC_TASKS : 1u;
                 mbar_init(a_full + s, count);
             }
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -181,106 +219,202 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
         const uint32_t b_bytes = (uint32_t)(TC_S * np * 32);
         for (int i = tid; i < 2 * TC_M; i += TC_THREADS) s_rows[i] = sg.rows[(size_t)it.rt * 2 * TC_M + i];
         __syncthreads();
+        // Seed rows of the item: quad o starts at (h0, k0) = rows[4 o]; the distinct h0 (Ex rows), the distinct k0
+        // (Ey rows) and Ey[1] are what the generators need per atom -- the loader warp keeps them in a shared-memory
+        // ring, TC_SEED_MAX K-steps ahead, so no generator ever waits on a global load.
+        if (warp == TC_W_SEED) {
+            const int h0 = s_rows[8 * lane], k0 = s_rows[8 * lane + 1];
+            const unsigned mh = __match_any_sync(0xffffffffu, h0), mk = __match_any_sync(0xffffffffu, k0);
+            const int lh = __ffs(mh) - 1, lk = __ffs(mk) - 1;  // leader lane of my value
+            const unsigned leaders_h = __ballot_sync(0xffffffffu, lh == lane), leaders_k = __ballot_sync(0xffffffffu, lk == lane);
+            const int ih = __popc(leaders_h & ((1u << lh) - 1u)), ik = __popc(leaders_k & ((1u << lk) - 1u));
+            const int n_uh = __popc(leaders_h), n_uk = __popc(leaders_k);
+            s_quad[2 * lane] = (uint8_t)ih;
+            s_quad[2 * lane + 1] = (uint8_t)(n_uh + ik);
+            if (lh == lane) s_seedrow[ih] = (uint16_t)h0;
+            if (lk == lane) s_seedrow[n_uh + ik] = (uint16_t)(k0 | 0x8000);
+            if (lane < 3) s_seedrow[n_uh + n_uk + lane] = (uint16_t)(min(lane + 1, sg.rows1 - 1) | 0x8000);  // Ey[1..3]
+            if (lane == 0) {
+                s_nseed[0] = n_uh;
+                s_nseed[1] = n_uk;
+            }
+        }
+        __syncthreads();
+        const int n_seed = s_nseed[0] + s_nseed[1] + 3;          // rows per seed stage
+        const int seed_stage = n_seed * 256;                      // bytes: 16 atoms x double2 per row
+        const int seed_shift = seed_stage * 8 <= TC_SEED_BYTES ? 3 : seed_stage * 4 <= TC_SEED_BYTES ? 2 : 1;  // 8, 4 or 2 K-steps
+        const int seed_depth = 1 << seed_shift;
 
         if (is_gen) {
             // ---- generators: thread (ap, o) -> atoms 2 ap, 2 ap + 1 of the K-step, rows 4 o .. 4 o + 3 ----
-            // The plan pads every run of consecutive k to a multiple of four rows, so a quad is always one run:
-            // row 0 is seeded from the FP64 tables, rows 1..3 follow by P *= Ey[1].  Padding rows are computed
-            // and never referenced.
-            const int ap = tid & 7, o = tid >> 3;
-            const int h0 = s_rows[2 * (4 * o)], k0 = s_rows[2 * (4 * o) + 1];
-            const int off0 = tc_canon_a(4 * o, 4 * ap);  // K' = 4 ap .. 4 ap + 3; rows 4 o + r: + 16 r bytes
-            // seeds of row 0 and the k-step factor are prefetched one K-step ahead; their table addresses advance
-            // by a constant stride per K-step (two 8-atom blocks)
-            const int row1 = 1 < sg.rows1 ? 1 : 0;
-            const double2 *px[2], *py[2], *py1[2];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int jf = it.j0 + 2 * ap + c;
-                px[c] = sg.ex + tab_index(jf, h0, sg.rows0);
-                py[c] = sg.ey + tab_index(jf, k0, sg.rows1);
-                py1[c] = sg.ey + tab_index(jf, row1, sg.rows1);
-            }
-            const size_t sx = (size_t)sg.rows0 * 16, sy = (size_t)sg.rows1 * 16;
-            double2 nx[2], ny[2], ny1[2];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) { nx[c] = *px[c]; ny[c] = *py[c]; ny1[c] = *py1[c]; }
-            for (int t = 0; t < n_steps; ++t) {
-                const int st = t & (TC_NSTG - 1);
-                double2 y1[2], p[2];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    y1[c] = ny1[c];
-                    p[c].x = nx[c].x * ny[c].x - nx[c].y * ny[c].y;
-                    p[c].y = nx[c].x * ny[c].y + nx[c].y * ny[c].x;
-                }
-                if (t + 1 < n_steps) {
+            // The plan pads every run of consecutive k to a multiple of four rows, so a quad is always one run
+            // (h0, k0 .. k0 + 3):  P_r = (w Ex[h0] Ey[k0]) Ey[r], four independent products per atom (no recurrence
+            // chain: eight independent digit pipelines per thread).  Padding rows are computed and never referenced.
+            // Tasks (K-step t, pass j = 4 row quads x 8 atom pairs) are handed out in order from a shared counter:
+            // the warps of a scheduler that is held up (the MMA warp's UTCIMMA issue stalls the FP64 instructions
+            // of its scheduler) simply take fewer of them.
+            const int ap = lane & 7;
+            const int n_tasks = n_steps * TC_TASKS;
+            for (;;) {
+                int task = 0;
+                if (lane == 0) task = atomicAdd(s_task, 1);
+                task = __shfl_sync(0xffffffffu, task, 0);
+                if (task >= n_tasks) break;
+                const int t = task >> 3, o = 4 * (task & 7) + (lane >> 3);
+                const int off0 = tc_canon_a(4 * o, 4 * ap);  // K' = 4 ap .. 4 ap + 3; rows 4 o + r: + 16 r bytes
+                // seeds Ex[h0], Ey[k0] and the factors Ey[1..3] of my two atoms, from the seed ring
+                const int sx = (s_quad[2 * o] * 16 + 2 * ap) * 16, sy = (s_quad[2 * o + 1] * 16 + 2 * ap) * 16,
+                          se = ((n_seed - 3) * 16 + 2 * ap) * 16;
+                const int st = t & (TC_NSTG - 1), ss = t & (seed_depth - 1);
+                double2 e[3][2], p[2];
+                mbar_wait(seed_full + ss, (unsigned)(t >> seed_shift) & 1u);
+                if (lane == 0) TC_STAMP((task & 7) * 3);
+                {
+                    const unsigned char *sd = sSeed + ss * seed_stage;
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        px[c] += sx; py[c] += sy; py1[c] += sy;
-                        nx[c] = *px[c]; ny[c] = *py[c]; ny1[c] = *py1[c];
+                        const double2 x = *reinterpret_cast<const double2 *>(sd + sx + 16 * c);
+                        const double2 y = *reinterpret_cast<const double2 *>(sd + sy + 16 * c);
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) e[r][c] = *reinterpret_cast<const double2 *>(sd + se + 256 * r + 16 * c);
+                        p[c].x = x.x * y.x - x.y * y.y;
+                        p[c].y = x.x * y.y + x.y * y.x;
                     }
                 }
                 if (t >= TC_NSTG) mbar_wait(s_free + st, (unsigned)((t / TC_NSTG) - 1) & 1u);
+                if (lane == 0) TC_STAMP((task & 7) * 3 + 1);
                 int8_t *dstA = sA + st * A_STAGE + off0;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    if (r > 0) {
+                    // biased fixed point of (re0, im0, re1, im1): the low 40 mantissa bits hold the five digits + 128
+                    unsigned long long b[4];
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const double nr = p[c].x * y1[c].x - p[c].y * y1[c].y, ni = p[c].x * y1[c].y + p[c].y * y1[c].x;
-                            p[c].x = nr; p[c].y = ni;
+                    for (int c = 0; c < 2; ++c) {
+                        double pr = p[c].x, pi = p[c].y;
+                        if (r > 0) {
+                            pr = p[c].x * e[r - 1][c].x - p[c].y * e[r - 1][c].y;
+                            pi = p[c].x * e[r - 1][c].y + p[c].y * e[r - 1][c].x;
                         }
+                        b[2 * c] = (unsigned long long)__double_as_longlong(pr + TC_MAGIC);
+                        b[2 * c + 1] = (unsigned long long)__double_as_longlong(pi + TC_MAGIC);
                     }
-                    unsigned lo[2][2], hi[2][2];  // [atom][re / im]
+                    // 4 x 4 byte transpose of the low words: word i = byte i of (re0, im0, re1, im1) = slice 5 - i
+                    const unsigned t0 = __byte_perm((unsigned)b[0], (unsigned)b[1], 0x5140), t1 = __byte_perm((unsigned)b[0], (unsigned)b[1], 0x7362),
+                                   t2 = __byte_perm((unsigned)b[2], (unsigned)b[3], 0x5140), t3 = __byte_perm((unsigned)b[2], (unsigned)b[3], 0x7362);
+                    const unsigned h0 = __byte_perm((unsigned)(b[0] >> 32), (unsigned)(b[1] >> 32), 0x0040),
+                                   h1 = __byte_perm((unsigned)(b[2] >> 32), (unsigned)(b[3] >> 32), 0x0040);
+                    unsigned w[TC_S];
+                    w[0] = __byte_perm(h0, h1, 0x5410);  // slice 1 (most significant digit)
+                    w[1] = __byte_perm(t1, t3, 0x7632);  // slice 2 = byte 3
+                    w[2] = __byte_perm(t1, t3, 0x5410);  // slice 3 = byte 2
+                    w[3] = __byte_perm(t0, t2, 0x7632);  // slice 4 = byte 1
+                    w[4] = __byte_perm(t0, t2, 0x5410);  // slice 5 = byte 0
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) { tc_digits(p[c].x, lo[c][0], hi[c][0]); tc_digits(p[c].y, lo[c][1], hi[c][1]); }
-#pragma unroll
-                    for (int s = 0; s < TC_S; ++s) {
-                        const unsigned w0 = tc_pair(s + 1, lo[0][0], hi[0][0], lo[0][1], hi[0][1]);
-                        const unsigned w1 = tc_pair(s + 1, lo[1][0], hi[1][0], lo[1][1], hi[1][1]);
-                        *reinterpret_cast<uint32_t *>(dstA + s * TC_A_SLICE + 16 * r) = __byte_perm(w0, w1, 0x5410);
-                    }
+                    for (int s = 0; s < TC_S; ++s)       // xor 0x80: biased byte -> balanced int8 digit
+                        *reinterpret_cast<uint32_t *>(dstA + s * TC_A_SLICE + 16 * r) = w[s] ^ 0x80808080u;
                 }
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes -> visible to the tensor core
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_full + st);
+                if (lane == 0) {
+                    mbar_arrive(a_full + st);
+                    mbar_arrive(seed_free + ss);  // the seeds were consumed long ago: the loader may refill the slot
+                    TC_STAMP((task & 7) * 3 + 2);
+                }
             }
-        } else if (lane == 0) {
-            // ---- control: B image loads + MMA issue ----
+        } else if (warp == TC_W_SEED) {
+            // ---- seed loader: 16-byte cp.async gathers of the item's seed rows, seed_depth K-steps ahead ----
+            // lane -> atom a = lane & 15 of the K-step and seed rows (lane >> 4) + 2 i; source pointers of the first
+            // eight rows per lane live in registers and advance by a constant per K-step
+            const int a = lane & 15, r0 = lane >> 4;
+            const char *ex = reinterpret_cast<const char *>(sg.ex), *ey = reinterpret_cast<const char *>(sg.ey);
+            const unsigned step_x = (unsigned)sg.rows0 * 256u, step_y = (unsigned)sg.rows1 * 256u;  // two 8-atom blocks per K-step
+            auto seed_src = [&](int ri) -> const char * {
+                const int code = s_seedrow[ri], row = code & 0x7fff;
+                return (code & 0x8000) ? ey + tab_index(it.j0 + a, row, sg.rows1) * 16 : ex + tab_index(it.j0 + a, row, sg.rows0) * 16;
+            };
+            const char *src[8];
+            unsigned stp[8];
+            const int n_mine = (n_seed - r0 + 1) >> 1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int ri = min(r0 + 2 * i, n_seed - 1);
+                src[i] = seed_src(ri);
+                stp[i] = (s_seedrow[ri] & 0x8000) ? step_y : step_x;
+            }
+            const int dst0 = (r0 * 16 + a) * 16;
+            for (int t = 0; t < n_steps; ++t) {
+                const int ss = t & (seed_depth - 1);
+                if (t >= seed_depth) mbar_wait(seed_free + ss, (unsigned)((t >> seed_shift) - 1) & 1u);
+                unsigned char *dst = sSeed + ss * seed_stage + dst0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < n_mine) cp_async16(dst + i * 512, src[i]);
+                    src[i] += stp[i];
+                }
+                for (int i = 8; i < n_mine; ++i) {  // more than 16 seed rows: the rest are located on the fly
+                    const int ri = r0 + 2 * i;
+                    cp_async16(dst + i * 512, seed_src(ri) + (size_t)t * ((s_seedrow[ri] & 0x8000) ? step_y : step_x));
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(seed_full + ss)) : "memory");
+            }
+        } else if (warp == TC_W_BLOAD) {
+            // ---- B loader: one bulk copy of the pre-sliced Z image per K-step, as soon as the stage is free ----
+            // (the whole warp walks the loop and waits; one elected lane issues the copy)
             const int8_t *bsrc = sg.bimg + ((size_t)it.lt * (sg.ld / TC_KA) + it.j0 / TC_KA) * (size_t)b_bytes;
-            auto load_b = [&](int t) {
-                if (t < n_steps) {
-                    const int st = t % TC_NSTG;
-                    if (t >= TC_NSTG) mbar_wait(s_free + st, (unsigned)((t / TC_NSTG) - 1) & 1u);
+            for (int t = 0; t < n_steps; ++t) {
+                const int st = t & (TC_NSTG - 1);
+                if (t >= TC_NSTG) mbar_wait(s_free + st, (unsigned)((t / TC_NSTG) - 1) & 1u);
+                if (tc_elect_one()) {
                     mbar_arrive_expect_tx(b_full + st, b_bytes);
                     bulk_g2s(sB + st * B_STAGE, bsrc + (size_t)t * b_bytes, b_bytes, b_full + st);
                 }
-            };
-            load_b(0);
-            load_b(1);
-            for (int t = 0; t < n_steps; ++t) {
-                const int st = t % TC_NSTG;
-                const unsigned par = (unsigned)(t / TC_NSTG) & 1u;
-                mbar_wait(a_full + st, par);
-                mbar_wait(b_full + st, par);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t a_base = smem_u32(sA + st * A_STAGE), b_base = smem_u32(sB + st * B_STAGE);
-                const int per = max(1, 256 / np);  // B slices per MMA (N <= 256)
-#pragma unroll 1
-                for (int s = 1; s <= TC_S; ++s) {
-                    const uint64_t da = tc_desc(a_base + (uint32_t)((s - 1) * TC_A_SLICE), TC_A_LBO, TC_A_SBO);
-                    for (int t_lo = 1; t_lo <= 6 - s; t_lo += per) {
+                __syncwarp();
+            }
+        } else if (warp == TC_W_MMA) {
+            // ---- MMA issue: the (A slice s) x (B slices t_lo .. t_hi) products of a K-step; everything that does not
+            // depend on the stage is tabulated once per item so that the serial issue path is a handful of adds.  The
+            // whole warp walks the loop; one elected lane issues (the compiler then keeps the operands in uniform
+            // registers).  One commit per K-step: commits are expensive, and so is issuing from more than one warp. ----
+            const int per = max(1, 256 / np);  // B slices per MMA (N <= 256)
+            uint32_t m_a[15], m_b[15], m_d[15], m_i[15];
+            int n_mma = 0;
+            {
+                int s = 1, t_lo = 1;
+#pragma unroll
+                for (int i = 0; i < 15; ++i) {
+                    m_a[i] = m_b[i] = m_d[i] = m_i[i] = 0;
+                    if (s <= TC_S) {
                         const int t_hi = min(6 - s, t_lo + per - 1);
-                        const uint64_t db = tc_desc(b_base + (uint32_t)((t_lo - 1) * np * 32));
-                        // column blocks g = s + t; on the first K-step the s = 1 MMAs initialise every block
-                        tc_mma(tmem + (uint32_t)((s + t_lo - 2) * np), da, db, (t_hi - t_lo + 1) * np, (t > 0 || s > 1) ? 1u : 0u);
+                        m_a[i] = (uint32_t)((s - 1) * TC_A_SLICE) >> 4;
+                        m_b[i] = (uint32_t)((t_lo - 1) * np * 32) >> 4;
+                        m_d[i] = (uint32_t)((s + t_lo - 2) * np);          // column block g = s + t
+                        m_i[i] = tc_idesc((t_hi - t_lo + 1) * np) | (s > 1 ? 1u : 0u);  // bit 0 (masked off at issue):
+                        n_mma = i + 1;                                     // accumulate at t = 0
+                        t_lo = t_hi + 1;
+                        if (t_lo > 6 - s) { ++s; t_lo = 1; }
                     }
                 }
-                tc_commit(s_free + st);  // frees the A and B stage when these MMAs have read them
-                load_b(t + 2);           // after the issue: waiting for step t-1's stage overlaps with step t's MMAs
             }
-            tc_commit(acc_done);
+            const uint64_t da0 = tc_desc(smem_u32(sA), TC_A_LBO, TC_A_SBO), db0 = tc_desc(smem_u32(sB));
+            for (int t = 0; t < n_steps; ++t) {
+                const int st = t & (TC_NSTG - 1);
+                const unsigned par = (unsigned)(t / TC_NSTG) & 1u;
+                mbar_wait(b_full + st, par);
+                mbar_wait(a_full + st, par);
+                TC_STAMP(24);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint64_t da = da0 + (uint64_t)(st * (A_STAGE >> 4)), db = db0 + (uint64_t)(st * (B_STAGE >> 4));
+                if (tc_elect_one()) {
+#pragma unroll
+                    for (int i = 0; i < 15; ++i)
+                        if (i < n_mma) tc_mma(tmem + m_d[i], da + m_a[i], db + m_b[i], m_i[i] & ~1u, t > 0 ? 1u : (m_i[i] & 1u));
+                    tc_commit(s_free + st);  // frees the A and B stage when these MMAs have read them
+                }
+                __syncwarp();
+                TC_STAMP(26);
+            }
+            if (tc_elect_one()) tc_commit(acc_done);
+            __syncwarp();
         }
 
         // ---- epilogue: TMEM -> FP64 partial amplitudes (generator warps; warp w reads lanes 32 (w % 4) ..) ----
@@ -314,13 +448,17 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         }
         __syncthreads();  // TMEM and the rings are free for the next item
+#ifdef MB200_TC_TRACE
+        first_item = false;
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (warp == TC_GEN_WARPS)
+    if (warp == TC_W_MMA)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-constexpr int TC_SMEM = TC_NSTG * (TC_S * TC_A_SLICE + TC_S * 2 * TC_MAX_LT * 32) + (3 * TC_NSTG + 1) * 8 + 2 * TC_M + 16 + 1024;
+constexpr int TC_SMEM = TC_NSTG * (TC_S * TC_A_SLICE + TC_S * 2 * TC_MAX_LT * 32) + (3 * TC_NSTG + 1 + 2 * TC_SEED_MAX + 8) * 8 + 2 * TC_M + 16 + 16 + 64 + 136 +
+                        128 + TC_SEED_BYTES + 1024;
 
 }  // namespace mb200
