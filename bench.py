@@ -41,8 +41,10 @@ N_MOL = 33_333          # 99 999 atoms
 BOX = 99.97             # Å, SPC/E liquid density
 QMAX, DQ = 2.0, 0.1     # 20 nm^-1
 SEED = 20261019
-FP64_DMMA_PEAK_TFLOPS = 37.0   # tools/microbench/fp64_peaks on this pool's B200 (gpurun_out/fp64_peaks.log)
-FLOP_PER_ATOMQ = 8.0
+FP64_DMMA_PEAK_TFLOPS = 37.0   # tools/microbench/fp64_peaks on this pool's B200 (profiles/r01_fp64_peaks.log)
+FLOP_PER_ATOMQ = 8.0           # one complex multiply-accumulate per atom*q
+I8_PEAK_TOPS = 4359.0          # tcgen05 kind::i8 dense, M=128 N=256, tools/microbench/umma_i8 (profiles/r01_umma_i8.log)
+I8_OPS_PER_ATOMQ = 120.0       # 4 real MACs x 15 digit products (s + t <= 6 of 5 x 5) x 2 ops
 
 
 def parse():
@@ -55,9 +57,10 @@ def parse():
     ap.add_argument("--pool-steps", type=int, default=7, help="distinct batches resident in HBM (pool > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--precision", default="fp64", choices=["fp64", "i8x5"],
-                    help="arithmetic of the headline numbers (fp64 = parity mode; the other mode is always reported "
-                         "under split_precision)")
+    ap.add_argument("--precision", default="i8x5", choices=["i8x5", "fp64"],
+                    help="arithmetic of the contraction for the headline numbers (i8x5 = the library default: split "
+                         "precision on the tcgen05 tensor cores; fp64 = FP64 DMMA); the other mode is always measured too "
+                         "and reported under other_precision_mode")
     return ap.parse_args()
 
 
@@ -113,8 +116,16 @@ def config_dict(args, wl, n_gpus):
         "l2": f"inputs larger than L2: pool of {args.pool_steps * args.frames_per_step} distinct frames "
               f"({args.pool_steps * args.frames_per_step * wl['n_atoms'] * 12 / 1e6:.0f} MB) resident, every step reads a "
               "different batch; phase tables (>1 GB per step) are rewritten every step",
-        "precision": "FP64 tables, FP64 DMMA accumulation (parity mode, rel err <= 1e-6 vs reference)",
+        "precision": PRECISION_TEXT[args.precision],
     }
+
+
+PRECISION_TEXT = {
+    "i8x5": "split precision (library default): FP64 phase tables cut into five int8 digits (40-bit fixed point), exact int32 "
+            "accumulation on tcgen05 kind::i8 (TMEM), FP64 recombination; measured rel err <= 5e-9 per S cell, 3e-13 binned "
+            "(stated tolerance 1e-6)",
+    "fp64": "FP64 tables, FP64 DMMA accumulation (rel err ~1e-12 vs the reference kernel; stated tolerance 1e-6)",
+}
 
 
 def run_reference(args, wl, rank):
@@ -297,23 +308,40 @@ def main():
         parallel.shutdown()
         return
     kern_s = kern_ns * 1e-9
-    flops_per_launch = FLOP_PER_ATOMQ * B * wl["atomq_per_frame"]
-    achieved = flops_per_launch * kern_launches / kern_s / 1e12 if kern_s > 0 else None
-    roofline = {
-        "kernel": "k_sf_contract", "bound": "tensor", "pipe": "FP64 DMMA (mma.sync.m8n8k4.f64)",
-        "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-        "frac": achieved / FP64_DMMA_PEAK_TFLOPS if achieved else None,
-        "peak_source": "measured FP64 DMMA burst on this pool's B200 (tools/microbench/fp64_peaks.cu, "
-                       "profiles/r01_fp64_peaks.log); MEASURED_PEAKS.json has no FP64 entry",
-        "algorithmic_flop_per_atomq": FLOP_PER_ATOMQ, "kernel_ms_per_launch": kern_s / max(kern_launches, 1) * 1e3,
-        "kernel_share_of_step": kern_s / (ms * 1e-3), "traffic": None,
-        "hbm_gbs_measured_peak": json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs")
-        if (ROOT / "MEASURED_PEAKS.json").exists() else None,
-    }
+    atomq_per_launch = B * wl["atomq_per_frame"]
+    peaks_file = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    common = {"kernel_ms_per_launch": kern_s / max(kern_launches, 1) * 1e3, "kernel_share_of_step": kern_s / (ms * 1e-3),
+              "traffic": None, "hbm_gbs_measured_peak": peaks_file.get("hbm_gbs"),
+              "fp64_equivalent_tflops": FLOP_PER_ATOMQ * atomq_per_launch * kern_launches / kern_s / 1e12 if kern_s > 0 else None,
+              "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS}
+    if args.precision == "fp64":
+        achieved = common["fp64_equivalent_tflops"]
+        roofline = {
+            "kernel": "k_sf_contract", "bound": "tensor", "pipe": "FP64 DMMA (mma.sync.m8n8k4.f64)",
+            "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+            "frac": achieved / FP64_DMMA_PEAK_TFLOPS if achieved else None,
+            "peak_source": "measured FP64 DMMA burst on this pool's B200 (tools/microbench/fp64_peaks.cu, "
+                           "profiles/r01_fp64_peaks.log); MEASURED_PEAKS.json has no FP64 entry",
+            "algorithmic_flop_per_atomq": FLOP_PER_ATOMQ, **common}
+    else:
+        achieved = I8_OPS_PER_ATOMQ * atomq_per_launch * kern_launches / kern_s / 1e12 if kern_s > 0 else None
+        roofline = {
+            "kernel": "k_sf_contract_tc", "bound": "tensor", "pipe": "tcgen05.mma kind::i8 (UTCIMMA), int32 accumulators in TMEM",
+            "achieved": achieved, "peak": I8_PEAK_TOPS, "unit": "TFLOP/s",
+            "unit_note": "int8 tensor ops (multiply-add = 2), i.e. TOP/s; MEASURED_PEAKS.json carries only the bf16 figure "
+                         f"({peaks_file.get('bf16_tflops')} TFLOP/s), the int8 peak is our own probe of the same pipe",
+            "frac": achieved / I8_PEAK_TOPS if achieved else None,
+            "peak_source": "measured tcgen05 kind::i8 dense rate on this pool's B200, 148 CTAs x 128x256x32 MMAs from shared "
+                           "memory (tools/microbench/umma_i8.cu, profiles/r01_umma_i8.log); nominal 4500",
+            "algorithmic_int8_ops_per_atomq": I8_OPS_PER_ATOMQ,
+            "co_limiters": "shared-memory data pipe (operand reads of the MMAs + digit stores, ~73 % busy) and the digit "
+                           "generators' issue slots (~48 %): profiles/r01_tc_notes.md",
+            **common}
     line = {
         "metric": "saxs_atom_q_evals_per_s", "value": value, "unit": "atom*q/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": config_dict(args, wl, world),
+        "dtype": "i8x5->s32 (40-bit fixed point, FP64 tables and recombination)" if args.precision == "i8x5" else "f64",
+        "data": "synthetic", "config": config_dict(args, wl, world),
         "frames_per_s": K * B * world / (ms * 1e-3), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "precision": args.precision, "other_precision_mode": other_mode,
     }
@@ -331,7 +359,7 @@ def main():
             "max_rel_err_S_binned": float(np.max(np.abs(s1[0].sum(0)[nz] / ref_obs["structure_factors"][nz] - 1))),
             "max_rel_err_I_binned": float(np.max(np.abs(i1[0].sum(0)[nz] / ref_obs["scattering_intensities"][nz] - 1))),
             "bincount_equal": bool(np.array_equal(c1[0, -1], ref_obs["bincount"])),
-            "tolerance": "rel <= 1e-6 (FP64 mode), counts exact",
+            "tolerance": "rel <= 1e-6, counts exact",
         }
     if world == 1 and not args.no_e2e:
         line["path2_profile_hist"] = path2_summary(ctx, lib, torch)

@@ -15,13 +15,14 @@ from .modules import __all__ as _modules_all  # noqa: E402
 
 
 
-def set_precision(mode: str = "fp64", device: int | None = None) -> None:
-    """Arithmetic of the fused S(q) paths (``Saxs``, ``DiporderStructureFactor``) on this process' GPU.
+def set_precision(mode: str = "i8x5", device: int | None = None) -> None:
+    """Arithmetic of the S(q) contraction (``Saxs``, ``DiporderStructureFactor``, ``lib.math.structure_factor``).
 
-    ``"fp64"`` -- FP64 phase tables and FP64 DMMA accumulation: the parity mode and the default.
-    ``"i8x5"`` -- split precision on the tcgen05 tensor cores (five int8 digits per component, exact
-    int32 accumulation in TMEM): several times faster, ~1e-9 relative on binned S(q); isolated weak
-    cells of the raw cube can exceed 1e-6, so ``lib.math.structure_factor`` always stays FP64.
+    ``"i8x5"`` -- the default: split precision on the tcgen05 tensor cores (five int8 digits per component =
+    40-bit fixed point, exact int32 accumulation in TMEM, FP64 recombination).  Measured max relative error
+    on any nonzero cell of the raw S cube 4.4e-9 (1.5k .. 1M atoms), 3e-13 on binned S(q); stated tolerance 1e-6.
+    ``"fp64"`` -- FP64 phase tables and FP64 DMMA accumulation (~1e-12 against the reference kernel), ~2.6x slower.
+    The environment variable ``MAICOS_B200_PRECISION`` selects the mode for the CLI.
     """
     from . import _cabi
 

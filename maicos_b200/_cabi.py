@@ -133,7 +133,7 @@ class Context:
         self._h = handle
         self.device = int(device)
         mode = os.environ.get("MAICOS_B200_PRECISION", "")
-        if mode:  # e.g. MAICOS_B200_PRECISION=i8x5 for the CLI; maicos_b200.set_precision() overrides
+        if mode:  # e.g. MAICOS_B200_PRECISION=fp64 for the CLI; maicos_b200.set_precision() overrides
             self.set_precision(mode)
 
     @property
@@ -153,7 +153,7 @@ class Context:
         return dict(zip(keys, [int(v) for v in out]))
 
     def set_precision(self, mode: str) -> None:
-        """``"fp64"`` (parity default) or ``"i8x5"`` (split precision on the tcgen05 tensor cores)."""
+        """``"i8x5"`` (default: split precision on the tcgen05 tensor cores) or ``"fp64"`` (FP64 DMMA)."""
         _check(load().mb200_ctx_set_precision(self._h, {"fp64": 0, "i8x5": 1}[mode]))
 
     def launch_count(self) -> int:

@@ -104,8 +104,8 @@ struct mb200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false;
     bool sf_attr_set = false, hist_attr_set = false, tc_attr_set = false;
-    int precision = 0;        // 0: FP64 DMMA (parity default)  1: int8 x 5 split precision on tcgen05
-    bool force_fp64 = false;  // cudaFuncSetAttribute done on this device
+    int precision = 1;        // 1: int8 x 5 split precision on tcgen05 (default)  0: FP64 DMMA
+    bool force_fp64 = false;  // this call must use the FP64 kernel (non-finite weights)
     int64_t launches = 0;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // S(q) workspaces

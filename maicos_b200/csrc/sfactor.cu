@@ -1154,7 +1154,30 @@ extern "C" int mb200_structure_factor_block(mb200_ctx *ctx, const double *positi
     double *hp = ctx->h_out.as<double>();
     for (size_t j = 0; j < n; ++j)
         for (int d = 0; d < 3; ++d) hp[j * 3 + d] = positions[(int64_t)j * stride_atom + d * stride_xyz];
-    if (n) std::memcpy(hp + n * 3, weights, n * 8);
+    // Split-precision mode works on table entries in [-1, 1]: the weights are divided by a power of two >= max|w|
+    // (exact) and S is multiplied back by its square (exact).  Non-finite weights take the FP64 kernel.
+    double wscale = 1.0;
+    bool tc_weights = ctx->precision == 1;
+    if (tc_weights) {
+        double wmax = 0.0;
+        for (size_t j = 0; j < n; ++j) {
+            const double a = std::fabs(weights[j]);
+            if (!(a <= 1.7e308)) { tc_weights = false; break; }
+            wmax = std::max(wmax, a);
+        }
+        if (tc_weights && wmax > 1.0) {
+            int ex = 0;
+            std::frexp(wmax, &ex);  // wmax = f * 2^ex, 0.5 <= f < 1
+            wscale = std::ldexp(1.0, ex);
+        }
+    }
+    if (n) {
+        if (wscale == 1.0) std::memcpy(hp + n * 3, weights, n * 8);
+        else {
+            const double inv = 1.0 / wscale;
+            for (size_t j = 0; j < n; ++j) hp[n * 3 + j] = weights[j] * inv;
+        }
+    }
     MB_TRY(ctx->d_pos.ensure(std::max<size_t>(n, 1) * 32));
     if (n) MB_CUDA(cudaMemcpyAsync(ctx->d_pos.p, hp, n * 32, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -1168,7 +1191,7 @@ extern "C" int mb200_structure_factor_block(mb200_ctx *ctx, const double *positi
     for (int d = 0; d < 3; ++d) { sp.job.box[d] = dimensions[d]; sp.job.boxf[d] = (float)dimensions[d]; }
     sp.job.n = (int32_t)n; sp.job.is_f32 = 0; sp.job.wrap_mode = 0;
     std::vector<SegDesc> segs;
-    ctx->force_fp64 = true;  // the raw-cube API carries arbitrary weights and is the parity reference: FP64 only
+    ctx->force_fp64 = !tc_weights;
     const int rc_seg = run_segments(ctx, specs, block, n_blocks, segs);
     ctx->force_fp64 = false;
     MB_TRY(rc_seg);
@@ -1181,7 +1204,8 @@ extern "C" int mb200_structure_factor_block(mb200_ctx *ctx, const double *positi
     MB_CUDA(cudaMemcpyAsync(hp, ctx->d_sval.p, nv * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
     MB_TRY(finish_timing(ctx));
-    for (size_t e = 0; e < nv; ++e) structure_factors[plan->cell[e]] = hp[e];
+    const double s_scale = wscale * wscale;
+    for (size_t e = 0; e < nv; ++e) structure_factors[plan->cell[e]] = hp[e] * s_scale;
     return MB200_OK;
 }
 

@@ -166,8 +166,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
     unsigned long long *acc_done = s_free + TC_NSTG;                                             // [1]
     unsigned long long *seed_full = acc_done + 1;                                                // [SEED_MAX] loader -> generators
     unsigned long long *seed_free = seed_full + TC_SEED_MAX;                                     // [SEED_MAX] generators -> loader
-    unsigned long long *init_done = seed_free + TC_SEED_MAX;                                     // [1] K-step 0 issued (+ 7 spare)
-    uint8_t *s_rows = reinterpret_cast<uint8_t *>(init_done + 8);                                     // [128][2]
+    uint8_t *s_rows = reinterpret_cast<uint8_t *>(seed_free + TC_SEED_MAX);                                     // [128][2]
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_rows + 2 * TC_M);
     int *s_item = reinterpret_cast<int *>(s_tmem + 1);
     int *s_nseed = s_item + 1;                                                                   // [2] unique h, unique k0
@@ -197,10 +196,10 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
         if (tid == 0) {
             *s_item = atomicAdd(counter, 1);
             *s_task = 0;
-            for (int s = 0; s < 3 * TC_NSTG + 1 + 2 * TC_SEED_MAX + 8; ++s) {  // re-arm: every item starts at phase 0
+            for (int s = 0; s < 3 * TC_NSTG + 1 + 2 * TC_SEED_MAX; ++s) {  // re-arm: every item starts at phase 0
                 if (bars_live) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(a_full + s)) : "memory");
-                // a_full: one arrive per generator task; b_full / s_free / acc_done: 1; seed_full: one cp.async arrive per
-                // loader lane; seed_free: one arrive per generator task
+                // a_full: one arrive per generator task; b_full / s_free / acc_done: 1; seed_full: one cp.async
+                // arrive per loader lane; seed_free: one arrive per generator task
                 const unsigned count = s < TC_NSTG ? TC_TASKS : s < 3 * TC_NSTG + 1 ? 1u : s < 3 * TC_NSTG + 1 + TC_SEED_MAX ? 32u :
                                        s < 3 * TC_NSTG + 1 + 2 * TC_SEED_MAX ? TC_TASKS : 1u;
                 mbar_init(a_full + s, count);
@@ -233,14 +232,14 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
             s_quad[2 * lane + 1] = (uint8_t)(n_uh + ik);
             if (lh == lane) s_seedrow[ih] = (uint16_t)h0;
             if (lk == lane) s_seedrow[n_uh + ik] = (uint16_t)(k0 | 0x8000);
-            if (lane < 3) s_seedrow[n_uh + n_uk + lane] = (uint16_t)(min(lane + 1, sg.rows1 - 1) | 0x8000);  // Ey[1..3]
+            if (lane == 0) s_seedrow[n_uh + n_uk] = (uint16_t)(min(1, sg.rows1 - 1) | 0x8000);  // Ey[1]
             if (lane == 0) {
                 s_nseed[0] = n_uh;
                 s_nseed[1] = n_uk;
             }
         }
         __syncthreads();
-        const int n_seed = s_nseed[0] + s_nseed[1] + 3;          // rows per seed stage
+        const int n_seed = s_nseed[0] + s_nseed[1] + 1;          // rows per seed stage
         const int seed_stage = n_seed * 256;                      // bytes: 16 atoms x double2 per row
         const int seed_shift = seed_stage * 8 <= TC_SEED_BYTES ? 3 : seed_stage * 4 <= TC_SEED_BYTES ? 2 : 1;  // 8, 4 or 2 K-steps
         const int seed_depth = 1 << seed_shift;
@@ -263,8 +262,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                 const int t = task >> 3, o = 4 * (task & 7) + (lane >> 3);
                 const int off0 = tc_canon_a(4 * o, 4 * ap);  // K' = 4 ap .. 4 ap + 3; rows 4 o + r: + 16 r bytes
                 // seeds Ex[h0], Ey[k0] and the factors Ey[1..3] of my two atoms, from the seed ring
-                const int sx = (s_quad[2 * o] * 16 + 2 * ap) * 16, sy = (s_quad[2 * o + 1] * 16 + 2 * ap) * 16,
-                          se = ((n_seed - 3) * 16 + 2 * ap) * 16;
+                const int sx = (s_quad[2 * o] * 16 + ap) * 16, sy = (s_quad[2 * o + 1] * 16 + ap) * 16, se = ((n_seed - 1) * 16 + ap) * 16;
                 const int st = t & (TC_NSTG - 1), ss = t & (seed_depth - 1);
                 double2 e[3][2], p[2];
                 mbar_wait(seed_full + ss, (unsigned)(t >> seed_shift) & 1u);
@@ -272,13 +270,15 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                 {
                     const unsigned char *sd = sSeed + ss * seed_stage;
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const double2 x = *reinterpret_cast<const double2 *>(sd + sx + 16 * c);
-                        const double2 y = *reinterpret_cast<const double2 *>(sd + sy + 16 * c);
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) e[r][c] = *reinterpret_cast<const double2 *>(sd + se + 256 * r + 16 * c);
+                    for (int c = 0; c < 2; ++c) {  // atom 2 ap + c sits at slot 8 c + ap of its seed row
+                        const double2 x = *reinterpret_cast<const double2 *>(sd + sx + 128 * c);
+                        const double2 y = *reinterpret_cast<const double2 *>(sd + sy + 128 * c);
+                        const double2 e1 = *reinterpret_cast<const double2 *>(sd + se + 128 * c);
                         p[c].x = x.x * y.x - x.y * y.y;
                         p[c].y = x.x * y.y + x.y * y.x;
+                        e[0][c] = e1;  // Ey[1], Ey[2] = Ey[1]^2, Ey[3] = Ey[1]^3 (unit-modulus table entries)
+                        e[1][c] = make_double2(e1.x * e1.x - e1.y * e1.y, 2.0 * e1.x * e1.y);
+                        e[2][c] = make_double2(e[1][c].x * e1.x - e[1][c].y * e1.y, e[1][c].x * e1.y + e[1][c].y * e1.x);
                     }
                 }
                 if (t >= TC_NSTG) mbar_wait(s_free + st, (unsigned)((t / TC_NSTG) - 1) & 1u);
@@ -341,7 +341,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                 src[i] = seed_src(ri);
                 stp[i] = (s_seedrow[ri] & 0x8000) ? step_y : step_x;
             }
-            const int dst0 = (r0 * 16 + a) * 16;
+            const int dst0 = (r0 * 16 + (a & 1) * 8 + (a >> 1)) * 16;  // row layout [atom parity][atom pair]: conflict-free reads
             for (int t = 0; t < n_steps; ++t) {
                 const int ss = t & (seed_depth - 1);
                 if (t >= seed_depth) mbar_wait(seed_free + ss, (unsigned)((t >> seed_shift) - 1) & 1u);
@@ -374,7 +374,8 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
             // ---- MMA issue: the (A slice s) x (B slices t_lo .. t_hi) products of a K-step; everything that does not
             // depend on the stage is tabulated once per item so that the serial issue path is a handful of adds.  The
             // whole warp walks the loop; one elected lane issues (the compiler then keeps the operands in uniform
-            // registers).  One commit per K-step: commits are expensive, and so is issuing from more than one warp. ----
+            // registers).  One commit per K-step and one issuing warp: per-MMA commits, MMAs dealt to four warps and even /
+            // odd K-steps on two warps were all measured slower or equal (profiles/r01_tc_notes.md). ----
             const int per = max(1, 256 / np);  // B slices per MMA (N <= 256)
             uint32_t m_a[15], m_b[15], m_d[15], m_i[15];
             int n_mma = 0;
@@ -458,7 +459,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-constexpr int TC_SMEM = TC_NSTG * (TC_S * TC_A_SLICE + TC_S * 2 * TC_MAX_LT * 32) + (3 * TC_NSTG + 1 + 2 * TC_SEED_MAX + 8) * 8 + 2 * TC_M + 16 + 16 + 64 + 136 +
+constexpr int TC_SMEM = TC_NSTG * (TC_S * TC_A_SLICE + TC_S * 2 * TC_MAX_LT * 32) + (3 * TC_NSTG + 1 + 2 * TC_SEED_MAX) * 8 + 2 * TC_M + 16 + 16 + 64 + 136 +
                         128 + TC_SEED_BYTES + 1024;
 
 }  // namespace mb200
