@@ -418,41 +418,43 @@ class AnalysisBase(_Runner):
     def _flush_staged(self, wait: bool = True) -> None:
         """Hand the staged frames to the device.
 
-        The device call runs on a worker thread (the C ABI releases the GIL) so that the host can
-        stage the next batch meanwhile; at most one batch is in flight, batches complete in order
-        and the statistics are updated by the worker in frame order.
+        The device call runs on a worker thread (the C ABI releases the GIL) so that the host can stage the
+        next batch meanwhile.  A new batch is queued *behind* the one in flight before the host waits for the
+        latter, so the worker goes from one device call straight into the next; batches complete in order,
+        and their statistics are accumulated on the calling thread, in frame order, while the device works.
         """
         if self._staged:
             staged, self._staged = self._staged, []
-            self._drain()
             if self._pool is None:
                 from concurrent.futures import ThreadPoolExecutor
 
                 self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mb200-batch")
-            self._inflight = self._pool.submit(self._process_batch, staged)
-            self._stage_parity ^= 1  # the next batch is staged into the other pinned buffer
+            previous, self._inflight = self._inflight, self._pool.submit(self._device_batch, staged)
+            self._stage_parity ^= 1  # the next batch is staged into the other pinned buffer (free once `previous` is done)
+            self._finish_batch(previous)
         if wait:
             self._drain()
 
     def _drain(self) -> None:
         fut, self._inflight = self._inflight, None
-        if fut is not None:
-            t0 = time.perf_counter()
-            last = fut.result()  # re-raises worker exceptions
-            self.timings["wait_device_s"] += time.perf_counter() - t0
-            if last is not None:
-                self._frame_index, self._obs = last
+        self._finish_batch(fut)
 
-    def _process_batch(self, staged: list):
+    def _device_batch(self, staged: list):
         t0 = time.perf_counter()
         out = self._compute_staged([s for _, s in staged])
         self.timings["device_call_s"] += time.perf_counter() - t0
-        last = None
+        return staged, out
+
+    def _finish_batch(self, fut) -> None:
+        if fut is None:
+            return
+        t0 = time.perf_counter()
+        staged, out = fut.result()  # re-raises worker exceptions
+        self.timings["wait_device_s"] += time.perf_counter() - t0
         for (slot, _), (obs, value) in zip(staged, out):
             obs = Results(obs)
             self._accumulate(slot, value, obs)
-            last = (slot, obs)
-        return last
+            self._frame_index, self._obs = slot, obs
 
     def _call_single_frame(self, ts, current_frame_index) -> None:
         """Serial entry point with the reference's signature (one frame, statistics updated)."""
