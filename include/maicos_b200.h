@@ -177,11 +177,36 @@ int mb200_compound_prologue(mb200_ctx *ctx, const float *positions, int position
                             int wrap_center, int weight_mode, int pdim, double *centers_dev,
                             double *weights_dev);
 
+/* Per-atom quantities of the "virtual cut" estimator of the dielectric profile modules:
+ *   testpos_i = centre of |charge| of atom i's compound along the profile coordinate
+ *               (planar: x[dim], dielectricplanar.py:183-185; cylinder: the radial coordinate itself is averaged,
+ *               dielectriccylinder.py:167-173), compounds = contiguous runs of atoms;
+ *   w_ij      = q_i * (n_j - np.digitize(x_i[cut_dims[j]], arange(n_j)[1:] * step_j))   for cut direction j.
+ * Binning testpos with weights w_j through mb200_profile_hist(MB200_GEOM_SCALAR | MB200_BIN_DIGITIZE) gives
+ * n_j * mean_c(cumsum_c(curQ[c, :])) of dielectricplanar.py:203-213 / dielectriccylinder.py:180-189 without the
+ * (n_j x n_bins) table.
+ *   positions : float32 [n_frames][n_atoms][3] (host, or device if positions_on_device)
+ *   geometry  : 0 planar, 1 cylinder (center float64 [n_frames][3] required)
+ *   cut_bins  : host int32 [n_frames][n_cut], cut_step host float64 [n_frames][n_cut] (= L / n_j)
+ * outputs (DEVICE): coord_dev float64 [n_frames][n_atoms], weights_dev float64 [n_frames][n_cut][n_atoms]. */
+int mb200_dielectric_prepare(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                             int64_t n_atoms, const int64_t *compound_ptr, int64_t n_c, const double *charges,
+                             int geometry, int dim, const double *center, int n_cut, const int32_t *cut_dims,
+                             const int32_t *cut_bins, const double *cut_step, double *coord_dev,
+                             double *weights_dev);
+
 /* ---- path 2: weighted slab / shell histograms --------------------------------- */
 
 #define MB200_GEOM_PLANAR 0   /* np.histogram(pos[:, dim])            core/planar.py:235-243   */
 #define MB200_GEOM_CYLINDER 1 /* transform_cylinder + np.histogram2d  core/cylinder.py:229-243 */
 #define MB200_GEOM_SPHERE 2   /* transform_sphere + np.histogram      core/sphere.py:215-223   */
+#define MB200_GEOM_SCALAR 3   /* `positions` is the binned coordinate itself, [n_frames][n] (f32 or f64) */
+/* or-ed into `geometry`: np.digitize(x, edges[1:-1]) instead of np.histogram -- nothing is dropped, values
+ * left / right of the range (and NaN) land in the first / last bin; the cylinder has no axial window.
+ * Replaces the digitize + bincount pairs of the dielectric modules:
+ *   modules/dielectricplanar.py:170-176, 203-213, modules/dielectriccylinder.py:134-151, 180-190,
+ *   modules/dielectricsphere.py:113-133. */
+#define MB200_BIN_DIGITIZE 0x10
 
 /* Fused weighted + count histogram of ProfileBase._single_frame (core/base.py:815-818),
  * batched over frames.  numpy semantics (numpy/lib/_histograms_impl.py:816-873, 1037-1069):

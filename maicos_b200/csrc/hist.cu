@@ -47,7 +47,7 @@ struct HistParams {
     double *acc_f;                        // [F][n_bins] float64 fallback sums
     unsigned long long *acc_c;            // [F][n_bins] counts
     long long n;
-    int n_bins, dim, geometry, is_f32, w_per_frame;
+    int n_bins, dim, geometry, is_f32, w_per_frame, digitize;
 };
 
 // exponent k with 2^k >= wmax (wmax finite, > 0), clamped so that Q = 2^(k-52) stays normal
@@ -65,6 +65,19 @@ __device__ __forceinline__ int bin_of(double x, const double *__restrict__ edges
     // right edge inclusive)
     int idx = (int)((x - first) * inv_width);
     idx = min(max(idx, 0), n_bins - 1);
+    while (idx > 0 && x < edges[idx]) --idx;
+    while (idx < n_bins - 1 && x >= edges[idx + 1]) ++idx;
+    return idx;
+}
+
+// np.digitize(x, edges[1:-1]) (dielectric modules: dielectricplanar.py:170-172, dielectriccylinder.py:134,
+// dielectricsphere.py:113): the bin is the number of interior edges <= x, i.e. values left of the range go to bin 0,
+// values right of it (and NaN, which searchsorted orders last) to bin n_bins - 1.  Nothing is dropped.
+__device__ __forceinline__ int bin_digitize(double x, const double *__restrict__ edges, int n_bins, double first,
+                                            double inv_width) {
+    if (x != x) return n_bins - 1;
+    const double gd = (x - first) * inv_width;
+    int idx = gd <= 0.0 ? 0 : (gd >= (double)(n_bins - 1) ? n_bins - 1 : (int)gd);
     while (idx > 0 && x < edges[idx]) --idx;
     while (idx < n_bins - 1 && x >= edges[idx + 1]) ++idx;
     return idx;
@@ -89,7 +102,7 @@ __global__ void __launch_bounds__(256) k_hist_wmax(const double *__restrict__ w,
 
 struct FrameGeom {
     double cx, cy, cz, zlo, zhi, first, last, inv_width;
-    int d0, d1, d2, geometry, nb;
+    int d0, d1, d2, geometry, nb, digitize;
 };
 
 __device__ __forceinline__ double pick(double x, double y, double z, int d) { return d == 0 ? x : (d == 1 ? y : z); }
@@ -100,7 +113,7 @@ __device__ __forceinline__ int atom_bin(const FrameGeom &g, double x, double y, 
         v = pick(x, y, z, g.d0);
     } else if (g.geometry == MB200_GEOM_CYLINDER) {
         const double ax = pick(x, y, z, g.d0);
-        if (!(ax >= g.zlo && ax <= g.zhi)) return -1;  // histogram2d drops outliers of either dimension
+        if (!g.digitize && !(ax >= g.zlo && ax <= g.zhi)) return -1;  // histogram2d drops outliers of either dimension
         const double a = __dsub_rn(pick(x, y, z, g.d1), pick(g.cx, g.cy, g.cz, g.d1));
         const double b = __dsub_rn(pick(x, y, z, g.d2), pick(g.cx, g.cy, g.cz, g.d2));
         v = sqrt(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
@@ -108,7 +121,10 @@ __device__ __forceinline__ int atom_bin(const FrameGeom &g, double x, double y, 
         const double a = __dsub_rn(x, g.cx), b = __dsub_rn(y, g.cy), c = __dsub_rn(z, g.cz);
         v = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c)));
     }
-    return bin_of(v, edges, g.nb, g.first, g.last, g.inv_width);
+    return g.digitize ? bin_digitize(v, edges, g.nb, g.first, g.inv_width) : bin_of(v, edges, g.nb, g.first, g.last, g.inv_width);
+}
+__device__ __forceinline__ int scalar_bin(const FrameGeom &g, double v, const double *edges) {
+    return g.digitize ? bin_digitize(v, edges, g.nb, g.first, g.inv_width) : bin_of(v, edges, g.nb, g.first, g.last, g.inv_width);
 }
 
 // MODE 0: shared-memory privatised, fixed-point weights   1: shared counts only (no weights)
@@ -130,11 +146,11 @@ __global__ void __launch_bounds__(H_THREADS) k_hist(HistParams p) {
         __syncthreads();
     }
     FrameGeom g;
-    g.geometry = p.geometry; g.nb = nb;
+    g.geometry = p.geometry; g.nb = nb; g.digitize = p.digitize;
     g.d0 = p.dim; g.d1 = (p.dim + 1) % 3; g.d2 = (p.dim + 2) % 3;  // odims = roll(arange(3), -dim)[1:]
     g.cx = g.cy = g.cz = g.zlo = g.zhi = 0;
-    if (p.geometry != MB200_GEOM_PLANAR) { g.cx = p.center[f * 3]; g.cy = p.center[f * 3 + 1]; g.cz = p.center[f * 3 + 2]; }
-    if (p.geometry == MB200_GEOM_CYLINDER) { g.zlo = p.zrange[f * 2]; g.zhi = p.zrange[f * 2 + 1]; }
+    if (p.geometry == MB200_GEOM_CYLINDER || p.geometry == MB200_GEOM_SPHERE) { g.cx = p.center[f * 3]; g.cy = p.center[f * 3 + 1]; g.cz = p.center[f * 3 + 2]; }
+    if (p.geometry == MB200_GEOM_CYLINDER && p.zrange) { g.zlo = p.zrange[f * 2]; g.zhi = p.zrange[f * 2 + 1]; }
     g.first = g_edges[0]; g.last = g_edges[nb];
     g.inv_width = (double)nb / (g.last - g.first);
     const double *w = p.weights ? p.weights + (p.w_per_frame ? (size_t)f * p.n : 0) : nullptr;
@@ -175,7 +191,16 @@ __global__ void __launch_bounds__(H_THREADS) k_hist(HistParams p) {
     };
 
     const long long n = p.n;
-    if (p.is_f32) {
+    if (p.geometry == MB200_GEOM_SCALAR) {  // the binned coordinate itself, [F][n]
+        const long long gtid = (long long)blockIdx.x * H_THREADS + threadIdx.x, gstride = (long long)gridDim.x * H_THREADS;
+        if (p.is_f32) {
+            const float *base = reinterpret_cast<const float *>(p.pos) + (size_t)f * n;
+            for (long long j = gtid; j < n; j += gstride) deposit(scalar_bin(g, (double)base[j], edges), j);
+        } else {
+            const double *base = reinterpret_cast<const double *>(p.pos) + (size_t)f * n;
+            for (long long j = gtid; j < n; j += gstride) deposit(scalar_bin(g, base[j], edges), j);
+        }
+    } else if (p.is_f32) {
         const float *base = reinterpret_cast<const float *>(p.pos) + (size_t)f * n * 3;
         // scalar head up to 16-byte alignment, float4 body (4 atoms = 3 x float4), scalar tail
         const unsigned long long addr = (unsigned long long)(uintptr_t)base;
@@ -263,24 +288,28 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
                                   int weights_per_frame, int weights_on_device, const double *edges, int32_t n_bins,
                                   const double *center, const double *zrange, double *hist_w, int64_t *hist_c) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
-    if (geometry < 0 || geometry > 2 || n_frames < 0 || n < 0 || n_bins <= 0 || dim < 0 || dim > 2 || !edges || !hist_c ||
+    const int digitize = (geometry & MB200_BIN_DIGITIZE) ? 1 : 0;
+    geometry &= ~MB200_BIN_DIGITIZE;
+    if (geometry < 0 || geometry > 3 || n_frames < 0 || n < 0 || n_bins <= 0 || dim < 0 || dim > 2 || !edges || !hist_c ||
         (n && !positions) || (weights && !hist_w))
         return fail(MB200_EINVAL, "invalid argument to mb200_profile_hist");
-    if (geometry != MB200_GEOM_PLANAR && !center) return fail(MB200_EINVAL, "center required for radial geometries");
-    if (geometry == MB200_GEOM_CYLINDER && !zrange) return fail(MB200_EINVAL, "zrange required for cylinder geometry");
+    if ((geometry == MB200_GEOM_CYLINDER || geometry == MB200_GEOM_SPHERE) && !center)
+        return fail(MB200_EINVAL, "center required for radial geometries");
+    if (geometry == MB200_GEOM_CYLINDER && !zrange && !digitize) return fail(MB200_EINVAL, "zrange required for cylinder geometry");
     if (n_frames == 0) return MB200_OK;
     if (n_frames > 65535) return fail(MB200_EINVAL, "at most 65535 frames per call");
     MB_CUDA(cudaSetDevice(ctx->device));
     const size_t F = (size_t)n_frames, N = (size_t)n, NB = (size_t)n_bins;
     const size_t esz = pos_is_f32 ? 4 : 8;
+    const size_t ncomp = geometry == MB200_GEOM_SCALAR ? 1 : 3;  // values per element in `positions`
 
     HistParams p;
     std::memset(&p, 0, sizeof(p));
     if (positions_on_device || N == 0) {
         p.pos = positions;
     } else {
-        MB_TRY(ctx->d_hpos.ensure(F * N * 3 * esz));
-        MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * 3 * esz, cudaMemcpyHostToDevice, ctx->stream));
+        MB_TRY(ctx->d_hpos.ensure(F * N * ncomp * esz));
+        MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * ncomp * esz, cudaMemcpyHostToDevice, ctx->stream));
         p.pos = ctx->d_hpos.p;
     }
     const bool weighted = weights && N;
@@ -320,7 +349,7 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
     double *d_ow = reinterpret_cast<double *>(p.acc_c + acc);
     long long *d_oc = reinterpret_cast<long long *>(d_ow + acc);
     MB_CUDA(cudaMemsetAsync(p.acc_lo, 0, acc * 8 * 4, ctx->stream));
-    p.n = n; p.n_bins = n_bins; p.dim = dim; p.geometry = geometry; p.is_f32 = pos_is_f32; p.w_per_frame = weights_per_frame;
+    p.n = n; p.n_bins = n_bins; p.dim = dim; p.geometry = geometry; p.is_f32 = pos_is_f32; p.w_per_frame = weights_per_frame; p.digitize = digitize;
 
     const long long total = (long long)(F * NB);
     {

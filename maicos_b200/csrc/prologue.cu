@@ -213,3 +213,136 @@ extern "C" int mb200_compound_prologue(mb200_ctx *ctx, const float *positions, i
     MB_CUDA(cudaStreamSynchronize(ctx->stream));  // host topology arrays may be reused by the caller
     return MB200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Dielectric profile modules: per-atom quantities of the "virtual cut" estimator.
+//
+// Reference, per frame (modules/dielectricplanar.py:180-213, modules/dielectriccylinder.py:163-190):
+//   testpos = centre of |charge| of the atom's compound along the profile coordinate (planar: x[dim];
+//             cylinder: the radial coordinate r itself is averaged, sum(r |q|) / sum(|q|)),
+//   cbin    = np.digitize(x[cut direction], arange(n_cut)[1:] * (L / n_cut)),
+//   curQ    = bincount(zbin(testpos) + n_bins * cbin, charges).reshape(n_cut, n_bins),
+//   m       = -cumsum(curQ / A, axis=0).mean(axis=0).
+// Since  mean_c cumsum_c curQ[c, z] = (1 / n_cut) sum_c (n_cut - c) curQ[c, z],  the two-dimensional table is a
+// one-dimensional weighted histogram over testpos with weights  q_i (n_cut - cbin_i):  this kernel writes
+// testpos and those weights per atom, mb200_profile_hist(MB200_GEOM_SCALAR | MB200_BIN_DIGITIZE) bins them
+// (exact fixed-point accumulation), the host applies -1 / (A n_cut).  One thread owns one compound (contiguous
+// atoms, float64 sequential sums in atom order like AtomGroup.center / accumulate of the shim).
+// ---------------------------------------------------------------------------------------------------------
+namespace mb200 {
+
+struct DielParams {
+    const float *pos;        // [F][n_atoms][3]
+    const long long *ptr;    // [n_c + 1]
+    const double *charge;    // [n_atoms]
+    const double *center;    // [F][3] (cylinder) or null
+    const int *cut_bins;     // [F][n_cut]
+    const double *cut_step;  // [F][n_cut]
+    double *coord;           // [F][n_atoms]
+    double *weights;         // [F][n_cut][n_atoms]
+    long long n_atoms, n_c;
+    int geometry, dim, n_cut, cut_dims[2];
+};
+
+__global__ void __launch_bounds__(128) k_dielectric_prepare(DielParams p) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long f = blockIdx.y;
+    if (c >= p.n_c) return;
+    const long long a0 = p.ptr[c], a1 = p.ptr[c + 1];
+    const float *q = p.pos + ((size_t)f * p.n_atoms + a0) * 3;
+    const int d1 = (p.dim + 1) % 3, d2 = (p.dim + 2) % 3;  // odims = roll(arange(3), -dim)[1:]
+    double cx1 = 0.0, cx2 = 0.0;
+    if (p.geometry == 1) { cx1 = p.center[f * 3 + d1]; cx2 = p.center[f * 3 + d2]; }
+    auto profile_coord = [&](long long i) -> double {
+        if (p.geometry == 0) return (double)q[i * 3 + p.dim];
+        const double a = __dsub_rn((double)q[i * 3 + d1], cx1), b = __dsub_rn((double)q[i * 3 + d2], cx2);
+        return sqrt(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));  // transform_cylinder: norm of the odims components
+    };
+    double num = 0.0, den = 0.0;
+    for (long long i = 0; i < a1 - a0; ++i) {
+        const double w = fabs(p.charge[a0 + i]);
+        num = __dadd_rn(num, __dmul_rn(w, profile_coord(i)));
+        den = __dadd_rn(den, w);
+    }
+    const double testpos = __ddiv_rn(num, den);
+    for (long long i = 0; i < a1 - a0; ++i) {
+        p.coord[(size_t)f * p.n_atoms + a0 + i] = testpos;
+        const double qi = p.charge[a0 + i];
+        for (int j = 0; j < p.n_cut; ++j) {
+            const int nb = p.cut_bins[f * p.n_cut + j];
+            const double step = p.cut_step[f * p.n_cut + j];
+            const double x = (double)q[i * 3 + p.cut_dims[j]];
+            // np.digitize(x, arange(nb)[1:] * step): number of edges k * step, k = 1 .. nb - 1, that are <= x
+            int b;
+            if (x != x) {
+                b = nb - 1;
+            } else {
+                const double g = x / step;
+                b = g <= 0.0 ? 0 : (g >= (double)(nb - 1) ? nb - 1 : (int)g);
+                while (b > 0 && x < __dmul_rn((double)b, step)) --b;
+                while (b < nb - 1 && x >= __dmul_rn((double)(b + 1), step)) ++b;
+            }
+            p.weights[((size_t)f * p.n_cut + j) * p.n_atoms + a0 + i] = __dmul_rn(qi, (double)(nb - b));
+        }
+    }
+}
+
+}  // namespace mb200
+
+extern "C" int mb200_dielectric_prepare(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                                        int64_t n_atoms, const int64_t *compound_ptr, int64_t n_c, const double *charges,
+                                        int geometry, int dim, const double *center, int n_cut, const int32_t *cut_dims,
+                                        const int32_t *cut_bins, const double *cut_step, double *coord_dev,
+                                        double *weights_dev) {
+    using namespace mb200;
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    if (n_frames < 0 || n_atoms < 0 || n_c < 0 || !compound_ptr || !charges || !coord_dev || (n_atoms && !positions) ||
+        geometry < 0 || geometry > 1 || dim < 0 || dim > 2 || n_cut < 0 || n_cut > 2 ||
+        (n_cut && (!cut_dims || !cut_bins || !cut_step || !weights_dev)) || (geometry == 1 && !center))
+        return fail(MB200_EINVAL, "invalid argument to mb200_dielectric_prepare");
+    if (n_frames == 0 || n_c == 0) return MB200_OK;
+    if (n_frames > 65535) return fail(MB200_EINVAL, "at most 65535 frames per call");
+    if (compound_ptr[0] != 0 || compound_ptr[n_c] != n_atoms) return fail(MB200_EINVAL, "compound_ptr must cover all atoms");
+    for (int64_t c = 0; c < n_c; ++c)
+        if (compound_ptr[c + 1] <= compound_ptr[c]) return fail(MB200_EINVAL, "empty compound %lld", (long long)c);
+    for (int j = 0; j < n_cut; ++j)
+        if (cut_dims[j] < 0 || cut_dims[j] > 2) return fail(MB200_EINVAL, "cut direction out of range");
+    for (int64_t i = 0; i < n_frames * n_cut; ++i)
+        if (cut_bins[i] < 1 || !(cut_step[i] > 0.0)) return fail(MB200_EINVAL, "virtual cuts need n >= 1 and a positive spacing");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const size_t F = (size_t)n_frames, N = (size_t)n_atoms, NC = (size_t)n_c;
+    DielParams p;
+    std::memset(&p, 0, sizeof(p));
+    if (positions_on_device) {
+        p.pos = positions;
+    } else {
+        MB_TRY(ctx->d_pos.ensure(F * N * 12));
+        MB_CUDA(cudaMemcpyAsync(ctx->d_pos.p, positions, F * N * 12, cudaMemcpyHostToDevice, ctx->stream));
+        p.pos = ctx->d_pos.as<float>();
+    }
+    // ptr | charge | center | cut_bins | cut_step
+    const size_t b_ptr = (NC + 1) * 8, b_q = N * 8, b_c = F * 24, b_nb = ((F * 2 * 4 + 7) / 8) * 8, b_st = F * 2 * 8;
+    MB_TRY(ctx->d_ctopo.ensure(b_ptr + b_q + b_c + b_nb + b_st + 64));
+    char *base = ctx->d_ctopo.as<char>();
+    MB_CUDA(cudaMemcpyAsync(base, compound_ptr, b_ptr, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(cudaMemcpyAsync(base + b_ptr, charges, b_q, cudaMemcpyHostToDevice, ctx->stream));
+    if (center) MB_CUDA(cudaMemcpyAsync(base + b_ptr + b_q, center, b_c, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_cut) {
+        MB_CUDA(cudaMemcpyAsync(base + b_ptr + b_q + b_c, cut_bins, F * n_cut * 4, cudaMemcpyHostToDevice, ctx->stream));
+        MB_CUDA(cudaMemcpyAsync(base + b_ptr + b_q + b_c + b_nb, cut_step, F * n_cut * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    p.ptr = reinterpret_cast<const long long *>(base);
+    p.charge = reinterpret_cast<const double *>(base + b_ptr);
+    p.center = center ? reinterpret_cast<const double *>(base + b_ptr + b_q) : nullptr;
+    p.cut_bins = reinterpret_cast<const int *>(base + b_ptr + b_q + b_c);
+    p.cut_step = reinterpret_cast<const double *>(base + b_ptr + b_q + b_c + b_nb);
+    p.coord = coord_dev; p.weights = weights_dev;
+    p.n_atoms = n_atoms; p.n_c = n_c; p.geometry = geometry; p.dim = dim; p.n_cut = n_cut;
+    for (int j = 0; j < n_cut; ++j) p.cut_dims[j] = cut_dims[j];
+    dim3 grid((unsigned)((NC + 127) / 128), (unsigned)F);
+    k_dielectric_prepare<<<grid, 128, 0, ctx->stream>>>(p);
+    MB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));  // host arrays may be reused by the caller
+    return MB200_OK;
+}

@@ -13,13 +13,17 @@ import numpy as np
 
 from .. import _cabi
 
-PLANAR, CYLINDER, SPHERE = 0, 1, 2
+PLANAR, CYLINDER, SPHERE, SCALAR = 0, 1, 2, 3
+DIGITIZE = 0x10  # or-ed into the geometry: np.digitize(x, edges[1:-1]) semantics (nothing dropped, ends clamp)
 
 
 def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights: np.ndarray | None, edges: np.ndarray,
                  center: np.ndarray | None = None, zrange: np.ndarray | None = None, device: int | None = None,
-                 device_positions: tuple | None = None, device_weights: tuple | None = None):
+                 device_positions: tuple | None = None, device_weights: tuple | None = None, digitize: bool = False):
     """Histogram ``positions [F, n, 3]`` (float32 or float64) into ``edges [F, n_bins + 1]``.
+
+    ``geometry = SCALAR``: ``positions [F, n]`` is the binned coordinate itself.  ``digitize=True``: the bin is
+    ``np.digitize(x, edges[1:-1])`` (dielectric modules) instead of ``np.histogram``'s.
 
     ``weights``: ``None`` (counts only), ``[1, n]`` (same for all frames) or ``[F, n]``.
     ``device_positions = (pointer, F, n)``: float64 ``[F, n, 3]`` already in HBM (output of the
@@ -31,7 +35,10 @@ def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights:
         pos_is_f32, pos_on_dev = 0, 1
     else:
         positions = np.ascontiguousarray(positions)
-        if positions.ndim != 3 or positions.shape[2] != 3:
+        if geometry == SCALAR:
+            if positions.ndim != 2:
+                raise ValueError("a scalar coordinate must have shape (n_frames, n)")
+        elif positions.ndim != 3 or positions.shape[2] != 3:
             raise ValueError("positions must have shape (n_frames, n, 3)")
         if positions.dtype not in (np.float32, np.float64):
             raise ValueError("positions must be float32 or float64")
@@ -60,7 +67,7 @@ def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights:
     ctx = _cabi.context(device)
     _cabi.check(
         _cabi.load().mb200_profile_hist(
-            ctx.handle, int(geometry), pos_ptr, pos_is_f32, pos_on_dev, F, n, int(dim),
+            ctx.handle, int(geometry) | (DIGITIZE if digitize else 0), pos_ptr, pos_is_f32, pos_on_dev, F, n, int(dim),
             w_ptr, per_frame, w_on_dev, _cabi.ptr(edges), n_bins, _cabi.ptr(center), _cabi.ptr(zrange),
             _cabi.ptr(hist_w), _cabi.ptr(hist_c),
         )

@@ -8,6 +8,7 @@ header helpers ``get_cli_input`` / ``atomgroup_header`` / ``get_module_input_str
 
 from __future__ import annotations
 
+import functools
 import inspect
 import logging
 import sys
@@ -58,6 +59,46 @@ def unit_vectors_sphere(atomgroup, grouping: str, bin_method: str) -> np.ndarray
     rel -= atomgroup.universe.dimensions[:3] / 2
     rel /= np.linalg.norm(rel, axis=1)[:, np.newaxis]
     return rel
+
+
+def get_compound(atomgroup) -> str:
+    """Highest-order topology attribute: "molecules", "fragments", "residues" (lib/util.py:359-388)."""
+    if hasattr(atomgroup, "molnums"):
+        return "molecules"
+    if hasattr(atomgroup, "fragments"):
+        logging.info("Cannot use 'molecules'. Falling back to 'fragments'")
+        return "fragments"
+    if hasattr(atomgroup, "residues"):
+        logging.info("Cannot use 'fragments'. Falling back to 'residues'")
+        return "residues"
+    raise AttributeError("Missing any connection information in `atomgroup`.")
+
+
+def charge_neutral(filter: str):
+    """Class decorator: warn (``filter``) about free charges in the AtomGroup, refuse a non-neutral universe
+    (lib/util.py:470-517; tolerance 1e-4 e)."""
+
+    def inner(original_class):
+        original_prepare = original_class._prepare
+
+        @functools.wraps(original_prepare)
+        def wrapped(self):
+            if not np.allclose(self.atomgroup.total_charge(compound=get_compound(self.atomgroup)), 0, atol=1e-4):
+                with warnings.catch_warnings():
+                    warnings.simplefilter(filter)
+                    warnings.warn(
+                        "At least one AtomGroup has free charges. Analysis for systems with free charges could lead "
+                        "to severe artifacts!",
+                        stacklevel=1,
+                    )
+            if not np.allclose(self.atomgroup.universe.atoms.total_charge(), 0, atol=1e-4):
+                raise ValueError("Analysis for non-neutral systems is not supported.")
+            return original_prepare(self)
+
+        original_class._prepare = wrapped
+        return original_class
+
+    return inner
 
 
 def correlation_analysis(timeseries: np.ndarray) -> float:

@@ -11,5 +11,8 @@ from .dipordersphere import DiporderSphere
 from .velocityplanar import VelocityPlanar
 from .velocitycylinder import VelocityCylinder
 from .temperatureplanar import TemperaturePlanar
+from .dielectricplanar import DielectricPlanar
+from .dielectriccylinder import DielectricCylinder
+from .dielectricsphere import DielectricSphere
 
-__all__ = ['Saxs', 'DiporderStructureFactor', 'DensityPlanar', 'DensityCylinder', 'DensitySphere', 'DiporderPlanar', 'DiporderCylinder', 'DiporderSphere', 'VelocityPlanar', 'VelocityCylinder', 'TemperaturePlanar']
+__all__ = ['Saxs', 'DiporderStructureFactor', 'DensityPlanar', 'DensityCylinder', 'DensitySphere', 'DiporderPlanar', 'DiporderCylinder', 'DiporderSphere', 'VelocityPlanar', 'VelocityCylinder', 'TemperaturePlanar', 'DielectricPlanar', 'DielectricCylinder', 'DielectricSphere']

@@ -75,3 +75,23 @@ def compact_to_cube(g, name):
     q[g[f"{name}__cells"]] = g[f"{name}__q"]
     s[g[f"{name}__cells"]] = g[f"{name}__s"]
     return q.reshape(shape), s.reshape(shape)
+
+
+def dipole_universe(positions, orientations, box=10.0):
+    """The reference's ``dipoles()`` fixture (tests/modules/test_dielectricplanar.py:33-60) on the shim: one molecule
+    per dipole, charges -1 / +1 one Angstrom apart (tests/data/dipole.gro / dipole.itp), moment 1 e A along
+    ``orientation``, cubic box of 10 A."""
+    from maicos_b200.mdshim import MemoryTrajectory, Universe
+
+    pos = []
+    for p, o in zip(positions, orientations):
+        o = np.asarray(o, dtype=np.float64)
+        o = o / np.linalg.norm(o)
+        pos += [np.asarray(p, dtype=np.float64) - 0.5 * o, np.asarray(p, dtype=np.float64) + 0.5 * o]
+    n = len(pos)
+    res = np.arange(n) // 2
+    traj = MemoryTrajectory(np.asarray(pos, dtype=np.float32)[None], np.float32([box, box, box, 90, 90, 90]))
+    names = np.array(["A", "B"] * (n // 2), dtype=object)
+    return Universe(n, traj, names=names, types=np.array(["X"] * n, dtype=object), masses=np.ones(n),
+                    charges=np.array([-1.0, 1.0] * (n // 2)), resindices=res, molnums=res,
+                    bonds=np.stack([np.arange(0, n, 2), np.arange(1, n, 2)], 1))

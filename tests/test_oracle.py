@@ -206,3 +206,25 @@ def test_density_cylinder_reference_means(water_gro):
         w = density_weights(u.atoms, "atoms", dens)
         prof = restatement.hist_cylinder(u.atoms.positions, w, 2, nb, 0.0, rmax, 0.0, L[2], L / 2) / vol
         assert_allclose(prof.mean(), mean, atol=1e-4, rtol=1e-2)
+
+
+@pytest.mark.parametrize("orientation,M_par,M_perp", [([0, 0, 1], [0, 0], 1), ([1, 0, 0], [1, 0], 0), ([0, 1, 0], [0, 1], 0),
+                                                      ([1, 1, 1], [1 / np.sqrt(3), 1 / np.sqrt(3)], 1 / np.sqrt(3))])
+def test_dielectric_restatement_dipole_known_answers(orientation, M_par, M_perp):
+    """Pins oracle.restatement.dielectric_planar_frame: tests/modules/test_dielectricplanar.py:104-196 (single dipole and
+    5 x 5 x 5 grid: total dipole moment, and the volume integral of the virtual-cut dipole density equals it)."""
+    from conftest import dipole_universe
+
+    xx, yy, zz = np.meshgrid(np.arange(0, 10, 2) + 1, np.arange(0, 10, 2) + 1, np.arange(0, 10, 2) + 1)
+    grid = np.array([xx.flatten(), yy.flatten(), zz.flatten()]).T.tolist()
+    for centres in ([[5, 5, 5]], grid):
+        u = dipole_universe(centres, [orientation] * len(centres))
+        pos, q = u.atoms.positions, np.asarray(u.atoms.charges, dtype=np.float64)
+        inv = np.unique(u.atoms.molnums, return_inverse=True)[1]
+        obs, _ = restatement.dielectric_planar_frame(pos, q, inv, pos, q, u.dimensions, 2, 1000, 0.01)
+        n = len(centres)
+        assert_allclose(obs["M_par"], np.multiply(M_par, n), rtol=0.1, atol=1e-5)
+        assert_allclose(obs["M_perp"], np.multiply(M_perp, n), rtol=0.1, atol=1e-5)
+        bv = obs["bin_volume"][0]
+        assert_allclose(np.sum(obs["m_par"], axis=0) * bv, np.multiply(M_par, n), rtol=0.1, atol=1e-5)
+        assert_allclose(np.sum(obs["m_perp"], axis=0) * bv, np.multiply(M_perp, n), rtol=0.1, atol=1e-5)
