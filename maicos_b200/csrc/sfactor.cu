@@ -30,6 +30,7 @@
 #include <map>
 
 #include "common.cuh"
+#include "sfactor_digits.cuh"
 
 namespace mb200 {
 
@@ -98,6 +99,10 @@ struct TableJob {
     float boxf[3];
     int32_t n, ld, rows[3];
     int32_t is_f32, wrap_mode;  // wrap_mode: 0 none, 1 saxs float32 wrap, 2 pack + saxs wrap
+    // split-precision mode: the z axis is written as the int8 digit image of the tensor-core kernel instead of an FP64
+    // table (sfactor_tc.cuh: [l tile][K-step][5 slices][2 L_t rows x 32 B], UMMA canonical K-major layout)
+    int8_t *bimg;
+    int32_t img_n_lt, img_lt, img_maxn;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -140,7 +145,33 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= jb.ld) return;
     const int rows = jb.rows[axis];
+    // split-precision mode, z axis: digits of Z = Ez[l] straight into the image of the tensor-core kernel, rows
+    // 2 l (real part of A: (Zr, -Zi)) and 2 l + 1 (imaginary part: (Zi, Zr)) of l tile l / L_t, K position 2 (j % 16)
+    const bool to_image = axis == 2 && jb.bimg != nullptr;
+    const int np = 2 * jb.img_lt;
+    int8_t *img = nullptr;
+    if (to_image) img = jb.bimg + (size_t)(j / TC_KA) * (size_t)(TC_S * np * 32) + tc_canon(0, 2 * (j % TC_KA));
+    const size_t img_tile = (size_t)(jb.ld / TC_KA) * (size_t)(TC_S * np * 32);
+    auto put_image = [&](int l, double zr, double zi) {
+        unsigned rlo, rhi, ilo, ihi, nlo, nhi;
+        tc_digits(zr, rlo, rhi);
+        tc_digits(zi, ilo, ihi);
+        tc_digits(-zi, nlo, nhi);
+        int8_t *b = img + (size_t)(l / jb.img_lt) * img_tile;
+        const int li = l % jb.img_lt;
+        const int o0 = tc_canon(2 * li, 0), o1 = tc_canon(2 * li + 1, 0);
+#pragma unroll
+        for (int t = 1; t <= TC_S; ++t) {
+            *reinterpret_cast<uint16_t *>(b + o0) = (uint16_t)tc_pair(t, rlo, rhi, nlo, nhi);
+            *reinterpret_cast<uint16_t *>(b + o1) = (uint16_t)tc_pair(t, ilo, ihi, rlo, rhi);
+            b += np * 32;
+        }
+    };
     if (j >= jb.n) {  // zero padding up to the leading dimension
+        if (to_image) {
+            for (int l = 0; l < jb.img_n_lt * jb.img_lt; ++l) put_image(l, 0.0, 0.0);
+            return;
+        }
         for (int r = 0; r < rows; ++r) tab[tab_index(j, r, rows)] = make_double2(0.0, 0.0);
         return;
     }
@@ -171,12 +202,18 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
             t -= rint(t);
             sincospi(2.0 * t, &ci, &cr);
         }
-        tab[tab_index(j, r, rows)] = make_double2(w * cr, w * ci);
+        if (to_image) {
+            if (r < jb.img_maxn) put_image(r, cr, ci);  // the z axis never carries weights
+        } else {
+            tab[tab_index(j, r, rows)] = make_double2(w * cr, w * ci);
+        }
         const double nr = cr * c1 - ci * s1;
         const double ni = cr * s1 + ci * c1;
         cr = nr;
         ci = ni;
     }
+    if (to_image)  // l values of the last tile beyond the cube edge
+        for (int l = jb.img_maxn; l < jb.img_n_lt * jb.img_lt; ++l) put_image(l, 0.0, 0.0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -792,7 +829,7 @@ struct SegSpec {       // one contraction problem (one reference structure_facto
 
 
 
-// Split-precision variant of run_segments: FP64 tables -> int8 Z image -> tcgen05 contraction.
+// Split-precision variant of run_segments: FP64 x / y tables + int8 Z image (one kernel) -> tcgen05 contraction.
 static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t block, int32_t n_blocks,
                            std::vector<SegDesc> &segs_host) {
     const int ns = (int)specs.size();
@@ -815,7 +852,7 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
             off_y[s] = off_y[sp.share_yz_with]; off_z[s] = off_z[sp.share_yz_with]; off_img[s] = off_img[sp.share_yz_with];
         } else {
             off_y[s] = tab_elems; tab_elems += (size_t)pl.rows[1] * ld;
-            off_z[s] = tab_elems; tab_elems += (size_t)pl.rows[2] * ld;
+            off_z[s] = off_y[s];  // no FP64 z table in this mode: k_sf_tables writes the digit image instead
             off_img[s] = img_bytes;
             img_bytes += (size_t)pl.tc_n_lt * (ld / TC_KA) * (size_t)(TC_S * 2 * pl.tc_lt * 32);
         }
@@ -852,8 +889,6 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
     if (n_blocks > 1 || items.empty())
         MB_CUDA(cudaMemsetAsync(ctx->d_amp.p, 0, std::max<size_t>(amp_elems, 1) * 16, ctx->stream));
     std::vector<TcSeg> tsegs(ns);
-    std::vector<BimgJob> bjobs;
-    int max_steps = 0, max_nlt = 1;
     for (int s = 0; s < ns; ++s) {
         SegSpec &sp = specs[s];
         const SfPlan &pl = *sp.plan;
@@ -879,48 +914,37 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
         ts.amp = sd.amp;
         ts.rows0 = pl.rows[0]; ts.rows1 = pl.rows[1]; ts.ld = sp.job.ld;
         ts.n_rt = pl.tc_n_rt; ts.n_lt = pl.tc_n_lt; ts.lt_size = pl.tc_lt; ts.n_pairs = pl.tc_n_pairs; ts.n_split = n_split[s];
-        if (sp.share_yz_with < 0 && sp.job.ld > 0) {
-            BimgJob bj;
-            bj.ez = sd.ez; bj.bimg = ctx->d_bimg.as<int8_t>() + off_img[s];
-            bj.rows2 = pl.rows[2]; bj.ld = sp.job.ld; bj.maxn2 = pl.maxn[2]; bj.n_lt = pl.tc_n_lt; bj.lt_size = pl.tc_lt;
-            bjobs.push_back(bj);
-            max_steps = std::max(max_steps, sp.job.ld / TC_KA);
-            max_nlt = std::max(max_nlt, pl.tc_n_lt);
+        if (sp.share_yz_with < 0) {  // the z axis goes straight into the digit image (k_sf_tables)
+            sp.job.bimg = ctx->d_bimg.as<int8_t>() + off_img[s];
+            sp.job.img_n_lt = pl.tc_n_lt; sp.job.img_lt = pl.tc_lt; sp.job.img_maxn = pl.maxn[2];
         }
     }
     // ---- descriptors to the device through the pinned staging buffer
     const size_t b_jobs = (size_t)ns * sizeof(TableJob), b_segs = (size_t)ns * sizeof(SegDesc), b_tsegs = (size_t)ns * sizeof(TcSeg),
-                 b_bj = bjobs.size() * sizeof(BimgJob), b_items = items.size() * sizeof(TcItem);
-    MB_TRY(ctx->h_stage.ensure(b_jobs + b_segs + b_tsegs + b_bj + b_items + 64));
+                 b_items = items.size() * sizeof(TcItem);
+    MB_TRY(ctx->h_stage.ensure(b_jobs + b_segs + b_tsegs + b_items + 64));
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
     char *hs = ctx->h_stage.as<char>();
     for (int s = 0; s < ns; ++s) std::memcpy(hs + (size_t)s * sizeof(TableJob), &specs[s].job, sizeof(TableJob));
     std::memcpy(hs + b_jobs, segs_host.data(), b_segs);
     std::memcpy(hs + b_jobs + b_segs, tsegs.data(), b_tsegs);
-    if (b_bj) std::memcpy(hs + b_jobs + b_segs + b_tsegs, bjobs.data(), b_bj);
-    if (b_items) std::memcpy(hs + b_jobs + b_segs + b_tsegs + b_bj, items.data(), b_items);
+    if (b_items) std::memcpy(hs + b_jobs + b_segs + b_tsegs, items.data(), b_items);
     MB_TRY(ctx->d_jobs.ensure(b_jobs));
     MB_TRY(ctx->d_segs.ensure(b_segs));
-    MB_TRY(ctx->d_tcdesc.ensure(b_tsegs + b_bj + 64));
+    MB_TRY(ctx->d_tcdesc.ensure(b_tsegs + 64));
     MB_TRY(ctx->d_items.ensure(std::max<size_t>(b_items, 16)));
     MB_TRY(ctx->d_counter.ensure(16));
     MB_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, hs, b_jobs, cudaMemcpyHostToDevice, ctx->stream));
     MB_CUDA(cudaMemcpyAsync(ctx->d_segs.p, hs + b_jobs, b_segs, cudaMemcpyHostToDevice, ctx->stream));
-    MB_CUDA(cudaMemcpyAsync(ctx->d_tcdesc.p, hs + b_jobs + b_segs, b_tsegs + b_bj, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(cudaMemcpyAsync(ctx->d_tcdesc.p, hs + b_jobs + b_segs, b_tsegs, cudaMemcpyHostToDevice, ctx->stream));
     if (b_items)
-        MB_CUDA(cudaMemcpyAsync(ctx->d_items.p, hs + b_jobs + b_segs + b_tsegs + b_bj, b_items, cudaMemcpyHostToDevice, ctx->stream));
+        MB_CUDA(cudaMemcpyAsync(ctx->d_items.p, hs + b_jobs + b_segs + b_tsegs, b_items, cudaMemcpyHostToDevice, ctx->stream));
     // ---- launches
     int max_ld = 0;
     for (int s = 0; s < ns; ++s) max_ld = std::max(max_ld, specs[s].job.ld);
     int64_t launched = 0;
     if (max_ld > 0) {
         k_sf_tables<<<dim3((max_ld + 127) / 128, 3, ns), 128, 0, ctx->stream>>>(ctx->d_jobs.as<TableJob>());
-        MB_CUDA(cudaGetLastError());
-        ++launched;
-    }
-    if (!bjobs.empty()) {
-        const BimgJob *d_bj = reinterpret_cast<const BimgJob *>(ctx->d_tcdesc.as<char>() + b_tsegs);
-        k_sf_bimage<<<dim3((unsigned)max_steps, (unsigned)max_nlt, (unsigned)bjobs.size()), 256, 0, ctx->stream>>>(d_bj);
         MB_CUDA(cudaGetLastError());
         ++launched;
     }

@@ -21,16 +21,15 @@
 //                seeded from the FP64 tables at the start of a run of consecutive k and advanced by the
 //                recurrence P *= Ey[1] inside the run; digits are written as (re, im) byte pairs into the
 //                canonical K-major no-swizzle UMMA layout (cute ((8,n),2):((1,SBO),LBO), LBO = 128, SBO = 256);
-//   control    : lane 0 bulk-copies the pre-sliced Z image of the K-step (k_sf_bimage) and issues the MMAs;
+//   control    : lane 0 bulk-copies the pre-sliced Z image of the K-step (written by k_sf_tables) and issues the MMAs;
 //                tcgen05.commit frees the stage.  At the end of an item the generator warps read TMEM
 //                (tcgen05.ld), rescale and write the partial amplitudes that the usual finalisers consume.
 #pragma once
+#include "sfactor_digits.cuh"
 
 namespace mb200 {
 
 constexpr int TC_M = 128;          // rows ((h,k) pairs) per tile
-constexpr int TC_KA = 16;          // atoms per MMA K-step
-constexpr int TC_S = 5;            // digits per component
 constexpr int TC_NSTG = 4;         // A / B stages (power of two: cheap stage / phase arithmetic)
 #ifndef MB200_TC_GEN_WARPS
 #define MB200_TC_GEN_WARPS 16
@@ -50,13 +49,12 @@ struct TcItem {
 
 struct TcSeg {
     const double2 *ex, *ey;     // FP64 phase tables (blocked layout)
-    const int8_t *bimg;         // pre-sliced Z image [n_lt][K-step][5][NP x 32]
+    const int8_t *bimg;         // pre-sliced Z image [n_lt][K-step][5][NP x 32], written by k_sf_tables
     const uint8_t *rows;        // [n_rt * 128][2] packed (h, k) pairs
     double2 *amp;               // [n_split][n_rt * n_lt][128][L_t]
     int32_t rows0, rows1, ld, n_rt, n_lt, lt_size, n_pairs, n_split;
 };
 
-__device__ __host__ __forceinline__ int tc_canon(int row, int k) { return (row >> 3) * 256 + (k >> 4) * 128 + (row & 7) * 16 + (k & 15); }
 
 // K-major, no swizzle, descriptor version 1; LBO = distance of the two 16-byte K chunks, SBO = distance of 8-row groups
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo = 128, uint32_t sbo = 256) {
@@ -68,61 +66,6 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo = 128, 
 // slots: the 32 lanes of a warp store (2 row groups x 2 quads x 2 K chunks x 4 atom pairs) hit 32 distinct banks.
 constexpr int TC_A_SBO = 144, TC_A_LBO = 2336, TC_A_SLICE = 4672;
 __device__ __forceinline__ int tc_canon_a(int row, int k) { return (row >> 3) * TC_A_SBO + (k >> 4) * TC_A_LBO + (row & 7) * 16 + (k & 15); }
-
-// Digits: y = x + TC_MAGIC lies in [2^14, 2^15) (ulp 2^-38), so the low 40 mantissa bits of y are
-// U = rint(x * 2^38) + 128 * (256^4 + 256^3 + 256^2 + 256 + 1); byte i of U xor 0x80 is the balanced digit of
-// weight 256^i.  Returned: lo = digits 5, 4, 3, 2 (bytes 0..3), hi = digit 1 (byte 0), already re-centred.
-#define TC_MAGIC (16384.0 + 551911719040.0 / 274877906944.0)
-__device__ __forceinline__ void tc_digits(double x, unsigned &lo, unsigned &hi) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(x + TC_MAGIC);
-    lo = (unsigned)b ^ 0x80808080u;
-    hi = ((unsigned)(b >> 32) ^ 0x80u) & 0xffu;
-}
-// (re, im) digit pair of slice s (1 = most significant) as a 16-bit value, re in the low byte
-__device__ __forceinline__ unsigned tc_pair(int s, unsigned rlo, unsigned rhi, unsigned ilo, unsigned ihi) {
-    switch (s) {
-        case 1: return __byte_perm(rhi, ihi, 0x0040);
-        case 2: return __byte_perm(rlo, ilo, 0x0073);
-        case 3: return __byte_perm(rlo, ilo, 0x0062);
-        case 4: return __byte_perm(rlo, ilo, 0x0051);
-        default: return __byte_perm(rlo, ilo, 0x0040);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_sf_bimage: Z = Ez rows of an l tile -> int8 digit image in the UMMA smem layout, per K-step
-//   grid (K-steps, n_lt, segments); thread = (l, atom) pairs of the K-step
-// ---------------------------------------------------------------------------------------------
-struct BimgJob {
-    const double2 *ez;
-    int8_t *bimg;
-    int32_t rows2, ld, maxn2, n_lt, lt_size;
-};
-
-__global__ void __launch_bounds__(256) k_sf_bimage(const BimgJob *__restrict__ jobs) {
-    const BimgJob &jb = jobs[blockIdx.z];
-    const int ks = blockIdx.x, lt = blockIdx.y;
-    if (ks * TC_KA >= jb.ld || lt >= jb.n_lt) return;
-    const int np = 2 * jb.lt_size;
-    int8_t *out = jb.bimg + ((size_t)lt * (jb.ld / TC_KA) + ks) * (size_t)(TC_S * np * 32);
-    for (int e = threadIdx.x; e < jb.lt_size * TC_KA; e += blockDim.x) {
-        const int li = e / TC_KA, a = e % TC_KA;
-        const int l = lt * jb.lt_size + li;
-        double2 z = make_double2(0.0, 0.0);
-        if (l < jb.maxn2) z = jb.ez[tab_index(ks * TC_KA + a, l, jb.rows2)];
-        unsigned rlo, rhi, ilo, ihi, nlo, nhi;
-        tc_digits(z.x, rlo, rhi);
-        tc_digits(z.y, ilo, ihi);
-        tc_digits(-z.y, nlo, nhi);
-#pragma unroll
-        for (int t = 1; t <= TC_S; ++t) {
-            int8_t *b = out + (size_t)(t - 1) * np * 32;
-            // row 2l (real part of A): (Zr, -Zi); row 2l + 1 (imaginary part): (Zi, Zr)
-            *reinterpret_cast<uint16_t *>(b + tc_canon(2 * li, 2 * a)) = (uint16_t)tc_pair(t, rlo, rhi, nlo, nhi);
-            *reinterpret_cast<uint16_t *>(b + tc_canon(2 * li + 1, 2 * a)) = (uint16_t)tc_pair(t, ilo, ihi, rlo, rhi);
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // k_sf_contract_tc
