@@ -73,6 +73,11 @@ int mb200_ctx_set_timing(mb200_ctx *ctx, int enable);
 int mb200_ctx_set_precision(mb200_ctx *ctx, int mode);
 /* Total kernels launched by this context since creation. */
 int64_t mb200_ctx_launch_count(mb200_ctx *ctx);
+/* Announce the host buffer the NEXT mb200_saxs_frames call will read its positions from: the frames are copied to
+ * the device on a separate copy stream while the current call computes (host staging -> PCIe -> HBM overlap across
+ * calls).  The next call recognises the pointer and skips its own copy.  May be called from another thread than the
+ * one inside a compute call; at most two announcements are kept.  The buffer must stay untouched until that call. */
+int mb200_prefetch_frames(mb200_ctx *ctx, const void *host_frames, size_t bytes);
 /* Page-locked host memory for frame staging (full-rate asynchronous H2D / D2H).  Any host pointer
  * is accepted by the compute calls; pinned ones avoid the driver's bounce buffer. */
 int mb200_host_alloc(size_t bytes, void **out);

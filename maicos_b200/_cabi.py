@@ -33,6 +33,7 @@ SIGNATURES = {
     "mb200_ctx_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "mb200_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "mb200_ctx_set_precision": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "mb200_prefetch_frames": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "mb200_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mb200_host_free": (None, [ctypes.c_void_p]),
     "mb200_sfactor_maxn": (ctypes.c_int, [c_double_p, ctypes.c_double, c_i32_p]),

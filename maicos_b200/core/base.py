@@ -344,6 +344,11 @@ class AnalysisBase(_Runner):
         """Turn staged frames into ``[(obs dict, correlation scalar), ...]`` with one device call."""
         raise NotImplementedError
 
+    def _announce_staged(self, staged: list) -> None:
+        """Hook called when a batch is complete, before it is queued: classes whose device call reads the pinned
+        staging buffer directly announce it (``mb200_prefetch_frames``) so that its host -> device copy overlaps with
+        the device call still running."""
+
     def _conclude(self) -> None:
         """Finalise ``results`` from ``sums / means / sems``."""
 
@@ -429,6 +434,7 @@ class AnalysisBase(_Runner):
                 from concurrent.futures import ThreadPoolExecutor
 
                 self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mb200-batch")
+            self._announce_staged([st for _, st in staged])
             previous, self._inflight = self._inflight, self._pool.submit(self._device_batch, staged)
             self._stage_parity ^= 1  # the next batch is staged into the other pinned buffer (free once `previous` is done)
             self._finish_batch(previous)

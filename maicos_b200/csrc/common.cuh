@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <list>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <vector>
@@ -94,6 +95,7 @@ struct PinBuf {
 };
 
 struct SfPlan;  // sfactor.cu
+const void *take_prefetched(mb200_ctx *ctx, const void *host, size_t bytes);  // context.cu
 
 }  // namespace mb200
 
@@ -113,6 +115,14 @@ struct mb200_ctx {
     mb200::PinBuf h_stage, h_out;
     // histogram workspaces
     mb200::DevBuf d_hpos, d_hw, d_hw2, d_hedges, d_hpar, d_hout, d_ctopo;
+    // host -> device prefetch of the next batch of frames (mb200_prefetch_frames): copy stream, two buffers
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t pref_ev[2] = {nullptr, nullptr};
+    mb200::DevBuf d_pref[2];
+    const void *pref_src[2] = {nullptr, nullptr};
+    size_t pref_bytes[2] = {0, 0};
+    int pref_next = 0;
+    std::mutex pref_mutex;
     std::list<std::shared_ptr<mb200::SfPlan>> plans;  // small LRU cache keyed by box + q window
     ~mb200_ctx();
 };

@@ -10,6 +10,9 @@ mb200_ctx::~mb200_ctx() {
     plans.clear();
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    for (int i = 0; i < 2; ++i)
+        if (pref_ev[i]) cudaEventDestroy(pref_ev[i]);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -44,6 +47,8 @@ extern "C" int mb200_ctx_create(int device, mb200_ctx **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->pref_ev[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete ctx;
         return fail(MB200_ECUDA, "context creation failed: %s", cudaGetErrorString(e));
@@ -80,6 +85,37 @@ extern "C" int mb200_ctx_set_timing(mb200_ctx *ctx, int enable) {
 }
 
 extern "C" int64_t mb200_ctx_launch_count(mb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int mb200_prefetch_frames(mb200_ctx *ctx, const void *host_frames, size_t bytes) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    if (!host_frames || bytes == 0) return MB200_OK;
+    MB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lock(ctx->pref_mutex);
+    const int slot = ctx->pref_next;
+    ctx->pref_next ^= 1;
+    ctx->pref_src[slot] = nullptr;
+    MB_TRY(ctx->d_pref[slot].ensure(bytes));
+    MB_CUDA(cudaMemcpyAsync(ctx->d_pref[slot].p, host_frames, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    MB_CUDA(cudaEventRecord(ctx->pref_ev[slot], ctx->copy_stream));
+    ctx->pref_src[slot] = host_frames;
+    ctx->pref_bytes[slot] = bytes;
+    return MB200_OK;
+}
+
+namespace mb200 {
+// Device copy of `host` if it was announced with mb200_prefetch_frames (the compute stream is made to wait for the
+// copy), else nullptr.  A slot is consumed by the first call that takes it.
+const void *take_prefetched(mb200_ctx *ctx, const void *host, size_t bytes) {
+    std::lock_guard<std::mutex> lock(ctx->pref_mutex);
+    for (int slot = 0; slot < 2; ++slot)
+        if (ctx->pref_src[slot] == host && ctx->pref_bytes[slot] >= bytes && host) {
+            ctx->pref_src[slot] = nullptr;
+            if (cudaStreamWaitEvent(ctx->stream, ctx->pref_ev[slot], 0) != cudaSuccess) return nullptr;
+            return ctx->d_pref[slot].p;
+        }
+    return nullptr;
+}
+}  // namespace mb200
 
 extern "C" int mb200_host_alloc(size_t bytes, void **out) {
     if (!out) return fail(MB200_EINVAL, "null output pointer");

@@ -1266,6 +1266,8 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
     // frames are processed in chunks bounded by the table workspace
     const size_t frame_elems = (size_t)n_atoms_total * 3;
     size_t done = 0;
+    const float *pref = nullptr;
+    bool pref_checked = false;
     while (done < (size_t)n_frames) {
         // chunk size: keep tables under ~12 GB
         size_t chunk = 0, tab_bytes = 0;
@@ -1291,7 +1293,14 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
         const float *dpos;
         if (positions_on_device) {
             dpos = positions + done * frame_elems;
+        } else if (!pref_checked && (pref = reinterpret_cast<const float *>(
+                                         take_prefetched(ctx, positions, (size_t)n_frames * frame_elems * 4))) != nullptr) {
+            pref_checked = true;
+            dpos = pref + done * frame_elems;  // the whole call was copied ahead by mb200_prefetch_frames
+        } else if (pref != nullptr) {
+            dpos = pref + done * frame_elems;
         } else {
+            pref_checked = true;
             MB_TRY(ctx->d_pos.ensure(std::max<size_t>(chunk * frame_elems, 1) * 4));
             if (frame_elems)
                 MB_CUDA(cudaMemcpyAsync(ctx->d_pos.p, positions + done * frame_elems, chunk * frame_elems * 4,

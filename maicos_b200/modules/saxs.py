@@ -113,6 +113,15 @@ class Saxs(AnalysisBase):
         positions_into(self.atomgroup, buf[row])
         return buf, row, box
 
+    def _announce_staged(self, staged: list) -> None:
+        if not self.bin_spectrum or not staged:
+            return
+        base = staged[0][0].ctypes.data
+        if any(st[0].ctypes.data != base or st[1] != f for f, st in enumerate(staged)):
+            return  # not one contiguous staging run: the call copies by itself
+        nbytes = len(staged) * self.atomgroup.n_atoms * 12
+        _cabi.check(_cabi.load().mb200_prefetch_frames(_cabi.context().handle, base, nbytes))
+
     def _device_packs(self) -> bool:
         return bool(self.pack and self._universe.dimensions is not None)
 
