@@ -21,7 +21,7 @@ from maicos_b200.lib.math import sfactor_maxn  # noqa: E402
 from maicos_b200.mdshim import MemoryTrajectory, Universe  # noqa: E402
 
 import os
-out = {"precision": os.environ.get("MAICOS_B200_PRECISION", "fp64")}
+out = {"precision": os.environ.get("MAICOS_B200_PRECISION", "i8x5")}
 ctx = _cabi.context()
 
 
@@ -71,6 +71,7 @@ a, dt = timed(lambda: mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.1, unwr
 out["C4_densityplanar_1M"] = {"frames": a.n_frames, "frames_per_s": a.n_frames / dt, "n_atoms": int(fr.shape[1]),
                               "n_bins": a.n_bins, "timings": a.timings}
 water = u.select_atoms("element O H")
+mb.DiporderPlanar(water, bin_width=0.1, unwrap=False, pack=False).run()  # warm-up (pinned staging, device buffers)
 a, dt = timed(lambda: mb.DiporderPlanar(water, bin_width=0.1, unwrap=False, pack=False).run())
 out["C4_diporderplanar_300k_mol"] = {"frames": a.n_frames, "frames_per_s": a.n_frames / dt, "n_bins": a.n_bins,
                                      "timings": a.timings, "note": "COM + dipole per molecule on the host (numpy)"}
