@@ -45,6 +45,10 @@ FP64_DMMA_PEAK_TFLOPS = 37.0   # tools/microbench/fp64_peaks on this pool's B200
 FLOP_PER_ATOMQ = 8.0           # one complex multiply-accumulate per atom*q
 I8_PEAK_TOPS = 4359.0          # tcgen05 kind::i8 dense, M=128 N=256, tools/microbench/umma_i8 (profiles/r01_umma_i8.log)
 I8_OPS_PER_ATOMQ = 120.0       # 4 real MACs x 15 digit products (s + t <= 6 of 5 x 5) x 2 ops
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the contraction kernel (one `ncu --set full` capture of
+# `bench.py --steps 2 --warmup 1`, 40 frames per launch): profiles/r01_tc_ncu_details.txt, r01_contract_v2_ncu_details.txt
+NCU_TRAFFIC_BYTES = {"i8x5": 5.238e9 + 0.256e9, "fp64": 17.944e9 + 0.093e9}
+NCU_TRAFFIC_FRAMES = 40
 
 
 def parse():
@@ -311,7 +315,10 @@ def main():
     atomq_per_launch = B * wl["atomq_per_frame"]
     peaks_file = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     common = {"kernel_ms_per_launch": kern_s / max(kern_launches, 1) * 1e3, "kernel_share_of_step": kern_s / (ms * 1e-3),
-              "traffic": None, "hbm_gbs_measured_peak": peaks_file.get("hbm_gbs"),
+              "traffic": NCU_TRAFFIC_BYTES[args.precision] * B / NCU_TRAFFIC_FRAMES,
+              "traffic_note": "DRAM bytes per launch from the committed ncu capture (not measured in this run): the tables are "
+                              "re-read from HBM by every row tile; the kernel is compute-side bound (DRAM < 10 % of peak)",
+              "hbm_gbs_measured_peak": peaks_file.get("hbm_gbs"),
               "fp64_equivalent_tflops": FLOP_PER_ATOMQ * atomq_per_launch * kern_launches / kern_s / 1e12 if kern_s > 0 else None,
               "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS}
     if args.precision == "fp64":
