@@ -235,6 +235,11 @@ class AtomGroup:
     def n_atoms(self) -> int:
         return len(self.indices)
 
+    @property
+    def ix(self) -> np.ndarray:
+        """Topology indices of the atoms (MDAnalysis ``AtomGroup.ix``)."""
+        return self.indices
+
     def __len__(self) -> int:
         return len(self.indices)
 

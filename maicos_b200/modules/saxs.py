@@ -24,6 +24,33 @@ from ..lib import tables
 from ..lib.math import atomic_form_factor, structure_factor
 
 
+def _element_groups(atomgroup):
+    """``(sorted unique element names, group id per atom)`` -- what ``np.unique(elements, return_inverse=True)`` gives.
+
+    Topology arrays hold a handful of distinct ``str`` objects referenced a million times, so the atoms are first
+    grouped by object identity (integers) and only the few representatives are compared as strings; the result is
+    kept on the universe for further analyses of the same selection.
+    """
+    elements = np.asarray(atomgroup.elements)
+    universe = atomgroup.universe
+    cache = universe.__dict__.setdefault("_mb200_element_groups", {}) if hasattr(universe, "__dict__") else {}
+    ix = getattr(atomgroup, "ix", None)
+    key = (len(elements), hash(np.asarray(ix).tobytes()) if ix is not None else None, id(atomgroup.universe))
+    if ix is not None and key in cache:
+        return cache[key]
+    if elements.dtype == object and len(elements) > 4096:
+        ids = np.fromiter(map(id, elements), dtype=np.int64, count=len(elements))
+        _, first, inv = np.unique(ids, return_index=True, return_inverse=True)
+        names = np.array([str(elements[i]) for i in first])
+        unique, remap = np.unique(names, return_inverse=True)
+        inverse = remap[inv]
+    else:
+        unique, inverse = np.unique(elements.astype(str), return_inverse=True)
+    if ix is not None:
+        cache[key] = (unique, inverse)
+    return unique, inverse
+
+
 class Saxs(AnalysisBase):
     r"""Small angle X-ray scattering intensities :math:`I(q) = \sum_e f_e(q)^2 S_e(q)`.
 
@@ -79,8 +106,7 @@ class Saxs(AnalysisBase):
         self.thetamax *= np.pi / 180
 
         # one group per element; weights are ones, form factors are applied after the kernel
-        elements = np.asarray(self.atomgroup.elements).astype(str)  # fixed-width strings sort fast
-        unique, inverse = np.unique(elements, return_inverse=True)
+        unique, inverse = _element_groups(self.atomgroup)
         self.groups, self.weights, self.elements, self._group_index = [], [], [], []
         for g, element in enumerate(unique):
             idx = np.flatnonzero(inverse == g).astype(np.int32)
