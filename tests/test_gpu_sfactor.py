@@ -286,3 +286,24 @@ def test_split_precision_against_fp64_mode(water_gro, water_frames, precision):
         assert not np.isfinite(s_bad[s_bad != 0]).any()
     finally:
         mb.set_precision("i8x5")
+
+
+def test_batched_pipeline_is_independent_of_the_batch_size():
+    """Frame staging, queued device calls and the announced host->device prefetch (mb200_prefetch_frames): seven frames in
+    batches of two (four device calls, three of them prefetched under the previous call) give the numbers of one batch."""
+    u = mb.synthetic.spce_universe(900, 20261026, n_frames=7)
+    ref = mb.Saxs(u.atoms, qmax=2.5).run()
+    old = mb.Saxs._batch_size
+    try:
+        mb.Saxs._batch_size = 2
+        got = mb.Saxs(u.atoms, qmax=2.5).run()
+        mb.Saxs._batch_size = 1
+        one = mb.Saxs(u.atoms, qmax=2.5).run(step=2)
+    finally:
+        mb.Saxs._batch_size = old
+    for k in ("structure_factors", "scattering_intensities", "dstructure_factors", "dscattering_intensities"):
+        assert_array_equal(got.results[k], ref.results[k])
+    assert_array_equal(got.sums.bincount, ref.sums.bincount)
+    assert_array_equal(got.timeseries, ref.timeseries)
+    assert_array_equal(one.frames, [0, 2, 4, 6])
+    assert_allclose(one.timeseries, ref.timeseries[::2], rtol=0, atol=0)
