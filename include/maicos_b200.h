@@ -55,7 +55,8 @@ uint64_t mb200_ctx_stream(mb200_ctx *ctx);
 /* Statistics of the last S(q) call on this context (for bench.py / DESIGN.md):
  *   out[0] = kernels launched, out[1] = n_valid q, out[2] = CTAs of the contraction kernel,
  *   out[3] = DMMA tile-steps issued (8x8x4 MMAs), out[4] = atom*q evaluations,
- *   out[5] = last contraction-kernel time in ns (0 unless timing enabled),
+ *   out[5] = last contraction-kernel time in ns (0 unless timing enabled); after mb200_profile_hist: time of
+ *            the histogram kernel of that call,
  *   out[6] = k-splits, out[7] = warp tiles in the plan. */
 int mb200_ctx_stats(mb200_ctx *ctx, int64_t out[8]);
 /* Enable (1) / disable (0) CUDA-event timing of the contraction kernel inside calls. */
@@ -212,6 +213,11 @@ int mb200_dielectric_prepare(mb200_ctx *ctx, const float *positions, int positio
  *   modules/dielectricplanar.py:170-176, 203-213, modules/dielectriccylinder.py:134-151, 180-190,
  *   modules/dielectricsphere.py:113-133. */
 #define MB200_BIN_DIGITIZE 0x10
+
+/* Kernel used for WEIGHTED histograms with finite weights (results are bitwise identical, both accumulate the same
+ * exact fixed-point integers):  0 (default) counting-sort tiles, one shared-memory atomic per element;
+ * 1 three shared-memory atomics per element (the round-1 kernel, kept for A/B measurements). */
+int mb200_ctx_set_hist_mode(mb200_ctx *ctx, int mode);
 
 /* Fused weighted + count histogram of ProfileBase._single_frame (core/base.py:815-818),
  * batched over frames.  numpy semantics (numpy/lib/_histograms_impl.py:816-873, 1037-1069):

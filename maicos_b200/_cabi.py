@@ -33,6 +33,7 @@ SIGNATURES = {
     "mb200_ctx_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "mb200_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "mb200_ctx_set_precision": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "mb200_ctx_set_hist_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "mb200_prefetch_frames": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "mb200_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mb200_host_free": (None, [ctypes.c_void_p]),
@@ -142,6 +143,9 @@ class Context:
         mode = os.environ.get("MAICOS_B200_PRECISION", "")
         if mode:  # e.g. MAICOS_B200_PRECISION=fp64 for the CLI; maicos_b200.set_precision() overrides
             self.set_precision(mode)
+        mode = os.environ.get("MAICOS_B200_HIST", "")
+        if mode:
+            self.set_hist_mode(mode)
 
     @property
     def handle(self):
@@ -162,6 +166,10 @@ class Context:
     def set_precision(self, mode: str) -> None:
         """``"i8x5"`` (default: split precision on the tcgen05 tensor cores) or ``"fp64"`` (FP64 DMMA)."""
         _check(load().mb200_ctx_set_precision(self._h, {"fp64": 0, "i8x5": 1}[mode]))
+
+    def set_hist_mode(self, mode: str) -> None:
+        """Weighted-histogram kernel: ``"sorted"`` (default, one shared atomic per element) or ``"atomics"``."""
+        _check(load().mb200_ctx_set_hist_mode(self._h, {"sorted": 0, "atomics": 1}[mode]))
 
     def launch_count(self) -> int:
         return int(load().mb200_ctx_launch_count(self._h))

@@ -106,6 +106,8 @@ struct mb200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false;
     bool sf_attr_set = false, hist_attr_set = false, tc_attr_set = false;
+    unsigned hs_attr_set = 0;  // k_hist_sorted<B> instantiations whose shared-memory limit is raised
+    int hist_mode = 0;         // weighted histograms: 0 counting-sort kernel (default), 1 three-atomics kernel
     int precision = 1;        // 1: int8 x 5 split precision on tcgen05 (default)  0: FP64 DMMA
     bool force_fp64 = false;  // this call must use the FP64 kernel (non-finite weights)
     int64_t launches = 0;

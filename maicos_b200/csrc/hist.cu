@@ -247,6 +247,386 @@ __global__ void __launch_bounds__(H_THREADS) k_hist(HistParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_hist_sorted: the weighted mode with ONE shared-memory atomic per element (default for finite weights).
+//
+// k_hist<0> spends three native ATOMS per element (count, low limb, middle limb) and the shared-memory atomic unit
+// retires about one lane per cycle per SM, which caps it near 20 % of the HBM rate.  Here a CTA of 512 threads works on
+// tiles of 4096 elements and counting-sorts each tile by bin:
+//   1. bin of the element and rank = atomicAdd(&cnt[bin], 1) -- the only atomic, it is also the count.  The bin is
+//      idx = trunc((x - first) * n / (last - first)) whenever the fractional part of that product is further than
+//      `eps` from 0 and 1, eps being a bound on everything that separates the product from the position of x among
+//      the float64 edges (three roundings of the product, two of each np.linspace edge); otherwise -- values sitting
+//      on an edge, about one element in 1e11 for continuous data -- the edges decide exactly as in k_hist<0>, either
+//      evaluated the way np.linspace does (fl(fl(i * step) + first), after the CTA has verified that the table it was
+//      given is exactly that) or read from the table;
+//   2. block scan of the tile counts -> segment offsets (order: thread, round; thread t owns bins t + 512 r);
+//   3. scatter of the 54-bit fixed-point weights (same fixed(w) as k_hist<0>) to offset[bin] + rank;
+//   4. the owner of a bin sums its segment with plain 64-bit adds and folds it into the CTA's private
+//      {sum, carry, count} record of the bin (plain read-modify-write, the owner is the only writer).
+// Integer sums are exact and order independent, so the result is BITWISE the one of k_hist<0>; the flush into the
+// 128-bit global accumulators and k_hist_merge are shared.  Frames with non-finite weights take float64 global atomics.
+constexpr int HS_THREADS = 512;
+constexpr int HS_PER = 8;
+constexpr int HS_TILE = HS_THREADS * HS_PER;
+
+// shared memory through 32-bit window addresses (keeps the address arithmetic out of the generic space)
+__device__ __forceinline__ unsigned int lds32(unsigned int a) { unsigned int v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(unsigned int a, unsigned int v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long lds64(unsigned int a) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts64(unsigned int a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ double ldsf64(unsigned int a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned int atoms_inc(unsigned int a) { unsigned int v; asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(a) : "memory"); return v; }
+// per-bin record of a CTA: 96-bit sum (three limbs) + 32-bit count
+__device__ __forceinline__ void lds_acc(unsigned int a, unsigned int &s0, unsigned int &s1, unsigned int &s2, unsigned int &count) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(count) : "r"(a));
+}
+__device__ __forceinline__ void sts_acc(unsigned int a, unsigned int s0, unsigned int s1, unsigned int s2, unsigned int count) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(s0), "r"(s1), "r"(s2), "r"(count) : "memory");
+}
+// {s2, s1, s0} += {carry, sum}
+__device__ __forceinline__ void add96(unsigned int &s0, unsigned int &s1, unsigned int &s2, unsigned long long sum, unsigned int carry) {
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, %5;"
+        : "+r"(s0), "+r"(s1), "+r"(s2)
+        : "r"((unsigned int)sum), "r"((unsigned int)(sum >> 32)), "r"(carry));
+}
+
+struct EdgeRef {
+    unsigned int tab;  // shared-memory address of the edge table
+    double first, last, step, inv_width, eps;
+    int nb, arith;
+    __device__ __forceinline__ double at(int i) const {
+        if (arith) return i == nb ? last : __dadd_rn(__dmul_rn((double)i, step), first);
+        return ldsf64(tab + 8u * (unsigned int)i);
+    }
+};
+
+// same decisions as bin_of / bin_digitize above, edges through EdgeRef (rare path: kept out of line, scalar arguments
+// so that the caller's EdgeRef stays in registers)
+__device__ __noinline__ int find_bin_exact(unsigned int tab, double first, double last, double step, double inv_width,
+                                           int nb, int arith, double x, int digitize) {
+    EdgeRef e;
+    e.tab = tab; e.first = first; e.last = last; e.step = step; e.inv_width = inv_width; e.nb = nb; e.arith = arith;
+    int idx;
+    if (digitize) {
+        if (x != x) return nb - 1;
+        const double gd = (x - first) * inv_width;
+        idx = gd <= 0.0 ? 0 : (gd >= (double)(nb - 1) ? nb - 1 : (int)gd);
+    } else {
+        if (!(x >= first && x <= last)) return -1;
+        idx = (int)((x - first) * inv_width);
+        idx = min(max(idx, 0), nb - 1);
+    }
+    while (idx > 0 && x < e.at(idx)) --idx;
+    while (idx < nb - 1 && x >= e.at(idx + 1)) ++idx;
+    return idx;
+}
+
+__device__ __forceinline__ int find_bin(const EdgeRef &e, double x, int digitize) {
+    const double gd = __dmul_rn(__dsub_rn(x, e.first), e.inv_width);
+    const int idx = (int)gd;
+    const double fr = gd - (double)idx;
+    // strictly inside bin idx whatever the roundings (this also excludes NaN, out-of-range values and x == last)
+    if (fr > e.eps && fr < 1.0 - e.eps && gd > 0.0 && idx < e.nb) return idx;
+    return find_bin_exact(e.tab, e.first, e.last, e.step, e.inv_width, e.nb, e.arith, x, digitize);
+}
+
+// binned coordinate of an atom given as float32; false when histogram2d's axial window drops it
+__device__ __forceinline__ bool atom_value_f32(const FrameGeom &g, float x, float y, float z, double &v) {
+    if (g.geometry == MB200_GEOM_PLANAR) {
+        v = (double)(g.d0 == 0 ? x : (g.d0 == 1 ? y : z));
+        return true;
+    }
+    const double dx = (double)x, dy = (double)y, dz = (double)z;
+    if (g.geometry == MB200_GEOM_CYLINDER) {
+        const double ax = pick(dx, dy, dz, g.d0);
+        if (!g.digitize && !(ax >= g.zlo && ax <= g.zhi)) return false;
+        const double a = __dsub_rn(pick(dx, dy, dz, g.d1), pick(g.cx, g.cy, g.cz, g.d1));
+        const double b = __dsub_rn(pick(dx, dy, dz, g.d2), pick(g.cx, g.cy, g.cz, g.d2));
+        v = sqrt(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+    } else {
+        const double a = __dsub_rn(dx, g.cx), b = __dsub_rn(dy, g.cy), c = __dsub_rn(dz, g.cz);
+        v = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c)));
+    }
+    return true;
+}
+__device__ __forceinline__ bool atom_value(const FrameGeom &g, double x, double y, double z, double &v) {
+    if (g.geometry == MB200_GEOM_PLANAR) {
+        v = pick(x, y, z, g.d0);
+    } else if (g.geometry == MB200_GEOM_CYLINDER) {
+        const double ax = pick(x, y, z, g.d0);
+        if (!g.digitize && !(ax >= g.zlo && ax <= g.zhi)) return false;
+        const double a = __dsub_rn(pick(x, y, z, g.d1), pick(g.cx, g.cy, g.cz, g.d1));
+        const double b = __dsub_rn(pick(x, y, z, g.d2), pick(g.cx, g.cy, g.cz, g.d2));
+        v = sqrt(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+    } else {
+        const double a = __dsub_rn(x, g.cx), b = __dsub_rn(y, g.cy), c = __dsub_rn(z, g.cz);
+        v = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c)));
+    }
+    return true;
+}
+
+template <int BPT>
+__global__ void __launch_bounds__(HS_THREADS, 2) k_hist_sorted(HistParams p) {
+    extern __shared__ __align__(16) unsigned char hsm[];
+    const int f = blockIdx.y, nb = p.n_bins, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // shared layout: sorted [HS_TILE] x 8 B | warp totals [16] x 4 B | acc [nb] x 16 B | edges [nb + 1] x 8 B |
+    // cnt [nb + 1] x 4 B (the last counter collects the dropped elements).  The window addresses are made opaque to
+    // the compiler so that they stay in registers instead of being rebuilt at every use.
+    unsigned int s_sorted = (unsigned int)__cvta_generic_to_shared(hsm);
+    unsigned int s_wt = s_sorted + 8u * HS_TILE;
+    unsigned int s_acc = s_wt + 64u;
+    unsigned int s_edges = s_acc + 16u * (unsigned int)nb;
+    unsigned int s_cnt = s_edges + 8u * (unsigned int)(nb + 1);
+    asm volatile("" : "+r"(s_sorted), "+r"(s_wt), "+r"(s_acc), "+r"(s_cnt));
+
+    const double *g_edges = p.edges + (size_t)f * (nb + 1);
+    EdgeRef E;
+    E.tab = s_edges; E.nb = nb;
+    E.first = g_edges[0]; E.last = g_edges[nb];
+    const double width = __dsub_rn(E.last, E.first);
+    E.step = __ddiv_rn(width, (double)nb);
+    E.inv_width = (double)nb / width;
+    {
+        // |gd - t(x)| <= 3 nb u and |t(edge_i) - i| <= nb u (1 + 6 A / width), u = 2^-53, A = max(|first|, |last|); x2 margin
+        const double A = fmax(fabs(E.first), fabs(E.last));
+        const double e = 8.0 * (double)nb * 1.1102230246251565e-16 * (1.0 + 2.0 * A / fabs(width));
+        E.eps = (width > 0.0 && e < 0.25) ? e : 2.0;  // 2: the quick test never passes
+    }
+    int lin = 1;
+    for (int i = t; i <= nb; i += HS_THREADS) {
+        const double e = g_edges[i];
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(s_edges + 8u * (unsigned int)i), "d"(e) : "memory");
+        lin &= (e == (i == nb ? E.last : __dadd_rn(__dmul_rn((double)i, E.step), E.first))) ? 1 : 0;
+    }
+    for (int i = t; i <= nb; i += HS_THREADS) {
+        sts32(s_cnt + 4u * (unsigned int)i, 0u);
+        if (i < nb) sts_acc(s_acc + 16u * (unsigned int)i, 0u, 0u, 0u, 0u);
+    }
+    E.arith = __syncthreads_and(lin);
+    if (!E.arith) E.eps = 2.0;  // hand-made edges: always decided by the table
+
+    FrameGeom g;
+    g.geometry = p.geometry; g.nb = nb; g.digitize = p.digitize;
+    g.d0 = p.dim; g.d1 = (p.dim + 1) % 3; g.d2 = (p.dim + 2) % 3;
+    g.cx = g.cy = g.cz = g.zlo = g.zhi = 0;
+    if (p.geometry == MB200_GEOM_CYLINDER || p.geometry == MB200_GEOM_SPHERE) { g.cx = p.center[f * 3]; g.cy = p.center[f * 3 + 1]; g.cz = p.center[f * 3 + 2]; }
+    if (p.geometry == MB200_GEOM_CYLINDER && p.zrange) { g.zlo = p.zrange[f * 2]; g.zhi = p.zrange[f * 2 + 1]; }
+    const int dig = p.digitize;
+    if (dig) E.eps = 2.0;  // digitize clamps instead of dropping: exact path
+    const long long n = p.n;
+    const double *w = p.weights + (p.w_per_frame ? (size_t)f * n : 0);
+    double *gf = p.acc_f + (size_t)f * nb;
+    unsigned long long *gc = p.acc_c + (size_t)f * nb;
+    unsigned long long *glo = p.acc_lo + (size_t)f * nb, *ghi = p.acc_hi + (size_t)f * nb;
+
+    const unsigned long long wb = p.wmax_bits[p.w_per_frame ? f : 0];
+    const bool fx = wb < 0x7ff0000000000000ull;
+    const double wmax = __longlong_as_double((long long)wb);
+    const int kexp = bias_exponent(fx && wmax > 0.0 ? wmax : 1.0);
+    const double bias = ldexp(1.0, kexp), inv_q = ldexp(1.0, 52 - kexp);
+
+    // element j of the frame -> bin (or -1); generic fetch for every layout
+    auto bin_generic = [&](long long j) -> int {
+        double v;
+        if (p.geometry == MB200_GEOM_SCALAR) {
+            v = p.is_f32 ? (double)(reinterpret_cast<const float *>(p.pos) + (size_t)f * n)[j]
+                         : (reinterpret_cast<const double *>(p.pos) + (size_t)f * n)[j];
+        } else {
+            double x, y, z;
+            if (p.is_f32) {
+                const float *b = reinterpret_cast<const float *>(p.pos) + ((size_t)f * n + j) * 3;
+                x = (double)b[0]; y = (double)b[1]; z = (double)b[2];
+            } else {
+                const double *b = reinterpret_cast<const double *>(p.pos) + ((size_t)f * n + j) * 3;
+                x = b[0]; y = b[1]; z = b[2];
+            }
+            if (!atom_value(g, x, y, z, v)) return -1;
+        }
+        return find_bin(E, v, dig);
+    };
+    auto fixed = [&](double wj) -> unsigned long long {
+        return (unsigned long long)__double2ll_rn(__dmul_rn(__dadd_rn(wj, bias), inv_q));
+    };
+
+    if (!fx) {  // inf / nan weights in this frame: float64 atomics keep numpy's result
+        for (long long j = (long long)blockIdx.x * HS_THREADS + t; j < n; j += (long long)gridDim.x * HS_THREADS) {
+            const int b = bin_generic(j);
+            if (b < 0) continue;
+            atomicAdd(&gc[b], 1ull);
+            atomicAdd(&gf[b], w[j]);
+        }
+        return;
+    }
+
+    // float32 [n][3] frames: 16-byte aligned body of 4-atom groups (3 x float4), at most 3 + 3 atoms around it
+    long long a0 = 0, n_quads = 0;
+    const bool fast = p.geometry != MB200_GEOM_SCALAR && p.is_f32 &&
+                      (((unsigned long long)(uintptr_t)p.pos) & 3ull) == 0;
+    const float *fbase = reinterpret_cast<const float *>(p.pos) + (size_t)f * n * 3;
+    if (fast) {
+        const unsigned long long addr = (unsigned long long)(uintptr_t)fbase;
+        while (a0 < n && ((addr + (unsigned long long)a0 * 12ull) & 15ull)) ++a0;
+        n_quads = (n - a0) / 4;
+    }
+    const long long n_tiles = fast ? (n_quads + HS_TILE / 4 - 1) / (HS_TILE / 4) : (n + HS_TILE - 1) / HS_TILE;
+
+    if (fast && blockIdx.x == 0) {  // the unaligned head and the tail of the frame: straight into the global accumulators
+        const long long tail0 = a0 + n_quads * 4;
+        const long long n_extra = a0 + (n - tail0);
+        if (t < n_extra) {
+            const long long j = t < a0 ? t : tail0 + (t - a0);
+            const int b = bin_generic(j);
+            if (b >= 0) {
+                const unsigned long long v = fixed(w[j]);
+                atomicAdd(&gc[b], 1ull);
+                const unsigned long long old = atomicAdd(&glo[b], v);
+                if ((old + v) < old) atomicAdd(&ghi[b], 1ull);
+            }
+        }
+    }
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        unsigned int pk[HS_PER];
+        unsigned long long val[HS_PER];
+        int bins[HS_PER];
+        if (fast) {
+            const float4 *vb = reinterpret_cast<const float4 *>(fbase + a0 * 3);
+            if (t == 0 && tile + gridDim.x < n_tiles) {  // the CTA's next tile on its way into L2 while this one is sorted
+                const long long q0 = (tile + gridDim.x) * (HS_TILE / 4);
+                const long long nq = min((long long)(HS_TILE / 4), n_quads - q0);
+                const unsigned long long wa = (unsigned long long)(uintptr_t)(w + a0 + q0 * 4) & ~15ull;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vb + q0 * 3), "r"((unsigned int)(nq * 48)) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wa), "r"((unsigned int)(nq * 32)) : "memory");
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long long qd = tile * (HS_TILE / 4) + h * HS_THREADS + t;
+                if (qd < n_quads) {
+                    const float4 v0 = __ldg(vb + qd * 3), v1 = __ldg(vb + qd * 3 + 1), v2 = __ldg(vb + qd * 3 + 2);
+                    const double *wq = w + a0 + qd * 4;
+                    const double w0 = __ldg(wq), w1 = __ldg(wq + 1), w2 = __ldg(wq + 2), w3 = __ldg(wq + 3);
+                    double c;
+                    bins[h * 4 + 0] = atom_value_f32(g, v0.x, v0.y, v0.z, c) ? find_bin(E, c, dig) : -1;
+                    bins[h * 4 + 1] = atom_value_f32(g, v0.w, v1.x, v1.y, c) ? find_bin(E, c, dig) : -1;
+                    bins[h * 4 + 2] = atom_value_f32(g, v1.z, v1.w, v2.x, c) ? find_bin(E, c, dig) : -1;
+                    bins[h * 4 + 3] = atom_value_f32(g, v2.y, v2.z, v2.w, c) ? find_bin(E, c, dig) : -1;
+                    val[h * 4 + 0] = fixed(w0); val[h * 4 + 1] = fixed(w1); val[h * 4 + 2] = fixed(w2); val[h * 4 + 3] = fixed(w3);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { bins[h * 4 + i] = -1; val[h * 4 + i] = 0ull; }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < HS_PER; ++s) {
+                const long long j = tile * HS_TILE + s * HS_THREADS + t;
+                bins[s] = -1; val[s] = 0ull;
+                if (j < n) {
+                    bins[s] = bin_generic(j);
+                    val[s] = fixed(w[j]);
+                }
+            }
+        }
+        __syncthreads();  // E: the previous tile's owners are done with cnt[] and sorted[]
+        // dropped elements (and the empty slots of a partial tile) are counted in cnt[nb] and sorted behind everything
+#pragma unroll
+        for (int s = 0; s < HS_PER; ++s) {
+            const unsigned int b = bins[s] >= 0 ? (unsigned int)bins[s] : (unsigned int)nb;
+            pk[s] = (b << 13) | atoms_inc(s_cnt + 4u * b);
+        }
+        __syncthreads();  // A
+
+        // segment offsets, order (thread, round): thread t owns bins t + 512 r
+        unsigned int c[BPT];
+        unsigned int mine = 0;
+#pragma unroll
+        for (int r = 0; r < BPT; ++r) {
+            const int b = t + r * HS_THREADS;
+            c[r] = b < nb ? lds32(s_cnt + 4u * (unsigned int)b) : 0u;
+            mine += c[r];
+        }
+        unsigned int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) sts32(s_wt + 4u * (unsigned int)warp, incl);
+        __syncthreads();  // B
+        unsigned int base;
+        {
+            const unsigned int wv = lane < HS_THREADS / 32 ? lds32(s_wt + 4u * (unsigned int)lane) : 0u;
+            unsigned int wi = wv;
+#pragma unroll
+            for (int o = 1; o < HS_THREADS / 32; o <<= 1) {
+                const unsigned int up = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += up;
+            }
+            base = __shfl_sync(0xffffffffu, wi - wv, warp) + incl - mine;
+            unsigned int o = base;
+#pragma unroll
+            for (int r = 0; r < BPT; ++r) {
+                const int b = t + r * HS_THREADS;
+                if (b < nb) sts32(s_cnt + 4u * (unsigned int)b, o);
+                o += c[r];
+            }
+            if (t == HS_THREADS - 1) sts32(s_cnt + 4u * (unsigned int)nb, o);  // the dropped elements go last
+        }
+        __syncthreads();  // C
+#pragma unroll
+        for (int s = 0; s < HS_PER; ++s)
+            sts64(s_sorted + 8u * (lds32(s_cnt + ((pk[s] >> 11) & 0x1ffffcu)) + (pk[s] & 8191u)), val[s]);
+        __syncthreads();  // D
+        unsigned int src = s_sorted + 8u * base;
+        if (t == HS_THREADS - 1) sts32(s_cnt + 4u * (unsigned int)nb, 0u);
+        const bool wide = mine > 2048u;  // 2048 values below 2^53 cannot wrap a 64-bit sum
+#pragma unroll
+        for (int r = 0; r < BPT; ++r) {
+            const int b = t + r * HS_THREADS;
+            if (c[r]) {
+                unsigned long long sum = 0ull;
+                unsigned int carry = 0u;
+                const unsigned int end = src + 8u * c[r];
+                if (!wide) {
+#pragma unroll 1
+                    for (; src != end; src += 8u) sum += lds64(src);
+                } else {
+#pragma unroll 1
+                    for (; src != end; src += 8u) {
+                        const unsigned long long x = lds64(src);
+                        sum += x;
+                        carry += sum < x ? 1u : 0u;
+                    }
+                }
+                unsigned int s0, s1, s2, cn;
+                const unsigned int aa = s_acc + 16u * (unsigned int)b;
+                lds_acc(aa, s0, s1, s2, cn);
+                add96(s0, s1, s2, sum, carry);
+                sts_acc(aa, s0, s1, s2, cn + c[r]);
+            }
+            if (b < nb) sts32(s_cnt + 4u * (unsigned int)b, 0u);  // it held the segment offset
+        }
+    }
+    __syncthreads();
+
+    // owners flush their bins into the 128-bit global accumulators
+#pragma unroll
+    for (int r = 0; r < BPT; ++r) {
+        const int b = t + r * HS_THREADS;
+        if (b >= nb) continue;
+        unsigned int s0, s1, s2, cn;
+        lds_acc(s_acc + 16u * (unsigned int)b, s0, s1, s2, cn);
+        if (!cn) continue;
+        atomicAdd(&gc[b], (unsigned long long)cn);
+        const unsigned long long lo64 = ((unsigned long long)s1 << 32) | s0;
+        const unsigned long long old = atomicAdd(&glo[b], lo64);
+        const unsigned long long hi = (unsigned long long)s2 + ((old + lo64) < old ? 1ull : 0ull);
+        if (hi) atomicAdd(&ghi[b], hi);
+    }
+}
+
 // out_w = (acc - count * 2^52) * Q  (exact in __int128), or the float64 fallback sums
 __global__ void k_hist_merge(HistParams p, int fixed_point, double *__restrict__ out_w, long long *__restrict__ out_c,
                              long long total) {
@@ -376,10 +756,33 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
         long long want = ((long long)ctx->n_sm * 4 + (long long)F - 1) / (long long)F;
         unsigned bx = (unsigned)std::max<long long>(1, std::min(per_frame, std::max<long long>(want, 1)));
         dim3 grid(bx, (unsigned)F);
-        if (mode == 0) k_hist<0><<<grid, H_THREADS, smem, ctx->stream>>>(p);
+        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        if (mode == 0 && ctx->hist_mode == 0) {
+            // counting-sort kernel: one or two resident CTAs of 512 threads per SM, the grid fills them once
+            const size_t ssm = NB * 16 + (size_t)HS_TILE * 8 + (NB + 1) * 8 + (NB + 1) * 4 + 64 + 16;
+            const long long slots = (long long)ctx->n_sm * (ssm <= 112 * 1024 ? 2 : 1);
+            const long long n_tiles = (long long)((N + HS_TILE - 1) / HS_TILE);
+            const unsigned sbx = (unsigned)std::max<long long>(1, std::min(n_tiles, slots / (long long)F));
+            const dim3 sgrid(sbx, (unsigned)F);
+            const int bpt = (int)((NB + HS_THREADS - 1) / HS_THREADS);
+#define MB_HS_CASE(B)                                                                                              \
+    case B:                                                                                                        \
+        if (!(ctx->hs_attr_set & (1u << B))) {                                                                     \
+            MB_CUDA(cudaFuncSetAttribute(k_hist_sorted<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
+            ctx->hs_attr_set |= 1u << B;                                                                           \
+        }                                                                                                          \
+        k_hist_sorted<B><<<sgrid, HS_THREADS, ssm, ctx->stream>>>(p);                                              \
+        break;
+            switch (bpt) {
+                MB_HS_CASE(1) MB_HS_CASE(2) MB_HS_CASE(3) MB_HS_CASE(4) MB_HS_CASE(5) MB_HS_CASE(6) MB_HS_CASE(7) MB_HS_CASE(8)
+                default: return fail(MB200_EINVAL, "internal: bins per thread out of range");
+            }
+#undef MB_HS_CASE
+        } else if (mode == 0) k_hist<0><<<grid, H_THREADS, smem, ctx->stream>>>(p);
         else if (mode == 1) k_hist<1><<<grid, H_THREADS, smem, ctx->stream>>>(p);
         else k_hist<2><<<grid, H_THREADS, 0, ctx->stream>>>(p);
         MB_CUDA(cudaGetLastError());
+        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
         ctx->launches += 1;
     }
     k_hist_merge<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(p, mode == 0, hist_w ? d_ow : nullptr, d_oc, total);
@@ -389,5 +792,18 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
     if (hist_w) MB_CUDA(cudaMemcpyAsync(hist_w, d_ow, F * NB * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(cudaMemcpyAsync(hist_c, d_oc, F * NB * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats[5] = 0;
+    if (ctx->timing && N) {  // time of the histogram kernel proper (mb200_ctx_stats, out[5])
+        float ms = 0.f;
+        MB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->stats[5] = (int64_t)(ms * 1.0e6);
+    }
+    return MB200_OK;
+}
+
+extern "C" int mb200_ctx_set_hist_mode(mb200_ctx *ctx, int mode) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    if (mode < 0 || mode > 1) return fail(MB200_EINVAL, "histogram mode must be 0 (counting sort) or 1 (three atomics)");
+    ctx->hist_mode = mode;
     return MB200_OK;
 }

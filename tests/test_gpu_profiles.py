@@ -86,6 +86,55 @@ def test_heavy_collisions_unaligned_frames_and_nonfinite_weights():
     assert_array_equal(hc[1], restatement.hist_planar(pos[1], None, 2, nb, 0.0, 50.0))
 
 
+@pytest.mark.parametrize("n_bins", [1, 31, 512, 513, 1024, 1537, 2154, 3000, 4096])
+def test_sorted_kernel_bitwise_equals_atomics_kernel(n_bins):
+    """Counting-sort kernel (default) vs the three-atomics kernel: identical exact integer sums, every bins-per-thread
+    instantiation, every layout (float32 aligned / unaligned, float64, scalar, digitize, cylinder, sphere, hand-made
+    edges that are not numpy's linspace), tiles that are not full, weights of mixed sign and magnitude."""
+    from maicos_b200 import _cabi
+    ctx = _cabi.context(None)
+    rng = np.random.default_rng(n_bins)
+    F, n = 3, 29_999  # n * 12 B is not a multiple of 16
+    pos32 = rng.uniform(-2, 52, (F, n, 3)).astype(np.float32)
+    pos32[0, : n // 3, 2] = np.float32(11.7)  # heavy collisions: segment sums longer than one tile share
+    w = rng.normal(size=(F, n)) * np.exp(rng.uniform(-20, 20, (F, n)))
+    lin = np.stack([np.linspace(np.float64(0), np.float64(50 + f), n_bins + 1) for f in range(F)])
+    hand = lin.copy()
+    if n_bins > 2:
+        hand[:, 1:-1] += rng.uniform(-0.3, 0.3, (F, n_bins - 1)) * (50.0 / n_bins)  # still increasing, not a linspace
+    center = np.tile([25.0, 26.0, 27.0], (F, 1))
+    zr = np.tile([3.0, 45.0], (F, 1))
+    radial = np.stack([np.linspace(np.float64(0.25), np.float64(24 + f), n_bins + 1) for f in range(F)])
+    cases = [
+        (0, pos32, 2, w, lin, None, None, False),
+        (0, pos32, 0, w[:1], hand, None, None, False),
+        (0, pos32.astype(np.float64), 1, w, lin, None, None, False),
+        (3, np.ascontiguousarray(pos32[:, :, 1]), 0, w, lin, None, None, True),
+        (3, np.ascontiguousarray(pos32[:, :, 1]).astype(np.float64), 0, w, hand, None, None, False),
+        (1, pos32, 1, w, radial, center, zr, False),
+        (2, pos32, 0, w, radial, center, None, False),
+        (0, pos32[:, :4097], 2, w[:, :4097], lin, None, None, True),
+        (0, pos32[:, :5], 2, w[:, :5], lin, None, None, False),
+    ]
+    try:
+        for geom, p, dim, ww, e, c, z, dig in cases:
+            ctx.set_hist_mode("atomics")
+            ref_w, ref_c = profile_hist(geom, np.ascontiguousarray(p), dim, np.ascontiguousarray(ww), e, c, z, digitize=dig)
+            ctx.set_hist_mode("sorted")
+            hw, hc = profile_hist(geom, np.ascontiguousarray(p), dim, np.ascontiguousarray(ww), e, c, z, digitize=dig)
+            assert_array_equal(hc, ref_c)
+            assert_array_equal(hw, ref_w)
+            assert hc.sum() > 0
+    finally:
+        ctx.set_hist_mode("sorted")
+    # and against numpy for the linspace case
+    hw, hc = profile_hist(0, pos32, 2, w, lin)
+    for f in range(F):
+        assert_array_equal(hc[f], restatement.hist_planar(pos32[f], None, 2, n_bins, lin[f, 0], lin[f, -1]))
+        assert_allclose(hw[f], restatement.hist_planar(pos32[f], w[f], 2, n_bins, lin[f, 0], lin[f, -1]), rtol=WTOL,
+                        atol=WTOL * np.abs(w[f]).sum())
+
+
 def test_empty_and_ragged_inputs():
     e = np.linspace(0.0, 1.0, 11)[None]
     hw, hc = profile_hist(0, np.zeros((1, 0, 3), np.float32), 2, np.zeros((1, 0)), e)

@@ -53,6 +53,28 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps * 1e-3, (time.perf_counter() - t0) / reps
 
 
+def kernel_ms(mode, weighted=True, reps=10):
+    """CUDA-event time of the histogram kernel alone (mb200_ctx_stats out[5]), median over calls."""
+    ctx.set_hist_mode(mode)
+    ctx.set_timing(True)
+    ts = []
+    for _ in range(reps + 3):
+        call(d_pos.data_ptr(), 1, d_w.data_ptr() if weighted else None, 1)
+        ts.append(ctx.stats()["contract_ns"] * 1e-6)
+    ctx.set_timing(False)
+    return float(np.median(ts[3:]))
+
+
+variants = {}
+for mode in ("atomics", "sorted"):
+    ctx.set_hist_mode(mode)
+    s_call, _ = timed(lambda: call(d_pos.data_ptr(), 1, d_w.data_ptr(), 1), 20)
+    k = kernel_ms(mode)
+    variants[mode] = {"ms_per_call": s_call * 1e3, "kernel_ms": k, "kernel_gbs": 12.0 * N * F / k / 1e6,
+                      "call_gbs": 12.0 * N * F / s_call / 1e9}
+variants["counts_only"] = {"kernel_ms": kernel_ms("sorted", weighted=False)}
+variants["counts_only"]["kernel_gbs"] = 12.0 * N * F / variants["counts_only"]["kernel_ms"] / 1e6
+ctx.set_hist_mode("sorted")
 dev_s, dev_wall = timed(lambda: call(d_pos.data_ptr(), 1, d_w.data_ptr(), 1), 20)
 ref_c = np.histogram(pos[0, :, 2], NB, (np.float64(0), np.float64(LZ)))[0]  # float64 range as planar.py:107-110
 assert np.array_equal(hc[0], ref_c)
@@ -71,6 +93,8 @@ print(json.dumps({
                  "wall_ms_per_call": dev_wall * 1e3},
     "e2e_host_pinned": {"frames_per_s": F / host_wall, "h2d_gbs": 12.0 * N * F / host_wall / 1e9},
     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                 "algorithmic_bytes_per_atom_frame": 12},
+                 "algorithmic_bytes_per_atom_frame": 12,
+                 "kernel_only_frac": variants["sorted"]["kernel_gbs"] / peak},
+    "variants": variants,
     "cpu_baseline": {"frames_per_s": 1 / cpu, "cores": 1, "kind": "numpy np.histogram weighted + count (reference call)"},
 }))
