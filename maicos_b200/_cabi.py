@@ -37,6 +37,7 @@ SIGNATURES = {
     "mb200_prefetch_frames": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "mb200_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mb200_host_free": (None, [ctypes.c_void_p]),
+    "mb200_host_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
     "mb200_sfactor_maxn": (ctypes.c_int, [c_double_p, ctypes.c_double, c_i32_p]),
     "mb200_structure_factor": (
         ctypes.c_int,
@@ -305,3 +306,11 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+def host_copy(dst: np.ndarray, src: np.ndarray, n_threads: int = 0) -> None:
+    """``dst[...] = src`` for C-contiguous arrays of the same dtype and size, copied by a few threads (GIL released)."""
+    if dst.nbytes != src.nbytes or dst.dtype != src.dtype or not (dst.flags.c_contiguous and src.flags.c_contiguous):
+        np.copyto(dst, src)
+        return
+    _check(load().mb200_host_copy(dst.ctypes.data, src.ctypes.data, dst.nbytes, int(n_threads)))

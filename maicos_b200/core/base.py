@@ -60,14 +60,33 @@ class Results(dict):
         return Results(self)
 
 
+def _is_arange(atomgroup, idx) -> bool:
+    """``idx`` is ``arange(idx[0], idx[-1] + 1)`` (checked once per atom group object)."""
+    cached = getattr(atomgroup, "_mb200_contiguous", None)
+    if cached is None or cached[0] != len(idx):
+        ok = bool(np.array_equal(idx, np.arange(int(idx[0]), int(idx[0]) + len(idx))))
+        cached = (len(idx), ok)
+        try:
+            atomgroup._mb200_contiguous = cached
+        except AttributeError:
+            pass
+    return cached[1]
+
+
 def positions_into(atomgroup, out: np.ndarray) -> np.ndarray:
     """Copy the current positions of ``atomgroup`` into ``out`` (one pass, no temporary)."""
     try:
         src = atomgroup.universe.trajectory.ts.positions
         idx = atomgroup.indices
-        if len(idx) == len(src) and (len(idx) == 0 or (idx[0] == 0 and idx[-1] == len(src) - 1 and
-                                                      getattr(atomgroup, "_all", False))):
-            np.copyto(out, src)
+        n = len(idx)
+        if n and int(idx[-1]) - int(idx[0]) == n - 1 and (getattr(atomgroup, "_all", False) or _is_arange(atomgroup, idx)):
+            block = src[int(idx[0]):int(idx[0]) + n]  # a contiguous run of atoms: one block copy
+            if n * 12 >= (1 << 20) and block.dtype == out.dtype:
+                from .. import _cabi
+
+                _cabi.host_copy(out, block)
+            else:
+                np.copyto(out, block)
         else:
             np.take(src, idx, axis=0, out=out)
     except (AttributeError, TypeError, ValueError):
@@ -177,11 +196,15 @@ class _Runner:
         trajectory = first._trajectory
         for slot in local:
             ts = trajectory[int(first.frames_selected[slot])]
-            ts_original = ts.copy() if len(analysis_instances) > 1 else None
+            # every analysis starts from the untouched frame; frames of the in-memory shim are copy-on-write views
+            # of the trajectory, so "untouched" is the view itself and nothing is copied unless an analysis transforms
+            shared = len(analysis_instances) > 1 and not ts.positions.flags.writeable
+            ts_original = ts.positions if shared else (ts.copy().positions if len(analysis_instances) > 1 else None)
             for a in analysis_instances:
-                if ts_original is not None:
-                    # every analysis starts from the untouched frame
-                    ts.positions[...] = ts_original.positions
+                if shared:
+                    ts.positions = ts_original
+                elif ts_original is not None:
+                    ts.positions[...] = ts_original
                 a._enqueue_frame(ts, int(slot))
         for a in analysis_instances:
             a._flush_staged()
@@ -297,11 +320,8 @@ class AnalysisBase(_Runner):
         """Slots (positions in the selected-frame list) this rank analyses."""
         slots = np.arange(self.n_frames)
         if parallel.frame_sharded():
-            if self.n_frames < parallel.world():
-                raise ValueError(
-                    f"{self.n_frames} frames cannot be sharded over {parallel.world()} ranks; "
-                    "use parallel.init(mode='qblocks') for single huge frames"
-                )
+            # fewer frames than ranks: the surplus ranks analyse nothing and join the final merge with n = 0
+            # (parallel.init(mode='qblocks') is the mode that spreads a single huge frame)
             slots = slots[parallel.rank()::parallel.world()]
         return slots
 
@@ -397,7 +417,8 @@ class AnalysisBase(_Runner):
         ):
             self._universe.atoms.wrap(compound=self.wrap_compound)
         if self.jitter != 0.0:
-            ts.positions += np.random.random(size=(len(ts.positions), 3)) * self.jitter
+            pos = ts.writable_positions() if hasattr(ts, "writable_positions") else ts.positions
+            pos += np.random.random(size=(len(pos), 3)) * self.jitter
 
     def _begin_frame(self, ts, slot: int) -> None:
         self._frame_index = slot
@@ -504,6 +525,18 @@ class AnalysisBase(_Runner):
             return
         mine = np.zeros(self.n_frames, dtype=bool)
         mine[self._local_frame_slots()] = True
+        # ranks without frames (more ranks than frames) take the observables' shapes from a rank that has some and
+        # enter the merge with n = 0
+        have = hasattr(self, "sums")
+        layout = parallel.share_layout(
+            {k: (np.shape(v), np.asarray(v).dtype.str) for k, v in self.sums.items()} if have else None)
+        if layout is None:
+            raise ValueError("No frame was analysed on any rank.")
+        if not have:
+            zeros = {k: np.zeros(shape, dtype=np.dtype(dt)) if shape else np.dtype(dt).type(0) for k, (shape, dt) in layout.items()}
+            self.sums = Results({k: np.copy(v) for k, v in zeros.items()})
+            self.means = Results({k: np.asarray(v, dtype=np.float64).copy() for k, v in zeros.items()})
+            self.sems = Results({k: np.asarray(v, dtype=np.float64).copy() for k, v in zeros.items()})
         dtypes = {k: np.asarray(v).dtype for k, v in self.sums.items()}
         extra = {
             "timeseries": np.where(mine, self.timeseries, 0.0),

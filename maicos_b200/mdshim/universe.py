@@ -46,6 +46,13 @@ class Timestep:
     def volume(self) -> float:
         return float(np.prod(self.dimensions[:3].astype(np.float64)))
 
+    def writable_positions(self) -> np.ndarray:
+        """``positions`` for in-place modification.  Frames of a :class:`MemoryTrajectory` alias the trajectory's
+        own storage (read-only view, no per-frame copy); the first transformation that writes takes a private copy."""
+        if not self.positions.flags.writeable:
+            self.positions = self.positions.copy()
+        return self.positions
+
     @property
     def n_atoms(self) -> int:
         return len(self.positions)
@@ -118,7 +125,15 @@ class MemoryTrajectory:
             f += self.n_frames
         if not 0 <= f < self.n_frames:
             raise IndexError(f"frame {f} out of range (0..{self.n_frames - 1})")
-        pos = self.frame_source(f) if self.coordinates is None else self.coordinates[f].copy()
+        if self.coordinates is None:
+            pos = self.frame_source(f)
+        else:  # copy-on-write: a read-only view until something modifies the frame (Timestep.writable_positions)
+            pos = self.coordinates[f]
+            if pos.flags.c_contiguous:
+                pos = pos.view()
+                pos.flags.writeable = False
+            else:
+                pos = pos.copy()
         vel = None if self.velocities is None else self.velocities[f].copy()
         dims = None if self.dimensions is None else np.array(self.dimensions[f], dtype=np.float32)
         t = self.times[f] if self.times is not None else f * self.dt
@@ -276,7 +291,7 @@ class AtomGroup:
 
     @positions.setter
     def positions(self, value):
-        self.universe.trajectory.ts.positions[self.indices] = value
+        self.universe.trajectory.ts.writable_positions()[self.indices] = value
 
     @property
     def velocities(self) -> np.ndarray:
@@ -293,9 +308,9 @@ class AtomGroup:
         ts = self.universe.trajectory.ts
         t = np.asarray(t, dtype=np.float32)
         if self._all:
-            ts.positions += t
+            ts.writable_positions()[...] += t
         else:
-            ts.positions[self.indices] += t
+            ts.writable_positions()[self.indices] += t
         return self
 
     # ---- selections -----------------------------------------------------------------------
@@ -399,7 +414,7 @@ class AtomGroup:
         """Move atoms (or whole compounds, by their centre of mass) into the primary cell, in place."""
         box = self._box()
         ts = self.universe.trajectory.ts
-        pos = ts.positions if self._all else ts.positions[self.indices]
+        pos = ts.writable_positions() if self._all else ts.positions[self.indices]
         if compound.lower() == "atoms":
             pos -= np.floor(pos / box) * box
         else:
@@ -409,14 +424,14 @@ class AtomGroup:
             shift = (-np.floor(com / box.astype(np.float64)) * box).astype(np.float32)
             pos += shift[ids]
         if not self._all:
-            ts.positions[self.indices] = pos
+            ts.writable_positions()[self.indices] = pos
         return pos
 
     def unwrap(self, compound: str = "fragments") -> np.ndarray:
         """Make compounds whole (minimum image about their first atom) and put their COM in the cell."""
         box = self._box()
         ts = self.universe.trajectory.ts
-        pos = ts.positions if self._all else ts.positions[self.indices]
+        pos = ts.writable_positions() if self._all else ts.positions[self.indices]
         ids = self._compound_ids(compound)
         first = np.full(int(ids.max()) + 1 if len(ids) else 0, -1, dtype=np.int64)
         order = np.arange(len(ids))[::-1]
@@ -426,5 +441,5 @@ class AtomGroup:
         delta -= box * np.round(delta / box)
         pos[...] = anchor + delta
         if not self._all:
-            ts.positions[self.indices] = pos
+            ts.writable_positions()[self.indices] = pos
         return self.wrap(compound=compound)

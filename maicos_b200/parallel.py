@@ -113,6 +113,24 @@ def barrier() -> None:
         dist.barrier()
 
 
+def share_layout(layout):
+    """First non-``None`` ``layout`` (a small picklable object) among the ranks.
+
+    A rank whose share of the frames is empty (more ranks than frames) has no observables to derive the packed
+    buffer of :func:`merge_welford` from; it adopts the layout of a rank that has.
+    """
+    if _state["world"] <= 1:
+        return layout
+    import torch.distributed as dist
+
+    gathered = [None] * _state["world"]
+    dist.all_gather_object(gathered, layout)
+    for item in gathered:
+        if item is not None:
+            return item
+    return None
+
+
 def merge_welford(n_local: int, means: dict, sems: dict, sums: dict, extra: dict[str, np.ndarray]):
     """Merge per-rank running statistics with ONE allreduce.
 

@@ -15,6 +15,7 @@ def main(out):
     parallel.init(mode="frames", backend="gloo")
     u = small_universe(n_frames=23)
     ana = Series(u.atoms).run(start=1, step=2)
+    few = Series(u.atoms).run(start=3, stop=5)  # two frames: with three ranks one of them has nothing to analyse
     # q-block style reduction of a per-frame partial sum
     buf = np.full(7, float(parallel.rank() + 1))
     parallel.allreduce_sum(buf)
@@ -22,7 +23,8 @@ def main(out):
         np.savez(out, mean=ana.means.observable, sem=ana.sems.observable, total=ana.sums.observable,
                  vec_mean=ana.means.vec, vec_sem=ana.sems.vec, count=ana.sums.count, frames=ana.frames,
                  times=ana.times, timeseries=ana.timeseries, index=ana._index, result=ana.results.mean,
-                 corrtime=ana.corrtime, buf=buf, world=parallel.world())
+                 corrtime=ana.corrtime, buf=buf, world=parallel.world(), few_mean=few.means.observable,
+                 few_sem=few.sems.observable, few_count=few.sums.count, few_index=few._index, few_vec=few.means.vec)
     parallel.barrier()
     parallel.shutdown()
 

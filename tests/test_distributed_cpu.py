@@ -6,6 +6,7 @@ import sys
 from pathlib import Path
 
 import numpy as np
+import pytest
 from numpy.testing import assert_allclose, assert_array_equal
 
 from maicos_b200 import parallel
@@ -33,16 +34,24 @@ def test_merge_welford_single_process_is_identity():
     assert_array_equal(ex["ts"], np.arange(5.0))
 
 
-def test_two_ranks_frame_sharding_matches_serial(tmp_path):
+@pytest.mark.parametrize("world", [2, 3])
+def test_ranks_frame_sharding_matches_serial(tmp_path, world):
     out = tmp_path / "dist.npz"
     env = dict(os.environ, OMP_NUM_THREADS="1")
     env.pop("WORLD_SIZE", None)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), str(HERE / "_dist_worker.py"), str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     d = np.load(out)
-    assert int(d["world"]) == 2
+    assert int(d["world"]) == world
+    # two frames on `world` ranks: with three ranks one has no frame and joins the merge with n = 0
+    few = Series(small_universe(n_frames=23).atoms).run(start=3, stop=5)
+    assert int(d["few_index"]) == few.n_frames == 2
+    assert_allclose(d["few_mean"], few.means.observable, rtol=1e-13)
+    assert_allclose(d["few_sem"], few.sems.observable, rtol=1e-10)
+    assert_allclose(d["few_vec"], few.means.vec, rtol=1e-13)
+    assert int(d["few_count"]) == few.sums.count
     serial = Series(small_universe(n_frames=23).atoms).run(start=1, step=2)
     assert int(d["index"]) == serial.n_frames == 11
     assert_array_equal(d["frames"], serial.frames)
@@ -56,4 +65,4 @@ def test_two_ranks_frame_sharding_matches_serial(tmp_path):
     assert int(d["count"]) == serial.sums.count  # integer observables stay exact
     assert_allclose(d["result"], serial.results.mean, rtol=1e-13)
     assert_allclose(d["corrtime"], serial.corrtime)
-    assert_array_equal(d["buf"], np.full(7, 3.0))
+    assert_array_equal(d["buf"], np.full(7, world * (world + 1) / 2.0))
