@@ -399,12 +399,24 @@ def path2_summary(ctx, lib, torch):
     e1.record(stream)
     torch.cuda.synchronize()
     sec = e0.elapsed_time(e1) / 10 * 1e-3
+    # the histogram kernel alone: CUDA events around it inside the call (mb200_ctx_stats out[5])
+    lib.mb200_ctx_set_timing(ctx.handle, 1)
+    ks = []
+    for _ in range(5):
+        call()
+        ks.append(ctx.stats()["contract_ns"] * 1e-9)
+    lib.mb200_ctx_set_timing(ctx.handle, 0)
+    ksec = float(np.median(ks))
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     peak = peaks.get("hbm_gbs", 6650.0)
     gbs = 12.0 * n * F / sec / 1e9
     return {"workload": f"weighted + count slab histogram, {n} atoms x {F} frames resident, {nb} bins",
             "frames_per_s": F / sec, "atoms_per_s": n * F / sec,
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+            "roofline": {"kernel": "k_hist_sorted", "bound": "hbm", "achieved": 12.0 * n * F / ksec / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": 12.0 * n * F / ksec / 1e9 / peak, "kernel_ms_per_launch": ksec * 1e3,
+                         "whole_call": {"achieved": gbs, "frac": gbs / peak, "ms_per_call": sec * 1e3,
+                                        "note": "call = edges upload + max|w| + histogram + merge kernels + per-frame results to host"},
+                         "co_limiter": "shared-memory atomic unit: one ATOMS lane per clock and SM (profiles/r01_hist_notes.md)",
                          "algorithmic_bytes_per_atom_frame": 12,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}}
 

@@ -81,7 +81,7 @@ def positions_into(atomgroup, out: np.ndarray) -> np.ndarray:
         n = len(idx)
         if n and int(idx[-1]) - int(idx[0]) == n - 1 and (getattr(atomgroup, "_all", False) or _is_arange(atomgroup, idx)):
             block = src[int(idx[0]):int(idx[0]) + n]  # a contiguous run of atoms: one block copy
-            if n * 12 >= (1 << 20) and block.dtype == out.dtype:
+            if n * 12 >= (1 << 22) and block.dtype == out.dtype:
                 from .. import _cabi
 
                 _cabi.host_copy(out, block)
@@ -394,6 +394,7 @@ class AnalysisBase(_Runner):
             logging.info(f"Using {self.n_bins} bins.")
         self.timeseries = np.zeros(self.n_frames)
         self._n_local = 0
+        self._n_flushed = 0
         self._staged = []
         self._inflight = None
         #: host-side time split of the last run: staging, waiting for the device, inside the C-ABI call
@@ -434,12 +435,19 @@ class AnalysisBase(_Runner):
             t0 = time.perf_counter()
             self._staged.append((slot, self._stage_frame()))
             self.timings["stage_s"] += time.perf_counter() - t0
-            if len(self._staged) >= max(1, self._batch_size):
+            if len(self._staged) >= self._flush_threshold():
                 self._flush_staged(wait=False)
         else:
             self._obs = Results()
             value = self._single_frame()
             self._accumulate(slot, value, self._obs)
+
+    def _flush_threshold(self) -> int:
+        """Frames per device call: the first two batches of a run are a quarter and a half of ``_batch_size`` so
+        that the device starts after a few staged frames instead of a whole batch (shorter pipeline fill)."""
+        b = max(1, self._batch_size)
+        k = getattr(self, "_n_flushed", 2)
+        return b if k >= 2 else max(1, b >> (2 - k))
 
     def _flush_staged(self, wait: bool = True) -> None:
         """Hand the staged frames to the device.
@@ -451,6 +459,7 @@ class AnalysisBase(_Runner):
         """
         if self._staged:
             staged, self._staged = self._staged, []
+            self._n_flushed = getattr(self, "_n_flushed", 0) + 1
             if self._pool is None:
                 from concurrent.futures import ThreadPoolExecutor
 

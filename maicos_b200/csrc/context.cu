@@ -144,7 +144,7 @@ extern "C" int mb200_host_copy(void *dst, const void *src, size_t bytes, int n_t
     if (!dst || !src) return fail(MB200_EINVAL, "null pointer in mb200_host_copy");
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     int nt = std::max(1, std::min<int>(n_threads > 0 ? n_threads : 4, (int)hw));
-    if (bytes < ((size_t)1 << 20)) nt = 1;
+    if (bytes < ((size_t)1 << 22)) nt = 1;
     if (nt == 1) {
         std::memcpy(dst, src, bytes);
         return MB200_OK;
