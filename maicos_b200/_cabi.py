@@ -166,7 +166,7 @@ class Context:
 
     def set_precision(self, mode: str) -> None:
         """``"i8x5"`` (default: split precision on the tcgen05 tensor cores) or ``"fp64"`` (FP64 DMMA)."""
-        _check(load().mb200_ctx_set_precision(self._h, {"fp64": 0, "i8x5": 1}[mode]))
+        _check(load().mb200_ctx_set_precision(self._h, {"fp64": 0, "i8x5": 1, "i8x5-smem": 2}[mode]))
 
     def set_hist_mode(self, mode: str) -> None:
         """Weighted-histogram kernel: ``"sorted"`` (default, one shared atomic per element) or ``"atomics"``."""

@@ -109,6 +109,7 @@ struct mb200_ctx {
     unsigned hs_attr_set = 0;  // k_hist_sorted<B> instantiations whose shared-memory limit is raised
     int hist_mode = 0;         // weighted histograms: 0 counting-sort kernel (default), 1 three-atomics kernel
     int precision = 1;        // 1: int8 x 5 split precision on tcgen05 (default)  0: FP64 DMMA
+    bool tc_a_tmem = true;    // split-precision kernel: generated A operand in tensor memory when the l tile allows it
     bool force_fp64 = false;  // this call must use the FP64 kernel (non-finite weights)
     int64_t launches = 0;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};

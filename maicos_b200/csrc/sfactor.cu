@@ -950,14 +950,22 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
     }
     if (!items.empty()) {
         if (!ctx->tc_attr_set) {
-            MB_CUDA(cudaFuncSetAttribute(k_sf_contract_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+            MB_CUDA(cudaFuncSetAttribute(k_sf_contract_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+            MB_CUDA(cudaFuncSetAttribute(k_sf_contract_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
             ctx->tc_attr_set = true;
         }
+        // l tiles of at most 32 values leave room in tensor memory for the generated A operand (sfactor_tc.cuh)
+        bool a_in_tmem = ctx->tc_a_tmem;
+        for (int s = 0; s < ns; ++s) a_in_tmem = a_in_tmem && specs[s].plan->tc_lt <= TC_ATM_MAX_LT;
         if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
         MB_CUDA(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
         const unsigned n_cta = (unsigned)std::min<size_t>(items.size(), (size_t)ctx->n_sm);
-        k_sf_contract_tc<<<n_cta, TC_THREADS, TC_SMEM, ctx->stream>>>(ctx->d_items.as<TcItem>(), (int)items.size(),
-                                                                     ctx->d_tcdesc.as<TcSeg>(), ctx->d_counter.as<int>());
+        if (a_in_tmem)
+            k_sf_contract_tc<true><<<n_cta, TC_THREADS, TC_SMEM, ctx->stream>>>(ctx->d_items.as<TcItem>(), (int)items.size(),
+                                                                               ctx->d_tcdesc.as<TcSeg>(), ctx->d_counter.as<int>());
+        else
+            k_sf_contract_tc<false><<<n_cta, TC_THREADS, TC_SMEM, ctx->stream>>>(ctx->d_items.as<TcItem>(), (int)items.size(),
+                                                                                ctx->d_tcdesc.as<TcSeg>(), ctx->d_counter.as<int>());
         MB_CUDA(cudaGetLastError());
         if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
         ++launched;
@@ -1141,8 +1149,9 @@ using namespace mb200;
 // ------------------------------------------------------------------------------------------
 extern "C" int mb200_ctx_set_precision(mb200_ctx *ctx, int mode) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
-    if (mode != 0 && mode != 1) return fail(MB200_EINVAL, "precision mode must be 0 (fp64) or 1 (i8x5 split precision)");
-    ctx->precision = mode;
+    if (mode < 0 || mode > 2) return fail(MB200_EINVAL, "precision mode must be 0 (fp64), 1 (i8x5 split precision) or 2 (i8x5, A operand in shared memory)");
+    ctx->precision = mode ? 1 : 0;
+    ctx->tc_a_tmem = mode != 2;
     return MB200_OK;
 }
 

@@ -84,6 +84,20 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t da, uint64_t db
                  "l"(da), "l"(db), "r"(idesc), "r"(acc)
                  : "memory");
 }
+// A operand from tensor memory (row = TMEM lane, four int8 along K per 32-bit column): tools/microbench/umma_i8_ts.cu
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+                 "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+// tcgen05.st.16x128b.x1: thread i of the warp writes r0 to (TMEM lane i / 4, column i % 4) and r1 to (lane i / 4 + 8,
+// column i % 4) of the 16-lane block at `addr` (tools/microbench/tmem_st_layout.cu)
+__device__ __forceinline__ void tc_st_16x128(uint32_t addr, uint32_t r0, uint32_t r1) {
+    asm volatile("tcgen05.st.sync.aligned.16x128b.x1.b32 [%0], {%1, %2};\n" ::"r"(addr), "r"(r0), "r"(r1) : "memory");
+}
+constexpr int TC_ATM_COL0 = 320;       // A-in-TMEM variant: accumulators in columns 0 .. 5 np - 1 (np <= 64), A stages behind
+constexpr int TC_ATM_MAX_LT = 32;
+
 // One lane of a converged warp (the compiler knows a single thread runs the guarded code: operands move to
 // uniform registers without a per-value loop).
 __device__ __forceinline__ bool tc_elect_one() {
@@ -95,6 +109,13 @@ __device__ __forceinline__ void tc_commit(unsigned long long *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ATM = true (l tiles of at most 32 values, i.e. np <= 64 accumulator columns per digit group): the generated A operand
+// goes to TENSOR MEMORY instead of shared memory -- tcgen05.st.16x128b from the generator registers, MMAs in the
+// "[d], [a], b-desc" form -- which takes the digit stores and the tensor core's A reads (358 of the ~830 wavefronts of a
+// K-step) off the shared-memory pipe.  Generator thread (L = lane / 4, pair = lane % 4 + 4 half) of the warp that owns
+// TMEM lane quarter `warp % 4` forms the same 4 rows x 2 atoms as before; row 4 o + r of quad o = 8 quarter + L lives in
+// TMEM lane 32 quarter + L + 8 r (the fragment layout of the store), and the epilogue undoes that permutation.
+template <bool ATM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__restrict__ segs, int *__restrict__ counter) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -113,8 +134,8 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_rows + 2 * TC_M);
     int *s_item = reinterpret_cast<int *>(s_tmem + 1);
     int *s_nseed = s_item + 1;                                                                   // [2] unique h, unique k0
-    int *s_task = s_nseed + 2;                                                                   // [1] generator task counter (+ pad)
-    uint8_t *s_quad = reinterpret_cast<uint8_t *>(s_task + 2);                                  // [32][2] quad -> seed row (x, y)
+    int *s_task = s_nseed + 2;                                                                   // [4] generator task counters
+    uint8_t *s_quad = reinterpret_cast<uint8_t *>(s_task + 4);                                  // [32][2] quad -> seed row (x, y)
     uint16_t *s_seedrow = reinterpret_cast<uint16_t *>(s_quad + 64);                             // [67] table row | axis << 15
     unsigned char *sSeed = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(s_seedrow + 68) + 127) & ~(uintptr_t)127);                  // [depth][n_seed rows][16 atoms] double2
@@ -138,7 +159,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
     for (;;) {
         if (tid == 0) {
             *s_item = atomicAdd(counter, 1);
-            *s_task = 0;
+            s_task[0] = s_task[1] = s_task[2] = s_task[3] = 0;
             for (int s = 0; s < 3 * TC_NSTG + 1 + 2 * TC_SEED_MAX; ++s) {  // re-arm: every item starts at phase 0
                 if (bars_live) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(a_full + s)) : "memory");
                 // a_full: one arrive per generator task; b_full / s_free / acc_done: 1; seed_full: one cp.async
@@ -187,7 +208,85 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
         const int seed_shift = seed_stage * 8 <= TC_SEED_BYTES ? 3 : seed_stage * 4 <= TC_SEED_BYTES ? 2 : 1;  // 8, 4 or 2 K-steps
         const int seed_depth = 1 << seed_shift;
 
-        if (is_gen) {
+        if (is_gen && ATM) {
+            // ---- generators, A in tensor memory: tasks (K-step t, column half) per TMEM lane quarter, handed out in
+            // order from the quarter's counter to the four warps that can reach it ----
+            const int qd = warp & 3, L = lane >> 2;
+            const int o = 8 * qd + L;  // quad of the item (rows 4 o .. 4 o + 3)
+            const int n_tasks = n_steps * 2;
+            const int rx = s_quad[2 * o], ry = s_quad[2 * o + 1], re1 = n_seed - 1;
+            for (;;) {
+                int task = 0;
+                if (lane == 0) task = atomicAdd(s_task + qd, 1);
+                task = __shfl_sync(0xffffffffu, task, 0);
+                if (task >= n_tasks) break;
+                const int t = task >> 1, ch = task & 1;
+                const int ap = (lane & 3) + 4 * ch;  // atom pair of the K-step = 32-bit column of the slice
+                // seed rows are rotated by four slots on odd rows (see the loader): the two quads of a quarter-warp read
+                // different bank halves when their rows differ in parity
+                const int sx = (rx * 16 + ((ap + 4 * (rx & 1)) & 7)) * 16, sy = (ry * 16 + ((ap + 4 * (ry & 1)) & 7)) * 16,
+                          se = (re1 * 16 + ((ap + 4 * (re1 & 1)) & 7)) * 16;
+                const int st = t & (TC_NSTG - 1), ss = t & (seed_depth - 1);
+                double2 e[3][2], p[2];
+                mbar_wait(seed_full + ss, (unsigned)(t >> seed_shift) & 1u);
+                {
+                    const unsigned char *sd = sSeed + ss * seed_stage;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const double2 x = *reinterpret_cast<const double2 *>(sd + sx + 128 * c);
+                        const double2 y = *reinterpret_cast<const double2 *>(sd + sy + 128 * c);
+                        const double2 e1 = *reinterpret_cast<const double2 *>(sd + se + 128 * c);
+                        p[c].x = x.x * y.x - x.y * y.y;
+                        p[c].y = x.x * y.y + x.y * y.x;
+                        e[0][c] = e1;
+                        e[1][c] = make_double2(e1.x * e1.x - e1.y * e1.y, 2.0 * e1.x * e1.y);
+                        e[2][c] = make_double2(e[1][c].x * e1.x - e[1][c].y * e1.y, e[1][c].x * e1.y + e[1][c].y * e1.x);
+                    }
+                }
+                if (t >= TC_NSTG) {
+                    mbar_wait(s_free + st, (unsigned)((t / TC_NSTG) - 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                }
+                const uint32_t a_dst = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(TC_ATM_COL0 + st * (TC_S * 8) + 4 * ch);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {  // rows r = 0, 1 -> TMEM lanes L, L + 8; r = 2, 3 -> L + 16, L + 24
+                    unsigned w[2][TC_S];
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int r = 2 * half + rr;
+                        unsigned long long b[4];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            double pr = p[c].x, pi = p[c].y;
+                            if (r > 0) {
+                                pr = p[c].x * e[r - 1][c].x - p[c].y * e[r - 1][c].y;
+                                pi = p[c].x * e[r - 1][c].y + p[c].y * e[r - 1][c].x;
+                            }
+                            b[2 * c] = (unsigned long long)__double_as_longlong(pr + TC_MAGIC);
+                            b[2 * c + 1] = (unsigned long long)__double_as_longlong(pi + TC_MAGIC);
+                        }
+                        const unsigned t0 = __byte_perm((unsigned)b[0], (unsigned)b[1], 0x5140), t1 = __byte_perm((unsigned)b[0], (unsigned)b[1], 0x7362),
+                                       t2 = __byte_perm((unsigned)b[2], (unsigned)b[3], 0x5140), t3 = __byte_perm((unsigned)b[2], (unsigned)b[3], 0x7362);
+                        const unsigned h0 = __byte_perm((unsigned)(b[0] >> 32), (unsigned)(b[1] >> 32), 0x0040),
+                                       h1 = __byte_perm((unsigned)(b[2] >> 32), (unsigned)(b[3] >> 32), 0x0040);
+                        w[rr][0] = __byte_perm(h0, h1, 0x5410) ^ 0x80808080u;
+                        w[rr][1] = __byte_perm(t1, t3, 0x7632) ^ 0x80808080u;
+                        w[rr][2] = __byte_perm(t1, t3, 0x5410) ^ 0x80808080u;
+                        w[rr][3] = __byte_perm(t0, t2, 0x7632) ^ 0x80808080u;
+                        w[rr][4] = __byte_perm(t0, t2, 0x5410) ^ 0x80808080u;
+                    }
+#pragma unroll
+                    for (int s = 0; s < TC_S; ++s) tc_st_16x128(a_dst + ((uint32_t)(16 * half) << 16) + (uint32_t)(8 * s), w[0][s], w[1][s]);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(a_full + st);
+                    mbar_arrive(seed_free + ss);
+                }
+            }
+        } else if (is_gen) {
             // ---- generators: thread (ap, o) -> atoms 2 ap, 2 ap + 1 of the K-step, rows 4 o .. 4 o + 3 ----
             // The plan pads every run of consecutive k to a multiple of four rows, so a quad is always one run
             // (h0, k0 .. k0 + 3):  P_r = (w Ex[h0] Ey[k0]) Ey[r], four independent products per atom (no recurrence
@@ -284,7 +383,8 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                 src[i] = seed_src(ri);
                 stp[i] = (s_seedrow[ri] & 0x8000) ? step_y : step_x;
             }
-            const int dst0 = (r0 * 16 + (a & 1) * 8 + (a >> 1)) * 16;  // row layout [atom parity][atom pair]: conflict-free reads
+            // row layout [atom parity][atom pair]: conflict-free reads; ATM: pairs rotated by four slots on odd rows
+            const int dst0 = (r0 * 16 + (a & 1) * 8 + (ATM ? (((a >> 1) + 4 * r0) & 7) : (a >> 1))) * 16;
             for (int t = 0; t < n_steps; ++t) {
                 const int ss = t & (seed_depth - 1);
                 if (t >= seed_depth) mbar_wait(seed_free + ss, (unsigned)((t >> seed_shift) - 1) & 1u);
@@ -329,7 +429,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                     m_a[i] = m_b[i] = m_d[i] = m_i[i] = 0;
                     if (s <= TC_S) {
                         const int t_hi = min(6 - s, t_lo + per - 1);
-                        m_a[i] = (uint32_t)((s - 1) * TC_A_SLICE) >> 4;
+                        m_a[i] = ATM ? (uint32_t)((s - 1) * 8) : (uint32_t)((s - 1) * TC_A_SLICE) >> 4;
                         m_b[i] = (uint32_t)((t_lo - 1) * np * 32) >> 4;
                         m_d[i] = (uint32_t)((s + t_lo - 2) * np);          // column block g = s + t
                         m_i[i] = tc_idesc((t_hi - t_lo + 1) * np) | (s > 1 ? 1u : 0u);  // bit 0 (masked off at issue):
@@ -351,7 +451,13 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                 if (tc_elect_one()) {
 #pragma unroll
                     for (int i = 0; i < 15; ++i)
-                        if (i < n_mma) tc_mma(tmem + m_d[i], da + m_a[i], db + m_b[i], m_i[i] & ~1u, t > 0 ? 1u : (m_i[i] & 1u));
+                        if (i < n_mma) {
+                            if (ATM)
+                                tc_mma_ts(tmem + m_d[i], tmem + (uint32_t)(TC_ATM_COL0 + st * (TC_S * 8)) + m_a[i], db + m_b[i], m_i[i] & ~1u,
+                                          t > 0 ? 1u : (m_i[i] & 1u));
+                            else
+                                tc_mma(tmem + m_d[i], da + m_a[i], db + m_b[i], m_i[i] & ~1u, t > 0 ? 1u : (m_i[i] & 1u));
+                        }
                     tc_commit(s_free + st);  // frees the A and B stage when these MMAs have read them
                 }
                 __syncwarp();
@@ -365,7 +471,8 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
         if (is_gen) {
             mbar_wait(acc_done, 0u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const int row = 32 * (warp & 3) + lane;
+            // ATM: TMEM lane 32 q + L + 8 r holds row 32 q + 4 L + r
+            const int row = 32 * (warp & 3) + (ATM ? 4 * (lane & 7) + (lane >> 3) : lane);
             const int n_tiles = sg.n_rt * sg.n_lt;
             double2 *out = sg.amp + (((size_t)it.split * n_tiles + (size_t)it.rt * sg.n_lt + it.lt) * TC_M + row) * lt_size;
             // column chunks of 16 (= 8 l values), dealt round robin to the four warps that share a lane quarter
@@ -402,7 +509,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-constexpr int TC_SMEM = TC_NSTG * (TC_S * TC_A_SLICE + TC_S * 2 * TC_MAX_LT * 32) + (3 * TC_NSTG + 1 + 2 * TC_SEED_MAX) * 8 + 2 * TC_M + 16 + 16 + 64 + 136 +
+constexpr int TC_SMEM = 16 + TC_NSTG * (TC_S * TC_A_SLICE + TC_S * 2 * TC_MAX_LT * 32) + (3 * TC_NSTG + 1 + 2 * TC_SEED_MAX) * 8 + 2 * TC_M + 16 + 16 + 64 + 136 +
                         128 + TC_SEED_BYTES + 1024;
 
 }  // namespace mb200
