@@ -229,6 +229,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                 const int st = t & (TC_NSTG - 1), ss = t & (seed_depth - 1);
                 double2 e[3][2], p[2];
                 mbar_wait(seed_full + ss, (unsigned)(t >> seed_shift) & 1u);
+                if (lane == 0) TC_STAMP((2 * qd + ch) * 3);
                 {
                     const unsigned char *sd = sSeed + ss * seed_stage;
 #pragma unroll
@@ -247,6 +248,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                     mbar_wait(s_free + st, (unsigned)((t / TC_NSTG) - 1) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 }
+                if (lane == 0) TC_STAMP((2 * qd + ch) * 3 + 1);
                 const uint32_t a_dst = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(TC_ATM_COL0 + st * (TC_S * 8) + 4 * ch);
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {  // rows r = 0, 1 -> TMEM lanes L, L + 8; r = 2, 3 -> L + 16, L + 24
@@ -284,6 +286,7 @@ k_sf_contract_tc(const TcItem *__restrict__ items, int n_items, const TcSeg *__r
                 if (lane == 0) {
                     mbar_arrive(a_full + st);
                     mbar_arrive(seed_free + ss);
+                    TC_STAMP((2 * qd + ch) * 3 + 2);
                 }
             }
         } else if (is_gen) {

@@ -34,3 +34,6 @@ print("commit(t) -> first generator past s_free wait of step t+4: mean %.0f min 
 for t in range(20, 32):
     print(t, "gen_seed", (gen_seed[t] - a_rdy[20]).tolist(), "\n   gen_free", (gen_free[t] - a_rdy[20]).tolist(), "\n   gen_done", (gen_done[t] - a_rdy[20]).tolist(),
           "\n   ctl ready,issued", int(a_rdy[t] - a_rdy[20]), int(issued[t] - a_rdy[20]))
+print("MMA warp per K-step (relative to step 20): operands seen, commit issued | first generator past the s_free wait of step t + 4")
+for t in range(20, 32):
+    print(t, int(T[t, 24] - a_rdy[20]), int(T[t, 26] - a_rdy[20]), "|", int(gen_free[t + 4].min() - a_rdy[20]))
