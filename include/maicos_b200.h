@@ -70,7 +70,9 @@ int mb200_ctx_set_timing(mb200_ctx *ctx, int enable);
  *   0  FP64 phase tables + FP64 DMMA (mma.sync m8n8k4) accumulation: ~1e-12 against the reference kernel.
  * Plans that cannot be tiled for the tensor cores (a reciprocal cube edge > 255) and calls with non-finite
  * weights use mode 0 automatically.  Weights of mb200_structure_factor[_block] are rescaled by an exact
- * power of two so that any finite weights are admissible in mode 1. */
+ * power of two so that any finite weights are admissible in mode 1.
+ *   2  as 1, but the generated operand always goes through shared memory (mode 1 writes it straight into tensor
+ *      memory when the l tiles of the plan have at most 32 values); same results bit for bit, for A/B measurements. */
 int mb200_ctx_set_precision(mb200_ctx *ctx, int mode);
 /* Total kernels launched by this context since creation. */
 int64_t mb200_ctx_launch_count(mb200_ctx *ctx);
