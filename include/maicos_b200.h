@@ -154,7 +154,7 @@ int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const double *we
                        double qmin, double qmax, int32_t n_bins, int32_t block, int32_t n_blocks,
                        double *s_binned, int64_t *bincount);
 
-/* Staging helper (host only): memcpy of `bytes` split over `n_threads` threads (<= 0: 4).  Used to move a frame from
+/* Staging helper (host only): memcpy of `bytes` split over `n_threads` threads (<= 0: 6).  Used to move a frame from
  * the trajectory reader's buffer (MDAnalysis `ts.positions`) into the pinned batch buffer faster than one core copies. */
 int mb200_host_copy(void *dst, const void *src, size_t bytes, int n_threads);
 

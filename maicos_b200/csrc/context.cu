@@ -143,7 +143,7 @@ extern "C" int mb200_host_copy(void *dst, const void *src, size_t bytes, int n_t
     if (bytes == 0) return MB200_OK;
     if (!dst || !src) return fail(MB200_EINVAL, "null pointer in mb200_host_copy");
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    int nt = std::max(1, std::min<int>(n_threads > 0 ? n_threads : 4, (int)hw));
+    int nt = std::max(1, std::min<int>(n_threads > 0 ? n_threads : 6, (int)hw));  // 6: best on the 16-core B200 hosts (tools/host_copy_bw.py)
     if (bytes < ((size_t)1 << 22)) nt = 1;
     if (nt == 1) {
         std::memcpy(dst, src, bytes);

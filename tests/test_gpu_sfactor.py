@@ -307,3 +307,33 @@ def test_batched_pipeline_is_independent_of_the_batch_size():
     assert_array_equal(got.timeseries, ref.timeseries)
     assert_array_equal(one.frames, [0, 2, 4, 6])
     assert_allclose(one.timeseries, ref.timeseries[::2], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("n,box,qmax", [
+    (1, (21.0, 22.0, 23.0), 2.0),           # one atom: every K-step but the first is padding
+    (17, (30.0, 30.0, 30.0), 3.0),          # ragged: 16 + 1 atoms
+    (4097, (25.0, 31.0, 37.0), 4.0),        # maxn up to 24: l tile of 24 values
+    (9000, (99.97, 99.97, 99.97), 2.0),     # the bench shape: maxn 32, l tile exactly 32 (the limit of the TMEM variant)
+    (3000, (103.0, 99.0, 104.0), 2.0),      # l extent 34 > 32: both settings take the shared-memory kernel
+])
+def test_tmem_operand_variant_bitwise_equals_shared_memory_variant(n, box, qmax, precision):
+    """Split-precision contraction with the generated A operand in tensor memory (default when the l tile has at most 32
+    values) vs the same arithmetic through shared memory: exact int32 accumulation, so the raw S cube is bit-identical."""
+    if precision != "i8x5":
+        pytest.skip("one arithmetic mode only")
+    from maicos_b200 import _cabi
+    rng = np.random.default_rng(n)
+    pos = rng.uniform(-3.0, 1.2 * max(box), (n, 3))
+    w = rng.normal(size=n)
+    ctx = _cabi.context(None)
+    try:
+        ctx.set_precision("i8x5-smem")
+        q0, s0 = structure_factor(pos, np.double(box), 0.0, qmax, 0.0, np.pi, w)
+        ctx.set_precision("i8x5")
+        q1, s1 = structure_factor(pos, np.double(box), 0.0, qmax, 0.0, np.pi, w)
+    finally:
+        ctx.set_precision("i8x5")
+    assert_array_equal(q1, q0)
+    assert_array_equal(s1, s0)
+    assert np.count_nonzero(s1) > 0
+    check(pos, np.double(box), 0.0, qmax, 0.0, np.pi, w)
