@@ -74,7 +74,7 @@ water = u.select_atoms("element O H")
 mb.DiporderPlanar(water, bin_width=0.1, unwrap=False, pack=False).run()  # warm-up (pinned staging, device buffers)
 a, dt = timed(lambda: mb.DiporderPlanar(water, bin_width=0.1, unwrap=False, pack=False).run())
 out["C4_diporderplanar_300k_mol"] = {"frames": a.n_frames, "frames_per_s": a.n_frames / dt, "n_bins": a.n_bins,
-                                     "timings": a.timings, "note": "COM + dipole per molecule on the host (numpy)"}
+                                     "timings": a.timings, "note": "unwrap-free water slab; COM + dipole per molecule formed on the device (mb200_compound_prologue)"}
 
 # ---- C5 ------------------------------------------------------------------------------------------
 n_mol = 333_333
