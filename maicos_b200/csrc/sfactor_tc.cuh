@@ -11,19 +11,22 @@
 //     MMAs "slice s of A" x "slices t = 1 .. 6 - s of B stacked along N" (N up to 256);
 //   * A = 16 * sum_g D_g * 256^-g in FP64 when an atom chunk (<= 8192 atoms, no int32 overflow) is flushed.
 //   Error: input quantisation 2^-39 and the dropped products (s + t >= 7, <= 2^-36 each) give |dA| ~ 1e-9 for
-//   1e5 atoms, i.e. ~1e-11 relative on binned S(q).  Single vanishing speckle cells of the raw cube can still
-//   exceed a relative 1e-6, so this is a separately selected mode (mb200_ctx_set_precision); the FP64 DMMA
-//   kernel stays the parity default and the only path of the raw-cube API.
+//   1e5 atoms: measured <= 5e-9 relative on EVERY nonzero cell of the raw S cube up to 1M atoms and ~1e-12 on binned
+//   S(q) (profiles/r01_tc_notes.md), against a stated tolerance of 1e-6 -- this is the default arithmetic
+//   (mb200_ctx_set_precision); the FP64 DMMA kernel stays selectable and takes the plans that cannot be tiled here.
 //
-// CTA = 8 generator warps + 1 control warp, one CTA per SM (512 TMEM columns):
-//   generators : thread (atom pair of the K-step, row quad o) walks 4 packed (h,k) rows for two atoms (two
-//                independent dependency chains, 32-bit stores); P = w Ex[h] Ey[k] is
-//                seeded from the FP64 tables at the start of a run of consecutive k and advanced by the
-//                recurrence P *= Ey[1] inside the run; digits are written as (re, im) byte pairs into the
-//                canonical K-major no-swizzle UMMA layout (cute ((8,n),2):((1,SBO),LBO), LBO = 128, SBO = 256);
-//   control    : lane 0 bulk-copies the pre-sliced Z image of the K-step (written by k_sf_tables) and issues the MMAs;
-//                tcgen05.commit frees the stage.  At the end of an item the generator warps read TMEM
-//                (tcgen05.ld), rescale and write the partial amplitudes that the usual finalisers consume.
+// CTA = 16 generator warps + MMA warp + seed loader warp + B loader warp, one CTA per SM (512 TMEM columns):
+//   generators : tasks (K-step, 4 row quads x 8 atom pairs) from a shared counter; thread = 2 atoms x the 4 packed (h,k)
+//                rows of a quad: P_r = (w Ex[h0] Ey[k0]) Ey[r] from the seed rows the loader warp keeps in a
+//                shared-memory ring; digits are written as (re, im) byte pairs either into the canonical K-major
+//                no-swizzle UMMA layout in shared memory (cute ((8,n),2):((1,SBO),LBO), SBO = 144, LBO = 2336) or --
+//                template parameter ATM, l tiles of at most 32 values -- straight into TENSOR MEMORY
+//                (tcgen05.st.16x128b; tasks per TMEM lane quarter);
+//   seed loader: 16-byte cp.async gathers of the item's distinct Ex[h0] / Ey[k0] rows and Ey[1], up to 8 K-steps ahead;
+//   B loader   : one bulk copy of the pre-sliced Z image of the K-step (written by k_sf_tables) per stage;
+//   MMA warp   : waits for A and B of the K-step, one elected lane issues its six MMAs and one tcgen05.commit that
+//                frees the stage.  At the end of an item the generator warps read TMEM (tcgen05.ld), rescale and
+//                write the partial amplitudes that the usual finalisers consume.
 #pragma once
 #include "sfactor_digits.cuh"
 
