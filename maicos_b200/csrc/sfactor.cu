@@ -478,6 +478,28 @@ __device__ __forceinline__ double s_of_entry(const SegDesc &sg, int e) {
     return re * re + im * im;
 }
 
+// Split-K partial amplitudes folded into slab 0, amp[0][i] = sum_s amp[s][i], in the fixed order of s_of_entry (the
+// result is bitwise the same).  For big frames (config 5: 123 slabs of 16 MB per segment) the finalisers' per-entry gathers
+// over all slabs cost more than the whole streaming pass: k_sf_binned 8.0 ms -> fold 0.5 ms + 0.3 ms.
+struct FoldDesc {
+    double2 *amp;
+    long long stride;  // elements per slab
+    int32_t n_split, pad;
+};
+__global__ void __launch_bounds__(256) k_sf_fold_splits(const FoldDesc *__restrict__ descs) {
+    const FoldDesc d = descs[blockIdx.y];
+    if (d.n_split < 2) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.stride; i += (long long)gridDim.x * blockDim.x) {
+        double re = 0.0, im = 0.0;
+        for (int sidx = 0; sidx < d.n_split; ++sidx) {
+            const double2 v = d.amp[(size_t)sidx * d.stride + i];
+            re += v.x;
+            im += v.y;
+        }
+        d.amp[i] = make_double2(re, im);
+    }
+}
+
 // compact S list: svals[seg][e]
 __global__ void __launch_bounds__(256) k_sf_svalues(const SegDesc *__restrict__ segs, double *__restrict__ svals,
                                                    int sval_stride) {
@@ -889,12 +911,19 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
     if (n_blocks > 1 || items.empty())
         MB_CUDA(cudaMemsetAsync(ctx->d_amp.p, 0, std::max<size_t>(amp_elems, 1) * 16, ctx->stream));
     std::vector<TcSeg> tsegs(ns);
+    std::vector<FoldDesc> folds(ns);
+    bool any_fold = false;
     for (int s = 0; s < ns; ++s) {
         SegSpec &sp = specs[s];
         const SfPlan &pl = *sp.plan;
         SegDesc &sd = segs_host[s];
         sd.ld = sp.job.ld; sd.n_split = n_split[s]; sd.n_wt = pl.n_wt; sd.n_valid = (int32_t)pl.cell.size();
         sd.amp_stride = (long long)pl.tc_n_rt * pl.tc_n_lt * TC_M * pl.tc_lt;
+        // many large slabs: fold them into slab 0 with one streaming pass (k_sf_fold_splits) before the finalisers gather
+        folds[s].stride = sd.amp_stride;
+        folds[s].n_split = (n_split[s] >= 2 && (size_t)n_split[s] * (size_t)sd.amp_stride * 16 >= ((size_t)96 << 20)) ? n_split[s] : 1;
+        folds[s].pad = 0;
+        if (folds[s].n_split > 1) { sd.n_split = 1; any_fold = true; }
         for (int a = 0; a < 3; ++a) sd.rows[a] = pl.rows[a];
         sd.tgs = nullptr;
         sd.ent_amp = pl.d_ent_amp_tc.as<int32_t>();
@@ -902,11 +931,12 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
         sd.ff2 = (sp.ff2_group >= 0 && pl.d_ff2.p) ? pl.d_ff2.as<double>() + (size_t)sp.ff2_group * sd.n_valid : nullptr;
         sd.ex = tab + off_x[s]; sd.ey = tab + off_y[s]; sd.ez = tab + off_z[s];
         sd.amp = ctx->d_amp.as<double2>() + off_amp[s];
+        folds[s].amp = sd.amp;
         sp.job.tab[0] = tab + off_x[s];
         sp.job.tab[1] = sp.share_yz_with >= 0 ? nullptr : tab + off_y[s];
         sp.job.tab[2] = sp.share_yz_with >= 0 ? nullptr : tab + off_z[s];
         if (sp.job.ld == 0 && amp_elems && n_blocks == 1 && !items.empty())
-            MB_CUDA(cudaMemsetAsync(sd.amp, 0, (size_t)sd.n_split * sd.amp_stride * 16, ctx->stream));
+            MB_CUDA(cudaMemsetAsync(sd.amp, 0, (size_t)n_split[s] * sd.amp_stride * 16, ctx->stream));
         TcSeg &ts = tsegs[s];
         ts.ex = sd.ex; ts.ey = sd.ey;
         ts.bimg = ctx->d_bimg.as<int8_t>() + off_img[s];
@@ -920,14 +950,16 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
         }
     }
     // ---- descriptors to the device through the pinned staging buffer
-    const size_t b_jobs = (size_t)ns * sizeof(TableJob), b_segs = (size_t)ns * sizeof(SegDesc), b_tsegs = (size_t)ns * sizeof(TcSeg),
-                 b_items = items.size() * sizeof(TcItem);
+    const size_t b_jobs = (size_t)ns * sizeof(TableJob), b_segs = (size_t)ns * sizeof(SegDesc),
+                 b_tsegs = ((size_t)ns * sizeof(TcSeg) + 15) / 16 * 16 + (size_t)ns * sizeof(FoldDesc),  // TcSeg[ns] | FoldDesc[ns]
+                 b_fold_off = ((size_t)ns * sizeof(TcSeg) + 15) / 16 * 16, b_items = items.size() * sizeof(TcItem);
     MB_TRY(ctx->h_stage.ensure(b_jobs + b_segs + b_tsegs + b_items + 64));
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
     char *hs = ctx->h_stage.as<char>();
     for (int s = 0; s < ns; ++s) std::memcpy(hs + (size_t)s * sizeof(TableJob), &specs[s].job, sizeof(TableJob));
     std::memcpy(hs + b_jobs, segs_host.data(), b_segs);
-    std::memcpy(hs + b_jobs + b_segs, tsegs.data(), b_tsegs);
+    std::memcpy(hs + b_jobs + b_segs, tsegs.data(), (size_t)ns * sizeof(TcSeg));
+    std::memcpy(hs + b_jobs + b_segs + b_fold_off, folds.data(), (size_t)ns * sizeof(FoldDesc));
     if (b_items) std::memcpy(hs + b_jobs + b_segs + b_tsegs, items.data(), b_items);
     MB_TRY(ctx->d_jobs.ensure(b_jobs));
     MB_TRY(ctx->d_segs.ensure(b_segs));
@@ -968,6 +1000,16 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
                                                                                 ctx->d_tcdesc.as<TcSeg>(), ctx->d_counter.as<int>());
         MB_CUDA(cudaGetLastError());
         if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        ++launched;
+    }
+    if (any_fold) {
+        long long max_stride = 0;
+        for (int s = 0; s < ns; ++s)
+            if (folds[s].n_split > 1) max_stride = std::max(max_stride, folds[s].stride);
+        const unsigned gx = (unsigned)std::min<long long>((max_stride + 255) / 256, (long long)ctx->n_sm * 8);
+        k_sf_fold_splits<<<dim3(gx, (unsigned)ns), 256, 0, ctx->stream>>>(
+            reinterpret_cast<const FoldDesc *>(ctx->d_tcdesc.as<char>() + b_fold_off));
+        MB_CUDA(cudaGetLastError());
         ++launched;
     }
     ctx->launches += launched;
