@@ -341,8 +341,11 @@ def main():
             "peak_source": "measured tcgen05 kind::i8 dense rate on this pool's B200, 148 CTAs x 128x256x32 MMAs from shared "
                            "memory (tools/microbench/umma_i8.cu, profiles/r01_umma_i8.log); nominal 4500",
             "algorithmic_int8_ops_per_atomq": I8_OPS_PER_ATOMQ,
-            "co_limiters": "shared-memory data pipe (operand reads of the MMAs + digit stores, ~73 % busy) and the digit "
-                           "generators' issue slots (~48 %): profiles/r01_tc_notes.md",
+            "kernel_variant": "k_sf_contract_tc<true>: generated A operand written to tensor memory (tcgen05.st), l tile <= 32",
+            "co_limiters": "no pipe is saturated (ncu: tensor 41 %, FP64 22 %, shared-memory pipe 42 %, issue slots 52 %): a K-step "
+                           "is paced by the MMA warp's serial loop -- ~620 cycles issuing six UTCIMMA (480 cycles of tensor work at "
+                           "N = 64 columns per digit slice) + ~550 cycles in two mbarrier try_waits; traces and the rejected "
+                           "variants in profiles/r01_tc_notes.md (session 4)",
             **common}
     line = {
         "metric": "saxs_atom_q_evals_per_s", "value": value, "unit": "atom*q/s", "n_gpus": world, "steps": K,
