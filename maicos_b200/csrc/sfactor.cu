@@ -103,6 +103,10 @@ struct TableJob {
     // table (sfactor_tc.cuh: [l tile][K-step][5 slices][2 L_t rows x 32 B], UMMA canonical K-major layout)
     int8_t *bimg;
     int32_t img_n_lt, img_lt, img_maxn;
+    // split-precision mode: the generators read only the seed rows of the y table (Ey[k0] of the row quads and Ey[1]);
+    // bit r of y_mask = row r is written (all rows when use_y_mask == 0).  The table kernel is HBM-write bound.
+    int32_t use_y_mask, pad_;
+    unsigned long long y_mask[4];
 };
 
 // ------------------------------------------------------------------------------------------
@@ -148,6 +152,8 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
     // split-precision mode, z axis: digits of Z = Ez[l] straight into the image of the tensor-core kernel, rows
     // 2 l (real part of A: (Zr, -Zi)) and 2 l + 1 (imaginary part: (Zi, Zr)) of l tile l / L_t, K position 2 (j % 16)
     const bool to_image = axis == 2 && jb.bimg != nullptr;
+    const bool masked = axis == 1 && jb.use_y_mask != 0;
+    auto wanted = [&](int r) -> bool { return !masked || ((jb.y_mask[(r >> 6) & 3] >> (r & 63)) & 1ull); };
     const int np = 2 * jb.img_lt;
     int8_t *img = nullptr;
     if (to_image) img = jb.bimg + (size_t)(j / TC_KA) * (size_t)(TC_S * np * 32) + tc_canon(0, 2 * (j % TC_KA));
@@ -172,7 +178,8 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
             for (int l = 0; l < jb.img_n_lt * jb.img_lt; ++l) put_image(l, 0.0, 0.0);
             return;
         }
-        for (int r = 0; r < rows; ++r) tab[tab_index(j, r, rows)] = make_double2(0.0, 0.0);
+        for (int r = 0; r < rows; ++r)
+            if (wanted(r)) tab[tab_index(j, r, rows)] = make_double2(0.0, 0.0);
         return;
     }
     const int64_t a = jb.index ? (int64_t)jb.index[j] : (int64_t)j;
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
         }
         if (to_image) {
             if (r < jb.img_maxn) put_image(r, cr, ci);  // the z axis never carries weights
-        } else {
+        } else if (wanted(r)) {
             tab[tab_index(j, r, rows)] = make_double2(w * cr, w * ci);
         }
         const double nr = cr * c1 - ci * s1;
@@ -570,6 +577,7 @@ struct SfPlan {
     int64_t n_mma_tiles = 0;  // valid 8x8 DMMA tiles
     // tensor-core (split precision) tiling: packed (h,k) rows in tiles of 128, l tiles of <= 48
     std::vector<uint8_t> tc_rows;       // [tc_n_rt * 128][2]
+    unsigned long long tc_ymask[4] = {0, 0, 0, 0};  // y-table rows the tensor-core generators read (k0 of every quad, row 1)
     std::vector<int32_t> ent_amp_tc;    // index into [tc_n_rt * tc_n_lt][128][tc_lt]
     int32_t tc_n_rt = 0, tc_n_lt = 0, tc_lt = 0, tc_n_pairs = 0;
     bool tc_ok = false;
@@ -747,6 +755,14 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
         pl->tc_n_pairs = (int32_t)(pl->tc_rows.size() / 2);
         pl->tc_n_rt = (pl->tc_n_pairs + TC_M - 1) / TC_M;
         pl->tc_rows.resize((size_t)pl->tc_n_rt * TC_M * 2, 0);
+        for (size_t o = 0; o + 7 < pl->tc_rows.size(); o += 8) {  // quad o / 8 starts at row 4 (o / 8): its k0
+            const int k0 = pl->tc_rows[o + 1];
+            pl->tc_ymask[k0 >> 6] |= 1ull << (k0 & 63);
+        }
+        {
+            const int r1 = std::min(1, std::max(0, (int)pl->rows[1] - 1));
+            pl->tc_ymask[r1 >> 6] |= 1ull << (r1 & 63);
+        }
         pl->tc_n_lt = (m2 + TC_MAX_LT - 1) / TC_MAX_LT;
         pl->tc_lt = (((m2 + pl->tc_n_lt - 1) / pl->tc_n_lt) + 7) / 8 * 8;
         pl->ent_amp_tc.resize(nv);
@@ -944,6 +960,8 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
         ts.amp = sd.amp;
         ts.rows0 = pl.rows[0]; ts.rows1 = pl.rows[1]; ts.ld = sp.job.ld;
         ts.n_rt = pl.tc_n_rt; ts.n_lt = pl.tc_n_lt; ts.lt_size = pl.tc_lt; ts.n_pairs = pl.tc_n_pairs; ts.n_split = n_split[s];
+        sp.job.use_y_mask = 1;
+        for (int i = 0; i < 4; ++i) sp.job.y_mask[i] = pl.tc_ymask[i];
         if (sp.share_yz_with < 0) {  // the z axis goes straight into the digit image (k_sf_tables)
             sp.job.bimg = ctx->d_bimg.as<int8_t>() + off_img[s];
             sp.job.img_n_lt = pl.tc_n_lt; sp.job.img_lt = pl.tc_lt; sp.job.img_maxn = pl.maxn[2];
@@ -1044,6 +1062,8 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
         const int ld = (sp.job.n + KT - 1) / KT * KT;
         sp.job.ld = ld;
         for (int a = 0; a < 3; ++a) sp.job.rows[a] = sp.plan->rows[a];
+        sp.job.use_y_mask = 0;  // the FP64 kernel reads every row
+        sp.job.bimg = nullptr;
         off_x[s] = tab_elems; tab_elems += (size_t)sp.plan->rows[0] * ld;
         if (sp.share_yz_with >= 0) {
             off_y[s] = off_y[sp.share_yz_with]; off_z[s] = off_z[sp.share_yz_with];
