@@ -283,7 +283,10 @@ def main():
     e2e = None
     if not args.no_e2e:
         def universe(n_frames, offset):
-            src = lambda f: pool[(offset + f) % len(pool)].copy()  # noqa: E731
+            def src(f):  # a frame of the in-memory pool as a read-only view (what MDAnalysis' MemoryReader hands out):
+                v = pool[(offset + f) % len(pool)].view()  # the one host copy of a frame is trajectory -> pinned staging
+                v.flags.writeable = False
+                return v
             traj = MemoryTrajectory(dimensions=np.float32([BOX, BOX, BOX, 90, 90, 90]), n_frames=n_frames,
                                     frame_source=src, n_atoms=n)
             return Universe(n, traj, **topo)

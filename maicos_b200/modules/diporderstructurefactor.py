@@ -105,15 +105,14 @@ class DiporderStructureFactor(AnalysisBase):
             parallel.allreduce_sum(packed)
             sb = packed[:sb.size].reshape(sb.shape)
             cb = np.rint(packed[sb.size:]).astype(np.int64).reshape(sb.shape)
-        out = []
-        for f in range(F):
-            total = np.zeros(self.n_bins)
-            for pdim in range(3):
-                with np.errstate(invalid="ignore", divide="ignore"):
-                    total += np.nan_to_num(sb[f, pdim] / cb[f, pdim])
-            total /= n
-            out.append(({"structure_factors": total}, total[-1]))
-        return out
+        # whole batch at once (this runs between two device calls): sum over pdim of nan_to_num(S / count), same order
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ratio = np.nan_to_num(sb / cb)
+        total = np.zeros((F, self.n_bins))
+        for pdim in range(3):
+            total += ratio[:, pdim]
+        total /= n
+        return [({"structure_factors": total[f]}, float(total[f, -1])) for f in range(F)]
 
     _single_frame = AnalysisBase._single_frame_from_batch
 
