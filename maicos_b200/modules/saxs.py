@@ -24,6 +24,25 @@ from ..lib import tables
 from ..lib.math import atomic_form_factor, structure_factor
 
 
+def _object_ids(objects: np.ndarray) -> np.ndarray:
+    """``id()`` of every entry of an object array.  In CPython ``id`` is the object's address and an object array stores
+    exactly those addresses, so the ids are the array's own buffer read as integers (microseconds instead of one Python
+    call per atom); any other interpreter / layout takes the generic route."""
+    try:
+        import ctypes
+        import sys
+
+        arr = np.ascontiguousarray(objects)
+        if sys.implementation.name == "cpython" and arr.dtype == object and arr.itemsize == ctypes.sizeof(ctypes.c_void_p) and len(arr):
+            raw = (ctypes.c_byte * arr.nbytes).from_address(arr.ctypes.data)
+            ids = np.frombuffer(raw, dtype=np.intp).astype(np.int64)
+            if ids[0] == id(arr[0]) and ids[-1] == id(arr[-1]):
+                return ids
+    except (TypeError, ValueError, AttributeError):
+        pass
+    return np.fromiter(map(id, objects), dtype=np.int64, count=len(objects))
+
+
 def _element_groups(atomgroup):
     """``(sorted unique element names, group id per atom)`` -- what ``np.unique(elements, return_inverse=True)`` gives.
 
@@ -39,8 +58,19 @@ def _element_groups(atomgroup):
     if ix is not None and key in cache:
         return cache[key]
     if elements.dtype == object and len(elements) > 4096:
-        ids = np.fromiter(map(id, elements), dtype=np.int64, count=len(elements))
-        _, first, inv = np.unique(ids, return_index=True, return_inverse=True)
+        ids = _object_ids(elements)
+        # a handful of distinct objects: peel them off one comparison pass at a time (np.unique sorts all atoms twice)
+        inv = np.full(len(ids), -1, dtype=np.int64)
+        first = []
+        while len(first) < 64:
+            todo = np.flatnonzero(inv < 0) if first else None
+            if todo is not None and len(todo) == 0:
+                break
+            i0 = 0 if todo is None else int(todo[0])
+            inv[ids == ids[i0]] = len(first)
+            first.append(i0)
+        if (inv < 0).any():  # many distinct string objects after all
+            _, first, inv = np.unique(ids, return_index=True, return_inverse=True)
         names = np.array([str(elements[i]) for i in first])
         unique, remap = np.unique(names, return_inverse=True)
         inverse = remap[inv]
