@@ -72,3 +72,43 @@ def test_reference_error_conventions():
         structure_factor(np.zeros((4, 2)), np.array([10.0, 10, 10]), 0, 2, 0, np.pi, np.ones(4))
     with pytest.raises(AssertionError):
         structure_factor(np.zeros((4, 3)), np.array([10.0, 10, 10]), 0, 2, 0, np.pi, np.ones(5))
+
+
+def test_library_sass_carries_the_claimed_instructions():
+    """The built library targets sm_100a and its hot kernels contain the instructions DESIGN.md names: tcgen05 int8 MMAs
+    (UTCIMMA) with one commit (UTCBAR), TMEM stores / loads (STTM / LDTM) and bulk copies (UBLKCP) in the split-precision
+    contraction, FP64 DMMA in the FP64 contraction, native shared-memory atomics in the histogram kernels."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    import maicos_b200
+
+    lib = Path(maicos_b200.__file__).parent / "_lib" / "libmaicos_b200.so"
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not lib.exists() or not Path(cuobjdump).exists():
+        pytest.skip("library or cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", str(lib)], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in out or "EF_CUDA_SM100" in out
+    kernels = {}
+    name = None
+    for line in out.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            kernels[name] = []
+        elif name is not None:
+            kernels[name].append(line)
+
+    def body(fragment):
+        hits = [k for k in kernels if fragment in k]
+        assert hits, f"no kernel named *{fragment}* in the library"
+        return "\n".join("\n".join(kernels[k]) for k in hits)
+
+    tc = body("k_sf_contract_tc")
+    for op in ("UTCIMMA", "UTCBAR", "LDTM", "UBLKCP", "SYNCS"):
+        assert op in tc, f"{op} missing from k_sf_contract_tc"
+    assert "STTM" in body("k_sf_contract_tcILb1"), "the TMEM-operand variant must store its A operand with tcgen05.st"
+    assert "DMMA" in body("13k_sf_contractE"), "FP64 contraction without DMMA"
+    assert "UBLKCP" in body("13k_sf_contractE"), "FP64 contraction without bulk-copy staging"
+    assert "ATOMS" in body("k_hist_sorted") and "ATOMS" in body("6k_histILi0")
+    assert "UBLKPF" in body("k_hist_sorted"), "the counting-sort histogram prefetches its next tile into L2 with a bulk prefetch"
