@@ -32,7 +32,8 @@ import numpy as np
 
 from .. import __version__, parallel
 from ..lib.math import center_cluster, new_mean, new_variance
-from ..lib.util import atomgroup_header, correlation_analysis, get_center, get_cli_input, get_module_input_str
+from ..lib.util import (atomgroup_header, correlation_analysis, get_center, get_cli_input, get_module_input_str,
+                        is_orthorhombic)
 
 _COMPATIBLE = (np.ndarray, float, int, list, np.float32, np.float64, np.int32, np.int64)
 _WRAP_COMPOUNDS = ["atoms", "group", "residues", "segments", "molecules", "fragments"]
@@ -414,7 +415,7 @@ class AnalysisBase(_Runner):
             com_refgroup = center_cluster(self.refgroup, self.ref_weights)
             self._universe.atoms.translate(self.box_center - com_refgroup)
         if self.pack and self._universe.dimensions is not None and not device_compounds and not (
-            self._device_pack and self.wrap_compound == "atoms"
+            self._device_pack and self.wrap_compound == "atoms" and is_orthorhombic(self._universe.dimensions)
         ):
             self._universe.atoms.wrap(compound=self.wrap_compound)
         if self.jitter != 0.0:

@@ -94,6 +94,8 @@ struct PinBuf {
     }
 };
 
+#define MB_LOCK(ctx) std::lock_guard<std::recursive_mutex> _mb_call_lock((ctx)->call_mutex)
+
 struct SfPlan;  // sfactor.cu
 const void *take_prefetched(mb200_ctx *ctx, const void *host, size_t bytes);  // context.cu
 
@@ -126,6 +128,14 @@ struct mb200_ctx {
     size_t pref_bytes[2] = {0, 0};
     int pref_next = 0;
     std::mutex pref_mutex;
+    // the device copy of a prefetch slot may be overwritten only after the call that consumed it has read it: recorded on
+    // the compute stream when the slot's last reader (k_sf_tables) has been queued, waited for by the copy stream
+    cudaEvent_t pref_done_ev[2] = {nullptr, nullptr};
+    bool pref_done_set[2] = {false, false};
+    int pref_taken = -1;  // slot taken by the compute call in progress (under call_mutex)
+    // Every compute entry point holds this for its whole duration: the workspaces above and the stream are shared by all
+    // callers of the context (several analysis instances each drive their own worker thread, AnalysisCollection).
+    std::recursive_mutex call_mutex;
     std::list<std::shared_ptr<mb200::SfPlan>> plans;  // small LRU cache keyed by box + q window
     ~mb200_ctx();
 };

@@ -15,6 +15,8 @@ mb200_ctx::~mb200_ctx() {
     if (ev1) cudaEventDestroy(ev1);
     for (int i = 0; i < 2; ++i)
         if (pref_ev[i]) cudaEventDestroy(pref_ev[i]);
+    for (int i = 0; i < 2; ++i)
+        if (pref_done_ev[i]) cudaEventDestroy(pref_done_ev[i]);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -52,6 +54,7 @@ extern "C" int mb200_ctx_create(int device, mb200_ctx **out) {
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->pref_ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->pref_done_ev[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete ctx;
         return fail(MB200_ECUDA, "context creation failed: %s", cudaGetErrorString(e));
@@ -69,6 +72,7 @@ extern "C" void mb200_ctx_destroy(mb200_ctx *ctx) {
 
 extern "C" int mb200_ctx_synchronize(mb200_ctx *ctx) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    MB_LOCK(ctx);
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
     return MB200_OK;
 }
@@ -97,6 +101,8 @@ extern "C" int mb200_prefetch_frames(mb200_ctx *ctx, const void *host_frames, si
     const int slot = ctx->pref_next;
     ctx->pref_next ^= 1;
     ctx->pref_src[slot] = nullptr;
+    if (ctx->pref_done_set[slot])  // the slot's previous content may still be read by a queued compute call
+        MB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pref_done_ev[slot], 0));
     MB_TRY(ctx->d_pref[slot].ensure(bytes));
     MB_CUDA(cudaMemcpyAsync(ctx->d_pref[slot].p, host_frames, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
     MB_CUDA(cudaEventRecord(ctx->pref_ev[slot], ctx->copy_stream));
@@ -114,6 +120,7 @@ const void *take_prefetched(mb200_ctx *ctx, const void *host, size_t bytes) {
         if (ctx->pref_src[slot] == host && ctx->pref_bytes[slot] >= bytes && host) {
             ctx->pref_src[slot] = nullptr;
             if (cudaStreamWaitEvent(ctx->stream, ctx->pref_ev[slot], 0) != cudaSuccess) return nullptr;
+            ctx->pref_taken = slot;
             return ctx->d_pref[slot].p;
         }
     return nullptr;

@@ -668,6 +668,7 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
                                   int weights_per_frame, int weights_on_device, const double *edges, int32_t n_bins,
                                   const double *center, const double *zrange, double *hist_w, int64_t *hist_c) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
     const int digitize = (geometry & MB200_BIN_DIGITIZE) ? 1 : 0;
     geometry &= ~MB200_BIN_DIGITIZE;
     if (geometry < 0 || geometry > 3 || n_frames < 0 || n < 0 || n_bins <= 0 || dim < 0 || dim > 2 || !edges || !hist_c ||

@@ -121,6 +121,7 @@ using namespace mb200;
 
 extern "C" int mb200_dev_alloc(mb200_ctx *ctx, size_t bytes, void **out) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    MB_LOCK(ctx);
     if (!out) return fail(MB200_EINVAL, "null output pointer");
     MB_CUDA(cudaSetDevice(ctx->device));
     *out = nullptr;
@@ -134,6 +135,7 @@ extern "C" int mb200_dev_alloc(mb200_ctx *ctx, size_t bytes, void **out) {
 
 extern "C" int mb200_dev_free(mb200_ctx *ctx, void *p) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    MB_LOCK(ctx);
     MB_CUDA(cudaSetDevice(ctx->device));
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (p) MB_CUDA(cudaFree(p));
@@ -142,6 +144,7 @@ extern "C" int mb200_dev_free(mb200_ctx *ctx, void *p) {
 
 extern "C" int mb200_dev_read(mb200_ctx *ctx, const void *dev, void *host, size_t bytes) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    MB_LOCK(ctx);
     MB_CUDA(cudaSetDevice(ctx->device));
     MB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -154,6 +157,7 @@ extern "C" int mb200_compound_prologue(mb200_ctx *ctx, const float *positions, i
                                        int make_whole, int wrap_center, int weight_mode, int pdim,
                                        double *centers_dev, double *weights_dev) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
     if (n_frames < 0 || n_atoms < 0 || n_c < 0 || !boxes || !compound_ptr || !centers_dev || (n_atoms && !positions) ||
         weight_mode < 0 || weight_mode > 4 || pdim < 0 || pdim > 2)
         return fail(MB200_EINVAL, "invalid argument to mb200_compound_prologue");
@@ -296,6 +300,7 @@ extern "C" int mb200_dielectric_prepare(mb200_ctx *ctx, const float *positions, 
                                         double *weights_dev) {
     using namespace mb200;
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
     if (n_frames < 0 || n_atoms < 0 || n_c < 0 || !compound_ptr || !charges || !coord_dev || (n_atoms && !positions) ||
         geometry < 0 || geometry > 1 || dim < 0 || dim > 2 || n_cut < 0 || n_cut > 2 ||
         (n_cut && (!cut_dims || !cut_bins || !cut_step || !weights_dev)) || (geometry == 1 && !center))

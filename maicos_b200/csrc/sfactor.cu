@@ -83,6 +83,7 @@ struct SegDesc {
     int32_t rows[3];               // table rows per axis (block stride = rows * 8 double2)
     int32_t pad_;
     long long amp_stride;          // double2 per split in `amp`
+    double s_scale;                // S = |A|^2 * s_scale: undoes the power-of-two rescaling of the weights (exact)
 };
 
 struct ItemDesc {
@@ -107,6 +108,9 @@ struct TableJob {
     // bit r of y_mask = row r is written (all rows when use_y_mask == 0).  The table kernel is HBM-write bound.
     int32_t use_y_mask, pad_;
     unsigned long long y_mask[4];
+    // weights are multiplied by this exact power of two before they enter the tables (split-precision mode works on
+    // entries in [-1, 1] with an ABSOLUTE quantisation of 2^-39: max|w| is brought into (0.5, 1])
+    double wscale;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
         double p = reinterpret_cast<const double *>(jb.pos)[a * jb.stride_atom + axis * jb.stride_xyz];
         u = p / jb.box[axis];
     }
-    const double w = (axis == 0 && jb.weights) ? jb.weights[j] : 1.0;
+    const double w = (axis == 0 && jb.weights) ? jb.weights[j] * jb.wscale : 1.0;
     double s1, c1;
     {
         double t = u - rint(u);
@@ -482,7 +486,7 @@ __device__ __forceinline__ double s_of_entry(const SegDesc &sg, int e) {
         re += v.x;
         im += v.y;
     }
-    return re * re + im * im;
+    return (re * re + im * im) * sg.s_scale;
 }
 
 // Split-K partial amplitudes folded into slab 0, amp[0][i] = sum_s amp[s][i], in the fixed order of s_of_entry (the
@@ -863,7 +867,42 @@ struct SegSpec {       // one contraction problem (one reference structure_facto
     TableJob job;       // table inputs (tab pointers filled by the engine)
     int share_yz_with;  // >= 0: reuse Ey/Ez tables of that earlier segment (same positions)
     int ff2_group;      // index into plan ff2, -1 none
+    double s_scale = 1.0;  // see SegDesc::s_scale
 };
+
+// max|w| of weight sets on the device, as the bit pattern of |w| (unsigned order: finite < inf < NaN)
+__global__ void __launch_bounds__(256) k_sf_wmax(const double *__restrict__ w, long long n, unsigned long long *__restrict__ out) {
+    const double *ws = w + (size_t)blockIdx.y * (size_t)n;
+    unsigned long long m = 0ull;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(ws[i]) & 0x7fffffffffffffffull;
+        m = b > m ? b : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_down_sync(0xffffffffu, m, o);
+        m = v > m ? v : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out + blockIdx.y, m);
+}
+
+// Power-of-two rescaling of a weight set with max|w| = wmax for the split-precision mode: w * wscale has its maximum in
+// (0.5, 1], S is multiplied back by s_scale = wscale^-2 (both exact).  false: the set cannot take that mode (non-finite
+// weights, or a scale whose square leaves the double range) and the call uses the FP64 kernel.
+static bool weight_scale(double wmax, double &wscale, double &s_scale) {
+    wscale = 1.0; s_scale = 1.0;
+    if (!(wmax <= 1.7e308)) return false;
+    if (wmax == 0.0) return true;
+    int ex = 0;
+    const double f = std::frexp(wmax, &ex);  // wmax = f * 2^ex, 0.5 <= f < 1
+    if (f == 0.5) --ex;                      // an exact power of two stays the maximum 1
+    if (ex == 0) return true;
+    if (ex > 480 || ex < -480) return false;
+    wscale = std::ldexp(1.0, -ex);
+    s_scale = std::ldexp(1.0, 2 * ex);
+    return true;
+}
+
 
 
 
@@ -954,6 +993,7 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
         SegDesc &sd = segs_host[s];
         sd.ld = sp.job.ld; sd.n_split = n_split[s]; sd.n_wt = pl.n_wt; sd.n_valid = (int32_t)pl.cell.size();
         sd.amp_stride = (long long)pl.tc_n_rt * pl.tc_n_lt * TC_M * pl.tc_lt;
+        sd.s_scale = sp.s_scale;
         // many large slabs: fold them into slab 0 with one streaming pass (k_sf_fold_splits) before the finalisers gather
         folds[s].stride = sd.amp_stride;
         folds[s].n_split = (n_split[s] >= 2 && (size_t)n_split[s] * (size_t)sd.amp_stride * 16 >= ((size_t)96 << 20)) ? n_split[s] : 1;
@@ -1121,6 +1161,7 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
         SegDesc &sd = segs_host[s];
         sd.ld = ld; sd.n_split = n_split; sd.n_wt = sp.plan->n_wt; sd.n_valid = (int32_t)sp.plan->cell.size();
         sd.amp_stride = (long long)sp.plan->n_wt * 512;
+        sd.s_scale = sp.s_scale;
         for (int a = 0; a < 3; ++a) sd.rows[a] = sp.plan->rows[a];
         sd.tgs = sp.plan->d_tgs.as<TileGroupDesc>();
         sd.ent_amp = sp.plan->d_ent_amp.as<int32_t>();
@@ -1248,6 +1289,7 @@ extern "C" int mb200_structure_factor_block(mb200_ctx *ctx, const double *positi
                                             const double *weights, int32_t block, int32_t n_blocks,
                                             double *scattering_vectors, double *structure_factors) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
     if (!dimensions || !scattering_vectors || !structure_factors || n_atoms < 0 || (n_atoms && (!positions || !weights)))
         return fail(MB200_EINVAL, "invalid argument to mb200_structure_factor");
     if (n_atoms > 2000000000LL) return fail(MB200_EINVAL, "too many atoms");
@@ -1268,30 +1310,22 @@ extern "C" int mb200_structure_factor_block(mb200_ctx *ctx, const double *positi
     double *hp = ctx->h_out.as<double>();
     for (size_t j = 0; j < n; ++j)
         for (int d = 0; d < 3; ++d) hp[j * 3 + d] = positions[(int64_t)j * stride_atom + d * stride_xyz];
-    // Split-precision mode works on table entries in [-1, 1]: the weights are divided by a power of two >= max|w|
-    // (exact) and S is multiplied back by its square (exact).  Non-finite weights take the FP64 kernel.
-    double wscale = 1.0;
+    // Split-precision mode works on table entries in [-1, 1] with an absolute quantisation: the weights are multiplied by
+    // the power of two that brings max|w| into (0.5, 1] (exact, applied by k_sf_tables) and S is multiplied back by its
+    // inverse square (exact, applied by the finalisers).  Non-finite weights take the FP64 kernel.
+    double wscale = 1.0, s_scale = 1.0;
     bool tc_weights = ctx->precision == 1;
     if (tc_weights) {
         double wmax = 0.0;
         for (size_t j = 0; j < n; ++j) {
             const double a = std::fabs(weights[j]);
-            if (!(a <= 1.7e308)) { tc_weights = false; break; }
+            if (!(a <= 1.7e308)) { wmax = a; break; }
             wmax = std::max(wmax, a);
         }
-        if (tc_weights && wmax > 1.0) {
-            int ex = 0;
-            std::frexp(wmax, &ex);  // wmax = f * 2^ex, 0.5 <= f < 1
-            wscale = std::ldexp(1.0, ex);
-        }
+        tc_weights = weight_scale(wmax, wscale, s_scale);
+        if (!tc_weights) { wscale = 1.0; s_scale = 1.0; }
     }
-    if (n) {
-        if (wscale == 1.0) std::memcpy(hp + n * 3, weights, n * 8);
-        else {
-            const double inv = 1.0 / wscale;
-            for (size_t j = 0; j < n; ++j) hp[n * 3 + j] = weights[j] * inv;
-        }
-    }
+    if (n) std::memcpy(hp + n * 3, weights, n * 8);
     MB_TRY(ctx->d_pos.ensure(std::max<size_t>(n, 1) * 32));
     if (n) MB_CUDA(cudaMemcpyAsync(ctx->d_pos.p, hp, n * 32, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -1299,11 +1333,13 @@ extern "C" int mb200_structure_factor_block(mb200_ctx *ctx, const double *positi
     SegSpec &sp = specs[0];
     sp.plan = plan.get(); sp.share_yz_with = -1; sp.ff2_group = -1;
     std::memset(&sp.job, 0, sizeof(TableJob));
+                sp.job.wscale = 1.0;
     sp.job.pos = ctx->d_pos.p; sp.job.index = nullptr;
     sp.job.weights = ctx->d_pos.as<double>() + n * 3;
     sp.job.stride_atom = 3; sp.job.stride_xyz = 1;
     for (int d = 0; d < 3; ++d) { sp.job.box[d] = dimensions[d]; sp.job.boxf[d] = (float)dimensions[d]; }
     sp.job.n = (int32_t)n; sp.job.is_f32 = 0; sp.job.wrap_mode = 0;
+    sp.job.wscale = wscale; sp.s_scale = s_scale;
     std::vector<SegDesc> segs;
     ctx->force_fp64 = !tc_weights;
     const int rc_seg = run_segments(ctx, specs, block, n_blocks, segs);
@@ -1318,8 +1354,7 @@ extern "C" int mb200_structure_factor_block(mb200_ctx *ctx, const double *positi
     MB_CUDA(cudaMemcpyAsync(hp, ctx->d_sval.p, nv * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
     MB_TRY(finish_timing(ctx));
-    const double s_scale = wscale * wscale;
-    for (size_t e = 0; e < nv; ++e) structure_factors[plan->cell[e]] = hp[e] * s_scale;
+    for (size_t e = 0; e < nv; ++e) structure_factors[plan->cell[e]] = hp[e];
     return MB200_OK;
 }
 
@@ -1338,6 +1373,7 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
                                  int32_t block, int32_t n_blocks, double *s_binned, double *i_binned,
                                  int64_t *bincount) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
     if (n_frames < 0 || n_groups < 0 || n_bins <= 0 || !boxes || !group_ptr || !cm_params || !s_binned || !i_binned ||
         !bincount || (n_atoms_total && !positions))
         return fail(MB200_EINVAL, "invalid argument to mb200_saxs_frames");
@@ -1403,6 +1439,7 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
                 SegSpec &sp = specs[f * n_groups + gi];
                 sp.plan = plans[f].get(); sp.share_yz_with = -1; sp.ff2_group = gi;
                 std::memset(&sp.job, 0, sizeof(TableJob));
+                sp.job.wscale = 1.0;
                 sp.job.pos = dpos + f * frame_elems;
                 sp.job.index = ctx->d_idx.as<int32_t>() + group_ptr[gi];
                 sp.job.weights = nullptr;
@@ -1431,6 +1468,12 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
         MB_TRY(finish_timing(ctx));
         done += chunk;
     }
+    if (ctx->pref_taken >= 0) {  // the prefetch slot this call read may be refilled from here on
+        std::lock_guard<std::mutex> lock(ctx->pref_mutex);
+        MB_CUDA(cudaEventRecord(ctx->pref_done_ev[ctx->pref_taken], ctx->stream));
+        ctx->pref_done_set[ctx->pref_taken] = true;
+        ctx->pref_taken = -1;
+    }
     return MB200_OK;
 }
 
@@ -1438,6 +1481,7 @@ extern "C" int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const
                                   int64_t n_frames, int64_t n, const double *boxes, double qmin, double qmax, int32_t n_bins,
                                   int32_t block, int32_t n_blocks, double *s_binned, int64_t *bincount) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
     if (n_frames < 0 || n < 0 || n_bins <= 0 || !boxes || !s_binned || !bincount || (n && (!positions || !weights)))
         return fail(MB200_EINVAL, "invalid argument to mb200_dipsf_frames");
     if (n_frames == 0) return MB200_OK;
@@ -1471,12 +1515,31 @@ extern "C" int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const
             MB_CUDA(cudaMemcpyAsync(dp, positions + done * nn * 3, chunk * nn * 24, cudaMemcpyHostToDevice, ctx->stream));
             MB_CUDA(cudaMemcpyAsync(dw, weights + done * nn * 3, chunk * nn * 24, cudaMemcpyHostToDevice, ctx->stream));
         }
+        // per (frame, component) max|w| -> power-of-two rescaling for the split-precision mode; a non-finite weight
+        // anywhere in the chunk (a zero dipole: mu / |mu| = NaN, the reference then returns NaN) sends it to FP64
+        std::vector<double> wsc(chunk * 3, 1.0), ssc(chunk * 3, 1.0);
+        bool tc_weights = ctx->precision == 1;
+        if (tc_weights && nn) {
+            MB_TRY(ctx->d_w.ensure(chunk * 3 * 8));
+            MB_TRY(ctx->h_out.ensure(chunk * 3 * 8 + 64));
+            MB_CUDA(cudaMemsetAsync(ctx->d_w.p, 0, chunk * 3 * 8, ctx->stream));
+            const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>((nn + 2047) / 2048, (size_t)ctx->n_sm * 8 / (chunk * 3) + 1));
+            k_sf_wmax<<<dim3(bx, (unsigned)(chunk * 3)), 256, 0, ctx->stream>>>(dw, (long long)nn, ctx->d_w.as<unsigned long long>());
+            MB_CUDA(cudaGetLastError());
+            ctx->launches += 1;
+            MB_CUDA(cudaMemcpyAsync(ctx->h_out.p, ctx->d_w.p, chunk * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MB_CUDA(cudaStreamSynchronize(ctx->stream));
+            const double *hm = ctx->h_out.as<double>();
+            for (size_t i = 0; i < chunk * 3 && tc_weights; ++i) tc_weights = weight_scale(hm[i], wsc[i], ssc[i]);
+        }
         std::vector<SegSpec> specs(chunk * 3);
         for (size_t f = 0; f < chunk; ++f)
             for (int c = 0; c < 3; ++c) {
                 SegSpec &sp = specs[f * 3 + c];
                 sp.plan = plans[f].get(); sp.share_yz_with = c == 0 ? -1 : (int)(f * 3); sp.ff2_group = -1;
                 std::memset(&sp.job, 0, sizeof(TableJob));
+                sp.job.wscale = tc_weights ? wsc[f * 3 + c] : 1.0;
+                sp.s_scale = tc_weights ? ssc[f * 3 + c] : 1.0;
                 sp.job.pos = dp + f * nn * 3; sp.job.index = nullptr;
                 sp.job.weights = dw + (f * 3 + c) * nn;
                 sp.job.stride_atom = 3; sp.job.stride_xyz = 1;
@@ -1484,7 +1547,10 @@ extern "C" int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const
                 sp.job.n = (int32_t)nn; sp.job.is_f32 = 0; sp.job.wrap_mode = 0;
             }
         std::vector<SegDesc> segs;
-        MB_TRY(run_segments(ctx, specs, block, n_blocks, segs));
+        ctx->force_fp64 = !tc_weights;
+        const int rc_seg = run_segments(ctx, specs, block, n_blocks, segs);
+        ctx->force_fp64 = false;
+        MB_TRY(rc_seg);
         const size_t ns = specs.size(), ob = ns * (size_t)n_bins;
         MB_TRY(ctx->d_out.ensure(ob * 16));
         double *d_s = ctx->d_out.as<double>();

@@ -20,6 +20,54 @@ import numpy as np
 from .math import correlation_time
 
 
+def triclinic_vectors(dimensions, dtype=np.float32) -> np.ndarray:
+    """Lower-triangular cell matrix of ``[lx, ly, lz, alpha, beta, gamma]`` (Å, degrees).
+
+    Restates ``MDAnalysis.lib.mdamath.triclinic_vectors`` (MDAnalysis >= 2.8.0, the reference's pinned dependency
+    ``pyproject.toml:63``; third party, not vendored): rows are the cell vectors a = (lx, 0, 0), b in the xy plane, c;
+    exact zeros for right angles, the zero matrix for an invalid cell, ``float32`` output like ``Timestep.dimensions``.
+    The reference takes its reciprocal lattice from the DIAGONAL of this matrix (``modules/saxs.py:169-176``,
+    ``modules/diporderstructurefactor.py:94``).
+    """
+    dim = np.asarray(dimensions, dtype=np.float64)
+    lx, ly, lz, alpha, beta, gamma = dim[:6]
+    if not (np.all(dim[:6] > 0.0) and alpha < 180.0 and beta < 180.0 and gamma < 180.0):
+        return np.zeros((3, 3), dtype=dtype)
+    if alpha == beta == gamma == 90.0:
+        return np.diag(dim[:3].astype(dtype, copy=False))
+    m = np.zeros((3, 3), dtype=np.float64)
+    m[0, 0] = lx
+    cos_alpha = 0.0 if alpha == 90.0 else np.cos(np.deg2rad(alpha))
+    cos_beta = 0.0 if beta == 90.0 else np.cos(np.deg2rad(beta))
+    if gamma == 90.0:
+        cos_gamma, sin_gamma = 0.0, 1.0
+    else:
+        g = np.deg2rad(gamma)
+        cos_gamma, sin_gamma = np.cos(g), np.sin(g)
+    m[1, 0] = ly * cos_gamma
+    m[1, 1] = ly * sin_gamma
+    m[2, 0] = lz * cos_beta
+    m[2, 1] = lz * (cos_alpha - cos_beta * cos_gamma) / sin_gamma
+    with np.errstate(invalid="ignore"):
+        m[2, 2] = np.sqrt(lz * lz - m[2, 0] ** 2 - m[2, 1] ** 2)
+    if m[2, 2] > 0.0:  # NaN or <= 0: two angles sum to no more than the third
+        return m.astype(dtype, copy=False)
+    return np.zeros((3, 3), dtype=dtype)
+
+
+def cell_diagonal(dimensions) -> np.ndarray:
+    """``np.diag(triclinic_vectors(dimensions))`` -- the box the S(q) modules work with (``saxs.py:176``)."""
+    dimensions = np.asarray(dimensions)
+    if dimensions.shape[-1] == 3:  # lengths only: an orthorhombic cell
+        return dimensions.astype(np.float32)
+    return np.diag(triclinic_vectors(dimensions))
+
+
+def is_orthorhombic(dimensions) -> bool:
+    dimensions = np.asarray(dimensions)
+    return dimensions.shape[-1] == 3 or bool(np.all(dimensions[3:6] == 90.0))
+
+
 def get_center(atomgroup, bin_method: str, compound: str) -> np.ndarray:
     """Per-compound centre: ``cog`` (geometry), ``com`` (mass) or ``coc`` (absolute charge)."""
     if bin_method == "cog":

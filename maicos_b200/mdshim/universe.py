@@ -408,6 +408,10 @@ class AtomGroup:
         dims = self.universe.dimensions
         if dims is None:
             raise ValueError("Universe has no dimensions")
+        if len(dims) >= 6 and not np.all(np.asarray(dims[3:6]) == 90.0):
+            raise NotImplementedError(
+                "the in-memory shim wraps / unwraps orthorhombic cells only; use pack=False, unwrap=False or an "
+                "MDAnalysis universe for triclinic cells")
         return dims[:3].astype(np.float32)
 
     def wrap(self, compound: str = "atoms") -> np.ndarray:

@@ -17,7 +17,7 @@ import numpy as np
 
 from .. import _cabi, parallel
 from ..core.base import AnalysisBase, CompoundPrologue, compound_runs, positions_into
-from ..lib.util import get_center
+from ..lib.util import cell_diagonal, get_center, is_orthorhombic
 
 
 class DiporderStructureFactor(AnalysisBase):
@@ -48,6 +48,7 @@ class DiporderStructureFactor(AnalysisBase):
         # centres and unit dipoles on the device when the compounds are eligible (contiguous, complete)
         self._prologue = None
         if (self.refgroup is None and not self.jitter and self.wrap_compound != "atoms"
+                and is_orthorhombic(self._universe.dimensions)  # the device prologue wraps orthorhombic cells
                 and compound_runs(self.atomgroup, self.wrap_compound) is not None):
             try:
                 self._prologue = CompoundPrologue(self.atomgroup, self.wrap_compound, self.bin_method,
@@ -58,7 +59,7 @@ class DiporderStructureFactor(AnalysisBase):
         self._batch_size = int(max(1, min(type(self)._batch_size, (128 << 20) // max(1, self.atomgroup.n_atoms * 12))))
 
     def _stage_frame(self):
-        box = np.double(np.array(self._ts.dimensions[:3], dtype=np.float32))
+        box = np.double(np.array(cell_diagonal(self._ts.dimensions), dtype=np.float32))  # diporderstructurefactor.py:94
         if self._prologue is not None:
             buf, row = self._staging_rows((self.atomgroup.n_atoms, 3), np.float32, "pos")
             positions_into(self.atomgroup, buf[row])

@@ -22,6 +22,7 @@ from .. import _cabi, parallel
 from ..core.base import AnalysisBase, positions_into
 from ..lib import tables
 from ..lib.math import atomic_form_factor, structure_factor
+from ..lib.util import cell_diagonal, is_orthorhombic
 
 
 def _object_ids(objects: np.ndarray) -> np.ndarray:
@@ -153,13 +154,13 @@ class Saxs(AnalysisBase):
         if self.bin_spectrum:
             self.n_bins = int(np.ceil((self.qmax - self.qmin) / self.dq))
         else:
-            self.box = np.asarray(self._universe.dimensions[:3])
+            self.box = cell_diagonal(self._universe.dimensions)
             self.scattering_vector_factors = 2 * np.pi / self.box
             self.max_n = np.ceil(self.qmax / self.scattering_vector_factors).astype(int)
 
     # ---- frame body ------------------------------------------------------------------------
     def _stage_frame(self):
-        box = np.array(self._ts.dimensions[:3], dtype=np.float32)
+        box = np.array(cell_diagonal(self._ts.dimensions), dtype=np.float32)  # saxs.py:176
         if not self.bin_spectrum and not np.all(box == self.box):
             raise ValueError(
                 f"Dimensions in frame {self._frame_index} are different from "
@@ -179,7 +180,9 @@ class Saxs(AnalysisBase):
         _cabi.check(_cabi.load().mb200_prefetch_frames(_cabi.context().handle, base, nbytes))
 
     def _device_packs(self) -> bool:
-        return bool(self.pack and self._universe.dimensions is not None)
+        # the kernel's pack is the orthorhombic ``x -= floor(x / L) L``; a triclinic cell is packed by the host
+        # (``atoms.wrap`` in ``_transform_frame``) before the frame is staged
+        return bool(self.pack and self._universe.dimensions is not None and is_orthorhombic(self._universe.dimensions))
 
     def _compute_staged(self, staged: list) -> list:
         if not self.bin_spectrum:

@@ -234,15 +234,52 @@ class RunningStats:
             self.sums[k] = self.sums[k] + x
 
 
+def box_diagonal(dimensions):
+    """``np.diag(mda.lib.mdamath.triclinic_vectors(ts.dimensions))`` (saxs.py:176, diporderstructurefactor.py:94).
+
+    MDAnalysis (>= 2.8.0, pyproject.toml:63) is a third-party dependency that is not in /root/reference; its published
+    construction puts a along x, b in the xy plane and c wherever the three angles require, in float64, and returns
+    float32.  The diagonal in closed form: (lx, ly sin(gamma), lz sqrt(1 - cos(beta)^2 - cy^2)) with
+    cy = (cos(alpha) - cos(beta) cos(gamma)) / sin(gamma); right angles use exact 0 / 1; an invalid cell gives zeros.
+    """
+    d = np.asarray(dimensions, dtype=np.float64)
+    if d.shape[-1] == 3:
+        return d.astype(np.float32)
+    lx, ly, lz, al, be, ga = d[:6]
+    if not (np.all(d[:6] > 0) and max(al, be, ga) < 180.0):
+        return np.zeros(3, dtype=np.float32)
+    if al == 90.0 and be == 90.0 and ga == 90.0:
+        return d[:3].astype(np.float32)
+    ca = 0.0 if al == 90.0 else np.cos(np.deg2rad(al))
+    cb = 0.0 if be == 90.0 else np.cos(np.deg2rad(be))
+    cg, sg = (0.0, 1.0) if ga == 90.0 else (np.cos(np.deg2rad(ga)), np.sin(np.deg2rad(ga)))
+    cx, cy = lz * cb, lz * (ca - cb * cg) / sg
+    with np.errstate(invalid="ignore"):
+        czz = np.sqrt(lz * lz - cx ** 2 - cy ** 2)
+    if not czz > 0.0:
+        return np.zeros(3, dtype=np.float32)
+    return np.array([lx, ly * sg, czz]).astype(np.float32)
+
+
 def run_saxs(frames, boxes, elements, qmin=0, qmax=6, dq=0.1, thetamin=0, thetamax=180, pack=True, sfactor=None):
     """``Saxs(ag, ...).run()`` restated end to end for in-memory frames (saxs.py:133-300 on top of
     core/base.py:417-499).  ``frames`` float32 [F, n, 3], ``boxes`` float32 [F, 3]."""
-    thetamin, thetamax = min(thetamin, thetamax) * np.pi / 180, max(thetamin, thetamax) * np.pi / 180  # :134-152
+    # saxs.py:136-137 assigns sequentially, so the second line sees the already replaced thetamin: swapped arguments
+    # (150, 30) become (30, 30), not (30, 150).  Kept as the reference has it.
+    thetamin = min(thetamin, thetamax)  # :136
+    thetamax = max(thetamin, thetamax)  # :137
+    for name, value in (("thetamin", thetamin), ("thetamax", thetamax)):  # :139-143
+        if value < 0 or value > 180:
+            raise ValueError(f"{name} ({value}°) has to between 0 and 180°.")
+    if thetamin > thetamax:  # :145-148 (unreachable after the two lines above; kept)
+        raise ValueError(f"thetamin ({thetamin}°) larger than thetamax ({thetamax}°).")
+    thetamin, thetamax = thetamin * np.pi / 180, thetamax * np.pi / 180  # :151-152
     n_bins = int(np.ceil((qmax - qmin) / dq))  # :167
     stats = RunningStats()
     series = []
     for pos, box in zip(frames, boxes):
         pos = np.asarray(pos, dtype=np.float32)
+        box = box_diagonal(box)  # saxs.py:176 (``boxes`` rows may be [lx, ly, lz] or full ``ts.dimensions``)
         if pack:  # base.py:446-448
             pos = wrap_atoms_f32(pos, box)
         obs, val = saxs_single_frame(pos, box, elements, qmin, qmax, thetamin, thetamax, n_bins, sfactor)
