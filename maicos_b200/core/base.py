@@ -192,26 +192,33 @@ class _Runner:
         for a in analysis_instances:
             a._call_prepare()
 
+        if progressbar_kwargs:
+            logging.getLogger(__name__).info("progressbar_kwargs are accepted for API compatibility and ignored "
+                                             "(frames are staged in batches; there is no per-frame progress bar).")
         first = analysis_instances[0]
         local = first._local_frame_slots()
         trajectory = first._trajectory
-        for slot in local:
-            ts = trajectory[int(first.frames_selected[slot])]
-            # every analysis starts from the untouched frame; frames of the in-memory shim are copy-on-write views
-            # of the trajectory, so "untouched" is the view itself and nothing is copied unless an analysis transforms
-            shared = len(analysis_instances) > 1 and not ts.positions.flags.writeable
-            ts_original = ts.positions if shared else (ts.copy().positions if len(analysis_instances) > 1 else None)
+        try:
+            for slot in local:
+                ts = trajectory[int(first.frames_selected[slot])]
+                # every analysis starts from the untouched frame; frames of the in-memory shim are copy-on-write views
+                # of the trajectory, so "untouched" is the view itself and nothing is copied unless an analysis transforms
+                shared = len(analysis_instances) > 1 and not ts.positions.flags.writeable
+                ts_original = ts.positions if shared else (ts.copy().positions if len(analysis_instances) > 1 else None)
+                for a in analysis_instances:
+                    if shared:
+                        ts.positions = ts_original
+                    elif ts_original is not None:
+                        ts.positions[...] = ts_original
+                    a._enqueue_frame(ts, int(slot))
             for a in analysis_instances:
-                if shared:
-                    ts.positions = ts_original
-                elif ts_original is not None:
-                    ts.positions[...] = ts_original
-                a._enqueue_frame(ts, int(slot))
-        for a in analysis_instances:
-            a._flush_staged()
-            a._merge_ranks()
-        for a in analysis_instances:
-            a._call_conclude()
+                a._flush_staged()
+                a._merge_ranks()
+            for a in analysis_instances:
+                a._call_conclude()
+        finally:
+            for a in analysis_instances:
+                a._release_run_resources()
         return self
 
 
@@ -524,17 +531,37 @@ class AnalysisBase(_Runner):
                 self.means[key] = new_mean(old_mean, x, n)
                 self.sems[key] = np.sqrt(new_variance(old_var, old_mean, self.means[key], x, n) / n)
                 self.sums[key] = self.sums[key] + x
-        if self.concfreq and n % self.concfreq == 0 and slot > 0 and not parallel.frame_sharded():
+        if self.concfreq and parallel.frame_sharded():
+            # frames are dealt round robin, so after n local frames the ranks together hold the first n * W frames of the
+            # selection: every `concfreq // W` local frames (while all ranks still have frames) the partial statistics
+            # are merged and concluded -- what a serial run shows at the same global frame count (base.py:496-499)
+            every = max(1, self.concfreq // parallel.world())
+            if n % every == 0 and n <= (self.n_frames // parallel.world()) // every * every:
+                self._sharded_checkpoint()
+        elif self.concfreq and n % self.concfreq == 0 and slot > 0:
             self._conclude()
             if self.module_has_save:
                 self.save()
+
+    def _sharded_checkpoint(self) -> None:
+        """``concfreq`` under frame sharding: Welford merge of the ranks' partial statistics (one allreduce),
+        ``_conclude`` + ``save`` on the merged state, then back to the rank-local state."""
+        keep = {k: getattr(self, k) for k in ("means", "sems", "sums", "timeseries", "frames", "times", "_index")}
+        keep = {k: (Results({kk: np.copy(vv) for kk, vv in v.items()}) if isinstance(v, dict) else np.copy(v))
+                for k, v in keep.items()}
+        self._merge_ranks()
+        self._conclude()
+        if self.module_has_save and parallel.rank() == 0:
+            self.save()
+        for k, v in keep.items():
+            setattr(self, k, v if isinstance(v, dict) or np.ndim(v) else v.item())
 
     def _merge_ranks(self) -> None:
         """Frame-sharded runs: merge the per-rank statistics with one allreduce."""
         if not parallel.frame_sharded():
             return
         mine = np.zeros(self.n_frames, dtype=bool)
-        mine[self._local_frame_slots()] = True
+        mine[self._local_frame_slots()[:self._n_local]] = True  # the frames analysed so far (all of them at the end)
         # ranks without frames (more ranks than frames) take the observables' shapes from a rank that has some and
         # enter the merge with n = 0
         have = hasattr(self, "sums")
@@ -571,6 +598,21 @@ class AnalysisBase(_Runner):
         self._conclude()
         if self.concfreq and self.module_has_save and parallel.rank() == 0:
             self.save()
+
+    def _release_run_resources(self) -> None:
+        """End of a run, also when a frame raised: wait for the batch in flight, stop the worker thread and hand the
+        pinned staging blocks (keyed by ``id(self)``) back, so that no later instance can be given a slot that a device
+        call still reads."""
+        fut, self._inflight = self._inflight, None
+        if fut is not None:
+            try:
+                fut.result()
+            except Exception:  # the original exception is already propagating
+                pass
+        self._staged = []
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         from .. import _cabi
 
         _cabi.release_pinned(self._slot_prefix())  # staging buffers live for one run

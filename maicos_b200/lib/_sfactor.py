@@ -85,5 +85,27 @@ def structure_factor(positions, dimensions, qmin, qmax, thetamin, thetamax, weig
     return q, s
 
 
+def sfactor_abs_error_bound(n_atoms: int, max_abs_weight: float = 1.0, precision: str = "i8x5") -> float:
+    r"""Worst-case absolute error of one complex amplitude :math:`A(\boldsymbol q) = \sum_k w_k e^{i q r_k}`.
+
+    ``S = |A|^2`` is what the kernel returns; its error is ``|dS| <= 2 |A| |dA| + |dA|^2``.  In the default
+    split-precision arithmetic every table entry is quantised to :math:`2^{-38}` *absolutely* (after ``max|w|`` has
+    been brought into ``(0.5, 1]`` by an exact power of two) and digit products below :math:`2^{-36}` are dropped:
+    per atom and amplitude component at most :math:`2^{-37}` (quantisation) + :math:`2^{-35}` (truncation), hence
+
+    .. math:: |dA| \le 16\, N\, 2^{-38}\, 2^{\lceil \log_2 \max|w| \rceil}.
+
+    On disordered input the errors add incoherently (measured :math:`\approx \sqrt N\,2^{-38}`, i.e. a relative error of
+    5e-9 on S where :math:`|A| \sim \sqrt N`); on a lattice the same few phase values repeat and the bound is what holds:
+    where amplitudes cancel (``|A|`` below the bound) the *relative* error of S is unbounded and the ``S != 0`` mask can
+    differ from the reference's, whose own rounding noise there is about ``N 2^-50`` (``tests/test_gpu_parity_r2.py``).
+    ``precision="fp64"``: FP64 tables and accumulation, about ``N 2^-50``.
+    """
+    n = float(max(int(n_atoms), 1))
+    w = float(max_abs_weight)
+    scale = 1.0 if not np.isfinite(w) or w <= 0 else 2.0 ** np.ceil(np.log2(w))
+    return (16.0 * n * 2.0 ** -38 if precision != "fp64" else n * 2.0 ** -50) * scale
+
+
 #: pre-v0.11 name of the same function (``CHANGELOG.rst:38-40``)
 compute_structure_factor = structure_factor

@@ -17,7 +17,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import tables
-from ._sfactor import compute_structure_factor, sfactor_maxn, structure_factor  # noqa: F401
+from ._sfactor import compute_structure_factor, sfactor_abs_error_bound, sfactor_maxn, structure_factor  # noqa: F401
 
 __all__ = [
     "structure_factor", "compute_structure_factor", "atomic_form_factor", "new_mean", "new_variance",

@@ -66,3 +66,13 @@ def test_ranks_frame_sharding_matches_serial(tmp_path, world):
     assert_allclose(d["result"], serial.results.mean, rtol=1e-13)
     assert_allclose(d["corrtime"], serial.corrtime)
     assert_array_equal(d["buf"], np.full(7, world * (world + 1) / 2.0))
+    # concfreq under frame sharding: partial results are merged and concluded every (concfreq // world) local frames,
+    # i.e. at the global frame counts a serial run with concfreq = (concfreq // world) * world concludes at
+    from _dist_worker import Checkpointed
+
+    every = max(1, 4 // world) * world
+    ser = Checkpointed(small_universe(n_frames=23).atoms, concfreq=every).run()
+    assert [c[0] for c in ser.log] == list(d["cp_index"]) and len(ser.log) == 23 // every + 1
+    assert_allclose(d["cp_mean"], [c[1] for c in ser.log], rtol=1e-13)
+    assert_allclose(d["cp_sem"], [c[2] for c in ser.log], rtol=1e-9)
+    assert_allclose(d["cp_vec"], np.stack([c[3] for c in ser.log]), rtol=1e-13)
