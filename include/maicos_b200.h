@@ -74,6 +74,12 @@ int mb200_ctx_set_timing(mb200_ctx *ctx, int enable);
  *   2  as 1, but the generated operand always goes through shared memory (mode 1 writes it straight into tensor
  *      memory when the l tiles of the plan have at most 32 values); same results bit for bit, for A/B measurements. */
 int mb200_ctx_set_precision(mb200_ctx *ctx, int mode);
+/* Peak probes of the pipes the roofline fractions of bench.py are quoted against, measured in the calling process
+ * (a few milliseconds each, best of three):
+ *   out[0] = tcgen05 kind::i8 dense rate in TOP/s (M = 128, N = 256, K = 32 from shared memory on every SM),
+ *   out[1] = FP64 DMMA rate in TFLOP/s (mma.sync m8n8k4), out[2] = device-to-device copy rate in GB/s
+ *   (read + write bytes of a 512 MiB copy), out[3] = 0 (reserved). */
+int mb200_probe_peaks(mb200_ctx *ctx, double out[4]);
 /* Total kernels launched by this context since creation. */
 int64_t mb200_ctx_launch_count(mb200_ctx *ctx);
 /* Announce the host buffer the NEXT mb200_saxs_frames call will read its positions from: the frames are copied to

@@ -32,6 +32,7 @@ SIGNATURES = {
     "mb200_ctx_stats": (ctypes.c_int, [ctypes.c_void_p, c_i64_p]),
     "mb200_ctx_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "mb200_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "mb200_probe_peaks": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "mb200_ctx_set_precision": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "mb200_ctx_set_hist_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "mb200_prefetch_frames": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
@@ -171,6 +172,12 @@ class Context:
     def set_hist_mode(self, mode: str) -> None:
         """Weighted-histogram kernel: ``"sorted"`` (default, one shared atomic per element) or ``"atomics"``."""
         _check(load().mb200_ctx_set_hist_mode(self._h, {"sorted": 0, "atomics": 1}[mode]))
+
+    def probe_peaks(self) -> dict:
+        """Measured ceilings of this device, in this process: ``i8_tops``, ``fp64_dmma_tflops``, ``hbm_copy_gbs``."""
+        out = (ctypes.c_double * 4)()
+        _check(load().mb200_probe_peaks(self._h, out))
+        return {"i8_tops": float(out[0]), "fp64_dmma_tflops": float(out[1]), "hbm_copy_gbs": float(out[2])}
 
     def launch_count(self) -> int:
         return int(load().mb200_ctx_launch_count(self._h))

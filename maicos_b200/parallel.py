@@ -18,6 +18,7 @@ are used directly (``SURVEY.md`` section 8(e)):
 
 from __future__ import annotations
 
+import contextlib
 import os
 
 import numpy as np
@@ -52,6 +53,25 @@ def init(mode: str = "frames", backend: str | None = None) -> None:
         else:
             dist.init_process_group(backend=backend)
     _state.update(initialised=True, rank=dist.get_rank(), world=dist.get_world_size(), backend=backend)
+
+
+def set_mode(mode: str) -> None:
+    """Switch the sharding axis of an initialised process group (``"frames"`` or ``"qblocks"``)."""
+    if mode not in ("frames", "qblocks"):
+        raise ValueError("mode must be 'frames' or 'qblocks'")
+    _state["mode"] = mode
+
+
+@contextlib.contextmanager
+def local_only():
+    """Inside the block this rank behaves like a single-process run (no sharding, no collectives) -- for work that one
+    rank does on its own while the group exists, e.g. a reference result to compare a sharded one with."""
+    keep = (_state["rank"], _state["world"])
+    _state["rank"], _state["world"] = 0, 1
+    try:
+        yield
+    finally:
+        _state["rank"], _state["world"] = keep
 
 
 def shutdown() -> None:

@@ -77,6 +77,14 @@ def _load_port():
             ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, dp, dp, dp,
         ]
         lib.oracle_structure_factor.restype = None
+        lib.oracle_structure_factor_slab.argtypes = [
+            dp, ctypes.c_ssize_t, ctypes.c_ssize_t, ctypes.c_ssize_t, dp,
+            ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, dp, ctypes.c_int32, ctypes.c_int32, dp, dp,
+        ]
+        lib.oracle_structure_factor_slab.restype = None
+        lib.oracle_set_threads.argtypes = [ctypes.c_int]
+        lib.oracle_set_threads.restype = None
+        lib.oracle_get_threads.restype = ctypes.c_int
         _port_lib = lib
     return _port_lib
 
@@ -113,6 +121,20 @@ def port_structure_factor(positions, dimensions, qmin, qmax, thetamin, thetamax,
     return q, s
 
 
+def port_structure_factor_slab(positions, dimensions, qmin, qmax, thetamin, thetamax, weights, h0, h1):
+    """The port restricted to Miller indices ``h0 <= h < h1`` (full-size parity checks on a slab of the cube)."""
+    lib = _load_port()
+    pos = np.ascontiguousarray(positions, dtype=np.float64)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    dims = np.ascontiguousarray(dimensions, dtype=np.float64)
+    maxn = port_maxn(dims, qmax)
+    q = np.empty(tuple(int(m) for m in maxn), dtype=np.float64)
+    s = np.empty_like(q)
+    lib.oracle_structure_factor_slab(_dp(pos), 3, 1, pos.shape[0], _dp(dims), float(qmin), float(qmax), float(thetamin),
+                                     float(thetamax), _dp(w), int(h0), int(h1), _dp(q), _dp(s))
+    return q, s
+
+
 def structure_factor(positions, dimensions, qmin, qmax, thetamin, thetamax, weights):
     """Best available CPU kernel: the compiled reference if present, else the port."""
     if have_reference():
@@ -128,5 +150,12 @@ def kind() -> str:
 
 
 def n_threads() -> int:
-    v = os.environ.get("OMP_NUM_THREADS")
-    return int(v) if v else (os.cpu_count() or 1)
+    """Size of the OpenMP pool both kernels run on (they share the process' libgomp)."""
+    return int(_load_port().oracle_get_threads())
+
+
+def set_threads(n: int | None = None) -> int:
+    """Give the OpenMP pool ``n`` threads (default: every core).  ``torch.distributed.run`` exports
+    ``OMP_NUM_THREADS=1`` to its workers, which would time the reference on one core."""
+    _load_port().oracle_set_threads(int(n or os.cpu_count() or 1))
+    return n_threads()

@@ -31,13 +31,15 @@ void oracle_sfactor_maxn(const double *dimensions, double qmax, int32_t *maxn) {
     }
 }
 
-/* _cmath.pyx:98-124.  positions is [n_atoms][3] with arbitrary element strides (in
- * doubles), outputs are dense C-contiguous [maxn0][maxn1][maxn2], zero where rejected. */
-void oracle_structure_factor(const double *positions, ptrdiff_t stride_atom, ptrdiff_t stride_xyz,
-                             ptrdiff_t n_atoms, const double *dimensions, double qmin,
-                             double qmax, double thetamin, double thetamax,
-                             const double *weights, double *scattering_vectors,
-                             double *structure_factors) {
+/* _cmath.pyx:98-124, restricted to the h-slab h0 <= h < h1 of the reciprocal cube (the full call is the slab
+ * [0, maxn0)); cells outside the slab stay zero.  positions is [n_atoms][3] with arbitrary element strides (in
+ * doubles), outputs are dense C-contiguous [maxn0][maxn1][maxn2], zero where rejected.  Cells are independent, so the
+ * (h, k) loops are shared among the threads (the reference's prange runs over h alone, :101). */
+void oracle_structure_factor_slab(const double *positions, ptrdiff_t stride_atom, ptrdiff_t stride_xyz,
+                                  ptrdiff_t n_atoms, const double *dimensions, double qmin,
+                                  double qmax, double thetamin, double thetamax,
+                                  const double *weights, int32_t h0, int32_t h1,
+                                  double *scattering_vectors, double *structure_factors) {
     int32_t maxn[3];
     double q_factor[3];
     oracle_sfactor_maxn(dimensions, qmax, maxn);
@@ -45,12 +47,13 @@ void oracle_structure_factor(const double *positions, ptrdiff_t stride_atom, ptr
     size_t cells = (size_t)maxn[0] * maxn[1] * maxn[2];
     memset(scattering_vectors, 0, cells * sizeof(double));
     memset(structure_factors, 0, cells * sizeof(double));
+    if (h0 < 0) h0 = 0;
+    if (h1 > maxn[0]) h1 = maxn[0];
 
-    /* _cmath.pyx:101 prange over h */
-#pragma omp parallel for schedule(static)
-    for (int h = 0; h < maxn[0]; ++h) {
-        double qx = h * q_factor[0];
+#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+    for (int h = h0; h < h1; ++h) {
         for (int k = 0; k < maxn[1]; ++k) {
+            double qx = h * q_factor[0];
             double qy = k * q_factor[1];
             for (int l = 0; l < maxn[2]; ++l) {
                 if (h + k + l == 0) continue;                      /* :108 */
@@ -73,3 +76,22 @@ void oracle_structure_factor(const double *positions, ptrdiff_t stride_atom, ptr
         }
     }
 }
+
+void oracle_structure_factor(const double *positions, ptrdiff_t stride_atom, ptrdiff_t stride_xyz,
+                             ptrdiff_t n_atoms, const double *dimensions, double qmin,
+                             double qmax, double thetamin, double thetamax,
+                             const double *weights, double *scattering_vectors,
+                             double *structure_factors) {
+    oracle_structure_factor_slab(positions, stride_atom, stride_xyz, n_atoms, dimensions, qmin, qmax, thetamin,
+                                 thetamax, weights, 0, INT32_MAX, scattering_vectors, structure_factors);
+}
+
+/* OpenMP pool size of this process (bench.py: torchrun exports OMP_NUM_THREADS=1 to its workers). */
+#ifdef _OPENMP
+#include <omp.h>
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_get_threads(void) { return omp_get_max_threads(); }
+#else
+void oracle_set_threads(int n) { (void)n; }
+int oracle_get_threads(void) { return 1; }
+#endif
