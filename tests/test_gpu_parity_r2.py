@@ -272,3 +272,75 @@ def test_device_compound_prologue_against_oracle(bin_method):
             # tighter: everything downstream of the (float32) whole-molecule coordinates is float64
             assert np.median(np.abs(centres[f] - c_ref)) < 1e-6
         cen.free(); wts.free()
+
+
+# ---- several analyses sharing one context (round-1 ADVICE, high) ------------------------------------------------
+def test_collection_of_batched_and_unbatched_members_equals_solo_runs():
+    """Saxs + DensityPlanar + DiporderPlanar (batched, each with its own worker thread) and DielectricPlanar (device calls
+    from the main thread) over 96 frames in ONE AnalysisCollection: the members interleave their calls on the shared
+    context (one stream, shared workspaces) -- results must equal the members' solo runs bit for bit."""
+    fr, topo = mb.synthetic.confined_slab_frames(1200, 300, 30.0, 30.0, 40.0, 24.0, 7, n_frames=96)
+    from maicos_b200.mdshim import MemoryTrajectory, Universe
+
+    def universe():
+        return Universe(fr.shape[1], MemoryTrajectory(fr.copy(), np.float32([30, 30, 40, 90, 90, 90])), **topo)
+
+    def members(u):
+        water = u.select_atoms("element O H")
+        return [mb.Saxs(u.atoms, qmax=2.0, dq=0.1),
+                mb.DensityPlanar(water, dens="mass", bin_width=0.2, unwrap=False, pack=False),
+                mb.DiporderPlanar(water, bin_width=0.5, unwrap=False, pack=False),
+                mb.DielectricPlanar(water, bin_width=0.5, unwrap=False, pack=False),
+                mb.DensitySphere(water, dens="number", bin_width=0.5, unwrap=False, pack=False)]
+
+    for m in members(universe()):
+        m._batch_size = 8  # many small batches: flushes of different members overlap all the time
+    together = members(universe())
+    for m in together:
+        m._batch_size = 8
+    type(together[0])._batch_size, keep = 8, type(together[0])._batch_size
+    try:
+        mb.AnalysisCollection(*together).run()
+        solo = members(universe())
+        for m in solo:
+            m.run()
+    finally:
+        type(together[0])._batch_size = keep
+    for a, b in zip(together, solo):
+        for key in b.sums:
+            assert_array_equal(np.asarray(a.sums[key]), np.asarray(b.sums[key]), err_msg=f"{type(a).__name__}.{key}")
+        for key in b.means:
+            assert_array_equal(np.asarray(a.means[key]), np.asarray(b.means[key]), err_msg=f"{type(a).__name__}.{key}")
+
+
+# ---- repeatability stress (compute-sanitizer is not available on the pool) ------------------------------------
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 255, 4097, 20011])
+def test_contraction_is_bitwise_repeatable_on_ragged_sizes(n, precision):
+    """Every launch of the contraction hands out items dynamically; split-K partials are summed in a fixed order, so the
+    result must not depend on scheduling: 60 repeats per size, bit-identical.  (racecheck stand-in)"""
+    rng = np.random.default_rng(n)
+    pos = rng.uniform(0, 33, (n, 3))
+    w = rng.normal(size=n)
+    box = np.array([33.0, 34.0, 35.0])
+    q0, s0 = structure_factor(pos, box, 0, 2.2, 0, np.pi, w)
+    for _ in range(60):
+        q, s = structure_factor(pos, box, 0, 2.2, 0, np.pi, w)
+        assert_array_equal(s, s0)
+
+
+def test_histograms_are_bitwise_repeatable_on_ragged_sizes():
+    from maicos_b200.lib._hist import profile_hist
+
+    rng = np.random.default_rng(3)
+    for n in (1, 511, 4096, 4097, 100003):
+        for nb in (1, 7, 512, 513, 4000):
+            pos = rng.uniform(-1, 21, (3, n, 3)).astype(np.float32)
+            w = rng.normal(size=(3, n)) * 10.0 ** rng.integers(-3, 4)
+            edges = np.tile(np.linspace(np.float64(0), 20.0, nb + 1), (3, 1))
+            hw0, hc0 = profile_hist(0, pos, 1, w, edges)
+            for _ in range(20):
+                hw, hc = profile_hist(0, pos, 1, w, edges)
+                assert_array_equal(hc, hc0)
+                assert_array_equal(hw, hw0)
+            for f in range(3):
+                assert_array_equal(hc0[f], restatement.hist_planar(np.double(pos[f]), None, 1, nb, 0.0, 20.0))
