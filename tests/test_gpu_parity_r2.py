@@ -162,7 +162,7 @@ def test_lattices_absolute_amplitude_bound(case, precision):
     if case.startswith("cubic"):
         box = np.array([40.0, 40.0, 40.0])
         pos = simple_cubic(20, 40.0, stretch=1.0 if case == "cubic" else 1.0007)
-        qmax = 2.0
+        qmax = 3.3  # the (1, 0, 0) Bragg peaks sit at 2 pi / 2 A = 3.14 / A
     else:
         pos, box = honeycomb_sheets(24, 14, stretch=1.0 if case == "graphene" else 0.9991)
         qmax = 3.2
