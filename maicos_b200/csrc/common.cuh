@@ -116,7 +116,7 @@ struct mb200_ctx {
     int64_t launches = 0;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // S(q) workspaces
-    mb200::DevBuf d_pos, d_w, d_idx, d_tables, d_amp, d_sval, d_jobs, d_segs, d_items, d_out, d_ff2, d_counter, d_bimg, d_tcdesc;
+    mb200::DevBuf d_pos, d_w, d_idx, d_tables, d_amp, d_sval, d_jobs, d_segs, d_items, d_out, d_ff2, d_counter, d_bimg, d_tcdesc, d_owned;
     mb200::PinBuf h_stage, h_out;
     // histogram workspaces
     mb200::DevBuf d_hpos, d_hw, d_hw2, d_hedges, d_hpar, d_hout, d_ctopo;

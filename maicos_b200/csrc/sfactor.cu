@@ -84,6 +84,10 @@ struct SegDesc {
     int32_t pad_;
     long long amp_stride;          // double2 per split in `amp`
     double s_scale;                // S = |A|^2 * s_scale: undoes the power-of-two rescaling of the weights (exact)
+    // q-block sharding of the tensor-core path: amplitude tiles (tile_elems double2 each) this rank did not compute read as
+    // zero without ever being cleared or folded (null: every tile is owned)
+    const uint8_t *tile_owned;
+    long long tile_elems;
 };
 
 struct ItemDesc {
@@ -479,6 +483,7 @@ k_sf_contract(const ItemDesc *__restrict__ items, int n_items, const SegDesc *__
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double s_of_entry(const SegDesc &sg, int e) {
     const int ai = sg.ent_amp[e];
+    if (sg.tile_owned && !sg.tile_owned[ai / (int)sg.tile_elems]) return 0.0;
     double re = 0.0, im = 0.0;
     const size_t stride = (size_t)sg.amp_stride;
     for (int s = 0; s < sg.n_split; ++s) {  // fixed order -> reproducible
@@ -495,12 +500,14 @@ __device__ __forceinline__ double s_of_entry(const SegDesc &sg, int e) {
 struct FoldDesc {
     double2 *amp;
     long long stride;  // elements per slab
-    int32_t n_split, pad;
+    int32_t n_split, tile_elems;
+    const uint8_t *owned;  // per tile of tile_elems elements: folded only when set (null: all)
 };
 __global__ void __launch_bounds__(256) k_sf_fold_splits(const FoldDesc *__restrict__ descs) {
     const FoldDesc d = descs[blockIdx.y];
     if (d.n_split < 2) return;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.stride; i += (long long)gridDim.x * blockDim.x) {
+        if (d.owned && !d.owned[i / d.tile_elems]) continue;
         double re = 0.0, im = 0.0;
         for (int sidx = 0; sidx < d.n_split; ++sidx) {
             const double2 v = d.amp[(size_t)sidx * d.stride + i];
@@ -583,7 +590,8 @@ struct SfPlan {
     std::vector<uint8_t> tc_rows;       // [tc_n_rt * 128][2]
     unsigned long long tc_ymask[4] = {0, 0, 0, 0};  // y-table rows the tensor-core generators read (k0 of every quad, row 1)
     std::vector<int32_t> ent_amp_tc;    // index into [tc_n_rt * tc_n_lt][128][tc_lt]
-    int32_t tc_n_rt = 0, tc_n_lt = 0, tc_lt = 0, tc_n_pairs = 0;
+    std::vector<uint8_t> tc_tile_used;  // [tc_n_rt * tc_n_lt] 1: the (row tile, l tile) block holds at least one valid q
+    int32_t tc_n_rt = 0, tc_n_lt = 0, tc_lt = 0, tc_n_pairs = 0, tc_n_used = 0;
     bool tc_ok = false;
     // device copies
     DevBuf d_tgs, d_ent_amp, d_bin_start, d_ff2, d_tc_rows, d_ent_amp_tc;
@@ -736,47 +744,71 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
     } else {
         pl->cell.swap(cell); pl->qrr.swap(qv); pl->ent_amp.swap(amp);
     }
-    // tensor-core tiling: (h,k) pairs with at least one valid l, in (h,k) order, 128 per row tile
+    // tensor-core tiling: (h,k) pairs with at least one valid l, packed in quads (h, k0 .. k0 + 3) -- the generators form the
+    // four rows of a quad from one seed product -- 32 quads = 128 rows per row tile, l tiles of <= 48 values
     if (m0 <= 255 && m1 <= 255 && m2 >= 1 && nv > 0) {
-        std::vector<int32_t> pos((size_t)m0 * m1, -1);
+        pl->tc_n_lt = (m2 + TC_MAX_LT - 1) / TC_MAX_LT;
+        pl->tc_lt = (((m2 + pl->tc_n_lt - 1) / pl->tc_n_lt) + 7) / 8 * 8;
+        const int n_lt = pl->tc_n_lt, lt_size = pl->tc_lt;
+        struct Quad { uint8_t h, k0; int8_t top; };
+        std::vector<Quad> quads;
+        std::vector<int32_t> quad_of((size_t)m0 * m1, -1);  // (h,k) -> quad (h-major order)
         for (int h = 0; h < m0; ++h) {
-            int prev_k = -2;
+            int prev_k = -2, run_k0 = 0;
             for (int k = 0; k < m1; ++k) {
-                bool any = false;
-                for (int l = 0; l < m2 && !any; ++l) any = qcube[((size_t)h * m1 + k) * m2 + l] != 0.0;
-                if (!any) continue;
-                if (k != prev_k + 1)  // a new run of consecutive k starts on a quad boundary (padding rows continue the old run)
-                    while ((pl->tc_rows.size() / 2) % 4) {
-                        pl->tc_rows.push_back(pl->tc_rows[pl->tc_rows.size() - 2]);
-                        pl->tc_rows.push_back((uint8_t)std::min(255, (int)pl->tc_rows[pl->tc_rows.size() - 2] + 1));
-                    }
-                pos[(size_t)h * m1 + k] = (int32_t)(pl->tc_rows.size() / 2);
-                pl->tc_rows.push_back((uint8_t)h);
-                pl->tc_rows.push_back((uint8_t)k);
+                int top = -1;  // highest l tile with a valid cell of this (h,k) pair
+                for (int l = m2 - 1; l >= 0; --l)
+                    if (qcube[((size_t)h * m1 + k) * m2 + l] != 0.0) { top = l / lt_size; break; }
+                if (top < 0) continue;
+                if (k != prev_k + 1) run_k0 = k;                     // a new run of consecutive k starts its own quads
+                if ((k - run_k0) % 4 == 0) quads.push_back({(uint8_t)h, (uint8_t)k, (int8_t)-1});
+                Quad &qd = quads.back();
+                qd.top = (int8_t)std::max<int>(qd.top, top);
+                quad_of[(size_t)h * m1 + k] = (int32_t)quads.size() - 1;
                 prev_k = k;
             }
+        }
+        // Cubes with several l tiles: quads whose highest populated l tile is the same go into the same row tiles (stable
+        // sort, h-major inside a class), so that most row tiles of the outer (h,k) region have no valid cell in the upper
+        // l tiles -- those (row tile, l tile) items are never launched (run_segments_tc) -- instead of every row tile
+        // touching every l tile: 204 -> 154 items at maxn = 103, 360 -> 287 at maxn = 138 (the generated operand is
+        // produced once per item, so items are what the contraction's cost counts).
+        std::vector<int32_t> order(quads.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
+        if (n_lt > 1)
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return quads[a].top > quads[b].top; });
+        std::vector<int32_t> slot_of(quads.size());
+        pl->tc_rows.reserve(quads.size() * 8 + 2 * TC_M);
+        for (size_t sidx = 0; sidx < order.size(); ++sidx) {
+            const Quad &qd = quads[order[sidx]];
+            slot_of[order[sidx]] = (int32_t)sidx;
+            for (int r = 0; r < 4; ++r) {
+                pl->tc_rows.push_back(qd.h);
+                pl->tc_rows.push_back((uint8_t)std::min(255, (int)qd.k0 + r));
+            }
+            pl->tc_ymask[qd.k0 >> 6] |= 1ull << (qd.k0 & 63);
         }
         pl->tc_n_pairs = (int32_t)(pl->tc_rows.size() / 2);
         pl->tc_n_rt = (pl->tc_n_pairs + TC_M - 1) / TC_M;
         pl->tc_rows.resize((size_t)pl->tc_n_rt * TC_M * 2, 0);
-        for (size_t o = 0; o + 7 < pl->tc_rows.size(); o += 8) {  // quad o / 8 starts at row 4 (o / 8): its k0
-            const int k0 = pl->tc_rows[o + 1];
-            pl->tc_ymask[k0 >> 6] |= 1ull << (k0 & 63);
-        }
+        pl->tc_ymask[0] |= 1ull;  // the padding quads of the last row tile start at k0 = 0
         {
             const int r1 = std::min(1, std::max(0, (int)pl->rows[1] - 1));
             pl->tc_ymask[r1 >> 6] |= 1ull << (r1 & 63);
         }
-        pl->tc_n_lt = (m2 + TC_MAX_LT - 1) / TC_MAX_LT;
-        pl->tc_lt = (((m2 + pl->tc_n_lt - 1) / pl->tc_n_lt) + 7) / 8 * 8;
         pl->ent_amp_tc.resize(nv);
+        pl->tc_tile_used.assign((size_t)pl->tc_n_rt * n_lt, 0);
         for (size_t e = 0; e < nv; ++e) {
             const int32_t ci = pl->cell[e];
             const int l = ci % m2, k = (ci / m2) % m1, h = ci / (m2 * m1);
-            const int32_t pp = pos[(size_t)h * m1 + k];
-            const int32_t tile = (pp / TC_M) * pl->tc_n_lt + l / pl->tc_lt;
-            pl->ent_amp_tc[e] = (tile * TC_M + pp % TC_M) * pl->tc_lt + l % pl->tc_lt;
+            const int32_t qi = quad_of[(size_t)h * m1 + k];
+            const int32_t pp = slot_of[qi] * 4 + (k - (int)quads[qi].k0);
+            const int32_t tile = (pp / TC_M) * n_lt + l / lt_size;
+            pl->tc_tile_used[tile] = 1;
+            pl->ent_amp_tc[e] = (tile * TC_M + pp % TC_M) * lt_size + l % lt_size;
         }
+        pl->tc_n_used = 0;
+        for (uint8_t u : pl->tc_tile_used) pl->tc_n_used += u;
         pl->tc_ok = true;
     }
     out = pl;
@@ -917,7 +949,7 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
     std::vector<TcItem> items;
     int64_t atomq = 0, n_mma = 0;
     int64_t total_tiles = 0;
-    for (int s = 0; s < ns; ++s) total_tiles += (int64_t)specs[s].plan->tc_n_rt * specs[s].plan->tc_n_lt;
+    for (int s = 0; s < ns; ++s) total_tiles += ((int64_t)specs[s].plan->tc_n_used + n_blocks - 1) / n_blocks;
     // Items are handed out in list order from one counter and all take about the same time, so the launch ends with up to
     // one item of idle time per CTA (3 % on the bench workload): the segments at the END of the list are cut into twice as
     // many atom chunks until the last 2 x n_sm items are half-size.
@@ -927,7 +959,7 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
         for (int s = ns - 1; s >= 0 && tail_items < 2 * (int64_t)ctx->n_sm; --s) {
             const SfPlan &pl = *specs[s].plan;
             const int ld = (specs[s].job.n + TC_KA - 1) / TC_KA * TC_KA;
-            const int64_t tiles = ((int64_t)pl.tc_n_rt * pl.tc_n_lt + n_blocks - 1) / n_blocks;
+            const int64_t tiles = ((int64_t)pl.tc_n_used + n_blocks - 1) / n_blocks;
             const int base = std::max<int>(1, (ld + TC_CHUNK - 1) / TC_CHUNK);
             if (ld / (2 * base) >= 64 * TC_KA) {
                 split_factor[s] = 2;
@@ -968,9 +1000,11 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
         for (int sp_i = 0; sp_i < n_split[s]; ++sp_i) {
             const int j0 = sp_i * steps_per * TC_KA, j1 = std::min(ld, (sp_i + 1) * steps_per * TC_KA);
             if (j1 <= j0) continue;
+            int used_idx = 0;  // q-blocks deal the populated (row tile, l tile) blocks round robin
             for (int rt = 0; rt < pl.tc_n_rt; ++rt)
                 for (int lt = 0; lt < pl.tc_n_lt; ++lt) {
-                    if ((rt * pl.tc_n_lt + lt) % n_blocks != block) continue;
+                    if (!pl.tc_tile_used[(size_t)rt * pl.tc_n_lt + lt]) continue;  // no valid q in this block: never launched
+                    if (used_idx++ % n_blocks != block) continue;
                     items.push_back({s, rt, lt, j0, j1, sp_i});
                     n_mma += (int64_t)((j1 - j0) / TC_KA) * 15;
                 }
@@ -981,8 +1015,25 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
     MB_TRY(ctx->d_bimg.ensure(std::max<size_t>(img_bytes, 16)));
     MB_TRY(ctx->d_amp.ensure(std::max<size_t>(amp_elems, 1) * 16));
     double2 *tab = ctx->d_tables.as<double2>();
-    // tiles that are not computed here (other q-blocks, empty segments) must read as zero
-    if (n_blocks > 1 || items.empty())
+    // q-blocks: per distinct plan, which (row tile, l tile) blocks this rank computes -- the finalisers and the fold pass
+    // skip the others, so nothing outside the rank's share of the amplitude workspace is ever touched
+    std::vector<uint8_t> owned_host;
+    std::vector<size_t> owned_off(ns, 0);
+    if (n_blocks > 1) {
+        std::map<const SfPlan *, size_t> seen;
+        for (int s = 0; s < ns; ++s) {
+            const SfPlan &pl = *specs[s].plan;
+            auto it = seen.find(&pl);
+            if (it != seen.end()) { owned_off[s] = it->second; continue; }
+            owned_off[s] = seen[&pl] = owned_host.size();
+            int used_idx = 0;
+            for (size_t t = 0; t < pl.tc_tile_used.size(); ++t)
+                owned_host.push_back(pl.tc_tile_used[t] && (used_idx++ % n_blocks) == block ? 1 : 0);
+        }
+        MB_TRY(ctx->d_owned.ensure(std::max<size_t>(owned_host.size(), 16)));
+    }
+    // empty segments (no atoms) are never written: they must read as zero
+    if (n_blocks == 1 && items.empty())
         MB_CUDA(cudaMemsetAsync(ctx->d_amp.p, 0, std::max<size_t>(amp_elems, 1) * 16, ctx->stream));
     std::vector<TcSeg> tsegs(ns);
     std::vector<FoldDesc> folds(ns);
@@ -997,7 +1048,10 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
         // many large slabs: fold them into slab 0 with one streaming pass (k_sf_fold_splits) before the finalisers gather
         folds[s].stride = sd.amp_stride;
         folds[s].n_split = (n_split[s] >= 2 && (size_t)n_split[s] * (size_t)sd.amp_stride * 16 >= ((size_t)96 << 20)) ? n_split[s] : 1;
-        folds[s].pad = 0;
+        folds[s].tile_elems = TC_M * pl.tc_lt;
+        folds[s].owned = n_blocks > 1 ? ctx->d_owned.as<uint8_t>() + owned_off[s] : nullptr;
+        sd.tile_owned = folds[s].owned;
+        sd.tile_elems = TC_M * pl.tc_lt;
         if (folds[s].n_split > 1) { sd.n_split = 1; any_fold = true; }
         for (int a = 0; a < 3; ++a) sd.rows[a] = pl.rows[a];
         sd.tgs = nullptr;
@@ -1010,7 +1064,7 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
         sp.job.tab[0] = tab + off_x[s];
         sp.job.tab[1] = sp.share_yz_with >= 0 ? nullptr : tab + off_y[s];
         sp.job.tab[2] = sp.share_yz_with >= 0 ? nullptr : tab + off_z[s];
-        if (sp.job.ld == 0 && amp_elems && n_blocks == 1 && !items.empty())
+        if (sp.job.ld == 0 && amp_elems)
             MB_CUDA(cudaMemsetAsync(sd.amp, 0, (size_t)n_split[s] * sd.amp_stride * 16, ctx->stream));
         TcSeg &ts = tsegs[s];
         ts.ex = sd.ex; ts.ey = sd.ey;
@@ -1030,7 +1084,8 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
     const size_t b_jobs = (size_t)ns * sizeof(TableJob), b_segs = (size_t)ns * sizeof(SegDesc),
                  b_tsegs = ((size_t)ns * sizeof(TcSeg) + 15) / 16 * 16 + (size_t)ns * sizeof(FoldDesc),  // TcSeg[ns] | FoldDesc[ns]
                  b_fold_off = ((size_t)ns * sizeof(TcSeg) + 15) / 16 * 16, b_items = items.size() * sizeof(TcItem);
-    MB_TRY(ctx->h_stage.ensure(b_jobs + b_segs + b_tsegs + b_items + 64));
+    const size_t b_owned = (owned_host.size() + 15) / 16 * 16;
+    MB_TRY(ctx->h_stage.ensure(b_jobs + b_segs + b_tsegs + b_items + b_owned + 64));
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
     char *hs = ctx->h_stage.as<char>();
     for (int s = 0; s < ns; ++s) std::memcpy(hs + (size_t)s * sizeof(TableJob), &specs[s].job, sizeof(TableJob));
@@ -1038,6 +1093,11 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
     std::memcpy(hs + b_jobs + b_segs, tsegs.data(), (size_t)ns * sizeof(TcSeg));
     std::memcpy(hs + b_jobs + b_segs + b_fold_off, folds.data(), (size_t)ns * sizeof(FoldDesc));
     if (b_items) std::memcpy(hs + b_jobs + b_segs + b_tsegs, items.data(), b_items);
+    if (!owned_host.empty()) {
+        std::memcpy(hs + b_jobs + b_segs + b_tsegs + b_items, owned_host.data(), owned_host.size());
+        MB_CUDA(cudaMemcpyAsync(ctx->d_owned.p, hs + b_jobs + b_segs + b_tsegs + b_items, owned_host.size(), cudaMemcpyHostToDevice,
+                                ctx->stream));
+    }
     MB_TRY(ctx->d_jobs.ensure(b_jobs));
     MB_TRY(ctx->d_segs.ensure(b_segs));
     MB_TRY(ctx->d_tcdesc.ensure(b_tsegs + 64));
