@@ -268,6 +268,10 @@ class AtomGroup:
         # per-atom topology attributes; absent ones raise AttributeError like MDAnalysis
         attrs = self.__dict__.get("universe")._attrs if "universe" in self.__dict__ else {}
         if name in attrs:
+            if self.__dict__.get("_all"):  # the whole universe: a read-only view instead of a gathered copy
+                view = attrs[name].view()
+                view.flags.writeable = False
+                return view
             return attrs[name][self.indices]
         raise AttributeError(f"AtomGroup has no attribute {name!r}")
 

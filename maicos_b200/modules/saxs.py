@@ -51,13 +51,16 @@ def _element_groups(atomgroup):
     grouped by object identity (integers) and only the few representatives are compared as strings; the result is
     kept on the universe for further analyses of the same selection.
     """
-    elements = np.asarray(atomgroup.elements)
     universe = atomgroup.universe
     cache = universe.__dict__.setdefault("_mb200_element_groups", {}) if hasattr(universe, "__dict__") else {}
     ix = getattr(atomgroup, "ix", None)
-    key = (len(elements), hash(np.asarray(ix).tobytes()) if ix is not None else None, id(atomgroup.universe))
+    if getattr(atomgroup, "_all", False):  # the whole universe: no need to fingerprint a million indices
+        key = ("all", atomgroup.n_atoms, id(universe))
+    else:
+        key = (atomgroup.n_atoms, hash(np.asarray(ix).tobytes()) if ix is not None else None, id(universe))
     if ix is not None and key in cache:
         return cache[key]
+    elements = np.asarray(atomgroup.elements)
     if elements.dtype == object and len(elements) > 4096:
         ids = _object_ids(elements)
         # a handful of distinct objects: peel them off one comparison pass at a time (np.unique sorts all atoms twice)
@@ -80,6 +83,40 @@ def _element_groups(atomgroup):
     if ix is not None:
         cache[key] = (unique, inverse)
     return unique, inverse
+
+
+class _GroupList:
+    """``Saxs.groups`` of the reference (one AtomGroup per element, saxs.py:158-164), built when somebody looks: the
+    device path works on the index arrays."""
+
+    def __init__(self, atomgroup, index):
+        self._atomgroup, self._index, self._made = atomgroup, index, {}
+
+    def __len__(self):
+        return len(self._index)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        i = range(len(self))[i]
+        if i not in self._made:
+            self._made[i] = self._atomgroup[self._index[i]]
+        return self._made[i]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class _OnesList(_GroupList):
+    """``Saxs.weights``: ones per group (the form factors are applied after the kernel, saxs.py:161-163)."""
+
+    def __init__(self, index):
+        self._index, self._made = index, {}
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        return np.ones(len(self._index[range(len(self))[i]]))
 
 
 class Saxs(AnalysisBase):
@@ -138,16 +175,19 @@ class Saxs(AnalysisBase):
 
         # one group per element; weights are ones, form factors are applied after the kernel
         unique, inverse = _element_groups(self.atomgroup)
-        self.groups, self.weights, self.elements, self._group_index = [], [], [], []
-        for g, element in enumerate(unique):
-            idx = np.flatnonzero(inverse == g).astype(np.int32)
-            self._group_index.append(idx)
-            self.groups.append(self.atomgroup[idx])
-            self.weights.append(np.ones(len(idx)))
-            self.elements.append(element)
-        self._group_ptr = np.concatenate([[0], np.cumsum([len(i) for i in self._group_index])]).astype(np.int64)
-        self._group_flat = np.ascontiguousarray(np.concatenate(self._group_index), dtype=np.int32)
-        self._cm = np.ascontiguousarray(np.stack([tables.cm_packed(str(el)) for el in self.elements]))
+        universe = self.atomgroup.universe
+        cache = universe.__dict__.setdefault("_mb200_saxs_groups", {}) if hasattr(universe, "__dict__") else {}
+        prepared = cache.get(id(inverse))  # `inverse` lives in the element-group cache: same selection, same object
+        if prepared is None or prepared[0] is not inverse:
+            index = [np.flatnonzero(inverse == g).astype(np.int32) for g in range(len(unique))]
+            ptr = np.concatenate([[0], np.cumsum([len(i) for i in index])]).astype(np.int64)
+            flat = np.ascontiguousarray(np.concatenate(index), dtype=np.int32)
+            cm = np.ascontiguousarray(np.stack([tables.cm_packed(str(el)) for el in unique]))
+            prepared = cache[id(inverse)] = (inverse, index, ptr, flat, cm)
+        _, self._group_index, self._group_ptr, self._group_flat, self._cm = prepared
+        self.elements = list(unique)
+        self.groups = _GroupList(self.atomgroup, self._group_index)
+        self.weights = _OnesList(self._group_index)
 
         # frames per device call: bounded by ~128 MB of staged positions (and by the table workspace)
         self._batch_size = int(max(1, min(type(self)._batch_size, (128 << 20) // max(1, self.atomgroup.n_atoms * 12))))
