@@ -170,6 +170,7 @@ int mb200_host_copy(void *dst, const void *src, size_t bytes, int n_threads);
 int mb200_dev_alloc(mb200_ctx *ctx, size_t bytes, void **out);
 int mb200_dev_free(mb200_ctx *ctx, void *p);
 int mb200_dev_read(mb200_ctx *ctx, const void *dev, void *host, size_t bytes);
+int mb200_dev_write(mb200_ctx *ctx, void *dev, const void *host, size_t bytes);
 
 /* Compound centres and dipole-derived weights from raw atom coordinates, for compounds that are
  * contiguous runs of atoms.  Replaces the per-frame host calls
@@ -194,6 +195,19 @@ int mb200_compound_prologue(mb200_ctx *ctx, const float *positions, int position
                             const double *masses, const double *charges, int make_whole,
                             int wrap_center, int weight_mode, int pdim, double *centers_dev,
                             double *weights_dev);
+
+/* The same with the topology side (compound_ptr, centre weights, masses, charges: 8 + 24 bytes per atom) uploaded ONCE:
+ * an analysis creates the handle in its _prepare and passes it with every batch of frames.  `positions` announced with
+ * mb200_prefetch_frames are taken from the prefetch slot (their copy ran under the previous call). */
+typedef struct mb200_topology mb200_topology;
+int mb200_topology_create(mb200_ctx *ctx, const int64_t *compound_ptr, int64_t n_c, int64_t n_atoms,
+                          const double *center_weights, const double *masses, const double *charges,
+                          mb200_topology **out);
+void mb200_topology_destroy(mb200_ctx *ctx, mb200_topology *topo);
+int mb200_compound_prologue_topo(mb200_ctx *ctx, const float *positions, int positions_on_device,
+                                 int64_t n_frames, const float *boxes, const mb200_topology *topo,
+                                 int make_whole, int wrap_center, int weight_mode, int pdim,
+                                 double *centers_dev, double *weights_dev);
 
 /* Per-atom quantities of the "virtual cut" estimator of the dielectric profile modules:
  *   testpos_i = centre of |charge| of atom i's compound along the profile coordinate

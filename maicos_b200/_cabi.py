@@ -62,10 +62,22 @@ SIGNATURES = {
     "mb200_dev_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mb200_dev_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "mb200_dev_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "mb200_dev_write": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "mb200_compound_prologue": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
          ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "mb200_topology_create": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.POINTER(ctypes.c_void_p)],
+    ),
+    "mb200_topology_destroy": (None, [ctypes.c_void_p, ctypes.c_void_p]),
+    "mb200_compound_prologue_topo": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p],
     ),
     "mb200_dielectric_prepare": (
@@ -302,6 +314,13 @@ class DeviceBuffer:
         out = np.empty(shape, dtype=dtype)
         _check(load().mb200_dev_read(self.ctx.handle, self.ptr, ptr(out), out.nbytes))
         return out
+
+    def write(self, array: np.ndarray) -> int:
+        """Upload a host array (grows the buffer as needed); returns the device pointer."""
+        array = np.ascontiguousarray(array)
+        self.ensure(array.nbytes)
+        _check(load().mb200_dev_write(self.ctx.handle, self.ptr, ptr(array), array.nbytes))
+        return self.ptr.value
 
     def free(self) -> None:
         if self.ptr:

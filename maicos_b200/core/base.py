@@ -95,6 +95,16 @@ def positions_into(atomgroup, out: np.ndarray) -> np.ndarray:
     return out
 
 
+def gather_rows(rows: list) -> np.ndarray:
+    """``[F, ...]`` array of staged rows ``(block, row)``: a view when they are consecutive rows of one block (the usual
+    case: one staging buffer, or consecutive frames of a page-locked trajectory), else a stacked copy."""
+    buf = rows[0][0]
+    base = buf.ctypes.data
+    if all(r[0].ctypes.data == base and r[1] == rows[0][1] + i for i, r in enumerate(rows)):
+        return buf[rows[0][1]:rows[0][1] + len(rows)]
+    return np.stack([b[r] for b, r in rows])
+
+
 _COMPOUND_ATTR = {"residues": "resindices", "molecules": "molnums", "segments": "segindices",
                   "fragments": "fragindices"}
 
@@ -111,6 +121,13 @@ def compound_runs(atomgroup, compound: str):
 
     if compound not in _COMPOUND_ATTR or not isinstance(atomgroup.universe, ShimUniverse):
         return None
+    cache = atomgroup.__dict__.setdefault("_mb200_compound_runs", {})  # topology does not change during a run
+    if compound not in cache:
+        cache[compound] = _compound_runs(atomgroup, compound)
+    return cache[compound]
+
+
+def _compound_runs(atomgroup, compound: str):
     ids = np.asarray(getattr(atomgroup, _COMPOUND_ATTR[compound]))
     if len(ids) == 0:
         return None
@@ -160,6 +177,13 @@ class CompoundPrologue:
         self.ctx = _cabi.context()
         self.centers = _cabi.DeviceBuffer(self.ctx)
         self.weights = _cabi.DeviceBuffer(self.ctx)
+        # compound_ptr, centre weights, masses and charges go to the device once per analysis, not with every batch
+        import ctypes
+
+        self._topo = ctypes.c_void_p()
+        _cabi.check(_cabi.load().mb200_topology_create(
+            self.ctx.handle, _cabi.ptr(self.ptr), self.n_c, self.n_atoms, _cabi.ptr(self.cw), _cabi.ptr(self.masses),
+            _cabi.ptr(self.charges), ctypes.byref(self._topo)))
 
     def run(self, positions: np.ndarray, boxes: np.ndarray):
         """positions float32 [F, n_atoms, 3] (pinned), boxes float32 [F, 3] -> device pointers (centres, weights)."""
@@ -170,11 +194,23 @@ class CompoundPrologue:
         n_w = {0: 0, 1: 1, 2: 1, 3: 1, 4: 3}[self.weight_mode]
         w_ptr = self.weights.ensure(F * self.n_c * 8 * n_w) if n_w else None
         boxes = np.ascontiguousarray(boxes, dtype=np.float32)
-        _cabi.check(_cabi.load().mb200_compound_prologue(
-            self.ctx.handle, _cabi.ptr(positions), 0, F, self.n_atoms, _cabi.ptr(boxes), _cabi.ptr(self.ptr), self.n_c,
-            _cabi.ptr(self.cw), _cabi.ptr(self.masses), _cabi.ptr(self.charges), int(self.make_whole),
+        _cabi.check(_cabi.load().mb200_compound_prologue_topo(
+            self.ctx.handle, _cabi.ptr(positions), 0, F, _cabi.ptr(boxes), self._topo, int(self.make_whole),
             int(self.wrap_center), self.weight_mode, self.pdim, c_ptr, w_ptr))
         return c_ptr, w_ptr
+
+    def close(self) -> None:
+        from .. import _cabi
+
+        topo, self._topo = getattr(self, "_topo", None), None
+        if topo:
+            _cabi.load().mb200_topology_destroy(self.ctx.handle, topo)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class _Runner:
@@ -355,6 +391,35 @@ class AnalysisBase(_Runner):
 
     def _slot_prefix(self) -> str:
         return f"{type(self).__name__}@{id(self):x}:"
+
+    def _stage_positions(self, tag: str = "pos") -> tuple[np.ndarray, int]:
+        """``(block, row)`` holding the float32 positions of ``self.atomgroup`` in the current frame.
+
+        Normally a row of the pinned batch buffer filled with one host copy.  When the trajectory itself lives in
+        page-locked memory (``trajectory.pinned_row``), the atom group is the whole system and nothing transformed the
+        frame, the row IS the trajectory's: no host copy, the device reads the frame where the reader put it."""
+        ag = self.atomgroup
+        pinned_row = getattr(self._trajectory, "pinned_row", None)
+        if pinned_row is not None and getattr(ag, "_all", False):
+            ts = self._universe.trajectory.ts
+            where = pinned_row(ts.frame)
+            if where is not None and where[0][where[1]].ctypes.data == ts.positions.ctypes.data:
+                return where
+        buf, row = self._staging_rows((ag.n_atoms, 3), np.float32, tag)
+        positions_into(ag, buf[row])
+        return buf, row
+
+    def _announce_rows(self, rows: list) -> None:
+        """Announce consecutive staged rows to the library (``mb200_prefetch_frames``): their host -> device copy then
+        runs on the copy stream while the device call before this batch is still computing."""
+        from .. import _cabi
+
+        if not rows:
+            return
+        block = gather_rows(rows)
+        if block.base is None and len(rows) > 1:
+            return  # a stacked copy: the call copies by itself
+        _cabi.check(_cabi.load().mb200_prefetch_frames(_cabi.context().handle, block.ctypes.data, block.nbytes))
 
     def _staging_rows(self, shape, dtype, tag: str) -> tuple[np.ndarray, int]:
         """``(pinned batch buffer [batch, *shape], row)`` for the frame being staged.
@@ -718,6 +783,7 @@ class ProfileBase:
         if not hasattr(self, "unwrap"):
             self.unwrap = True
         self._cached_weights = None
+        self._dev_static_w = None
         # frames per device call: bounded by ~64 MB of staged positions per batch
         n_pos = self.atomgroup.n_atoms
         self._batch_size = int(max(1, min(64, (64 << 20) // max(1, n_pos * 12))))
@@ -775,16 +841,13 @@ class ProfileBase:
         """
         st = dict(self._hist_geometry())
         if self._prologue is not None:  # raw atoms; centres and weights are formed on the device
-            buf, row = self._staging_rows((self.atomgroup.n_atoms, 3), np.float32, "pos")
-            positions_into(self.atomgroup, buf[row])
-            st["positions"] = (buf, row)
+            st["positions"] = self._stage_positions()
             st["box"] = np.array(self._universe.dimensions[:3], dtype=np.float32)
             st["weights"] = self._profile_weights() if self._static_weights else None
             st["obs"] = dict(self._obs)
             return st
         if self.grouping == "atoms":
-            buf, row = self._staging_rows((self.atomgroup.n_atoms, 3), np.float32, "pos")
-            positions_into(self.atomgroup, buf[row])
+            buf, row = self._stage_positions()
         else:
             centres = get_center(self.atomgroup, bin_method=self.bin_method, compound=self.grouping)
             buf, row = self._staging_rows(centres.shape, np.float64, "pos")
@@ -800,14 +863,23 @@ class ProfileBase:
         st["obs"] = dict(self._obs)
         return st
 
-    @staticmethod
-    def _gather_rows(rows: list) -> np.ndarray:
-        """``[F, ...]`` view of consecutively staged rows (copy only when they are not one run)."""
-        buf = rows[0][0]
-        base = buf.ctypes.data
-        if all(r[0].ctypes.data == base and r[1] == rows[0][1] + i for i, r in enumerate(rows)):
-            return buf[rows[0][1]:rows[0][1] + len(rows)]
-        return np.stack([b[r] for b, r in rows])
+    _gather_rows = staticmethod(gather_rows)
+
+    def _announce_profile_rows(self, staged: list) -> None:
+        """float32 atom positions of a batch (atoms grouping or the device prologue) are prefetched under the previous call."""
+        if staged and (self._prologue is not None or self.grouping == "atoms"):
+            self._announce_rows([s["positions"] for s in staged])
+
+    def _static_weights_on_device(self, weights: np.ndarray) -> int:
+        """Topology-only weights (masses, charges, ones) are uploaded once per run, not with every batch."""
+        from .. import _cabi
+
+        cached = getattr(self, "_dev_static_w", None)
+        if cached is None or cached[0] is not weights:
+            buf = _cabi.DeviceBuffer(_cabi.context())
+            buf.write(np.ascontiguousarray(weights, dtype=np.float64))
+            cached = self._dev_static_w = (weights, buf)
+        return cached[1].ptr.value
 
     def _compute_profiles(self, staged: list) -> list:
         from ..lib._hist import profile_hist
@@ -820,15 +892,17 @@ class ProfileBase:
         if self._prologue is not None:
             c_ptr, w_ptr = self._prologue.run(pos, np.stack([s["box"] for s in staged]))
             dev_w = (w_ptr, True) if w_ptr else None
-            w = g0["weights"][None] if (self._static_weights and not w_ptr) else None
-            hw, hc = profile_hist(g0["geometry"], None, g0["dim"], w, edges, center, zrange,
+            if self._static_weights and not w_ptr:
+                dev_w = (self._static_weights_on_device(g0["weights"]), False)
+            hw, hc = profile_hist(g0["geometry"], None, g0["dim"], None, edges, center, zrange,
                                   device_positions=(c_ptr, len(staged), self._prologue.n_c), device_weights=dev_w)
         else:
             if self._static_weights:
-                w = g0["weights"][None]
+                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange,
+                                      device_weights=(self._static_weights_on_device(g0["weights"]), False))
             else:
                 w = self._gather_rows([s["weights"] for s in staged])
-            hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], w, edges, center, zrange)
+                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], w, edges, center, zrange)
         out = []
         for f, s in enumerate(staged):
             obs = s["obs"]

@@ -114,6 +114,9 @@ class ProfileCylinderBase(CylinderBase, ProfileBase):
         CylinderBase._single_frame(self)
         return self._stage_profile()
 
+    def _announce_staged(self, staged: list) -> None:
+        self._announce_profile_rows(staged)
+
     _single_frame = AnalysisBase._single_frame_from_batch
 
     def _compute_staged(self, staged: list) -> list:

@@ -106,6 +106,9 @@ class ProfilePlanarBase(PlanarBase, ProfileBase):
         PlanarBase._single_frame(self)
         return self._stage_profile()
 
+    def _announce_staged(self, staged: list) -> None:
+        self._announce_profile_rows(staged)
+
     _single_frame = AnalysisBase._single_frame_from_batch
 
     def _compute_staged(self, staged: list) -> list:

@@ -686,8 +686,13 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
 
     HistParams p;
     std::memset(&p, 0, sizeof(p));
+    int pref_slot = -1;
     if (positions_on_device || N == 0) {
         p.pos = positions;
+    } else if (const void *pref = take_prefetched(ctx, positions, F * N * ncomp * esz)) {
+        p.pos = pref;  // announced with mb200_prefetch_frames: copied on the copy stream under the previous call
+        pref_slot = ctx->pref_taken;
+        ctx->pref_taken = -1;
     } else {
         MB_TRY(ctx->d_hpos.ensure(F * N * ncomp * esz));
         MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * ncomp * esz, cudaMemcpyHostToDevice, ctx->stream));
@@ -704,20 +709,23 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
             p.weights = ctx->d_hw.as<double>();
         }
     }
-    // small per-frame parameters: edges | center | zrange | wmax bits
+    // small per-frame parameters: edges | center | zrange | wmax bits -- gathered in the pinned staging block, ONE copy
     const size_t n_par = F * (NB + 1) + F * 3 + F * 2 + F;
     MB_TRY(ctx->d_hpar.ensure(n_par * 8));
+    MB_TRY(ctx->h_stage.ensure(n_par * 8));  // the previous call synchronised the stream before it returned
     double *dpar = ctx->d_hpar.as<double>();
-    MB_CUDA(cudaMemcpyAsync(dpar, edges, F * (NB + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    double *hpar = ctx->h_stage.as<double>();
+    std::memcpy(hpar, edges, F * (NB + 1) * 8);
     p.edges = dpar;
     if (center) {
-        MB_CUDA(cudaMemcpyAsync(dpar + F * (NB + 1), center, F * 24, cudaMemcpyHostToDevice, ctx->stream));
+        std::memcpy(hpar + F * (NB + 1), center, F * 24);
         p.center = dpar + F * (NB + 1);
     }
     if (zrange) {
-        MB_CUDA(cudaMemcpyAsync(dpar + F * (NB + 1) + F * 3, zrange, F * 16, cudaMemcpyHostToDevice, ctx->stream));
+        std::memcpy(hpar + F * (NB + 1) + F * 3, zrange, F * 16);
         p.zrange = dpar + F * (NB + 1) + F * 3;
     }
+    MB_CUDA(cudaMemcpyAsync(dpar, hpar, (F * (NB + 1) + F * 5) * 8, cudaMemcpyHostToDevice, ctx->stream));
     unsigned long long *d_wmax = reinterpret_cast<unsigned long long *>(dpar + F * (NB + 1) + F * 5);
     p.wmax_bits = d_wmax;
     // accumulators [F][NB]: lo, hi, f64, count + outputs [F][NB] (w, c)
@@ -790,9 +798,22 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
     MB_CUDA(cudaGetLastError());
     ctx->launches += 1;
     }
-    if (hist_w) MB_CUDA(cudaMemcpyAsync(hist_w, d_ow, F * NB * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    MB_CUDA(cudaMemcpyAsync(hist_c, d_oc, F * NB * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pref_slot >= 0) {  // the prefetch slot this call read may be refilled from here on
+        std::lock_guard<std::mutex> lock(ctx->pref_mutex);
+        MB_CUDA(cudaEventRecord(ctx->pref_done_ev[pref_slot], ctx->stream));
+        ctx->pref_done_set[pref_slot] = true;
+    }
+    // results: ONE device -> pinned copy of (weighted | counts), then into the caller's (pageable) arrays
+    MB_TRY(ctx->h_out.ensure(F * NB * 16));
+    char *hres = ctx->h_out.as<char>();
+    if (hist_w) {
+        MB_CUDA(cudaMemcpyAsync(hres, d_ow, F * NB * 16, cudaMemcpyDeviceToHost, ctx->stream));  // d_ow | d_oc are adjacent
+    } else {
+        MB_CUDA(cudaMemcpyAsync(hres + F * NB * 8, d_oc, F * NB * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hist_w) std::memcpy(hist_w, hres, F * NB * 8);
+    std::memcpy(hist_c, hres + F * NB * 8, F * NB * 8);
     ctx->stats[5] = 0;
     if (ctx->timing && N) {  // time of the histogram kernel proper (mb200_ctx_stats, out[5])
         float ms = 0.f;

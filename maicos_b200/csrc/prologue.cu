@@ -151,6 +151,125 @@ extern "C" int mb200_dev_read(mb200_ctx *ctx, const void *dev, void *host, size_
     return MB200_OK;
 }
 
+extern "C" int mb200_dev_write(mb200_ctx *ctx, void *dev, const void *host, size_t bytes) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
+    MB_LOCK(ctx);
+    if (bytes && (!dev || !host)) return fail(MB200_EINVAL, "null pointer in mb200_dev_write");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    MB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));  // `host` may be reused as soon as the call returns
+    return MB200_OK;
+}
+
+// Topology of the compounds, uploaded once per analysis (compound_ptr | centre weights | masses | charges): the per-call
+// variant below used to re-send these 8 + 24 bytes per atom with every batch of frames.
+struct mb200_topology {
+    mb200::DevBuf buf;
+    const long long *ptr = nullptr;
+    const double *cw = nullptr, *mass = nullptr, *charge = nullptr;
+    int64_t n_atoms = 0, n_c = 0;
+    int device = 0;
+};
+
+extern "C" int mb200_topology_create(mb200_ctx *ctx, const int64_t *compound_ptr, int64_t n_c, int64_t n_atoms,
+                                     const double *center_weights, const double *masses, const double *charges,
+                                     mb200_topology **out) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
+    if (!out) return fail(MB200_EINVAL, "null output pointer");
+    *out = nullptr;
+    if (n_atoms < 0 || n_c <= 0 || !compound_ptr) return fail(MB200_EINVAL, "invalid argument to mb200_topology_create");
+    if (compound_ptr[0] != 0 || compound_ptr[n_c] != n_atoms) return fail(MB200_EINVAL, "compound_ptr must cover all atoms");
+    for (int64_t c = 0; c < n_c; ++c) {
+        const int64_t m = compound_ptr[c + 1] - compound_ptr[c];
+        if (m <= 0 || m > MAX_COMPOUND_ATOMS)
+            return fail(MB200_EINVAL, "compound %lld has %lld atoms (supported: 1..%d)", (long long)c, (long long)m,
+                        MAX_COMPOUND_ATOMS);
+    }
+    MB_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<mb200_topology> t(new mb200_topology());
+    const size_t NC = (size_t)n_c, N = (size_t)n_atoms;
+    const size_t b_ptr = (NC + 1) * 8, b_at = N * 8;
+    MB_TRY(t->buf.ensure(b_ptr + 3 * b_at + 64));
+    char *base = t->buf.as<char>();
+    MB_CUDA(cudaMemcpyAsync(base, compound_ptr, b_ptr, cudaMemcpyHostToDevice, ctx->stream));
+    t->ptr = reinterpret_cast<const long long *>(base);
+    size_t off = b_ptr;
+    const double *src[3] = {center_weights, masses, charges};
+    const double **dst[3] = {&t->cw, &t->mass, &t->charge};
+    for (int i = 0; i < 3; ++i, off += b_at)
+        if (src[i] && b_at) {
+            MB_CUDA(cudaMemcpyAsync(base + off, src[i], b_at, cudaMemcpyHostToDevice, ctx->stream));
+            *dst[i] = reinterpret_cast<const double *>(base + off);
+        }
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));  // the host arrays may be reused by the caller
+    t->n_atoms = n_atoms; t->n_c = n_c; t->device = ctx->device;
+    *out = t.release();
+    return MB200_OK;
+}
+
+extern "C" void mb200_topology_destroy(mb200_ctx *ctx, mb200_topology *topo) {
+    if (!topo) return;
+    if (ctx) {
+        MB_LOCK(ctx);
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        delete topo;
+    } else {
+        delete topo;
+    }
+}
+
+extern "C" int mb200_compound_prologue_topo(mb200_ctx *ctx, const float *positions, int positions_on_device,
+                                            int64_t n_frames, const float *boxes, const mb200_topology *topo,
+                                            int make_whole, int wrap_center, int weight_mode, int pdim,
+                                            double *centers_dev, double *weights_dev) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
+    if (!topo || n_frames < 0 || !boxes || !centers_dev || (topo->n_atoms && !positions) || weight_mode < 0 || weight_mode > 4 ||
+        pdim < 0 || pdim > 2)
+        return fail(MB200_EINVAL, "invalid argument to mb200_compound_prologue");
+    if (topo->device != ctx->device) return fail(MB200_EINVAL, "topology belongs to another device");
+    if (weight_mode && (!topo->mass || !topo->charge || !weights_dev))
+        return fail(MB200_EINVAL, "dipole weights need masses, charges and an output buffer");
+    if (n_frames == 0) return MB200_OK;
+    if (n_frames > 65535) return fail(MB200_EINVAL, "at most 65535 frames per call");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const size_t F = (size_t)n_frames, N = (size_t)topo->n_atoms, NC = (size_t)topo->n_c;
+    CompoundParams p;
+    std::memset(&p, 0, sizeof(p));
+    int pref_slot = -1;
+    if (positions_on_device) {
+        p.pos = positions;
+    } else if (const void *pref = take_prefetched(ctx, positions, F * N * 12)) {
+        p.pos = reinterpret_cast<const float *>(pref);  // copied on the copy stream under the previous call
+        pref_slot = ctx->pref_taken;
+        ctx->pref_taken = -1;
+    } else {
+        MB_TRY(ctx->d_hpos.ensure(F * N * 12));
+        MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * 12, cudaMemcpyHostToDevice, ctx->stream));
+        p.pos = ctx->d_hpos.as<float>();
+    }
+    MB_TRY(ctx->d_ctopo.ensure(F * 12 + 64));
+    MB_CUDA(cudaMemcpyAsync(ctx->d_ctopo.p, boxes, F * 12, cudaMemcpyHostToDevice, ctx->stream));
+    p.boxes = ctx->d_ctopo.as<float>();
+    p.ptr = topo->ptr; p.cw = topo->cw; p.mass = topo->mass; p.charge = topo->charge;
+    p.centers = centers_dev; p.weights = weights_dev;
+    p.n_atoms = topo->n_atoms; p.n_c = topo->n_c;
+    p.make_whole = make_whole; p.wrap_center = wrap_center; p.weight_mode = weight_mode; p.pdim = pdim;
+    dim3 grid((unsigned)((NC + 127) / 128), (unsigned)F);
+    k_compound<<<grid, 128, 0, ctx->stream>>>(p);
+    MB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    if (pref_slot >= 0) {
+        std::lock_guard<std::mutex> lock(ctx->pref_mutex);
+        MB_CUDA(cudaEventRecord(ctx->pref_done_ev[pref_slot], ctx->stream));
+        ctx->pref_done_set[pref_slot] = true;
+    }
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));  // `positions` / `boxes` may be reused by the caller
+    return MB200_OK;
+}
+
 extern "C" int mb200_compound_prologue(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
                                        int64_t n_atoms, const float *boxes, const int64_t *compound_ptr, int64_t n_c,
                                        const double *center_weights, const double *masses, const double *charges,
@@ -164,58 +283,12 @@ extern "C" int mb200_compound_prologue(mb200_ctx *ctx, const float *positions, i
     if (weight_mode && (!masses || !charges || !weights_dev))
         return fail(MB200_EINVAL, "dipole weights need masses, charges and an output buffer");
     if (n_frames == 0 || n_c == 0) return MB200_OK;
-    if (n_frames > 65535) return fail(MB200_EINVAL, "at most 65535 frames per call");
-    if (compound_ptr[0] != 0 || compound_ptr[n_c] != n_atoms) return fail(MB200_EINVAL, "compound_ptr must cover all atoms");
-    for (int64_t c = 0; c < n_c; ++c) {
-        const int64_t m = compound_ptr[c + 1] - compound_ptr[c];
-        if (m <= 0 || m > MAX_COMPOUND_ATOMS)
-            return fail(MB200_EINVAL, "compound %lld has %lld atoms (supported: 1..%d)", (long long)c, (long long)m,
-                        MAX_COMPOUND_ATOMS);
-    }
-    MB_CUDA(cudaSetDevice(ctx->device));
-    const size_t F = (size_t)n_frames, N = (size_t)n_atoms, NC = (size_t)n_c;
-    CompoundParams p;
-    std::memset(&p, 0, sizeof(p));
-    if (positions_on_device) {
-        p.pos = positions;
-    } else {
-        MB_TRY(ctx->d_hpos.ensure(F * N * 12));
-        MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * 12, cudaMemcpyHostToDevice, ctx->stream));
-        p.pos = ctx->d_hpos.as<float>();
-    }
-    // topology side: ptr | cw | mass | charge | boxes
-    const size_t b_ptr = (NC + 1) * 8, b_at = N * 8;
-    MB_TRY(ctx->d_ctopo.ensure(b_ptr + 3 * b_at + F * 12 + 64));
-    char *base = ctx->d_ctopo.as<char>();
-    MB_CUDA(cudaMemcpyAsync(base, compound_ptr, b_ptr, cudaMemcpyHostToDevice, ctx->stream));
-    p.ptr = reinterpret_cast<const long long *>(base);
-    size_t off = b_ptr;
-    if (center_weights) {
-        MB_CUDA(cudaMemcpyAsync(base + off, center_weights, b_at, cudaMemcpyHostToDevice, ctx->stream));
-        p.cw = reinterpret_cast<const double *>(base + off);
-    }
-    off += b_at;
-    if (masses) {
-        MB_CUDA(cudaMemcpyAsync(base + off, masses, b_at, cudaMemcpyHostToDevice, ctx->stream));
-        p.mass = reinterpret_cast<const double *>(base + off);
-    }
-    off += b_at;
-    if (charges) {
-        MB_CUDA(cudaMemcpyAsync(base + off, charges, b_at, cudaMemcpyHostToDevice, ctx->stream));
-        p.charge = reinterpret_cast<const double *>(base + off);
-    }
-    off += b_at;
-    MB_CUDA(cudaMemcpyAsync(base + off, boxes, F * 12, cudaMemcpyHostToDevice, ctx->stream));
-    p.boxes = reinterpret_cast<const float *>(base + off);
-    p.centers = centers_dev; p.weights = weights_dev;
-    p.n_atoms = n_atoms; p.n_c = n_c;
-    p.make_whole = make_whole; p.wrap_center = wrap_center; p.weight_mode = weight_mode; p.pdim = pdim;
-    dim3 grid((unsigned)((NC + 127) / 128), (unsigned)F);
-    k_compound<<<grid, 128, 0, ctx->stream>>>(p);
-    MB_CUDA(cudaGetLastError());
-    ctx->launches += 1;
-    MB_CUDA(cudaStreamSynchronize(ctx->stream));  // host topology arrays may be reused by the caller
-    return MB200_OK;
+    mb200_topology *topo = nullptr;  // one-shot form: the topology travels with the call
+    MB_TRY(mb200_topology_create(ctx, compound_ptr, n_c, n_atoms, center_weights, masses, charges, &topo));
+    const int rc = mb200_compound_prologue_topo(ctx, positions, positions_on_device, n_frames, boxes, topo, make_whole,
+                                                wrap_center, weight_mode, pdim, centers_dev, weights_dev);
+    mb200_topology_destroy(ctx, topo);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -26,7 +26,9 @@
 //                  |q| histograms (S, f^2 S, count of S != 0) with one CTA per (segment, bin)
 //                  and a fixed-order reduction -> bitwise reproducible run to run.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 
 #include "common.cuh"
@@ -1439,6 +1441,15 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
         return fail(MB200_EINVAL, "invalid argument to mb200_saxs_frames");
     if (n_frames == 0 || n_groups == 0) return MB200_OK;
     MB_CUDA(cudaSetDevice(ctx->device));
+    // developer aid: MAICOS_B200_TRACE_HOST=1 prints the host-side time of every phase of the call to stderr
+    static const bool trace_host = std::getenv("MAICOS_B200_TRACE_HOST") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!trace_host) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[mb200_saxs_frames] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     const size_t n_idx = (size_t)group_ptr[n_groups];
     for (int gi = 0; gi < n_groups; ++gi)
         if (group_ptr[gi + 1] < group_ptr[gi]) return fail(MB200_EINVAL, "group_ptr must be non-decreasing");
@@ -1449,6 +1460,7 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
     MB_TRY(ctx->d_idx.ensure(std::max<size_t>(n_idx, 1) * 4));
     if (n_idx) MB_CUDA(cudaMemcpyAsync(ctx->d_idx.p, group_index, n_idx * 4, cudaMemcpyHostToDevice, ctx->stream));
 
+    mark("index check + upload");
     // frames are processed in chunks bounded by the table workspace
     const size_t frame_elems = (size_t)n_atoms_total * 3;
     size_t done = 0;
@@ -1474,7 +1486,9 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
             ++chunk;
             if (chunk >= 256) break;
         }
+        mark("plans");
         for (auto &pl : plans) MB_TRY(plan_ff2(ctx, *pl, cm_params, n_groups));
+        mark("form factors");
 
         const float *dpos;
         if (positions_on_device) {
@@ -1510,7 +1524,9 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
                 sp.job.is_f32 = 1; sp.job.wrap_mode = pack_atoms ? 2 : 1;
             }
         std::vector<SegDesc> segs;
+        mark("positions + specs");
         MB_TRY(run_segments(ctx, specs, block, n_blocks, segs));
+        mark("run_segments (host side)");
         const size_t ns = specs.size();
         const size_t ob = ns * (size_t)n_bins;
         MB_TRY(ctx->d_out.ensure(ob * 24));
@@ -1525,6 +1541,7 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
         MB_CUDA(cudaMemcpyAsync(i_binned + oo, d_i, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
         MB_CUDA(cudaMemcpyAsync(bincount + oo, d_c, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
         MB_CUDA(cudaStreamSynchronize(ctx->stream));
+        mark("device (wait)");
         MB_TRY(finish_timing(ctx));
         done += chunk;
     }

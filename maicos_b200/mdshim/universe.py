@@ -90,13 +90,27 @@ class MemoryTrajectory:
     """
 
     def __init__(self, coordinates=None, dimensions=None, velocities=None, dt=1.0, times=None,
-                 n_frames=None, frame_source=None, n_atoms=None):
+                 n_frames=None, frame_source=None, n_atoms=None, pinned=False, pinned_rows=None):
+        """``pinned=True`` keeps the coordinate block in page-locked memory (one copy at construction): the analysis
+        classes then hand frames to the device straight from the trajectory, without a staging copy.  A
+        ``frame_source`` that serves rows of a page-locked block says so with ``pinned_rows(frame) -> (block, row)``."""
+        self._pinned_block = None
+        self._pinned_rows = pinned_rows
         if coordinates is not None:
             coordinates = np.asarray(coordinates, dtype=np.float32)
             if coordinates.ndim == 2:
                 coordinates = coordinates[None]
             n_frames = coordinates.shape[0]
             n_atoms = coordinates.shape[1]
+            if pinned:
+                from .. import _cabi
+
+                if _cabi.device_count() > 0:
+                    self._pinned_block = _cabi._PinnedBlock(max(coordinates.nbytes, 1))
+                    block = np.frombuffer(self._pinned_block.buf, dtype=np.float32, count=coordinates.size)
+                    block = block.reshape(coordinates.shape)
+                    np.copyto(block, coordinates)
+                    coordinates = block
         elif frame_source is None or n_frames is None or n_atoms is None:
             raise ValueError("give either `coordinates` or `frame_source` with `n_frames` and `n_atoms`")
         self.coordinates = coordinates
@@ -139,6 +153,23 @@ class MemoryTrajectory:
         t = self.times[f] if self.times is not None else f * self.dt
         self.ts = Timestep(np.ascontiguousarray(pos, dtype=np.float32), dims, f, float(t), vel)
         return self.ts
+
+    def pinned_row(self, f: int):
+        """``(page-locked float32 block [*, n_atoms, 3], row)`` holding frame ``f``, or ``None``."""
+        if self._pinned_rows is not None:
+            return self._pinned_rows(int(f))
+        if self._pinned_block is not None:
+            return self.coordinates, int(f)
+        return None
+
+    def __del__(self):
+        block, self._pinned_block = getattr(self, "_pinned_block", None), None
+        if block is not None:
+            self.coordinates = None
+            try:
+                block.free()
+            except Exception:
+                pass
 
     def __len__(self):
         return self.n_frames

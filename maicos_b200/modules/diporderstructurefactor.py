@@ -16,7 +16,7 @@ import logging
 import numpy as np
 
 from .. import _cabi, parallel
-from ..core.base import AnalysisBase, CompoundPrologue, compound_runs, positions_into
+from ..core.base import AnalysisBase, CompoundPrologue, compound_runs, gather_rows
 from ..lib.util import cell_diagonal, get_center, is_orthorhombic
 
 
@@ -61,8 +61,7 @@ class DiporderStructureFactor(AnalysisBase):
     def _stage_frame(self):
         box = np.double(np.array(cell_diagonal(self._ts.dimensions), dtype=np.float32))  # diporderstructurefactor.py:94
         if self._prologue is not None:
-            buf, row = self._staging_rows((self.atomgroup.n_atoms, 3), np.float32, "pos")
-            positions_into(self.atomgroup, buf[row])
+            buf, row = self._stage_positions()
             return buf, row, box
         positions = np.ascontiguousarray(
             get_center(atomgroup=self.atomgroup, bin_method=self.bin_method, compound=self.wrap_compound),
@@ -74,16 +73,16 @@ class DiporderStructureFactor(AnalysisBase):
         unit = dipoles / np.linalg.norm(dipoles, axis=1)[:, np.newaxis]
         return positions, np.ascontiguousarray(unit.T, dtype=np.float64), box
 
+    def _announce_staged(self, staged: list) -> None:
+        if self._prologue is not None:
+            self._announce_rows([(st[0], st[1]) for st in staged])
+
     def _compute_staged(self, staged: list) -> list:
         F = len(staged)
         boxes = np.stack([s[2] for s in staged])
         on_device = 0
         if self._prologue is not None:
-            base = staged[0][0].ctypes.data
-            if all(st[0].ctypes.data == base and st[1] == staged[0][1] + f for f, st in enumerate(staged)):
-                raw = staged[0][0][staged[0][1]:staged[0][1] + F]
-            else:
-                raw = np.stack([buf[row] for buf, row, _ in staged])
+            raw = gather_rows([(st[0], st[1]) for st in staged])
             pos, w = self._prologue.run(raw, boxes.astype(np.float32))
             n, on_device = self._prologue.n_c, 1
         else:

@@ -19,7 +19,7 @@ import logging
 import numpy as np
 
 from .. import _cabi, parallel
-from ..core.base import AnalysisBase, positions_into
+from ..core.base import AnalysisBase, gather_rows
 from ..lib import tables
 from ..lib.math import atomic_form_factor, structure_factor
 from ..lib.util import cell_diagonal, is_orthorhombic
@@ -54,11 +54,13 @@ def _element_groups(atomgroup):
     universe = atomgroup.universe
     cache = universe.__dict__.setdefault("_mb200_element_groups", {}) if hasattr(universe, "__dict__") else {}
     ix = getattr(atomgroup, "ix", None)
-    if getattr(atomgroup, "_all", False):  # the whole universe: no need to fingerprint a million indices
-        key = ("all", atomgroup.n_atoms, id(universe))
+    if ix is None:
+        key = None
+    elif getattr(atomgroup, "_all", False):  # the whole universe: no need to fingerprint a million indices
+        key = ("all", len(ix), id(universe))
     else:
-        key = (atomgroup.n_atoms, hash(np.asarray(ix).tobytes()) if ix is not None else None, id(universe))
-    if ix is not None and key in cache:
+        key = (len(ix), hash(np.asarray(ix).tobytes()), id(universe))
+    if key is not None and key in cache:
         return cache[key]
     elements = np.asarray(atomgroup.elements)
     if elements.dtype == object and len(elements) > 4096:
@@ -206,18 +208,12 @@ class Saxs(AnalysisBase):
                 f"Dimensions in frame {self._frame_index} are different from "
                 "initial dimenions. Can not use `bin_spectrum=False`."
             )
-        buf, row = self._staging_rows((self.atomgroup.n_atoms, 3), np.float32, "pos")
-        positions_into(self.atomgroup, buf[row])
+        buf, row = self._stage_positions()
         return buf, row, box
 
     def _announce_staged(self, staged: list) -> None:
-        if not self.bin_spectrum or not staged:
-            return
-        base = staged[0][0].ctypes.data
-        if any(st[0].ctypes.data != base or st[1] != f for f, st in enumerate(staged)):
-            return  # not one contiguous staging run: the call copies by itself
-        nbytes = len(staged) * self.atomgroup.n_atoms * 12
-        _cabi.check(_cabi.load().mb200_prefetch_frames(_cabi.context().handle, base, nbytes))
+        if self.bin_spectrum:
+            self._announce_rows([(st[0], st[1]) for st in staged])
 
     def _device_packs(self) -> bool:
         # the kernel's pack is the orthorhombic ``x -= floor(x / L) L``; a triclinic cell is packed by the host
@@ -228,10 +224,7 @@ class Saxs(AnalysisBase):
         if not self.bin_spectrum:
             return [self._unbinned_frame(buf[row].copy(), box) for buf, row, box in staged]
         F, n, G = len(staged), self.atomgroup.n_atoms, len(self.groups)
-        pos = staged[0][0]
-        base = pos.ctypes.data
-        if any(st[0].ctypes.data != base or st[1] != f for f, st in enumerate(staged)):
-            pos = np.stack([buf[row] for buf, row, _ in staged])  # not one contiguous staging run
+        pos = gather_rows([(st[0], st[1]) for st in staged])  # a view of the staging buffer / pinned trajectory
         boxes = np.array([st[2] for st in staged], dtype=np.float32)
         s = np.zeros((F, G, self.n_bins))
         i = np.zeros((F, G, self.n_bins))
