@@ -305,24 +305,28 @@ def main():
     # ---- end to end through the public API (host trajectory -> Saxs.run()) ----------------------
     e2e = None
     if not args.no_e2e:
-        # the in-memory trajectory: the frame pool in PAGE-LOCKED host memory (frames go trajectory -> PCIe -> HBM with no
-        # staging copy), and the same pool in ordinary pageable memory (one host copy per frame into the pinned batch buffer)
-        pool_pinned = _cabi.pinned_empty(pool.shape, np.float32, slot="bench:pool")
-        np.copyto(pool_pinned, pool)
+        # the in-memory trajectory of this rank (K * B frames, the pool tiled) in PAGE-LOCKED host memory -- frames go
+        # trajectory -> PCIe -> HBM with no staging copy -- and the same frames served from ordinary pageable memory (one
+        # host copy per frame into the pinned batch buffer).  Rank r analyses frames r, r + W, ...: its local frame j is
+        # global frame j * W + r.
+        n_local = max(K, W) * B
+        traj_pinned = _cabi.pinned_empty((n_local, n, 3), np.float32, slot="bench:traj")
+        for j0 in range(0, n_local, len(pool)):
+            np.copyto(traj_pinned[j0:j0 + len(pool)], pool[:min(len(pool), n_local - j0)])
 
-        def universe(n_frames, offset, source):
-            def src(f):  # a frame of the in-memory pool as a read-only view (what MDAnalysis' MemoryReader hands out)
-                v = source[(offset + f) % len(source)].view()
+        def universe(n_frames, pinned):
+            def src(f):  # a frame as a read-only view (what MDAnalysis' MemoryReader hands out)
+                v = (traj_pinned[f // world] if pinned else pool[(f // world) % len(pool)]).view()
                 v.flags.writeable = False
                 return v
-            rows = (lambda f: (source, (offset + f) % len(source))) if source is pool_pinned else None
+            rows = (lambda f: (traj_pinned, f // world)) if pinned else None
             traj = MemoryTrajectory(dimensions=np.float32([BOX, BOX, BOX, 90, 90, 90]), n_frames=n_frames,
                                     frame_source=src, n_atoms=n, pinned_rows=rows)
             return Universe(n, traj, **topo)
 
-        def run_e2e(source):
-            mb.Saxs(universe(W * B * world, 0, source).atoms, qmax=QMAX, dq=DQ).run()  # warm-up: W steps per rank
-            u = universe(K * B * world, 17, source)
+        def run_e2e(pinned):
+            mb.Saxs(universe(W * B * world, pinned).atoms, qmax=QMAX, dq=DQ).run()  # warm-up: W steps per rank
+            u = universe(K * B * world, pinned)
             parallel.barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
             saxs = mb.Saxs(u.atoms, qmax=QMAX, dq=DQ).run()   # K steps per rank + one merging allreduce
@@ -338,8 +342,8 @@ def main():
         mb.Saxs._batch_size = B
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            dt, saxs = run_e2e(pool_pinned)
-            dt_pg, saxs_pg = run_e2e(pool)
+            dt, saxs = run_e2e(True)
+            dt_pg, saxs_pg = run_e2e(False)
         e2e = {"value": atomq_total / dt, "unit": "atom*q/s", "h2d_bytes_per_step": int(B * n * 12 + B * 12 + n * 4),
                "d2h_bytes_per_step": int(B * G * n_bins * 24), "frames_per_s": K * B * world / dt,
                "api": "maicos_b200.Saxs(atomgroup, qmax=2.0, dq=0.1).run()", "ms_per_step": dt / K * 1e3,
@@ -351,7 +355,7 @@ def main():
                                        "note": "same run with the trajectory in ordinary pageable memory: one host copy per "
                                                "frame into the pinned batch buffer, then the same H2D"}}
         mb.Saxs._batch_size = 32
-        _cabi.release_pinned("bench:pool")
+        _cabi.release_pinned("bench:traj")
 
     # ---- the other BASELINE configurations (bounded, with parity) -- every rank takes part in the sharded ones ----
     configs = None
@@ -596,7 +600,7 @@ def run_configs(args, ctx, lib, torch, rank, world, peaks):
 
     # ---- C4: DensityPlanar + DiporderPlanar on a 1M-atom graphene-confined slab (configs[3]) --------------------
     def c4():
-        n_c, n_w, F = 100_000, 300_000, 16
+        n_c, n_w, F = 100_000, 300_000, 64
         box = [215.0, 215.0, 215.4]
         fr, topo = confined_slab_frames(n_w, n_c, *box, 200.0, 20261021, n_frames=F)
         u_pg = Universe(fr.shape[1], MemoryTrajectory(fr, np.float32([*box, 90, 90, 90])), **topo)

@@ -204,10 +204,25 @@ int mb200_topology_create(mb200_ctx *ctx, const int64_t *compound_ptr, int64_t n
                           const double *center_weights, const double *masses, const double *charges,
                           mb200_topology **out);
 void mb200_topology_destroy(mb200_ctx *ctx, mb200_topology *topo);
+/*   compound_ptr NULL (n_c == n_atoms): every atom is its own compound (velocity / temperature weights per atom).
+ *   uv_mode / uv_dim (weight modes 1..3): the unit vector the dipole is projected on --
+ *     0 Cartesian e_pdim                                    src/maicos/lib/util.py:684-706
+ *     1 radial direction of a cylinder with axis uv_dim     src/maicos/lib/util.py:710-756  (DiporderCylinder, pdim "r")
+ *     2 radial direction of a sphere                        src/maicos/lib/util.py:760-786  (DiporderSphere)
+ *   both about the box centre dimensions[:3] / 2, from the compound's binned centre (bin_method). */
 int mb200_compound_prologue_topo(mb200_ctx *ctx, const float *positions, int positions_on_device,
                                  int64_t n_frames, const float *boxes, const mb200_topology *topo,
                                  int make_whole, int wrap_center, int weight_mode, int pdim,
-                                 double *centers_dev, double *weights_dev);
+                                 int uv_mode, int uv_dim, double *centers_dev, double *weights_dev);
+
+/* Velocity-derived weights from the raw velocities of a batch of frames; replaces the per-frame host calls
+ *   velocity_weights(ag, grouping, vdim)     src/maicos/lib/weights.py:195-225
+ *   temperature_weights(ag, grouping)        src/maicos/lib/weights.py:101-127
+ *   velocities : float32 [n_frames][n_atoms][3] (host, or device if velocities_on_device)
+ *   mode       : 0 v[:, vdim] per atom, 1 mass-weighted mean of v[:, vdim] per compound, 2 kinetic temperature per atom
+ * output (DEVICE): weights_dev float64 [n_frames][n_c], for mb200_profile_hist(weights_on_device=1, weights_per_frame=1). */
+int mb200_velocity_weights(mb200_ctx *ctx, const float *velocities, int velocities_on_device, int64_t n_frames,
+                           const mb200_topology *topo, int mode, int vdim, double *weights_dev);
 
 /* Per-atom quantities of the "virtual cut" estimator of the dielectric profile modules:
  *   testpos_i = centre of |charge| of atom i's compound along the profile coordinate

@@ -159,7 +159,7 @@ class CompoundPrologue:
     """Device-side unwrap / wrap / centre / dipole weights of an atom group's compounds."""
 
     def __init__(self, atomgroup, compound: str, bin_method: str, make_whole: bool, wrap_center: bool,
-                 weight_mode: int = 0, pdim: int = 0):
+                 weight_mode: int = 0, pdim: int = 0, uv_mode: int = 0, uv_dim: int = 0):
         from .. import _cabi
 
         self.ptr = compound_runs(atomgroup, compound)
@@ -174,6 +174,7 @@ class CompoundPrologue:
             raise ValueError("dipole weights need masses and charges")
         self.make_whole, self.wrap_center = bool(make_whole), bool(wrap_center)
         self.weight_mode, self.pdim = int(weight_mode), int(pdim)
+        self.uv_mode, self.uv_dim = int(uv_mode), int(uv_dim)  # unit vector of the projection: Cartesian / cylinder / sphere
         self.ctx = _cabi.context()
         self.centers = _cabi.DeviceBuffer(self.ctx)
         self.weights = _cabi.DeviceBuffer(self.ctx)
@@ -196,13 +197,60 @@ class CompoundPrologue:
         boxes = np.ascontiguousarray(boxes, dtype=np.float32)
         _cabi.check(_cabi.load().mb200_compound_prologue_topo(
             self.ctx.handle, _cabi.ptr(positions), 0, F, _cabi.ptr(boxes), self._topo, int(self.make_whole),
-            int(self.wrap_center), self.weight_mode, self.pdim, c_ptr, w_ptr))
+            int(self.wrap_center), self.weight_mode, self.pdim, self.uv_mode, self.uv_dim, c_ptr, w_ptr))
         return c_ptr, w_ptr
 
     def close(self) -> None:
         from .. import _cabi
 
         topo, self._topo = getattr(self, "_topo", None), None
+        if topo:
+            _cabi.load().mb200_topology_destroy(self.ctx.handle, topo)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class VelocityWeights:
+    """Device-side ``velocity_weights`` / ``temperature_weights`` (``lib/weights.py:101-127, 195-225``) from the raw
+    float32 velocities of a batch: mode 0 ``v[:, vdim]`` per atom, 1 mass-weighted compound mean, 2 kinetic temperature."""
+
+    def __init__(self, atomgroup, mode: int, vdim: int, prologue: CompoundPrologue | None = None):
+        import ctypes
+
+        from .. import _cabi
+
+        self.ctx = _cabi.context()
+        self.mode, self.vdim = int(mode), int(vdim)
+        self.n_atoms = atomgroup.n_atoms
+        self._own_topo = None
+        if prologue is not None:          # compounds: the prologue's topology (compound_ptr + masses)
+            self._topo, self.n_c = prologue._topo, prologue.n_c
+        else:                             # every atom its own compound
+            masses = np.ascontiguousarray(atomgroup.masses, dtype=np.float64) if mode == 2 else None
+            self._own_topo = ctypes.c_void_p()
+            _cabi.check(_cabi.load().mb200_topology_create(self.ctx.handle, None, self.n_atoms, self.n_atoms, None,
+                                                           _cabi.ptr(masses), None, ctypes.byref(self._own_topo)))
+            self._topo, self.n_c = self._own_topo, self.n_atoms
+        self.weights = _cabi.DeviceBuffer(self.ctx)
+
+    def run(self, velocities: np.ndarray) -> int:
+        """velocities float32 [F, n_atoms, 3] (pinned) -> device pointer of the weights float64 [F, n_c]."""
+        from .. import _cabi
+
+        F = velocities.shape[0]
+        w_ptr = self.weights.ensure(F * self.n_c * 8)
+        _cabi.check(_cabi.load().mb200_velocity_weights(self.ctx.handle, _cabi.ptr(velocities), 0, F, self._topo, self.mode,
+                                                        self.vdim, w_ptr))
+        return w_ptr
+
+    def close(self) -> None:
+        from .. import _cabi
+
+        topo, self._own_topo = self._own_topo, None
         if topo:
             _cabi.load().mb200_topology_destroy(self.ctx.handle, topo)
 
@@ -409,6 +457,19 @@ class AnalysisBase(_Runner):
         positions_into(ag, buf[row])
         return buf, row
 
+    def _gather_staged(self, rows: list, tag: str = "gather") -> np.ndarray:
+        """``[F, ...]`` array of staged rows for the device call: the rows themselves when they are consecutive (a view,
+        no copy), else gathered into a page-locked buffer (strided frame selections of a pinned trajectory)."""
+        from .. import _cabi
+
+        buf, base = rows[0][0], rows[0][0].ctypes.data
+        if all(r[0].ctypes.data == base and r[1] == rows[0][1] + i for i, r in enumerate(rows)):
+            return buf[rows[0][1]:rows[0][1] + len(rows)]
+        out = _cabi.pinned_empty((len(rows), *buf.shape[1:]), buf.dtype, slot=f"{self._slot_prefix()}{tag}")
+        for i, (b, r) in enumerate(rows):
+            _cabi.host_copy(out[i], b[r])
+        return out
+
     def _announce_rows(self, rows: list) -> None:
         """Announce consecutive staged rows to the library (``mb200_prefetch_frames``): their host -> device copy then
         runs on the copy stream while the device call before this batch is still computing."""
@@ -416,9 +477,10 @@ class AnalysisBase(_Runner):
 
         if not rows:
             return
-        block = gather_rows(rows)
-        if block.base is None and len(rows) > 1:
-            return  # a stacked copy: the call copies by itself
+        buf, base = rows[0][0], rows[0][0].ctypes.data
+        if not all(r[0].ctypes.data == base and r[1] == rows[0][1] + i for i, r in enumerate(rows)):
+            return  # not one run of rows: the call gathers and copies by itself
+        block = buf[rows[0][1]:rows[0][1] + len(rows)]
         _cabi.check(_cabi.load().mb200_prefetch_frames(_cabi.context().handle, block.ctypes.data, block.nbytes))
 
     def _staging_rows(self, shape, dtype, tag: str) -> tuple[np.ndarray, int]:
@@ -786,20 +848,34 @@ class ProfileBase:
         self._dev_static_w = None
         # frames per device call: bounded by ~64 MB of staged positions per batch
         n_pos = self.atomgroup.n_atoms
-        self._batch_size = int(max(1, min(64, (64 << 20) // max(1, n_pos * 12))))
+        self._batch_size = int(max(1, min(64, (128 << 20) // max(1, n_pos * 12))))
         # compounds: unwrap / wrap / centres / dipole weights on the device when they are eligible
         self._prologue = None
-        mode = getattr(self, "_device_weight_mode", None)
+        self._velocity = None
+        mode = getattr(self, "_device_weight_mode", None)          # (weight mode, pdim[, uv mode, uv dim]) of Diporder*
+        vmode = getattr(self, "_device_velocity_mode", None)       # (mode, vdim) of Velocity* / Temperature*
+        from ..mdshim import Universe as ShimUniverse
+
+        has_vel = vmode is not None and isinstance(self.atomgroup.universe, ShimUniverse) and (
+            getattr(self.atomgroup.universe.trajectory, "velocities", None) is not None)
         if (self.grouping != "atoms" and getattr(self, "refgroup", None) is None and not getattr(self, "jitter", 0.0)
-                and (self._static_weights or mode is not None) and compound_runs(self.atomgroup, self.grouping) is not None):
-            wm, pdim = mode if mode is not None else (0, 0)
+                and (self._static_weights or mode is not None or has_vel)
+                and is_orthorhombic(self.atomgroup.universe.dimensions)
+                and compound_runs(self.atomgroup, self.grouping) is not None):
+            wm, pdim, uvm, uvd = (tuple(mode) + (0, 0))[:4] if mode is not None else (0, 0, 0, 0)
             try:
                 self._prologue = CompoundPrologue(
                     self.atomgroup, self.grouping, self.bin_method, make_whole=bool(getattr(self, "unwrap", False)),
                     wrap_center=bool(getattr(self, "unwrap", False) or getattr(self, "pack", False)),
-                    weight_mode=wm, pdim=pdim)
+                    weight_mode=wm, pdim=pdim, uv_mode=uvm, uv_dim=uvd)
             except ValueError:
                 self._prologue = None
+        if has_vel and (self.grouping == "atoms" or self._prologue is not None):
+            try:
+                self._velocity = VelocityWeights(self.atomgroup, vmode[0] if self.grouping == "atoms" else 1, vmode[1],
+                                                 prologue=self._prologue)
+            except ValueError:
+                self._velocity = None
 
     # geometry classes provide these two
     def _hist_geometry(self) -> dict:
@@ -840,6 +916,14 @@ class ProfileBase:
         Positions (and per-frame weights) go straight into the pinned batch buffer of the frame's row.
         """
         st = dict(self._hist_geometry())
+        if self._velocity is not None:  # raw float32 velocities; the weights are formed on the device
+            vbuf, vrow = self._staging_rows((self.atomgroup.n_atoms, 3), np.float32, "vel")
+            vel = self._universe.trajectory.ts.velocities
+            if getattr(self.atomgroup, "_all", False):
+                np.copyto(vbuf[vrow], vel)
+            else:
+                np.take(vel, self.atomgroup.indices, axis=0, out=vbuf[vrow])
+            st["velocities"] = (vbuf, vrow)
         if self._prologue is not None:  # raw atoms; centres and weights are formed on the device
             st["positions"] = self._stage_positions()
             st["box"] = np.array(self._universe.dimensions[:3], dtype=np.float32)
@@ -855,6 +939,8 @@ class ProfileBase:
         st["positions"] = (buf, row)
         if self._static_weights:
             st["weights"] = self._profile_weights()
+        elif self._velocity is not None:
+            st["weights"] = None
         else:
             w = self._profile_weights()
             wbuf, wrow = self._staging_rows(w.shape, np.float64, "w")
@@ -885,13 +971,16 @@ class ProfileBase:
         from ..lib._hist import profile_hist
 
         g0 = staged[0]
-        pos = self._gather_rows([s["positions"] for s in staged])
+        pos = self._gather_staged([s["positions"] for s in staged])
         edges = np.stack([s["edges"] for s in staged])
         center = None if g0["center"] is None else np.stack([s["center"] for s in staged])
         zrange = None if g0["zrange"] is None else np.stack([s["zrange"] for s in staged])
+        vel_w = None
+        if self._velocity is not None:
+            vel_w = (self._velocity.run(self._gather_staged([s["velocities"] for s in staged], tag="velg")), True)
         if self._prologue is not None:
             c_ptr, w_ptr = self._prologue.run(pos, np.stack([s["box"] for s in staged]))
-            dev_w = (w_ptr, True) if w_ptr else None
+            dev_w = (w_ptr, True) if w_ptr else vel_w
             if self._static_weights and not w_ptr:
                 dev_w = (self._static_weights_on_device(g0["weights"]), False)
             hw, hc = profile_hist(g0["geometry"], None, g0["dim"], None, edges, center, zrange,
@@ -900,6 +989,8 @@ class ProfileBase:
             if self._static_weights:
                 hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange,
                                       device_weights=(self._static_weights_on_device(g0["weights"]), False))
+            elif vel_w is not None:
+                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange, device_weights=vel_w)
             else:
                 w = self._gather_rows([s["weights"] for s in staged])
                 hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], w, edges, center, zrange)

@@ -136,6 +136,11 @@ struct mb200_ctx {
     // Every compute entry point holds this for its whole duration: the workspaces above and the stream are shared by all
     // callers of the context (several analysis instances each drive their own worker thread, AnalysisCollection).
     std::recursive_mutex call_mutex;
+    // group-index array of the last mb200_saxs_frames call that is resident in d_idx (size, fingerprint, atom count)
+    bool idx_valid = false;
+    size_t idx_n = 0;
+    unsigned long long idx_fp = 0;
+    int64_t idx_natoms = 0;
     std::list<std::shared_ptr<mb200::SfPlan>> plans;  // small LRU cache keyed by box + q window
     ~mb200_ctx();
 };

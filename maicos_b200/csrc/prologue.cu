@@ -24,6 +24,9 @@ struct CompoundParams {
     double *weights;         // [F][n_c] or [F][3][n_c] or null
     long long n_atoms, n_c;
     int make_whole, wrap_center, weight_mode, pdim;
+    // unit vector the dipole is projected on: 0 Cartesian e_pdim (lib/util.py:684-706), 1 radial direction of a cylinder
+    // with axis uv_dim about the box centre (util.py:710-756), 2 radial direction of a sphere about the box centre (760-786)
+    int uv_mode, uv_dim;
 };
 
 constexpr int MAX_COMPOUND_ATOMS = 64;  // larger compounds take the host path
@@ -102,6 +105,23 @@ __global__ void __launch_bounds__(128) k_compound(CompoundParams p) {
         dz = __dadd_rn(dz, __dmul_rn(qi, __dsub_rn((double)z, rz)));
     }
     const double mu[3] = {dx, dy, dz};
+    if (p.uv_mode != 0 && p.weight_mode != 4) {
+        // e = (centre - box / 2), axial component dropped for the cylinder, normalised (numpy order: ((x^2 + y^2) + z^2));
+        // the centre is the binned one (bin_method), the box centre is dimensions[:3] / 2 in float32 (util.py:745-755, 779-785)
+        double e[3] = {__dsub_rn(out[0], (double)(bx * 0.5f)), __dsub_rn(out[1], (double)(by * 0.5f)),
+                       __dsub_rn(out[2], (double)(bz * 0.5f))};
+        if (p.uv_mode == 1) e[p.uv_dim] = 0.0;
+        const double en = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(e[0], e[0]), __dmul_rn(e[1], e[1])), __dmul_rn(e[2], e[2])));
+        for (int d = 0; d < 3; ++d) e[d] = __ddiv_rn(e[d], en);
+        double m3[3] = {mu[0], mu[1], mu[2]};
+        if (p.weight_mode != 1) {  // cos_theta: (mu / |mu|) . e  (weights.py:163-167)
+            const double norm = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            for (int d = 0; d < 3; ++d) m3[d] = __ddiv_rn(m3[d], norm);
+        }
+        const double w = __dadd_rn(__dadd_rn(__dmul_rn(m3[0], e[0]), __dmul_rn(m3[1], e[1])), __dmul_rn(m3[2], e[2]));
+        p.weights[(size_t)f * p.n_c + c] = p.weight_mode == 3 ? __dmul_rn(w, w) : w;
+        return;
+    }
     if (p.weight_mode == 1) {  // P0: mu . e
         p.weights[(size_t)f * p.n_c + c] = mu[p.pdim];
         return;
@@ -113,6 +133,46 @@ __global__ void __launch_bounds__(128) k_compound(CompoundParams p) {
     }
     const double cs = __ddiv_rn(mu[p.pdim], norm);
     p.weights[(size_t)f * p.n_c + c] = p.weight_mode == 3 ? __dmul_rn(cs, cs) : cs;
+}
+
+// Velocity-derived weights of the Velocity* / Temperature* profile modules from the raw float32 velocities of a batch of
+// frames (lib/weights.py:101-127, 195-225); one thread per compound:
+//   mode 0  v[:, vdim] per atom (grouping "atoms": compounds are single atoms)
+//   mode 1  sum_i m_i v_i[vdim] / sum_i m_i per compound, float64 sums in atom order
+//   mode 2  kinetic temperature per atom, ((vx^2 + vy^2) + vz^2 in float32) * m / 2 * prefac  (weights.py:125-127)
+struct VelocityParams {
+    const float *vel;       // [F][n_atoms][3]
+    const long long *ptr;   // [n_c + 1] or null (every atom its own compound)
+    const double *mass;     // [n_atoms] or null (mode 0)
+    double *weights;        // [F][n_c]
+    long long n_atoms, n_c;
+    double prefac;
+    int mode, vdim;
+};
+
+__global__ void __launch_bounds__(256) k_velocity_weights(VelocityParams p) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long f = blockIdx.y;
+    if (c >= p.n_c) return;
+    const long long a0 = p.ptr ? p.ptr[c] : c, a1 = p.ptr ? p.ptr[c + 1] : c + 1;
+    const float *v = p.vel + ((size_t)f * p.n_atoms) * 3;
+    double w;
+    if (p.mode == 0) {
+        w = (double)v[a0 * 3 + p.vdim];
+    } else if (p.mode == 1) {
+        double num = 0.0, den = 0.0;
+        for (long long a = a0; a < a1; ++a) {
+            const double m = p.mass[a];
+            num = __dadd_rn(num, __dmul_rn((double)v[a * 3 + p.vdim], m));
+            den = __dadd_rn(den, m);
+        }
+        w = __ddiv_rn(num, den);
+    } else {
+        const float vx = v[a0 * 3], vy = v[a0 * 3 + 1], vz = v[a0 * 3 + 2];
+        const float s = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+        w = __dmul_rn(__ddiv_rn(__dmul_rn((double)s, p.mass[a0]), 2.0), p.prefac);
+    }
+    p.weights[(size_t)f * p.n_c + c] = w;
 }
 
 }  // namespace mb200
@@ -178,22 +238,27 @@ extern "C" int mb200_topology_create(mb200_ctx *ctx, const int64_t *compound_ptr
     MB_LOCK(ctx);
     if (!out) return fail(MB200_EINVAL, "null output pointer");
     *out = nullptr;
-    if (n_atoms < 0 || n_c <= 0 || !compound_ptr) return fail(MB200_EINVAL, "invalid argument to mb200_topology_create");
-    if (compound_ptr[0] != 0 || compound_ptr[n_c] != n_atoms) return fail(MB200_EINVAL, "compound_ptr must cover all atoms");
-    for (int64_t c = 0; c < n_c; ++c) {
-        const int64_t m = compound_ptr[c + 1] - compound_ptr[c];
-        if (m <= 0 || m > MAX_COMPOUND_ATOMS)
-            return fail(MB200_EINVAL, "compound %lld has %lld atoms (supported: 1..%d)", (long long)c, (long long)m,
-                        MAX_COMPOUND_ATOMS);
+    if (n_atoms < 0 || n_c <= 0) return fail(MB200_EINVAL, "invalid argument to mb200_topology_create");
+    if (!compound_ptr && n_c != n_atoms) return fail(MB200_EINVAL, "without compound_ptr every atom is its own compound");
+    if (compound_ptr) {
+        if (compound_ptr[0] != 0 || compound_ptr[n_c] != n_atoms) return fail(MB200_EINVAL, "compound_ptr must cover all atoms");
+        for (int64_t c = 0; c < n_c; ++c) {
+            const int64_t m = compound_ptr[c + 1] - compound_ptr[c];
+            if (m <= 0 || m > MAX_COMPOUND_ATOMS)
+                return fail(MB200_EINVAL, "compound %lld has %lld atoms (supported: 1..%d)", (long long)c, (long long)m,
+                            MAX_COMPOUND_ATOMS);
+        }
     }
     MB_CUDA(cudaSetDevice(ctx->device));
     std::unique_ptr<mb200_topology> t(new mb200_topology());
     const size_t NC = (size_t)n_c, N = (size_t)n_atoms;
-    const size_t b_ptr = (NC + 1) * 8, b_at = N * 8;
+    const size_t b_ptr = compound_ptr ? (NC + 1) * 8 : 0, b_at = N * 8;
     MB_TRY(t->buf.ensure(b_ptr + 3 * b_at + 64));
     char *base = t->buf.as<char>();
-    MB_CUDA(cudaMemcpyAsync(base, compound_ptr, b_ptr, cudaMemcpyHostToDevice, ctx->stream));
-    t->ptr = reinterpret_cast<const long long *>(base);
+    if (compound_ptr) {
+        MB_CUDA(cudaMemcpyAsync(base, compound_ptr, b_ptr, cudaMemcpyHostToDevice, ctx->stream));
+        t->ptr = reinterpret_cast<const long long *>(base);
+    }
     size_t off = b_ptr;
     const double *src[3] = {center_weights, masses, charges};
     const double **dst[3] = {&t->cw, &t->mass, &t->charge};
@@ -223,11 +288,11 @@ extern "C" void mb200_topology_destroy(mb200_ctx *ctx, mb200_topology *topo) {
 extern "C" int mb200_compound_prologue_topo(mb200_ctx *ctx, const float *positions, int positions_on_device,
                                             int64_t n_frames, const float *boxes, const mb200_topology *topo,
                                             int make_whole, int wrap_center, int weight_mode, int pdim,
-                                            double *centers_dev, double *weights_dev) {
+                                            int uv_mode, int uv_dim, double *centers_dev, double *weights_dev) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
     MB_LOCK(ctx);
     if (!topo || n_frames < 0 || !boxes || !centers_dev || (topo->n_atoms && !positions) || weight_mode < 0 || weight_mode > 4 ||
-        pdim < 0 || pdim > 2)
+        pdim < 0 || pdim > 2 || uv_mode < 0 || uv_mode > 2 || uv_dim < 0 || uv_dim > 2 || !topo->ptr)
         return fail(MB200_EINVAL, "invalid argument to mb200_compound_prologue");
     if (topo->device != ctx->device) return fail(MB200_EINVAL, "topology belongs to another device");
     if (weight_mode && (!topo->mass || !topo->charge || !weights_dev))
@@ -257,6 +322,7 @@ extern "C" int mb200_compound_prologue_topo(mb200_ctx *ctx, const float *positio
     p.centers = centers_dev; p.weights = weights_dev;
     p.n_atoms = topo->n_atoms; p.n_c = topo->n_c;
     p.make_whole = make_whole; p.wrap_center = wrap_center; p.weight_mode = weight_mode; p.pdim = pdim;
+    p.uv_mode = uv_mode; p.uv_dim = uv_dim;
     dim3 grid((unsigned)((NC + 127) / 128), (unsigned)F);
     k_compound<<<grid, 128, 0, ctx->stream>>>(p);
     MB_CUDA(cudaGetLastError());
@@ -267,6 +333,42 @@ extern "C" int mb200_compound_prologue_topo(mb200_ctx *ctx, const float *positio
         ctx->pref_done_set[pref_slot] = true;
     }
     MB_CUDA(cudaStreamSynchronize(ctx->stream));  // `positions` / `boxes` may be reused by the caller
+    return MB200_OK;
+}
+
+extern "C" int mb200_velocity_weights(mb200_ctx *ctx, const float *velocities, int velocities_on_device, int64_t n_frames,
+                                      const mb200_topology *topo, int mode, int vdim, double *weights_dev) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
+    if (!topo || n_frames < 0 || !weights_dev || (topo->n_atoms && !velocities) || mode < 0 || mode > 2 || vdim < 0 || vdim > 2)
+        return fail(MB200_EINVAL, "invalid argument to mb200_velocity_weights");
+    if (topo->device != ctx->device) return fail(MB200_EINVAL, "topology belongs to another device");
+    if (mode != 0 && !topo->mass) return fail(MB200_EINVAL, "this mode needs masses in the topology");
+    if (mode != 1 && topo->n_c != topo->n_atoms) return fail(MB200_EINVAL, "per-atom modes need one compound per atom");
+    if (n_frames == 0 || topo->n_c == 0) return MB200_OK;
+    if (n_frames > 65535) return fail(MB200_EINVAL, "at most 65535 frames per call");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const size_t F = (size_t)n_frames, N = (size_t)topo->n_atoms;
+    VelocityParams p;
+    std::memset(&p, 0, sizeof(p));
+    if (velocities_on_device) {
+        p.vel = velocities;
+    } else {
+        MB_TRY(ctx->d_hw2.ensure(F * N * 12));
+        MB_CUDA(cudaMemcpyAsync(ctx->d_hw2.p, velocities, F * N * 12, cudaMemcpyHostToDevice, ctx->stream));
+        p.vel = ctx->d_hw2.as<float>();
+    }
+    p.ptr = topo->n_c == topo->n_atoms ? nullptr : topo->ptr;
+    p.mass = topo->mass; p.weights = weights_dev;
+    p.n_atoms = topo->n_atoms; p.n_c = topo->n_c;
+    // ((1 u * A^2) / ps^2) / k_B with scipy.constants' CODATA values (weights.py:125-126)
+    p.prefac = 1.66053906660e-27 * 1e4 / 1.380649e-23;
+    p.mode = mode; p.vdim = vdim;
+    dim3 grid((unsigned)((topo->n_c + 255) / 256), (unsigned)F);
+    k_velocity_weights<<<grid, 256, 0, ctx->stream>>>(p);
+    MB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));  // `velocities` may be reused by the caller
     return MB200_OK;
 }
 
@@ -286,7 +388,7 @@ extern "C" int mb200_compound_prologue(mb200_ctx *ctx, const float *positions, i
     mb200_topology *topo = nullptr;  // one-shot form: the topology travels with the call
     MB_TRY(mb200_topology_create(ctx, compound_ptr, n_c, n_atoms, center_weights, masses, charges, &topo));
     const int rc = mb200_compound_prologue_topo(ctx, positions, positions_on_device, n_frames, boxes, topo, make_whole,
-                                                wrap_center, weight_mode, pdim, centers_dev, weights_dev);
+                                                wrap_center, weight_mode, pdim, 0, 0, centers_dev, weights_dev);
     mb200_topology_destroy(ctx, topo);
     return rc;
 }

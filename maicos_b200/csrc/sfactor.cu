@@ -528,13 +528,17 @@ __global__ void __launch_bounds__(256) k_sf_svalues(const SegDesc *__restrict__ 
     if (e < sg.n_valid) svals[(size_t)blockIdx.y * sval_stride + e] = s_of_entry(sg, e);
 }
 
-// |q| histograms: one CTA per (bin, segment); out[seg][{S, f2S}][n_bins], cnt[seg][n_bins]
-__global__ void __launch_bounds__(128) k_sf_binned(const SegDesc *__restrict__ segs, double *__restrict__ out_s,
-                                                  double *__restrict__ out_i, long long *__restrict__ out_c,
-                                                  int n_bins) {
+// |q| histograms: out[seg][{S, f2S}][n_bins], cnt[seg][n_bins].  The entries of a (segment, bin) are cut into
+// gridDim.z equal parts; a CTA reduces its part in a fixed order (thread-strided sums, shuffle tree, four warp
+// partials) and writes the part's result to `part` [seg][bin][z][3]; k_sf_binned_final adds the parts in order.
+// The result depends on n_parts (a function of the plan size alone), never on scheduling: bitwise reproducible.
+__global__ void __launch_bounds__(128) k_sf_binned(const SegDesc *__restrict__ segs, double *__restrict__ part, int n_bins) {
     const SegDesc &sg = segs[blockIdx.y];
     const int b = blockIdx.x;
-    const int e0 = sg.bin_start[b], e1 = sg.bin_start[b + 1];
+    const int n_parts = gridDim.z, z = blockIdx.z;
+    const int e_lo = sg.bin_start[b], e_hi = sg.bin_start[b + 1];
+    const int per = (e_hi - e_lo + n_parts - 1) / n_parts;
+    const int e0 = e_lo + z * per, e1 = min(e_hi, e0 + per);
     double s = 0.0, si = 0.0;
     long long c = 0;
     for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
@@ -558,11 +562,29 @@ __global__ void __launch_bounds__(128) k_sf_binned(const SegDesc *__restrict__ s
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const size_t o = (size_t)blockIdx.y * n_bins + b;
-        out_s[o] = (sh_s[0] + sh_s[1]) + (sh_s[2] + sh_s[3]);
-        if (out_i) out_i[o] = (sh_i[0] + sh_i[1]) + (sh_i[2] + sh_i[3]);
-        out_c[o] = sh_c[0] + sh_c[1] + sh_c[2] + sh_c[3];
+        double *o = part + (((size_t)blockIdx.y * n_bins + b) * n_parts + z) * 3;
+        o[0] = (sh_s[0] + sh_s[1]) + (sh_s[2] + sh_s[3]);
+        o[1] = (sh_i[0] + sh_i[1]) + (sh_i[2] + sh_i[3]);
+        o[2] = __longlong_as_double(sh_c[0] + sh_c[1] + sh_c[2] + sh_c[3]);
     }
+}
+
+__global__ void __launch_bounds__(128) k_sf_binned_final(const double *__restrict__ part, double *__restrict__ out_s,
+                                                        double *__restrict__ out_i, long long *__restrict__ out_c,
+                                                        int n_parts, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    double s = 0.0, si = 0.0;
+    long long c = 0;
+    for (int z = 0; z < n_parts; ++z) {
+        const double *p = part + ((size_t)i * n_parts + z) * 3;
+        s += p[0];
+        si += p[1];
+        c += __double_as_longlong(p[2]);
+    }
+    out_s[i] = s;
+    if (out_i) out_i[i] = si;
+    out_c[i] = c;
 }
 
 }  // namespace mb200
@@ -1313,6 +1335,28 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
     return MB200_OK;
 }
 
+// |q| histograms of all segments of a call (k_sf_binned + k_sf_binned_final).  The number of parts per (segment, bin)
+// depends on the plan alone: about 2048 entries per part.
+static int launch_binned(mb200_ctx *ctx, const std::vector<SegSpec> &specs, double *d_s, double *d_i, long long *d_c,
+                         int32_t n_bins) {
+    const size_t ns = specs.size();
+    if (ns == 0) return MB200_OK;
+    size_t max_valid = 0;
+    for (const SegSpec &sp : specs) max_valid = std::max(max_valid, sp.plan->cell.size());
+    // a function of the plan alone (not of the batch size): the same frame gives the same bits in any batch
+    const size_t per_bin = max_valid / (size_t)std::max(n_bins, 1) + 1;
+    const int n_parts = (int)std::max<size_t>(1, std::min<size_t>({per_bin / 2048 + 1, (size_t)64, (size_t)8192 / (size_t)n_bins + 1}));
+    MB_TRY(ctx->d_sval.ensure(ns * (size_t)n_bins * n_parts * 24));
+    k_sf_binned<<<dim3((unsigned)n_bins, (unsigned)ns, (unsigned)n_parts), 128, 0, ctx->stream>>>(
+        ctx->d_segs.as<SegDesc>(), ctx->d_sval.as<double>(), n_bins);
+    MB_CUDA(cudaGetLastError());
+    const long long total = (long long)ns * n_bins;
+    k_sf_binned_final<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_sval.as<double>(), d_s, d_i, d_c, n_parts, total);
+    MB_CUDA(cudaGetLastError());
+    ctx->launches += 2; ctx->stats[0] += 2;
+    return MB200_OK;
+}
+
 static int finish_timing(mb200_ctx *ctx) {
     ctx->stats[5] = 0;
     if (ctx->timing && ctx->stats[2] > 0) {
@@ -1453,12 +1497,26 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
     const size_t n_idx = (size_t)group_ptr[n_groups];
     for (int gi = 0; gi < n_groups; ++gi)
         if (group_ptr[gi + 1] < group_ptr[gi]) return fail(MB200_EINVAL, "group_ptr must be non-decreasing");
-    for (size_t i = 0; i < n_idx; ++i)
-        if (group_index[i] < 0 || group_index[i] >= n_atoms_total) return fail(MB200_EINVAL, "group index out of range");
 
-    // group indices -> device
-    MB_TRY(ctx->d_idx.ensure(std::max<size_t>(n_idx, 1) * 4));
-    if (n_idx) MB_CUDA(cudaMemcpyAsync(ctx->d_idx.p, group_index, n_idx * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // group indices -> device (kept from the previous call when the array has the same content: a Saxs run sends the same
+    // selection with every batch; 64-bit multiply-xor fingerprint over the whole array, checked together with its size)
+    {
+        unsigned long long s1 = 0, s2 = 0;  // plain and position-weighted sums: no loop-carried multiply, vectorises
+        for (size_t i = 0; i < n_idx; ++i) {
+            const unsigned long long x = (unsigned)group_index[i];
+            s1 += x;
+            s2 += x * (unsigned long long)(2 * i + 1);
+        }
+        const unsigned long long fp = (s1 * 0x9e3779b97f4a7c15ull) ^ s2 ^ ((unsigned long long)n_idx << 40);
+        if (!(ctx->idx_valid && ctx->idx_n == n_idx && ctx->idx_fp == fp && ctx->idx_natoms == n_atoms_total)) {
+            for (size_t i = 0; i < n_idx; ++i)
+                if (group_index[i] < 0 || group_index[i] >= n_atoms_total) return fail(MB200_EINVAL, "group index out of range");
+            ctx->idx_valid = false;
+            MB_TRY(ctx->d_idx.ensure(std::max<size_t>(n_idx, 1) * 4));
+            if (n_idx) MB_CUDA(cudaMemcpyAsync(ctx->d_idx.p, group_index, n_idx * 4, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->idx_n = n_idx; ctx->idx_fp = fp; ctx->idx_natoms = n_atoms_total; ctx->idx_valid = true;
+        }
+    }
 
     mark("index check + upload");
     // frames are processed in chunks bounded by the table workspace
@@ -1532,10 +1590,7 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
         MB_TRY(ctx->d_out.ensure(ob * 24));
         double *d_s = ctx->d_out.as<double>(), *d_i = d_s + ob;
         long long *d_c = reinterpret_cast<long long *>(d_i + ob);
-        dim3 grid((unsigned)n_bins, (unsigned)ns);
-        k_sf_binned<<<grid, 128, 0, ctx->stream>>>(ctx->d_segs.as<SegDesc>(), d_s, d_i, d_c, n_bins);
-        MB_CUDA(cudaGetLastError());
-        ctx->launches += 1; ctx->stats[0] += 1;
+        MB_TRY(launch_binned(ctx, specs, d_s, d_i, d_c, n_bins));
         const size_t oo = done * (size_t)n_groups * n_bins;
         MB_CUDA(cudaMemcpyAsync(s_binned + oo, d_s, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
         MB_CUDA(cudaMemcpyAsync(i_binned + oo, d_i, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1632,10 +1687,7 @@ extern "C" int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const
         MB_TRY(ctx->d_out.ensure(ob * 16));
         double *d_s = ctx->d_out.as<double>();
         long long *d_c = reinterpret_cast<long long *>(d_s + ob);
-        dim3 grid((unsigned)n_bins, (unsigned)ns);
-        k_sf_binned<<<grid, 128, 0, ctx->stream>>>(ctx->d_segs.as<SegDesc>(), d_s, nullptr, d_c, n_bins);
-        MB_CUDA(cudaGetLastError());
-        ctx->launches += 1; ctx->stats[0] += 1;
+        MB_TRY(launch_binned(ctx, specs, d_s, nullptr, d_c, n_bins));
         const size_t oo = done * 3 * (size_t)n_bins;
         MB_CUDA(cudaMemcpyAsync(s_binned + oo, d_s, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
         MB_CUDA(cudaMemcpyAsync(bincount + oo, d_c, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));

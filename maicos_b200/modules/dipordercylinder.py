@@ -31,6 +31,10 @@ class DiporderCylinder(ProfileCylinderBase):
         float = 0.0
     ) -> None:
         self._locals = locals()
+        wm = {"P0": 1, "cos_theta": 2, "cos_2_theta": 3}.get(order_parameter)
+        if wm is not None and pdim in ("r", "z") and dim in (0, 1, 2):
+            # (weight mode, Cartesian pdim, unit-vector mode, cylinder axis): "z" projects on e_dim, "r" on the radial direction
+            self._device_weight_mode = (wm, dim, 0, 0) if pdim == "z" else (wm, 0, 1, dim)
 
         def get_unit_vectors(atomgroup, grouping: str):
             return unit_vectors_cylinder(atomgroup=atomgroup, grouping=grouping, bin_method=bin_method, dim=dim, pdim=pdim)

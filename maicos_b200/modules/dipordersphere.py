@@ -29,6 +29,9 @@ class DiporderSphere(ProfileSphereBase):
         str = "diporder_sphere.dat", concfreq: int = 0, order_parameter: str = "P0", jitter: float = 0.0
     ) -> None:
         self._locals = locals()
+        wm = {"P0": 1, "cos_theta": 2, "cos_2_theta": 3}.get(order_parameter)
+        if wm is not None:
+            self._device_weight_mode = (wm, 0, 2, 0)  # radial unit vectors about the box centre, formed on the device
 
         def get_unit_vectors(atomgroup, grouping: str):
             return unit_vectors_sphere(atomgroup=atomgroup, grouping=grouping, bin_method=bin_method)

@@ -82,7 +82,7 @@ class DiporderStructureFactor(AnalysisBase):
         boxes = np.stack([s[2] for s in staged])
         on_device = 0
         if self._prologue is not None:
-            raw = gather_rows([(st[0], st[1]) for st in staged])
+            raw = self._gather_staged([(st[0], st[1]) for st in staged])
             pos, w = self._prologue.run(raw, boxes.astype(np.float32))
             n, on_device = self._prologue.n_c, 1
         else:

@@ -224,7 +224,7 @@ class Saxs(AnalysisBase):
         if not self.bin_spectrum:
             return [self._unbinned_frame(buf[row].copy(), box) for buf, row, box in staged]
         F, n, G = len(staged), self.atomgroup.n_atoms, len(self.groups)
-        pos = gather_rows([(st[0], st[1]) for st in staged])  # a view of the staging buffer / pinned trajectory
+        pos = self._gather_staged([(st[0], st[1]) for st in staged])  # a view of the staging buffer / pinned trajectory
         boxes = np.array([st[2] for st in staged], dtype=np.float32)
         s = np.zeros((F, G, self.n_bins))
         i = np.zeros((F, G, self.n_bins))

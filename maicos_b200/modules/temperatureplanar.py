@@ -28,6 +28,8 @@ class TemperaturePlanar(ProfilePlanarBase):
         float = 0.0
     ) -> None:
         self._locals = locals()
+        if grouping == "atoms":  # other groupings raise in temperature_weights, as in the reference (weights.py:118-123)
+            self._device_velocity_mode = (2, 0)  # kinetic temperature per atom on the device (mb200_velocity_weights)
         super().__init__(
             atomgroup=atomgroup, unwrap=unwrap, pack=pack, refgroup=refgroup, jitter=jitter, concfreq=concfreq,
             dim=dim, zmin=zmin, zmax=zmax, bin_width=bin_width, sym=sym, sym_odd=False,

@@ -31,6 +31,7 @@ class VelocityPlanar(ProfilePlanarBase):
         self._locals = locals()
         if vdim not in [0, 1, 2]:
             raise ValueError("Velocity dimension can only be x=0, y=1 or z=2.")
+        self._device_velocity_mode = (0, vdim)  # velocity_weights on the device (mb200_velocity_weights)
         super().__init__(
             atomgroup=atomgroup, unwrap=unwrap, pack=pack, refgroup=refgroup, jitter=jitter, concfreq=concfreq,
             dim=dim, zmin=zmin, zmax=zmax, bin_width=bin_width, sym=sym, sym_odd=sym_odd,

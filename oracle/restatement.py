@@ -340,6 +340,59 @@ def compound_prologue(positions, box, compound_ptr, masses, charges, bin_method,
     return centres, w * w if weight_mode == 3 else w
 
 
+def unit_vectors_radial(centres, box, dim=None):
+    """lib/util.py:710-756 (cylinder, ``pdim="r"``: ``dim`` = axis) and 760-786 (sphere, ``dim=None``): the direction
+    from the box centre ``dimensions[:3] / 2`` (float32 halving) to every compound centre, axial component dropped for
+    the cylinder, normalised."""
+    rel = np.array(centres, dtype=np.float64)
+    rel -= np.asarray(box, dtype=np.float32) / 2  # util.py:745 / 779
+    if dim is not None:
+        rel[:, dim] = 0  # util.py:750
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rel /= np.linalg.norm(rel, axis=1)[:, np.newaxis]  # util.py:753 / 783
+    return rel
+
+
+def diporder_weights(dipoles, unit_vectors, order_parameter):
+    """lib/weights.py:131-178 for per-compound unit vectors ``[n, 3]`` or one Cartesian vector ``[3]``."""
+    if order_parameter == "P0":
+        return np.sum(dipoles * unit_vectors, axis=1)  # :160-161
+    with np.errstate(invalid="ignore", divide="ignore"):
+        w = np.sum(dipoles / np.linalg.norm(dipoles, axis=1)[:, np.newaxis] * unit_vectors, axis=1)  # :163-167
+    return w * w if order_parameter == "cos_2_theta" else w  # :168-169
+
+
+def compound_dipoles(positions, compound_ptr, masses, charges):
+    """``AtomGroup.dipole_vector(compound)``: sum_i q_i (r_i - R_com) per contiguous compound (whole molecules in)."""
+    n_c = len(compound_ptr) - 1
+    ids = np.repeat(np.arange(n_c), np.diff(compound_ptr))
+    pos = np.double(positions)
+    msum = np.bincount(ids, weights=masses, minlength=n_c)
+    com = np.stack([np.bincount(ids, weights=masses * pos[:, d], minlength=n_c) / msum for d in range(3)], 1)
+    rel = pos - com[ids]
+    return np.stack([np.bincount(ids, weights=charges * rel[:, d], minlength=n_c) for d in range(3)], 1)
+
+
+def velocity_weights(velocities, masses, compound_ptr, vdim):
+    """lib/weights.py:195-225: ``v[:, vdim]`` per atom (``compound_ptr=None``) or its mass-weighted compound mean."""
+    v = np.asarray(velocities, dtype=np.float32)[:, vdim]  # :213
+    if compound_ptr is None:
+        return v  # :215-216
+    n_c = len(compound_ptr) - 1
+    ids = np.repeat(np.arange(n_c), np.diff(compound_ptr))
+    mass_vels = np.bincount(ids, weights=v * np.asarray(masses), minlength=n_c)  # :218-220
+    group_mass = np.bincount(ids, weights=masses, minlength=n_c)  # :221-223
+    return mass_vels / group_mass  # :224
+
+
+def temperature_weights(velocities, masses):
+    """lib/weights.py:101-127: ``(v**2).sum(axis=1) * m / 2 * prefac`` with float32 velocities."""
+    atomic_mass, boltzmann = 1.66053906660e-27, 1.380649e-23  # scipy.constants (CODATA 2018)
+    prefac = atomic_mass * 1e4 / boltzmann  # :126
+    v = np.asarray(velocities, dtype=np.float32)
+    return (v ** 2).sum(axis=1) * np.asarray(masses) / 2 * prefac  # :127
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Dielectric profile modules (SURVEY.md 8(f) row 3): frame bodies with the reference's own digitize / bincount /
 # cumsum / mean sequence, including the (virtual cuts x bins) table the CUDA path never materialises.

@@ -344,3 +344,112 @@ def test_histograms_are_bitwise_repeatable_on_ragged_sizes():
                 assert_array_equal(hw, hw0)
             for f in range(3):
                 assert_array_equal(hc0[f], restatement.hist_planar(np.double(pos[f]), None, 1, nb, 0.0, 20.0))
+
+
+# ---- rest of the device prologue: velocity weights, cylinder / sphere unit vectors --------
+def _water_with_velocities(n_mol=900, L=30.0, F=5, seed=21):
+    from maicos_b200.mdshim import MemoryTrajectory, Universe
+
+    frames = mb.synthetic.spce_water_frames(n_mol, L, seed, n_frames=F)
+    rng = np.random.default_rng(seed)
+    vel = rng.normal(scale=5.0, size=frames.shape).astype(np.float32)
+    topo = mb.synthetic.spce_topology(n_mol)
+    u = Universe(3 * n_mol, MemoryTrajectory(frames, np.float32([L, L, L, 90, 90, 90]), velocities=vel), **topo)
+    return u, frames, vel, topo
+
+
+def test_velocity_and_temperature_weights_formed_on_the_device(precision):
+    if precision == "fp64":
+        pytest.skip("path 2 does not depend on the S(q) arithmetic")
+    u, frames, vel, topo = _water_with_velocities()
+    L, F, n = 30.0, len(frames), frames.shape[1]
+    masses = np.double(topo["masses"])
+    ptr = np.arange(0, n + 1, 3)
+    box = np.float32([L, L, L])
+
+    def reference(positions_fn, weights_fn, nb, normalization="number"):
+        st = restatement.RunningStats()
+        geo = restatement.planar_geometry(box, 2, nb)[2]
+        for f in range(F):
+            obs = dict(geo)
+            obs.update(restatement.profile_single_frame(
+                lambda p, w: restatement.hist_planar(p, w, 2, nb, 0.0, np.float64(box[2])), positions_fn(f), weights_fn(f),
+                normalization, geo["bin_volume"]))
+            st.update(obs)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return st.sums["profile"] / st.sums["bincount"] if normalization == "number" else st.means["profile"], st
+
+    # per atom
+    a = mb.VelocityPlanar(u.atoms, bin_width=1.5, vdim=1, unwrap=False, pack=False).run()
+    assert a._velocity is not None
+    ref, st = reference(lambda f: frames[f], lambda f: np.double(restatement.velocity_weights(vel[f], masses, None, 1)), a.n_bins)
+    assert_array_equal(a.sums.bincount, st.sums["bincount"])
+    assert_allclose(a.results.profile, ref, rtol=1e-12, atol=1e-14, equal_nan=True)
+    # flux (volume normalisation) and mass-weighted molecular velocities on device-made centres
+    a = mb.VelocityPlanar(u.atoms, bin_width=1.5, vdim=2, flux=True, grouping="molecules", unwrap=False, pack=False).run()
+    assert a._velocity is not None and a._prologue is not None
+    cen = [restatement.compound_prologue(frames[f], box, ptr, masses, topo["charges"], "com", False, False)[0] for f in range(F)]
+    ref, st = reference(lambda f: cen[f], lambda f: restatement.velocity_weights(vel[f], masses, ptr, 2), a.n_bins, "volume")
+    assert_array_equal(a.sums.bincount, st.sums["bincount"])
+    assert_allclose(a.results.profile, ref, rtol=1e-11, atol=1e-14)
+    # kinetic temperature
+    a = mb.TemperaturePlanar(u.atoms, bin_width=1.5, unwrap=False, pack=False).run()
+    assert a._velocity is not None
+    ref, st = reference(lambda f: frames[f], lambda f: restatement.temperature_weights(vel[f], masses), a.n_bins)
+    assert_array_equal(a.sums.bincount, st.sums["bincount"])
+    assert_allclose(a.results.profile, ref, rtol=1e-12, equal_nan=True)
+    # device path == host path of the same class, bit for bit in the counts and to rounding in the sums
+    import maicos_b200.core.base as base
+    keep = base.VelocityWeights
+    try:
+        base.VelocityWeights = lambda *args, **kw: (_ for _ in ()).throw(ValueError("host path"))
+        b = mb.TemperaturePlanar(u.atoms, bin_width=1.5, unwrap=False, pack=False).run()
+    finally:
+        base.VelocityWeights = keep
+    assert b._velocity is None
+    assert_array_equal(a.sums.bincount, b.sums.bincount)
+    assert_allclose(a.results.profile, b.results.profile, rtol=1e-13, equal_nan=True)
+
+
+@pytest.mark.parametrize("order_parameter", ["P0", "cos_theta", "cos_2_theta"])
+def test_diporder_cylinder_and_sphere_unit_vectors_formed_on_the_device(order_parameter, precision):
+    if precision == "fp64":
+        pytest.skip("path 2 does not depend on the S(q) arithmetic")
+    u, frames, vel, topo = _water_with_velocities(n_mol=1100, L=32.0, F=4, seed=5)
+    L, F, n = 32.0, len(frames), frames.shape[1]
+    masses, charges = np.double(topo["masses"]), np.double(topo["charges"])
+    ptr = np.arange(0, n + 1, 3)
+    box = np.float32([L, L, L])
+    center = np.double(box) / 2
+    norm = "volume" if order_parameter == "P0" else "number"
+
+    def check(ana, hist, unit_fn):
+        assert ana._prologue is not None, "centres, dipoles and unit vectors should be formed on the device"
+        st = restatement.RunningStats()
+        for f in range(F):
+            cen, _ = restatement.compound_prologue(frames[f], box, ptr, masses, charges, "com", True, True)
+            whole = restatement.compound_prologue(frames[f], box, ptr, masses, charges, "com", True, True, weight_mode=1)
+            # dipoles of the whole, wrapped molecules (what ag.dipole_vector sees after base.py:438-448)
+            pos = np.array(frames[f], dtype=np.float32)
+            anchor = pos[ptr[:-1]].repeat(3, axis=0)
+            d = pos - anchor
+            pos = (anchor + (d - box * np.round(d / box))).astype(np.float32)
+            mu = restatement.compound_dipoles(pos, ptr, masses, charges)
+            w = restatement.diporder_weights(mu, unit_fn(cen), order_parameter)
+            st.update({"profile": hist(cen, w), "bincount": hist(cen, None)})
+        assert_array_equal(ana.sums.bincount, st.sums["bincount"])
+        if norm == "number":
+            with np.errstate(invalid="ignore", divide="ignore"):
+                ref = st.sums["profile"] / st.sums["bincount"]
+            assert_allclose(ana.results.profile, ref, rtol=1e-9, atol=1e-12, equal_nan=True)
+        else:
+            assert_allclose(ana.sums.profile * ana.means.bin_volume, st.sums["profile"], rtol=1e-9, atol=1e-10)
+
+    for pdim in ("r", "z"):
+        a = mb.DiporderCylinder(u.atoms, bin_width=1.0, pdim=pdim, order_parameter=order_parameter).run()
+        nb, rmax = a.n_bins, a.rmax
+        unit = (lambda c: restatement.unit_vectors_radial(c, box, dim=2)) if pdim == "r" else (lambda c: np.array([0.0, 0, 1.0]))
+        check(a, lambda p, w: restatement.hist_cylinder(p, w, 2, nb, 0.0, rmax, 0.0, np.float64(L), center), unit)
+    a = mb.DiporderSphere(u.atoms, bin_width=1.0, order_parameter=order_parameter).run()
+    nb, rmax = a.n_bins, a.rmax
+    check(a, lambda p, w: restatement.hist_sphere(p, w, nb, 0.0, rmax, center), lambda c: restatement.unit_vectors_radial(c, box))
