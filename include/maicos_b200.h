@@ -146,6 +146,19 @@ int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int positions_on_d
                       double thetamax, int32_t n_bins, int pack_atoms, int32_t block,
                       int32_t n_blocks, double *s_binned, double *i_binned, int64_t *bincount);
 
+/* The same with the element groups uploaded ONCE (a selection of a million atoms is 4 MB of indices that the call above
+ * validates, fingerprints and -- when they changed -- copies with every batch): create the handle in _prepare, pass it
+ * with every batch, destroy it at the end of the run. */
+typedef struct mb200_groups mb200_groups;
+int mb200_groups_create(mb200_ctx *ctx, const int32_t *group_index, const int64_t *group_ptr, int32_t n_groups,
+                        int64_t n_atoms_total, mb200_groups **out);
+void mb200_groups_destroy(mb200_ctx *ctx, mb200_groups *groups);
+int mb200_saxs_frames_groups(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                             const float *boxes, const mb200_groups *groups, const double *cm_params, double qmin,
+                             double qmax, double thetamin, double thetamax, int32_t n_bins, int pack_atoms,
+                             int32_t block, int32_t n_blocks, double *s_binned, double *i_binned,
+                             int64_t *bincount);
+
 /* Fused DiporderStructureFactor frame body (replaces
  * src/maicos/modules/diporderstructurefactor.py:105-150): three weight sets on identical
  * positions share one set of phase tables; per frame and component S is binned by |q|.

@@ -59,6 +59,17 @@ SIGNATURES = {
          ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_int, ctypes.c_int32, ctypes.c_int32,
          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
     ),
+    "mb200_groups_create": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)],
+    ),
+    "mb200_groups_destroy": (None, [ctypes.c_void_p, ctypes.c_void_p]),
+    "mb200_saxs_frames_groups": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_int, ctypes.c_int32,
+         ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
+    ),
     "mb200_dev_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mb200_dev_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "mb200_dev_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
@@ -339,8 +350,18 @@ class DeviceBuffer:
             pass
 
 
+def _default_copy_threads() -> int:
+    """Staging-copy threads of this process: up to six, but no more than half of this rank's share of the host cores (one
+    process per GPU: eight ranks with six copy threads each oversubscribe a 32-core host and slow each other down)."""
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1))
+    share = max(1, (os.cpu_count() or 1) // ranks)
+    return int(max(1, min(6, share // 2)))
+
+
 def host_copy(dst: np.ndarray, src: np.ndarray, n_threads: int = 0) -> None:
     """``dst[...] = src`` for C-contiguous arrays of the same dtype and size, copied by a few threads (GIL released)."""
+    if n_threads <= 0:
+        n_threads = _default_copy_threads()
     if dst.nbytes != src.nbytes or dst.dtype != src.dtype or not (dst.flags.c_contiguous and src.flags.c_contiguous):
         np.copyto(dst, src)
         return

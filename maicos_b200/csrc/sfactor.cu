@@ -1472,6 +1472,73 @@ extern "C" int mb200_structure_factor(mb200_ctx *ctx, const double *positions, i
                                         thetamin, thetamax, weights, 0, 1, scattering_vectors, structure_factors);
 }
 
+// Element groups of a Saxs analysis, resident on the device for the whole run (mb200_groups_create).
+struct mb200_groups {
+    mb200::DevBuf idx;
+    std::vector<int64_t> ptr;
+    int64_t n_atoms_total = 0;
+    int device = 0;
+};
+
+static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                            int64_t n_atoms_total, const float *boxes, const int32_t *d_group_index,
+                            const int64_t *group_ptr, int32_t n_groups, const double *cm_params, double qmin,
+                            double qmax, double thetamin, double thetamax, int32_t n_bins, int pack_atoms,
+                            int32_t block, int32_t n_blocks, double *s_binned, double *i_binned, int64_t *bincount);
+
+extern "C" int mb200_groups_create(mb200_ctx *ctx, const int32_t *group_index, const int64_t *group_ptr, int32_t n_groups,
+                                   int64_t n_atoms_total, mb200_groups **out) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
+    if (!out) return fail(MB200_EINVAL, "null output pointer");
+    *out = nullptr;
+    if (n_groups < 0 || !group_ptr || n_atoms_total < 0) return fail(MB200_EINVAL, "invalid argument to mb200_groups_create");
+    for (int gi = 0; gi < n_groups; ++gi)
+        if (group_ptr[gi + 1] < group_ptr[gi]) return fail(MB200_EINVAL, "group_ptr must be non-decreasing");
+    const size_t n_idx = (size_t)group_ptr[n_groups];
+    if (n_idx && !group_index) return fail(MB200_EINVAL, "null group_index");
+    for (size_t i = 0; i < n_idx; ++i)
+        if (group_index[i] < 0 || group_index[i] >= n_atoms_total) return fail(MB200_EINVAL, "group index out of range");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<mb200_groups> g(new mb200_groups());
+    MB_TRY(g->idx.ensure(std::max<size_t>(n_idx, 1) * 4));
+    if (n_idx) {
+        MB_CUDA(cudaMemcpyAsync(g->idx.p, group_index, n_idx * 4, cudaMemcpyHostToDevice, ctx->stream));
+        MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    g->ptr.assign(group_ptr, group_ptr + n_groups + 1);
+    g->n_atoms_total = n_atoms_total;
+    g->device = ctx->device;
+    *out = g.release();
+    return MB200_OK;
+}
+
+extern "C" void mb200_groups_destroy(mb200_ctx *ctx, mb200_groups *groups) {
+    if (!groups) return;
+    if (ctx) {
+        MB_LOCK(ctx);
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        delete groups;
+    } else {
+        delete groups;
+    }
+}
+
+extern "C" int mb200_saxs_frames_groups(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                                        const float *boxes, const mb200_groups *groups, const double *cm_params, double qmin,
+                                        double qmax, double thetamin, double thetamax, int32_t n_bins, int pack_atoms,
+                                        int32_t block, int32_t n_blocks, double *s_binned, double *i_binned,
+                                        int64_t *bincount) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
+    if (!groups) return fail(MB200_EINVAL, "null groups handle");
+    if (groups->device != ctx->device) return fail(MB200_EINVAL, "groups belong to another device");
+    return saxs_frames_impl(ctx, positions, positions_on_device, n_frames, groups->n_atoms_total, boxes,
+                            groups->idx.as<int32_t>(), groups->ptr.data(), (int32_t)groups->ptr.size() - 1, cm_params, qmin, qmax,
+                            thetamin, thetamax, n_bins, pack_atoms, block, n_blocks, s_binned, i_binned, bincount);
+}
+
 extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
                                  int64_t n_atoms_total, const float *boxes, const int32_t *group_index,
                                  const int64_t *group_ptr, int32_t n_groups, const double *cm_params, double qmin,
@@ -1480,28 +1547,18 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
                                  int64_t *bincount) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
     MB_LOCK(ctx);
-    if (n_frames < 0 || n_groups < 0 || n_bins <= 0 || !boxes || !group_ptr || !cm_params || !s_binned || !i_binned ||
-        !bincount || (n_atoms_total && !positions))
-        return fail(MB200_EINVAL, "invalid argument to mb200_saxs_frames");
+    if (n_groups < 0 || !group_ptr) return fail(MB200_EINVAL, "invalid argument to mb200_saxs_frames");
     if (n_frames == 0 || n_groups == 0) return MB200_OK;
     MB_CUDA(cudaSetDevice(ctx->device));
-    // developer aid: MAICOS_B200_TRACE_HOST=1 prints the host-side time of every phase of the call to stderr
-    static const bool trace_host = std::getenv("MAICOS_B200_TRACE_HOST") != nullptr;
-    auto t_last = std::chrono::steady_clock::now();
-    auto mark = [&](const char *what) {
-        if (!trace_host) return;
-        const auto now = std::chrono::steady_clock::now();
-        std::fprintf(stderr, "[mb200_saxs_frames] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
-        t_last = now;
-    };
     const size_t n_idx = (size_t)group_ptr[n_groups];
     for (int gi = 0; gi < n_groups; ++gi)
         if (group_ptr[gi + 1] < group_ptr[gi]) return fail(MB200_EINVAL, "group_ptr must be non-decreasing");
-
+    if (n_idx && !group_index) return fail(MB200_EINVAL, "null group_index");
     // group indices -> device (kept from the previous call when the array has the same content: a Saxs run sends the same
-    // selection with every batch; 64-bit multiply-xor fingerprint over the whole array, checked together with its size)
+    // selection with every batch; size + plain and position-weighted sums as the fingerprint).  Callers that keep a
+    // selection for a whole run use mb200_groups_create + mb200_saxs_frames_groups and pay nothing per call.
     {
-        unsigned long long s1 = 0, s2 = 0;  // plain and position-weighted sums: no loop-carried multiply, vectorises
+        unsigned long long s1 = 0, s2 = 0;
         for (size_t i = 0; i < n_idx; ++i) {
             const unsigned long long x = (unsigned)group_index[i];
             s1 += x;
@@ -1517,8 +1574,31 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
             ctx->idx_n = n_idx; ctx->idx_fp = fp; ctx->idx_natoms = n_atoms_total; ctx->idx_valid = true;
         }
     }
+    return saxs_frames_impl(ctx, positions, positions_on_device, n_frames, n_atoms_total, boxes, ctx->d_idx.as<int32_t>(),
+                            group_ptr, n_groups, cm_params, qmin, qmax, thetamin, thetamax, n_bins, pack_atoms, block, n_blocks,
+                            s_binned, i_binned, bincount);
+}
 
-    mark("index check + upload");
+static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                            int64_t n_atoms_total, const float *boxes, const int32_t *d_group_index,
+                            const int64_t *group_ptr, int32_t n_groups, const double *cm_params, double qmin,
+                            double qmax, double thetamin, double thetamax, int32_t n_bins, int pack_atoms,
+                            int32_t block, int32_t n_blocks, double *s_binned, double *i_binned, int64_t *bincount) {
+    if (n_frames < 0 || n_groups < 0 || n_bins <= 0 || !boxes || !group_ptr || !cm_params || !s_binned || !i_binned ||
+        !bincount || (n_atoms_total && !positions))
+        return fail(MB200_EINVAL, "invalid argument to mb200_saxs_frames");
+    if (n_frames == 0 || n_groups == 0) return MB200_OK;
+    MB_CUDA(cudaSetDevice(ctx->device));
+    // developer aid: MAICOS_B200_TRACE_HOST=1 prints the host-side time of every phase of the call to stderr
+    static const bool trace_host = std::getenv("MAICOS_B200_TRACE_HOST") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!trace_host) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[mb200_saxs_frames] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    mark("entry");
     // frames are processed in chunks bounded by the table workspace
     const size_t frame_elems = (size_t)n_atoms_total * 3;
     size_t done = 0;
@@ -1573,7 +1653,7 @@ extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int pos
                 std::memset(&sp.job, 0, sizeof(TableJob));
                 sp.job.wscale = 1.0;
                 sp.job.pos = dpos + f * frame_elems;
-                sp.job.index = ctx->d_idx.as<int32_t>() + group_ptr[gi];
+                sp.job.index = d_group_index + group_ptr[gi];
                 sp.job.weights = nullptr;
                 sp.job.stride_atom = 3; sp.job.stride_xyz = 1;
                 const float *bx = boxes + (done + f) * 3;

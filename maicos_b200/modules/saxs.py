@@ -188,6 +188,7 @@ class Saxs(AnalysisBase):
             prepared = cache[id(inverse)] = (inverse, index, ptr, flat, cm)
         _, self._group_index, self._group_ptr, self._group_flat, self._cm = prepared
         self.elements = list(unique)
+        self._release_groups()
         self.groups = _GroupList(self.atomgroup, self._group_index)
         self.weights = _OnesList(self._group_index)
 
@@ -215,6 +216,23 @@ class Saxs(AnalysisBase):
         if self.bin_spectrum:
             self._announce_rows([(st[0], st[1]) for st in staged])
 
+    _groups_handle = None
+
+    def _release_groups(self) -> None:
+        handle, self._groups_handle = self._groups_handle, None
+        if handle:
+            _cabi.load().mb200_groups_destroy(_cabi.context().handle, handle)
+
+    def _release_run_resources(self) -> None:
+        super()._release_run_resources()
+        self._release_groups()
+
+    def __del__(self):
+        try:
+            self._release_groups()
+        except Exception:
+            pass
+
     def _device_packs(self) -> bool:
         # the kernel's pack is the orthorhombic ``x -= floor(x / L) L``; a triclinic cell is packed by the host
         # (``atoms.wrap`` in ``_transform_frame``) before the frame is staged
@@ -231,12 +249,17 @@ class Saxs(AnalysisBase):
         c = np.zeros((F, G, self.n_bins), dtype=np.int64)
         block, n_blocks = parallel.q_block()
         ctx = _cabi.context()
+        if self._groups_handle is None:  # the selection goes to the device once per run
+            import ctypes
+
+            self._groups_handle = ctypes.c_void_p()
+            _cabi.check(_cabi.load().mb200_groups_create(ctx.handle, _cabi.ptr(self._group_flat), _cabi.ptr(self._group_ptr), G, n,
+                                                         ctypes.byref(self._groups_handle)))
         _cabi.check(
-            _cabi.load().mb200_saxs_frames(
-                ctx.handle, _cabi.ptr(pos), 0, F, n, _cabi.ptr(boxes), _cabi.ptr(self._group_flat),
-                _cabi.ptr(self._group_ptr), G, _cabi.ptr(self._cm), float(self.qmin), float(self.qmax),
-                float(self.thetamin), float(self.thetamax), self.n_bins, int(self._device_packs()), block, n_blocks,
-                _cabi.ptr(s), _cabi.ptr(i), _cabi.ptr(c),
+            _cabi.load().mb200_saxs_frames_groups(
+                ctx.handle, _cabi.ptr(pos), 0, F, _cabi.ptr(boxes), self._groups_handle, _cabi.ptr(self._cm),
+                float(self.qmin), float(self.qmax), float(self.thetamin), float(self.thetamax), self.n_bins,
+                int(self._device_packs()), block, n_blocks, _cabi.ptr(s), _cabi.ptr(i), _cabi.ptr(c),
             )
         )
         if parallel.q_sharded():
