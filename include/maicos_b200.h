@@ -98,6 +98,15 @@ void mb200_host_free(void *p);
  * replaces: src/maicos/lib/_cmath.pyx:93-96 (NB the float32 cast of q_factor). */
 int mb200_sfactor_maxn(const double dimensions[3], double qmax, int32_t maxn[3]);
 
+/* Diagnostic, host only (no device needed): builds the q-plan of a box / q window -- the accepted Miller vectors with the
+ * reference's acceptance test (_cmath.pyx:93-115), their |q| bins, the DMMA and tensor-core tilings -- and describes it:
+ *   out[0] = accepted q vectors, out[1..3] = maxn, out[4] = tensor-core tiling possible, out[5] = row tiles (128 (h,k)
+ *   rows), out[6] = l tiles, out[7] = l values per tile, out[8] = populated (row tile, l tile) blocks = contraction items
+ *   per atom chunk, out[9] = DMMA warp tiles, out[10..15] = FNV-1a fingerprints of the plan's index tables.
+ * n_bins = 0: entries in C order of the cube (mb200_structure_factor), > 0: sorted by numpy |q| bin (the *_frames calls). */
+int mb200_plan_describe(const double dimensions[3], double qmin, double qmax, double thetamin, double thetamax,
+                        int32_t n_bins, int64_t out[16]);
+
 /* Drop-in for `_cmath.structure_factor` (src/maicos/lib/_cmath.pyx:21-126, re-exported
  * at src/maicos/lib/math.py:15; callers saxs.py:197-205, diporderstructurefactor.py:121-129).
  *   positions : host float64, element (j, d) at positions[j*stride_atom + d*stride_xyz]

@@ -39,6 +39,8 @@ SIGNATURES = {
     "mb200_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mb200_host_free": (None, [ctypes.c_void_p]),
     "mb200_host_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+    "mb200_plan_describe": (ctypes.c_int, [c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                           ctypes.c_int32, c_i64_p]),
     "mb200_sfactor_maxn": (ctypes.c_int, [c_double_p, ctypes.c_double, c_i32_p]),
     "mb200_structure_factor": (
         ctypes.c_int,
@@ -225,8 +227,19 @@ def default_device() -> int:
     return 0
 
 
+_tls = threading.local()
+
+
+def set_thread_device(device: int | None) -> None:
+    """Device that :func:`context` hands out on the calling thread when none is named (one worker thread per GPU in
+    single-process multi-GPU runs, ``maicos_b200.parallel.use_devices``)."""
+    _tls.device = device
+
+
 def context(device: int | None = None) -> Context:
     """Cached context for ``device``; raises :class:`MB200Error` when no GPU is visible."""
+    if device is None:
+        device = getattr(_tls, "device", None)
     if device is None:
         device = default_device()
     with _lock:

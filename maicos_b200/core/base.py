@@ -22,6 +22,7 @@ sharded over ranks and merged by one allreduce at the end.
 
 from __future__ import annotations
 
+import collections
 import logging
 import time
 import warnings
@@ -175,37 +176,50 @@ class CompoundPrologue:
         self.make_whole, self.wrap_center = bool(make_whole), bool(wrap_center)
         self.weight_mode, self.pdim = int(weight_mode), int(pdim)
         self.uv_mode, self.uv_dim = int(uv_mode), int(uv_dim)  # unit vector of the projection: Cartesian / cylinder / sphere
-        self.ctx = _cabi.context()
-        self.centers = _cabi.DeviceBuffer(self.ctx)
-        self.weights = _cabi.DeviceBuffer(self.ctx)
-        # compound_ptr, centre weights, masses and charges go to the device once per analysis, not with every batch
+        self._dev = {}  # device -> (context, topology handle, centres buffer, weights buffer), created on first use
+        self._on_device()  # fail early (ValueError / MB200Error) on the constructing thread's device
+
+    def _on_device(self):
+        """Per-device state of the calling thread's device: compound_ptr, centre weights, masses and charges go to a
+        device once per analysis, not with every batch."""
         import ctypes
 
-        self._topo = ctypes.c_void_p()
-        _cabi.check(_cabi.load().mb200_topology_create(
-            self.ctx.handle, _cabi.ptr(self.ptr), self.n_c, self.n_atoms, _cabi.ptr(self.cw), _cabi.ptr(self.masses),
-            _cabi.ptr(self.charges), ctypes.byref(self._topo)))
+        from .. import _cabi
+
+        ctx = _cabi.context()
+        st = self._dev.get(ctx.device)
+        if st is None:
+            topo = ctypes.c_void_p()
+            _cabi.check(_cabi.load().mb200_topology_create(
+                ctx.handle, _cabi.ptr(self.ptr), self.n_c, self.n_atoms, _cabi.ptr(self.cw), _cabi.ptr(self.masses),
+                _cabi.ptr(self.charges), ctypes.byref(topo)))
+            st = self._dev[ctx.device] = (ctx, topo, _cabi.DeviceBuffer(ctx), _cabi.DeviceBuffer(ctx))
+        return st
 
     def run(self, positions: np.ndarray, boxes: np.ndarray):
         """positions float32 [F, n_atoms, 3] (pinned), boxes float32 [F, 3] -> device pointers (centres, weights)."""
         from .. import _cabi
 
+        ctx, topo, centers, weights = self._on_device()
         F = positions.shape[0]
-        c_ptr = self.centers.ensure(F * self.n_c * 24)
+        c_ptr = centers.ensure(F * self.n_c * 24)
         n_w = {0: 0, 1: 1, 2: 1, 3: 1, 4: 3}[self.weight_mode]
-        w_ptr = self.weights.ensure(F * self.n_c * 8 * n_w) if n_w else None
+        w_ptr = weights.ensure(F * self.n_c * 8 * n_w) if n_w else None
         boxes = np.ascontiguousarray(boxes, dtype=np.float32)
         _cabi.check(_cabi.load().mb200_compound_prologue_topo(
-            self.ctx.handle, _cabi.ptr(positions), 0, F, _cabi.ptr(boxes), self._topo, int(self.make_whole),
+            ctx.handle, _cabi.ptr(positions), 0, F, _cabi.ptr(boxes), topo, int(self.make_whole),
             int(self.wrap_center), self.weight_mode, self.pdim, self.uv_mode, self.uv_dim, c_ptr, w_ptr))
         return c_ptr, w_ptr
 
     def close(self) -> None:
         from .. import _cabi
 
-        topo, self._topo = getattr(self, "_topo", None), None
-        if topo:
-            _cabi.load().mb200_topology_destroy(self.ctx.handle, topo)
+        dev, self._dev = getattr(self, "_dev", {}), {}
+        for ctx, topo, centers, weights in dev.values():
+            centers.free()
+            weights.free()
+            if topo:
+                _cabi.load().mb200_topology_destroy(ctx.handle, topo)
 
     def __del__(self):
         try:
@@ -219,40 +233,49 @@ class VelocityWeights:
     float32 velocities of a batch: mode 0 ``v[:, vdim]`` per atom, 1 mass-weighted compound mean, 2 kinetic temperature."""
 
     def __init__(self, atomgroup, mode: int, vdim: int, prologue: CompoundPrologue | None = None):
+        self.mode, self.vdim = int(mode), int(vdim)
+        self.n_atoms = atomgroup.n_atoms
+        self.prologue = prologue          # compounds: the prologue's topology (compound_ptr + masses)
+        self.n_c = prologue.n_c if prologue is not None else self.n_atoms
+        self.masses = np.ascontiguousarray(atomgroup.masses, dtype=np.float64) if (prologue is None and mode == 2) else None
+        self._dev = {}  # device -> (context, own topology handle or None, weights buffer)
+        self._on_device()
+
+    def _on_device(self):
         import ctypes
 
         from .. import _cabi
 
-        self.ctx = _cabi.context()
-        self.mode, self.vdim = int(mode), int(vdim)
-        self.n_atoms = atomgroup.n_atoms
-        self._own_topo = None
-        if prologue is not None:          # compounds: the prologue's topology (compound_ptr + masses)
-            self._topo, self.n_c = prologue._topo, prologue.n_c
-        else:                             # every atom its own compound
-            masses = np.ascontiguousarray(atomgroup.masses, dtype=np.float64) if mode == 2 else None
-            self._own_topo = ctypes.c_void_p()
-            _cabi.check(_cabi.load().mb200_topology_create(self.ctx.handle, None, self.n_atoms, self.n_atoms, None,
-                                                           _cabi.ptr(masses), None, ctypes.byref(self._own_topo)))
-            self._topo, self.n_c = self._own_topo, self.n_atoms
-        self.weights = _cabi.DeviceBuffer(self.ctx)
+        ctx = _cabi.context()
+        st = self._dev.get(ctx.device)
+        if st is None:
+            own = None
+            if self.prologue is None:     # every atom its own compound
+                own = ctypes.c_void_p()
+                _cabi.check(_cabi.load().mb200_topology_create(ctx.handle, None, self.n_atoms, self.n_atoms, None,
+                                                               _cabi.ptr(self.masses), None, ctypes.byref(own)))
+            st = self._dev[ctx.device] = (ctx, own, _cabi.DeviceBuffer(ctx))
+        return st
 
     def run(self, velocities: np.ndarray) -> int:
         """velocities float32 [F, n_atoms, 3] (pinned) -> device pointer of the weights float64 [F, n_c]."""
         from .. import _cabi
 
+        ctx, own, weights = self._on_device()
+        topo = own if own is not None else self.prologue._on_device()[1]
         F = velocities.shape[0]
-        w_ptr = self.weights.ensure(F * self.n_c * 8)
-        _cabi.check(_cabi.load().mb200_velocity_weights(self.ctx.handle, _cabi.ptr(velocities), 0, F, self._topo, self.mode,
-                                                        self.vdim, w_ptr))
+        w_ptr = weights.ensure(F * self.n_c * 8)
+        _cabi.check(_cabi.load().mb200_velocity_weights(ctx.handle, _cabi.ptr(velocities), 0, F, topo, self.mode, self.vdim, w_ptr))
         return w_ptr
 
     def close(self) -> None:
         from .. import _cabi
 
-        topo, self._own_topo = self._own_topo, None
-        if topo:
-            _cabi.load().mb200_topology_destroy(self.ctx.handle, topo)
+        dev, self._dev = getattr(self, "_dev", {}), {}
+        for ctx, own, weights in dev.values():
+            weights.free()
+            if own:
+                _cabi.load().mb200_topology_destroy(ctx.handle, own)
 
     def __del__(self):
         try:
@@ -375,8 +398,9 @@ class AnalysisBase(_Runner):
         self.results = Results()
         self._obs = Results()
         self._staged: list = []
-        self._pool = None
-        self._inflight = None
+        self._pools = None            # device -> single-worker executor of the device calls
+        self._inflight_q = collections.deque()
+        self._batch_device = None     # device of the batch being announced / submitted
         self._stage_parity = 0
         self.timings = {"stage_s": 0.0, "wait_device_s": 0.0, "device_call_s": 0.0}
 
@@ -481,7 +505,8 @@ class AnalysisBase(_Runner):
         if not all(r[0].ctypes.data == base and r[1] == rows[0][1] + i for i, r in enumerate(rows)):
             return  # not one run of rows: the call gathers and copies by itself
         block = buf[rows[0][1]:rows[0][1] + len(rows)]
-        _cabi.check(_cabi.load().mb200_prefetch_frames(_cabi.context().handle, block.ctypes.data, block.nbytes))
+        ctx = _cabi.context(self._batch_device)  # the device this batch is about to be submitted to
+        _cabi.check(_cabi.load().mb200_prefetch_frames(ctx.handle, block.ctypes.data, block.nbytes))
 
     def _staging_rows(self, shape, dtype, tag: str) -> tuple[np.ndarray, int]:
         """``(pinned batch buffer [batch, *shape], row)`` for the frame being staged.
@@ -531,7 +556,7 @@ class AnalysisBase(_Runner):
         self._n_local = 0
         self._n_flushed = 0
         self._staged = []
-        self._inflight = None
+        self._inflight_q = collections.deque()
         #: host-side time split of the last run: staging, waiting for the device, inside the C-ABI call
         self.timings = {"stage_s": 0.0, "wait_device_s": 0.0, "device_call_s": 0.0}
         for name in ("sums", "means", "sems"):
@@ -584,6 +609,11 @@ class AnalysisBase(_Runner):
         k = getattr(self, "_n_flushed", 2)
         return b if k >= 2 else max(1, b >> (2 - k))
 
+    def _run_devices(self) -> list:
+        """CUDA devices this run deals its batches to: ``parallel.use_devices`` or ``[None]`` (the default device)."""
+        devs = parallel.devices()
+        return list(devs) if devs else [None]
+
     def _flush_staged(self, wait: bool = True) -> None:
         """Hand the staged frames to the device.
 
@@ -591,24 +621,38 @@ class AnalysisBase(_Runner):
         next batch meanwhile.  A new batch is queued *behind* the one in flight before the host waits for the
         latter, so the worker goes from one device call straight into the next; batches complete in order,
         and their statistics are accumulated on the calling thread, in frame order, while the device works.
+        With ``parallel.use_devices`` batches go round robin to one worker per device; results still enter the
+        statistics in frame order.
         """
         if self._staged:
             staged, self._staged = self._staged, []
-            self._n_flushed = getattr(self, "_n_flushed", 0) + 1
-            if self._pool is None:
+            devs = self._run_devices()
+            k = self._n_flushed = getattr(self, "_n_flushed", 0) + 1
+            device = devs[(k - 1) % len(devs)]
+            if self._pools is None:
+                self._pools = {}
+            pool = self._pools.get(device)
+            if pool is None:
                 from concurrent.futures import ThreadPoolExecutor
 
-                self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mb200-batch")
+                from .. import _cabi
+
+                pool = self._pools[device] = ThreadPoolExecutor(
+                    max_workers=1, thread_name_prefix=f"mb200-batch-{device}", initializer=_cabi.set_thread_device,
+                    initargs=(device,))
+            self._batch_device = device
             self._announce_staged([st for _, st in staged])
-            previous, self._inflight = self._inflight, self._pool.submit(self._device_batch, staged)
-            self._stage_parity ^= 1  # the next batch is staged into the other pinned buffer (free once `previous` is done)
-            self._finish_batch(previous)
+            self._inflight_q.append(pool.submit(self._device_batch, staged))
+            # the next batch is staged into the next pinned buffer: one more buffer than batches in flight
+            self._stage_parity = (self._stage_parity + 1) % (len(devs) + 1)
+            while len(self._inflight_q) > len(devs):
+                self._finish_batch(self._inflight_q.popleft())
         if wait:
             self._drain()
 
     def _drain(self) -> None:
-        fut, self._inflight = self._inflight, None
-        self._finish_batch(fut)
+        while self._inflight_q:
+            self._finish_batch(self._inflight_q.popleft())
 
     def _device_batch(self, staged: list):
         t0 = time.perf_counter()
@@ -730,16 +774,15 @@ class AnalysisBase(_Runner):
         """End of a run, also when a frame raised: wait for the batch in flight, stop the worker thread and hand the
         pinned staging blocks (keyed by ``id(self)``) back, so that no later instance can be given a slot that a device
         call still reads."""
-        fut, self._inflight = self._inflight, None
-        if fut is not None:
+        while self._inflight_q:
             try:
-                fut.result()
+                self._inflight_q.popleft().result()
             except Exception:  # the original exception is already propagating
                 pass
         self._staged = []
-        if self._pool is not None:
-            self._pool.shutdown(wait=True)
-            self._pool = None
+        pools, self._pools = self._pools, None
+        for pool in (pools or {}).values():
+            pool.shutdown(wait=True)
         from .. import _cabi
 
         _cabi.release_pinned(self._slot_prefix())  # staging buffers live for one run
@@ -960,11 +1003,14 @@ class ProfileBase:
         """Topology-only weights (masses, charges, ones) are uploaded once per run, not with every batch."""
         from .. import _cabi
 
-        cached = getattr(self, "_dev_static_w", None)
+        ctx = _cabi.context()
+        if self._dev_static_w is None:
+            self._dev_static_w = {}
+        cached = self._dev_static_w.get(ctx.device)
         if cached is None or cached[0] is not weights:
-            buf = _cabi.DeviceBuffer(_cabi.context())
+            buf = _cabi.DeviceBuffer(ctx)
             buf.write(np.ascontiguousarray(weights, dtype=np.float64))
-            cached = self._dev_static_w = (weights, buf)
+            cached = self._dev_static_w[ctx.device] = (weights, buf)
         return cached[1].ptr.value
 
     def _compute_profiles(self, staged: list) -> list:

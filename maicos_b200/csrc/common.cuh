@@ -6,11 +6,13 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <list>
 #include <mutex>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/maicos_b200.h"
@@ -93,6 +95,28 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
     }
 };
+
+// fn(i0, i1) over [0, n) cut into contiguous chunks on a few host threads (q-plan construction for large reciprocal
+// cubes: an NPT trajectory needs a new plan for every box).  Serial below `min_parallel` items.
+template <typename F>
+inline void parallel_chunks(size_t n, size_t min_parallel, F fn) {
+    unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (const char *env = std::getenv("MAICOS_B200_HOST_THREADS")) nt = (unsigned)std::max(1, std::atoi(env));
+    if (n < min_parallel || nt < 2) {
+        fn((size_t)0, n);
+        return;
+    }
+    nt = (unsigned)std::min<size_t>(nt, n);
+    const size_t per = (n + nt - 1) / nt;
+    std::vector<std::thread> workers;
+    workers.reserve(nt - 1);
+    for (unsigned t = 1; t < nt; ++t) {
+        const size_t i0 = std::min(n, per * t), i1 = std::min(n, per * (t + 1));
+        if (i0 < i1) workers.emplace_back([=]() { fn(i0, i1); });
+    }
+    fn((size_t)0, std::min(n, per));
+    for (auto &w : workers) w.join();
+}
 
 #define MB_LOCK(ctx) std::lock_guard<std::recursive_mutex> _mb_call_lock((ctx)->call_mutex)
 

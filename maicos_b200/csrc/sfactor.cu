@@ -661,29 +661,34 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
     const size_t cells = (size_t)m0 * m1 * m2;
     std::vector<double> qcube(cells, 0.0);  // 0 = rejected
     const bool need_theta = !(thmin <= 0.0 && thmax >= 1.5707963267948968);
-    for (int h = 0; h < m0; ++h) {
-        const double qx = h * qf[0];
-        for (int k = 0; k < m1; ++k) {
-            const double qy = k * qf[1];
-            for (int l = 0; l < m2; ++l) {
-                if (h + k + l == 0) continue;
-                const double qz = l * qf[2];
-                const double qrr = std::sqrt(qx * qx + qy * qy + qz * qz);
-                if (!(qrr >= qmin && qrr <= qmax)) continue;
-                if (need_theta) {
-                    const double theta = std::acos(qz / qrr);
-                    if (!(theta >= thmin && theta <= thmax)) continue;
+    const size_t par_h = cells >= 200000 ? 2 : (size_t)m0 + 1;  // threads only for big cubes
+    parallel_chunks((size_t)m0, par_h, [&](size_t h_lo, size_t h_hi) {
+        for (int h = (int)h_lo; h < (int)h_hi; ++h) {
+            const double qx = h * qf[0];
+            for (int k = 0; k < m1; ++k) {
+                const double qy = k * qf[1];
+                for (int l = 0; l < m2; ++l) {
+                    if (h + k + l == 0) continue;
+                    const double qz = l * qf[2];
+                    const double qrr = std::sqrt(qx * qx + qy * qy + qz * qz);
+                    if (!(qrr >= qmin && qrr <= qmax)) continue;
+                    if (need_theta) {
+                        const double theta = std::acos(qz / qrr);
+                        if (!(theta >= thmin && theta <= thmax)) continue;
+                    }
+                    qcube[((size_t)h * m1 + k) * m2 + l] = qrr;
                 }
-                qcube[((size_t)h * m1 + k) * m2 + l] = qrr;
             }
         }
-    }
+    });
     // warp tiles: (quad, l-pair) with at least one valid q; DMMA-tile validity mask
     const int nqh = pl->rows[0] / QH, nqk = pl->rows[1] / QK, nlp = pl->rows[2] / NL;
     std::vector<int32_t> wt_of((size_t)nqh * nqk * nlp, -1);
     struct WT { int16_t h0, k0, l0; uint8_t mask; };
     std::vector<WT> wts;
-    for (int a = 0; a < nqh; ++a)
+    std::vector<std::vector<WT>> wts_a(nqh);  // per quad row a, in (b, c) order; concatenated in a order below
+    parallel_chunks((size_t)nqh, cells >= 200000 ? 2 : (size_t)nqh + 1, [&](size_t a_lo, size_t a_hi) {
+    for (int a = (int)a_lo; a < (int)a_hi; ++a)
         for (int b = 0; b < nqk; ++b)
             for (int c = 0; c < nlp; ++c) {
                 unsigned mask = 0;
@@ -704,12 +709,15 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
                         if (any) mask |= 1u << (2 * mt + nt);
                     }
                 }
-                if (mask) {
-                    wt_of[((size_t)a * nqk + b) * nlp + c] = (int32_t)wts.size();
-                    wts.push_back({(int16_t)(a * QH), (int16_t)(b * QK), (int16_t)(c * NL), (uint8_t)mask});
-                    pl->n_mma_tiles += __builtin_popcount(mask);
-                }
+                if (mask) wts_a[a].push_back({(int16_t)(a * QH), (int16_t)(b * QK), (int16_t)(c * NL), (uint8_t)mask});
             }
+    });
+    for (int a = 0; a < nqh; ++a)
+        for (const WT &t : wts_a[a]) {
+            wt_of[((size_t)a * nqk + t.k0 / QK) * nlp + t.l0 / NL] = (int32_t)wts.size();
+            wts.push_back(t);
+            pl->n_mma_tiles += __builtin_popcount(t.mask);
+        }
     pl->n_wt = (int32_t)wts.size();
     // pack consecutive warp tiles into CTAs
     for (size_t i = 0; i < wts.size(); i += WPC) {
@@ -732,16 +740,35 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
     }
     // entries
     std::vector<int32_t> cell; std::vector<double> qv; std::vector<int32_t> amp;
-    for (int h = 0; h < m0; ++h)
-        for (int k = 0; k < m1; ++k)
-            for (int l = 0; l < m2; ++l) {
-                const size_t ci = ((size_t)h * m1 + k) * m2 + l;
-                if (qcube[ci] == 0.0) continue;
-                const int32_t wt = wt_of[((size_t)(h / QH) * nqk + (k / QK)) * nlp + (l / NL)];
-                cell.push_back((int32_t)ci);
-                qv.push_back(qcube[ci]);
-                amp.push_back((wt * 32 + (h % QH) * 8 + (k % QK)) * 16 + (l % NL));
+    {
+        std::vector<size_t> h_start((size_t)m0 + 1, 0);  // entries are listed in C order of the cube: offsets per h slab
+        parallel_chunks((size_t)m0, par_h, [&](size_t h_lo, size_t h_hi) {
+            for (size_t h = h_lo; h < h_hi; ++h) {
+                size_t c = 0;
+                const double *slab = qcube.data() + h * (size_t)m1 * m2;
+                for (size_t i = 0; i < (size_t)m1 * m2; ++i) c += slab[i] != 0.0;
+                h_start[h + 1] = c;
             }
+        });
+        for (int h = 0; h < m0; ++h) h_start[h + 1] += h_start[h];
+        const size_t total = h_start[m0];
+        cell.resize(total); qv.resize(total); amp.resize(total);
+        parallel_chunks((size_t)m0, par_h, [&](size_t h_lo, size_t h_hi) {
+            for (int h = (int)h_lo; h < (int)h_hi; ++h) {
+                size_t o = h_start[h];
+                for (int k = 0; k < m1; ++k)
+                    for (int l = 0; l < m2; ++l) {
+                        const size_t ci = ((size_t)h * m1 + k) * m2 + l;
+                        if (qcube[ci] == 0.0) continue;
+                        const int32_t wt = wt_of[((size_t)(h / QH) * nqk + (k / QK)) * nlp + (l / NL)];
+                        cell[o] = (int32_t)ci;
+                        qv[o] = qcube[ci];
+                        amp[o] = (wt * 32 + (h % QH) * 8 + (k % QK)) * 16 + (l % NL);
+                        ++o;
+                    }
+            }
+        });
+    }
     const size_t nv = cell.size();
     if (n_bins > 0) {
         // np.histogram(a=|q|, bins=n_bins, range=(qmin, qmax)) -- saxs.py:222-233
@@ -753,10 +780,10 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
         edges[n_bins] = last;
         std::vector<int32_t> bin(nv);
         std::vector<int32_t> count(n_bins + 1, 0);
-        for (size_t e = 0; e < nv; ++e) {
-            bin[e] = numpy_bin(qv[e], first, last, n_bins, edges);
-            count[bin[e] + 1]++;
-        }
+        parallel_chunks(nv, 100000, [&](size_t e_lo, size_t e_hi) {
+            for (size_t e = e_lo; e < e_hi; ++e) bin[e] = numpy_bin(qv[e], first, last, n_bins, edges);
+        });
+        for (size_t e = 0; e < nv; ++e) count[bin[e] + 1]++;
         for (int b = 0; b < n_bins; ++b) count[b + 1] += count[b];
         pl->bin_start = count;
         std::vector<int32_t> pos(count.begin(), count.end() - 1);
@@ -777,12 +804,17 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
         struct Quad { uint8_t h, k0; int8_t top; };
         std::vector<Quad> quads;
         std::vector<int32_t> quad_of((size_t)m0 * m1, -1);  // (h,k) -> quad (h-major order)
+        std::vector<int8_t> top_hk((size_t)m0 * m1, -1);  // highest l tile with a valid cell of every (h,k) pair
+        parallel_chunks((size_t)m0, par_h, [&](size_t h_lo, size_t h_hi) {
+            for (size_t h = h_lo; h < h_hi; ++h)
+                for (int k = 0; k < m1; ++k)
+                    for (int l = m2 - 1; l >= 0; --l)
+                        if (qcube[(h * m1 + k) * m2 + l] != 0.0) { top_hk[h * m1 + k] = (int8_t)(l / lt_size); break; }
+        });
         for (int h = 0; h < m0; ++h) {
             int prev_k = -2, run_k0 = 0;
             for (int k = 0; k < m1; ++k) {
-                int top = -1;  // highest l tile with a valid cell of this (h,k) pair
-                for (int l = m2 - 1; l >= 0; --l)
-                    if (qcube[((size_t)h * m1 + k) * m2 + l] != 0.0) { top = l / lt_size; break; }
+                const int top = top_hk[(size_t)h * m1 + k];
                 if (top < 0) continue;
                 if (k != prev_k + 1) run_k0 = k;                     // a new run of consecutive k starts its own quads
                 if ((k - run_k0) % 4 == 0) quads.push_back({(uint8_t)h, (uint8_t)k, (int8_t)-1});
@@ -822,15 +854,17 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
         }
         pl->ent_amp_tc.resize(nv);
         pl->tc_tile_used.assign((size_t)pl->tc_n_rt * n_lt, 0);
-        for (size_t e = 0; e < nv; ++e) {
-            const int32_t ci = pl->cell[e];
-            const int l = ci % m2, k = (ci / m2) % m1, h = ci / (m2 * m1);
-            const int32_t qi = quad_of[(size_t)h * m1 + k];
-            const int32_t pp = slot_of[qi] * 4 + (k - (int)quads[qi].k0);
-            const int32_t tile = (pp / TC_M) * n_lt + l / lt_size;
-            pl->tc_tile_used[tile] = 1;
-            pl->ent_amp_tc[e] = (tile * TC_M + pp % TC_M) * lt_size + l % lt_size;
-        }
+        parallel_chunks(nv, 100000, [&](size_t e_lo, size_t e_hi) {
+            for (size_t e = e_lo; e < e_hi; ++e) {
+                const int32_t ci = pl->cell[e];
+                const int l = ci % m2, k = (ci / m2) % m1, h = ci / (m2 * m1);
+                const int32_t qi = quad_of[(size_t)h * m1 + k];
+                const int32_t pp = slot_of[qi] * 4 + (k - (int)quads[qi].k0);
+                const int32_t tile = (pp / TC_M) * n_lt + l / lt_size;
+                pl->ent_amp_tc[e] = (tile * TC_M + pp % TC_M) * lt_size + l % lt_size;
+            }
+        });
+        for (size_t e = 0; e < nv; ++e) pl->tc_tile_used[pl->ent_amp_tc[e] / (TC_M * lt_size)] = 1;
         pl->tc_n_used = 0;
         for (uint8_t u : pl->tc_tile_used) pl->tc_n_used += u;
         pl->tc_ok = true;
@@ -892,7 +926,8 @@ static int plan_ff2(mb200_ctx *ctx, SfPlan &pl, const double *cm, int n_groups) 
     const size_t nv = pl.qrr.size();
     std::vector<double> ff2((size_t)n_groups * nv);
     for (int gidx = 0; gidx < n_groups; ++gidx)
-        for (size_t e = 0; e < nv; ++e) {
+        parallel_chunks(nv, 50000, [&](size_t e_lo, size_t e_hi) {
+        for (size_t e = e_lo; e < e_hi; ++e) {
             const double q = pl.qrr[e] / (4 * M_PI);
             const double q2 = q * q;
             double f = 0.0;
@@ -905,6 +940,7 @@ static int plan_ff2(mb200_ctx *ctx, SfPlan &pl, const double *cm, int n_groups) 
             }
             ff2[(size_t)gidx * nv + e] = f * f;
         }
+        });
     if (!ff2.empty()) {
         MB_TRY(pl.d_ff2.ensure(ff2.size() * 8));
         MB_CUDA(cudaMemcpyAsync(pl.d_ff2.p, ff2.data(), ff2.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1380,6 +1416,32 @@ extern "C" int mb200_ctx_set_precision(mb200_ctx *ctx, int mode) {
     if (mode < 0 || mode > 2) return fail(MB200_EINVAL, "precision mode must be 0 (fp64), 1 (i8x5 split precision) or 2 (i8x5, A operand in shared memory)");
     ctx->precision = mode ? 1 : 0;
     ctx->tc_a_tmem = mode != 2;
+    return MB200_OK;
+}
+
+// Diagnostic (host only, no device needed): build the q-plan of a box / q window and describe it.
+extern "C" int mb200_plan_describe(const double dimensions[3], double qmin, double qmax, double thetamin, double thetamax,
+                                   int32_t n_bins, int64_t out[16]) {
+    if (!dimensions || !out) return fail(MB200_EINVAL, "null argument");
+    std::shared_ptr<SfPlan> pl;
+    MB_TRY(build_plan(dimensions, qmin, qmax, thetamin, thetamax, n_bins, pl));
+    auto fnv = [](const void *p, size_t bytes) {
+        unsigned long long h = 1469598103934665603ull;
+        const unsigned char *c = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < bytes; ++i) h = (h ^ c[i]) * 1099511628211ull;
+        return (int64_t)(h >> 1);
+    };
+    for (int i = 0; i < 16; ++i) out[i] = 0;
+    out[0] = (int64_t)pl->cell.size();
+    out[1] = pl->maxn[0]; out[2] = pl->maxn[1]; out[3] = pl->maxn[2];
+    out[4] = pl->tc_ok; out[5] = pl->tc_n_rt; out[6] = pl->tc_n_lt; out[7] = pl->tc_lt; out[8] = pl->tc_n_used;
+    out[9] = pl->n_wt;
+    out[10] = fnv(pl->cell.data(), pl->cell.size() * 4);
+    out[11] = fnv(pl->ent_amp.data(), pl->ent_amp.size() * 4);
+    out[12] = fnv(pl->ent_amp_tc.data(), pl->ent_amp_tc.size() * 4);
+    out[13] = fnv(pl->tc_rows.data(), pl->tc_rows.size());
+    out[14] = fnv(pl->bin_start.data(), pl->bin_start.size() * 4);
+    out[15] = fnv(pl->tgs.data(), pl->tgs.size() * sizeof(TileGroupDesc));
     return MB200_OK;
 }
 

@@ -216,12 +216,10 @@ class Saxs(AnalysisBase):
         if self.bin_spectrum:
             self._announce_rows([(st[0], st[1]) for st in staged])
 
-    _groups_handle = None
-
     def _release_groups(self) -> None:
-        handle, self._groups_handle = self._groups_handle, None
-        if handle:
-            _cabi.load().mb200_groups_destroy(_cabi.context().handle, handle)
+        handles, self._groups_handles = self.__dict__.get("_groups_handles", {}), {}
+        for device, handle in handles.items():
+            _cabi.load().mb200_groups_destroy(_cabi.context(device).handle, handle)
 
     def _release_run_resources(self) -> None:
         super()._release_run_resources()
@@ -249,15 +247,17 @@ class Saxs(AnalysisBase):
         c = np.zeros((F, G, self.n_bins), dtype=np.int64)
         block, n_blocks = parallel.q_block()
         ctx = _cabi.context()
-        if self._groups_handle is None:  # the selection goes to the device once per run
+        handle = self._groups_handles.get(ctx.device)
+        if handle is None:  # the selection goes to a device once per run
             import ctypes
 
-            self._groups_handle = ctypes.c_void_p()
+            handle = ctypes.c_void_p()
             _cabi.check(_cabi.load().mb200_groups_create(ctx.handle, _cabi.ptr(self._group_flat), _cabi.ptr(self._group_ptr), G, n,
-                                                         ctypes.byref(self._groups_handle)))
+                                                         ctypes.byref(handle)))
+            self._groups_handles[ctx.device] = handle
         _cabi.check(
             _cabi.load().mb200_saxs_frames_groups(
-                ctx.handle, _cabi.ptr(pos), 0, F, _cabi.ptr(boxes), self._groups_handle, _cabi.ptr(self._cm),
+                ctx.handle, _cabi.ptr(pos), 0, F, _cabi.ptr(boxes), handle, _cabi.ptr(self._cm),
                 float(self.qmin), float(self.qmax), float(self.thetamin), float(self.thetamax), self.n_bins,
                 int(self._device_packs()), block, n_blocks, _cabi.ptr(s), _cabi.ptr(i), _cabi.ptr(c),
             )

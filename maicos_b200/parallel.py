@@ -23,7 +23,7 @@ import os
 
 import numpy as np
 
-_state = {"initialised": False, "rank": 0, "world": 1, "mode": "frames", "device": None, "backend": None}
+_state = {"initialised": False, "rank": 0, "world": 1, "mode": "frames", "device": None, "backend": None, "devices": None}
 
 
 def init(mode: str = "frames", backend: str | None = None) -> None:
@@ -53,6 +53,31 @@ def init(mode: str = "frames", backend: str | None = None) -> None:
         else:
             dist.init_process_group(backend=backend)
     _state.update(initialised=True, rank=dist.get_rank(), world=dist.get_world_size(), backend=backend)
+
+
+def use_devices(devices=None) -> list[int] | None:
+    """Single-process multi-GPU: let every batched analysis of this process deal its batches of frames round robin to
+    these CUDA devices (one worker thread and one library context per device, no ``torchrun``, no collective: the
+    per-frame results come back to the one set of running statistics in frame order, so the numbers are those of a
+    single-GPU run).  ``devices``: a list of device indices, an integer count, ``"all"`` / ``None`` for every visible
+    device, ``[]`` / ``0`` to go back to one device.  Returns the list in use."""
+    from . import _cabi
+
+    if devices is None or devices == "all":
+        devices = list(range(_cabi.device_count()))
+    elif isinstance(devices, int):
+        devices = list(range(devices))
+    devices = [int(d) for d in devices]
+    n = _cabi.device_count()
+    if any(d < 0 or d >= max(n, 1) for d in devices):
+        raise ValueError(f"device index out of range (have {n} CUDA devices)")
+    _state["devices"] = devices if len(devices) > 0 else None
+    return _state["devices"]
+
+
+def devices() -> list[int] | None:
+    """Devices of the single-process multi-GPU mode (``None``: the process default device only)."""
+    return _state["devices"]
 
 
 def set_mode(mode: str) -> None:

@@ -112,3 +112,41 @@ def test_library_sass_carries_the_claimed_instructions():
     assert "UBLKCP" in body("13k_sf_contractE"), "FP64 contraction without bulk-copy staging"
     assert "ATOMS" in body("k_hist_sorted") and "ATOMS" in body("6k_histILi0")
     assert "UBLKPF" in body("k_hist_sorted"), "the counting-sort histogram prefetches its next tile into L2 with a bulk prefetch"
+
+
+@pytest.mark.parametrize("L,qmax,n_bins,window", [
+    (24.87, 6.0, 60, (0.0, 0.0, np.pi)),          # shipped water, default q range
+    (99.97, 2.0, 20, (0.0, 0.0, np.pi)),          # BASELINE config 2
+    (215.37, 2.0, 20, (0.0, 0.0, np.pi)),         # 1M atoms, two l tiles
+    (60.0, 3.0, 30, (0.5, 0.3, 1.2)),             # qmin and theta window
+    (50.0, 3.0, 0, (0.0, 0.0, np.pi)),            # raw-cube entry order
+])
+def test_q_plan_host_side(L, qmax, n_bins, window, monkeypatch):
+    """``mb200_plan_describe`` (host only): the plan accepts exactly the q vectors the reference kernel accepts
+    (_cmath.pyx:93-115 through the oracle's port), and the multi-threaded construction equals the serial one."""
+    import ctypes
+
+    from oracle import kernel
+
+    lib = _cabi.load()
+    dims = np.double(np.float32([L, L * 1.01, L * 0.99]))
+    qmin, tmin, tmax = window
+
+    def describe():
+        out = (ctypes.c_int64 * 16)()
+        _cabi.check(lib.mb200_plan_describe(dims.ctypes.data_as(_cabi.c_double_p), qmin, qmax, tmin, tmax, n_bins, out))
+        return list(out)
+
+    monkeypatch.setenv("MAICOS_B200_HOST_THREADS", "1")
+    serial = describe()
+    monkeypatch.setenv("MAICOS_B200_HOST_THREADS", "5")
+    threaded = describe()
+    assert serial == threaded
+    q, _ = kernel.port_structure_factor(np.zeros((1, 3)), dims, qmin, qmax, tmin, tmax, np.ones(1))
+    assert serial[0] == np.count_nonzero(q)
+    assert serial[1:4] == [int(m) for m in kernel.port_maxn(dims, qmax)]
+    n_rt, n_lt, lt, used = serial[5:9]
+    assert serial[4] == 1 and n_lt * lt >= serial[3] and lt % 8 == 0 and lt <= 48
+    assert 0 < used <= n_rt * n_lt
+    if n_lt > 1:  # quads sorted by their highest populated l tile: blocks without any valid q are never launched
+        assert used < n_rt * n_lt

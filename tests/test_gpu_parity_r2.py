@@ -453,3 +453,52 @@ def test_diporder_cylinder_and_sphere_unit_vectors_formed_on_the_device(order_pa
     a = mb.DiporderSphere(u.atoms, bin_width=1.0, order_parameter=order_parameter).run()
     nb, rmax = a.n_bins, a.rmax
     check(a, lambda p, w: restatement.hist_sphere(p, w, nb, 0.0, rmax, center), lambda c: restatement.unit_vectors_radial(c, box))
+
+
+# ---- single-process multi-GPU (parallel.use_devices) ------------------------------------------------------------
+def test_single_process_device_round_robin_equals_single_device(precision):
+    """Batches dealt round robin to one worker per device entry: with the one GPU of the test box listed twice the two
+    workers share a context (serialised by its lock) -- the pipeline, the per-device handles and the in-order
+    accumulation are exercised, and the results must be those of the plain run, bit for bit.  With more than one GPU
+    visible every GPU is used."""
+    from maicos_b200 import parallel
+
+    frames = mb.synthetic.spce_water_frames(500, 24.0, 9, n_frames=37)
+    topo = mb.synthetic.spce_topology(500)
+    from maicos_b200.mdshim import MemoryTrajectory, Universe
+
+    def universe():
+        return Universe(1500, MemoryTrajectory(frames, np.float32([24, 24, 24, 90, 90, 90])), **topo)
+
+    def run_all(u):
+        out = []
+        for make in (lambda: mb.Saxs(u.atoms, qmax=2.5, dq=0.1),
+                     lambda: mb.DiporderStructureFactor(u.atoms, qmax=2.0, dq=0.1),
+                     lambda: mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.5),
+                     lambda: mb.DiporderPlanar(u.atoms, bin_width=0.8)):
+            a = make()
+            a._batch_size = 4
+            type(a)._batch_size, keep = 4, type(a)._batch_size
+            try:
+                a.run()
+            finally:
+                type(a)._batch_size = keep
+            out.append(a)
+        return out
+
+    plain = run_all(universe())
+    n_dev = _cabi.device_count()
+    devices = list(range(n_dev)) if n_dev > 1 else [0, 0]
+    parallel.use_devices(devices)
+    try:
+        multi = run_all(universe())
+    finally:
+        parallel.use_devices([])
+    assert parallel.devices() is None
+    for a, b in zip(multi, plain):
+        assert a._index == b._index == 37
+        for key in b.sums:
+            assert_array_equal(np.asarray(a.sums[key]), np.asarray(b.sums[key]), err_msg=f"{type(a).__name__}.{key}")
+        for key in b.sems:
+            assert_array_equal(np.asarray(a.sems[key]), np.asarray(b.sems[key]), err_msg=f"{type(a).__name__}.{key}")
+        assert_array_equal(a.timeseries, b.timeseries)
