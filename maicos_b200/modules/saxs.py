@@ -87,6 +87,13 @@ def _element_groups(atomgroup):
     return unique, inverse
 
 
+def _destroy_groups(device: int, handle) -> None:
+    try:
+        _cabi.load().mb200_groups_destroy(_cabi.context(device).handle, handle)
+    except Exception:  # interpreter shutdown: the context is gone with the process
+        pass
+
+
 class _GroupList:
     """``Saxs.groups`` of the reference (one AtomGroup per element, saxs.py:158-164), built when somebody looks: the
     device path works on the index arrays."""
@@ -185,10 +192,9 @@ class Saxs(AnalysisBase):
             ptr = np.concatenate([[0], np.cumsum([len(i) for i in index])]).astype(np.int64)
             flat = np.ascontiguousarray(np.concatenate(index), dtype=np.int32)
             cm = np.ascontiguousarray(np.stack([tables.cm_packed(str(el)) for el in unique]))
-            prepared = cache[id(inverse)] = (inverse, index, ptr, flat, cm)
-        _, self._group_index, self._group_ptr, self._group_flat, self._cm = prepared
+            prepared = cache[id(inverse)] = (inverse, index, ptr, flat, cm, {})
+        _, self._group_index, self._group_ptr, self._group_flat, self._cm, self._groups_handles = prepared
         self.elements = list(unique)
-        self._release_groups()
         self.groups = _GroupList(self.atomgroup, self._group_index)
         self.weights = _OnesList(self._group_index)
 
@@ -216,20 +222,6 @@ class Saxs(AnalysisBase):
         if self.bin_spectrum:
             self._announce_rows([(st[0], st[1]) for st in staged])
 
-    def _release_groups(self) -> None:
-        handles, self._groups_handles = self.__dict__.get("_groups_handles", {}), {}
-        for device, handle in handles.items():
-            _cabi.load().mb200_groups_destroy(_cabi.context(device).handle, handle)
-
-    def _release_run_resources(self) -> None:
-        super()._release_run_resources()
-        self._release_groups()
-
-    def __del__(self):
-        try:
-            self._release_groups()
-        except Exception:
-            pass
 
     def _device_packs(self) -> bool:
         # the kernel's pack is the orthorhombic ``x -= floor(x / L) L``; a triclinic cell is packed by the host
@@ -251,10 +243,15 @@ class Saxs(AnalysisBase):
         if handle is None:  # the selection goes to a device once per run
             import ctypes
 
+            import weakref
+
             handle = ctypes.c_void_p()
             _cabi.check(_cabi.load().mb200_groups_create(ctx.handle, _cabi.ptr(self._group_flat), _cabi.ptr(self._group_ptr), G, n,
                                                          ctypes.byref(handle)))
+            # kept with the universe's prepared selection (further analyses of the same selection reuse it), destroyed
+            # with the universe
             self._groups_handles[ctx.device] = handle
+            weakref.finalize(self._universe, _destroy_groups, ctx.device, handle)
         _cabi.check(
             _cabi.load().mb200_saxs_frames_groups(
                 ctx.handle, _cabi.ptr(pos), 0, F, _cabi.ptr(boxes), handle, _cabi.ptr(self._cm),

@@ -23,6 +23,7 @@ import os
 
 import numpy as np
 
+_nccl_buffers: dict = {}
 _state = {"initialised": False, "rank": 0, "world": 1, "mode": "frames", "device": None, "backend": None, "devices": None}
 
 
@@ -105,6 +106,7 @@ def shutdown() -> None:
 
         if dist.is_initialized():
             dist.destroy_process_group()
+    _nccl_buffers.clear()
     _state.update(initialised=False, rank=0, world=1, device=None, backend=None)
 
 
@@ -143,9 +145,21 @@ def allreduce_sum(buf: np.ndarray) -> np.ndarray:
     assert buf.dtype == np.float64 and buf.flags.c_contiguous
     t = torch.from_numpy(buf.reshape(-1))
     if _state["backend"] == "nccl":
-        d = t.to(_state["device"], non_blocking=False)
+        # a persistent device tensor and a persistent pinned mirror per size: no allocation, no pageable staging per call
+        key = t.numel()
+        cached = _nccl_buffers.get(key)
+        if cached is None:
+            if len(_nccl_buffers) > 16:
+                _nccl_buffers.clear()
+            cached = _nccl_buffers[key] = (torch.empty(key, dtype=torch.float64, device=_state["device"]),
+                                           torch.empty(key, dtype=torch.float64).pin_memory())
+        d, h = cached
+        h.copy_(t)
+        d.copy_(h, non_blocking=True)
         dist.all_reduce(d, op=dist.ReduceOp.SUM)
-        t.copy_(d)
+        h.copy_(d, non_blocking=True)
+        torch.cuda.current_stream(_state["device"]).synchronize()
+        t.copy_(h)
     else:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return buf
