@@ -22,11 +22,15 @@ def set_precision(mode: str = "i8x5", device: int | None = None) -> None:
     40-bit fixed point, exact int32 accumulation in TMEM, FP64 recombination).  Measured max relative error
     on any nonzero cell of the raw S cube 4.4e-9 (1.5k .. 1M atoms), 3e-13 on binned S(q); stated tolerance 1e-6.
     ``"fp64"`` -- FP64 phase tables and FP64 DMMA accumulation (~1e-12 against the reference kernel), ~2.6x slower.
-    The environment variable ``MAICOS_B200_PRECISION`` selects the mode for the CLI.
+    The environment variable ``MAICOS_B200_PRECISION`` selects the mode for the CLI.  Without ``device`` the mode applies
+    to every device context of the process.
     """
     from . import _cabi
 
-    _cabi.context(device).set_precision(mode)
+    if device is not None:
+        _cabi.context(device).set_precision(mode)
+    else:  # every context of this process, existing and future (single-process multi-GPU runs use one per device)
+        _cabi.set_default_precision(mode)
 
 
 __all__ = ["AnalysisBase", "set_precision", "AnalysisCollection", "core", "lib", "mdshim", "parallel", "synthetic", *_modules_all]

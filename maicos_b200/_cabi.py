@@ -172,7 +172,7 @@ class Context:
         _check(lib.mb200_ctx_create(int(device), ctypes.byref(handle)))
         self._h = handle
         self.device = int(device)
-        mode = os.environ.get("MAICOS_B200_PRECISION", "")
+        mode = _default_precision or os.environ.get("MAICOS_B200_PRECISION", "")
         if mode:  # e.g. MAICOS_B200_PRECISION=fp64 for the CLI; maicos_b200.set_precision() overrides
             self.set_precision(mode)
         mode = os.environ.get("MAICOS_B200_HIST", "")
@@ -228,6 +228,21 @@ def default_device() -> int:
 
 
 _tls = threading.local()
+_default_precision = ""
+
+
+def set_default_precision(mode: str) -> None:
+    """Arithmetic mode of every context of this process: those that exist and those created later."""
+    global _default_precision
+    if mode not in ("fp64", "i8x5", "i8x5-smem"):
+        raise KeyError(mode)
+    _default_precision = mode
+    with _lock:
+        existing = list(_contexts.values())
+    if not existing:
+        existing = [context()]
+    for ctx in existing:
+        ctx.set_precision(mode)
 
 
 def set_thread_device(device: int | None) -> None:
