@@ -789,11 +789,11 @@ def path2_summary(ctx, lib, torch, peaks=None):
     gbs = 12.0 * n * F / sec / 1e9
     return {"workload": f"weighted + count slab histogram, {n} atoms x {F} frames resident, {nb} bins",
             "frames_per_s": F / sec, "atoms_per_s": n * F / sec,
-            "roofline": {"kernel": "k_hist_sorted", "bound": "hbm", "achieved": 12.0 * n * F / ksec / 1e9, "peak": peak,
+            "roofline": {"kernel": "k_hist_chunk", "bound": "hbm", "achieved": 12.0 * n * F / ksec / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": 12.0 * n * F / ksec / 1e9 / peak, "kernel_ms_per_launch": ksec * 1e3,
                          "whole_call": {"achieved": gbs, "frac": gbs / peak, "ms_per_call": sec * 1e3,
                                         "note": "call = parameter upload + max|w| + histogram + merge kernels + per-frame results to host"},
-                         "co_limiter": "shared-memory atomic unit: one ATOMS lane per clock and SM (profiles/r01_hist_notes.md)",
+                         "co_limiter": "four non-returning shared-memory atomics per element at ~9.7 lanes per clock and SM (profiles/r02_smem_atomics.log)",
                          "algorithmic_bytes_per_atom_frame": 12,
                          "hbm_copy_gbs_probed_in_this_run": (peaks or {}).get("hbm_copy_gbs"),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if pk else "fallback 6650 GB/s"}}

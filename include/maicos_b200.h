@@ -277,9 +277,11 @@ int mb200_dielectric_prepare(mb200_ctx *ctx, const float *positions, int positio
  *   modules/dielectricsphere.py:113-133. */
 #define MB200_BIN_DIGITIZE 0x10
 
-/* Kernel used for WEIGHTED histograms with finite weights (results are bitwise identical, both accumulate the same
- * exact fixed-point integers):  0 (default) counting-sort tiles, one shared-memory atomic per element;
- * 1 three shared-memory atomics per element (the round-1 kernel, kept for A/B measurements). */
+/* Kernel used for WEIGHTED histograms with finite weights (results are bitwise identical, all accumulate the same
+ * exact fixed-point integers):  0 (default) four non-returning shared-memory atomics per element on 18-bit chunks of
+ * the fixed-point weight, folded into wide per-bin records every 16384 elements;  1 three returning shared-memory
+ * atomics per element with carries (the round-1 kernel);  2 counting-sort tiles, one returning atomic per element (the
+ * round-1 default).  1 and 2 are kept for A/B measurements. */
 int mb200_ctx_set_hist_mode(mb200_ctx *ctx, int mode);
 
 /* Fused weighted + count histogram of ProfileBase._single_frame (core/base.py:815-818),

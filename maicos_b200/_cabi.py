@@ -200,8 +200,9 @@ class Context:
         _check(load().mb200_ctx_set_precision(self._h, {"fp64": 0, "i8x5": 1, "i8x5-smem": 2}[mode]))
 
     def set_hist_mode(self, mode: str) -> None:
-        """Weighted-histogram kernel: ``"sorted"`` (default, one shared atomic per element) or ``"atomics"``."""
-        _check(load().mb200_ctx_set_hist_mode(self._h, {"sorted": 0, "atomics": 1}[mode]))
+        """Weighted-histogram kernel: ``"chunks"`` (default: four non-returning shared atomics per element),
+        ``"atomics"`` (three returning atomics) or ``"sorted"`` (counting-sort tiles); bitwise identical results."""
+        _check(load().mb200_ctx_set_hist_mode(self._h, {"chunks": 0, "atomics": 1, "sorted": 2}[mode]))
 
     def probe_peaks(self) -> dict:
         """Measured ceilings of this device, in this process: ``i8_tops``, ``fp64_dmma_tflops``, ``hbm_copy_gbs``."""

@@ -131,9 +131,9 @@ struct mb200_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false;
-    bool sf_attr_set = false, hist_attr_set = false, tc_attr_set = false;
+    bool sf_attr_set = false, hist_attr_set = false, tc_attr_set = false, hc_attr_set = false;
     unsigned hs_attr_set = 0;  // k_hist_sorted<B> instantiations whose shared-memory limit is raised
-    int hist_mode = 0;         // weighted histograms: 0 counting-sort kernel (default), 1 three-atomics kernel
+    int hist_mode = 0;         // weighted histograms: 0 chunked non-returning atomics (default), 1 three returning atomics, 2 counting sort
     int precision = 1;        // 1: int8 x 5 split precision on tcgen05 (default)  0: FP64 DMMA
     bool tc_a_tmem = true;    // split-precision kernel: generated A operand in tensor memory when the l tile allows it
     bool force_fp64 = false;  // this call must use the FP64 kernel (non-finite weights)

@@ -627,6 +627,222 @@ __global__ void __launch_bounds__(HS_THREADS, 2) k_hist_sorted(HistParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k_hist_chunk: the weighted mode with FOUR non-returning shared-memory atomics per element and nothing else
+// (default for finite weights since round 2).
+//
+// Round 1 assumed that the shared-memory atomic unit retires one lane per clock and SM and built the counting sort
+// above around that.  tools/microbench/smem_atomics.cu (profiles/r02_smem_atomics.log) measures 8.5 - 10 lanes per clock
+// and SM for 32-bit adds on random bins, returning or not: what bounded k_hist<1> / k_hist_sorted was everything AROUND
+// the atomic (data-dependent edge loads, the sort's scan, scatter and segment sums on the shared-memory pipe).  So:
+//   * the bin comes from arithmetic alone (find_bin: the edge table is only consulted for values within eps of an edge);
+//   * the 54-bit fixed-point weight fixed(w) (same as k_hist<0>) is cut into three 18-bit chunks and each chunk is added
+//     to its own 32-bit counter of the bin with a plain `red.shared.add.u32`; the count is a fourth one.  16384 chunks
+//     below 2^18 cannot wrap a 32-bit counter, so after every four tiles of 4096 elements the owner of a bin (thread
+//     t owns bins t + 512 r) folds the four counters into the CTA's private {96-bit sum, count} record of the bin
+//     with plain loads and stores and clears them: no sort, no scan, two block barriers per 16384 elements;
+//   * the flush into the 128-bit global accumulators and k_hist_merge are the ones of the other kernels: integer sums
+//     are exact and order independent, the result is BITWISE theirs.
+// 5 x 4 lanes of atomics per element against ~9.7 lanes per clock: 2.4 elements per clock and SM = 8.4 TB/s of 12-byte
+// elements -- above what HBM delivers, so the kernel streams at the memory rate.
+constexpr int HC_THREADS = 512;
+constexpr int HC_PER = 8;
+constexpr int HC_TILE = HC_THREADS * HC_PER;
+constexpr int HC_FOLD_TILES = 4;  // 4 x 4096 = 16384 elements between folds: 16384 x (2^18 - 1) < 2^32
+
+__device__ __forceinline__ void red_add32(unsigned int a, unsigned int v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(HC_THREADS, 2) k_hist_chunk(HistParams p) {
+    extern __shared__ __align__(16) unsigned char hsm[];
+    const int f = blockIdx.y, nb = p.n_bins, t = threadIdx.x;
+    // shared layout: acc [nb] x 16 B | edges [nb + 1] x 8 B | cnt, c0, c1, c2 [nb] x 4 B each
+    unsigned int s_acc = (unsigned int)__cvta_generic_to_shared(hsm);
+    unsigned int s_edges = s_acc + 16u * (unsigned int)nb;
+    unsigned int s_cnt = s_edges + 8u * (unsigned int)(nb + 1);
+    const unsigned int plane = 4u * (unsigned int)nb;  // byte distance of the four counter planes
+    asm volatile("" : "+r"(s_acc), "+r"(s_cnt));
+
+    const double *g_edges = p.edges + (size_t)f * (nb + 1);
+    EdgeRef E;
+    E.tab = s_edges; E.nb = nb;
+    E.first = g_edges[0]; E.last = g_edges[nb];
+    const double width = __dsub_rn(E.last, E.first);
+    E.step = __ddiv_rn(width, (double)nb);
+    E.inv_width = (double)nb / width;
+    {
+        const double A = fmax(fabs(E.first), fabs(E.last));
+        const double e = 8.0 * (double)nb * 1.1102230246251565e-16 * (1.0 + 2.0 * A / fabs(width));
+        E.eps = (width > 0.0 && e < 0.25) ? e : 2.0;
+    }
+    int lin = 1;
+    for (int i = t; i <= nb; i += HC_THREADS) {
+        const double e = g_edges[i];
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(s_edges + 8u * (unsigned int)i), "d"(e) : "memory");
+        lin &= (e == (i == nb ? E.last : __dadd_rn(__dmul_rn((double)i, E.step), E.first))) ? 1 : 0;
+    }
+    for (int i = t; i < nb; i += HC_THREADS) {
+        sts_acc(s_acc + 16u * (unsigned int)i, 0u, 0u, 0u, 0u);
+#pragma unroll
+        for (unsigned int k = 0; k < 4u; ++k) sts32(s_cnt + k * plane + 4u * (unsigned int)i, 0u);
+    }
+    E.arith = __syncthreads_and(lin);
+    if (!E.arith) E.eps = 2.0;  // hand-made edges: always decided by the table
+
+    FrameGeom g;
+    g.geometry = p.geometry; g.nb = nb; g.digitize = p.digitize;
+    g.d0 = p.dim; g.d1 = (p.dim + 1) % 3; g.d2 = (p.dim + 2) % 3;
+    g.cx = g.cy = g.cz = g.zlo = g.zhi = 0;
+    if (p.geometry == MB200_GEOM_CYLINDER || p.geometry == MB200_GEOM_SPHERE) { g.cx = p.center[f * 3]; g.cy = p.center[f * 3 + 1]; g.cz = p.center[f * 3 + 2]; }
+    if (p.geometry == MB200_GEOM_CYLINDER && p.zrange) { g.zlo = p.zrange[f * 2]; g.zhi = p.zrange[f * 2 + 1]; }
+    const int dig = p.digitize;
+    if (dig) E.eps = 2.0;
+    const long long n = p.n;
+    const double *w = p.weights + (p.w_per_frame ? (size_t)f * n : 0);
+    double *gf = p.acc_f + (size_t)f * nb;
+    unsigned long long *gc = p.acc_c + (size_t)f * nb;
+    unsigned long long *glo = p.acc_lo + (size_t)f * nb, *ghi = p.acc_hi + (size_t)f * nb;
+
+    const unsigned long long wb = p.wmax_bits[p.w_per_frame ? f : 0];
+    const bool fx = wb < 0x7ff0000000000000ull;
+    const double wmax = __longlong_as_double((long long)wb);
+    const int kexp = bias_exponent(fx && wmax > 0.0 ? wmax : 1.0);
+    const double bias = ldexp(1.0, kexp), inv_q = ldexp(1.0, 52 - kexp);
+
+    auto bin_generic = [&](long long j) -> int {
+        double v;
+        if (p.geometry == MB200_GEOM_SCALAR) {
+            v = p.is_f32 ? (double)(reinterpret_cast<const float *>(p.pos) + (size_t)f * n)[j]
+                         : (reinterpret_cast<const double *>(p.pos) + (size_t)f * n)[j];
+        } else {
+            double x, y, z;
+            if (p.is_f32) {
+                const float *b = reinterpret_cast<const float *>(p.pos) + ((size_t)f * n + j) * 3;
+                x = (double)b[0]; y = (double)b[1]; z = (double)b[2];
+            } else {
+                const double *b = reinterpret_cast<const double *>(p.pos) + ((size_t)f * n + j) * 3;
+                x = b[0]; y = b[1]; z = b[2];
+            }
+            if (!atom_value(g, x, y, z, v)) return -1;
+        }
+        return find_bin(E, v, dig);
+    };
+    auto fixed = [&](double wj) -> unsigned long long {
+        return (unsigned long long)__double2ll_rn(__dmul_rn(__dadd_rn(wj, bias), inv_q));
+    };
+    auto deposit = [&](int b, unsigned long long v) {  // v <= 2^53: chunks of 18 bits
+        if (b < 0) return;
+        const unsigned int a = s_cnt + 4u * (unsigned int)b;
+        red_add32(a, 1u);
+        red_add32(a + plane, (unsigned int)v & 0x3ffffu);
+        red_add32(a + 2u * plane, (unsigned int)(v >> 18) & 0x3ffffu);
+        red_add32(a + 3u * plane, (unsigned int)(v >> 36));
+    };
+    auto fold = [&]() {  // between two block barriers: owners move the counters into the wide records
+        for (int b = t; b < nb; b += HC_THREADS) {
+            const unsigned int a = s_cnt + 4u * (unsigned int)b;
+            const unsigned int cn = lds32(a);
+            if (!cn) continue;
+            const unsigned long long c0 = lds32(a + plane), c1 = lds32(a + 2u * plane), c2 = lds32(a + 3u * plane);
+            // c0 + c1 2^18 + c2 2^36 < 2^69: low 64 bits with carry, then the top limb
+            const unsigned long long lo_a = c0 + (c1 << 18);                 // < 2^51
+            const unsigned long long lo_b = c2 << 36;                        // low 64 bits of c2 2^36
+            const unsigned long long lo = lo_a + lo_b;
+            const unsigned int top = (unsigned int)(c2 >> 28) + (lo < lo_a ? 1u : 0u);
+            unsigned int s0, s1, s2, count;
+            lds_acc(s_acc + 16u * (unsigned int)b, s0, s1, s2, count);
+            add96(s0, s1, s2, lo, top);
+            sts_acc(s_acc + 16u * (unsigned int)b, s0, s1, s2, count + cn);
+            sts32(a, 0u); sts32(a + plane, 0u); sts32(a + 2u * plane, 0u); sts32(a + 3u * plane, 0u);
+        }
+    };
+
+    if (!fx) {  // inf / nan weights in this frame: float64 atomics keep numpy's result
+        for (long long j = (long long)blockIdx.x * HC_THREADS + t; j < n; j += (long long)gridDim.x * HC_THREADS) {
+            const int b = bin_generic(j);
+            if (b < 0) continue;
+            atomicAdd(&gc[b], 1ull);
+            atomicAdd(&gf[b], w[j]);
+        }
+        return;
+    }
+
+    long long a0 = 0, n_quads = 0;
+    const bool fast = p.geometry != MB200_GEOM_SCALAR && p.is_f32 && (((unsigned long long)(uintptr_t)p.pos) & 3ull) == 0;
+    const float *fbase = reinterpret_cast<const float *>(p.pos) + (size_t)f * n * 3;
+    if (fast) {
+        const unsigned long long addr = (unsigned long long)(uintptr_t)fbase;
+        while (a0 < n && ((addr + (unsigned long long)a0 * 12ull) & 15ull)) ++a0;
+        n_quads = (n - a0) / 4;
+    }
+    const long long n_tiles = fast ? (n_quads + HC_TILE / 4 - 1) / (HC_TILE / 4) : (n + HC_TILE - 1) / HC_TILE;
+
+    if (fast && blockIdx.x == 0) {  // the unaligned head and the tail of the frame: straight into the global accumulators
+        const long long tail0 = a0 + n_quads * 4;
+        const long long n_extra = a0 + (n - tail0);
+        if (t < n_extra) {
+            const long long j = t < a0 ? t : tail0 + (t - a0);
+            const int b = bin_generic(j);
+            if (b >= 0) {
+                const unsigned long long v = fixed(w[j]);
+                atomicAdd(&gc[b], 1ull);
+                const unsigned long long old = atomicAdd(&glo[b], v);
+                if ((old + v) < old) atomicAdd(&ghi[b], 1ull);
+            }
+        }
+    }
+
+    int since_fold = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (fast) {
+            const float4 *vb = reinterpret_cast<const float4 *>(fbase + a0 * 3);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long long qd = tile * (HC_TILE / 4) + h * HC_THREADS + t;
+                if (qd < n_quads) {
+                    const float4 v0 = __ldg(vb + qd * 3), v1 = __ldg(vb + qd * 3 + 1), v2 = __ldg(vb + qd * 3 + 2);
+                    const double *wq = w + a0 + qd * 4;
+                    const double w0 = __ldg(wq), w1 = __ldg(wq + 1), w2 = __ldg(wq + 2), w3 = __ldg(wq + 3);
+                    double c;
+                    const int b0 = atom_value_f32(g, v0.x, v0.y, v0.z, c) ? find_bin(E, c, dig) : -1;
+                    const int b1 = atom_value_f32(g, v0.w, v1.x, v1.y, c) ? find_bin(E, c, dig) : -1;
+                    const int b2 = atom_value_f32(g, v1.z, v1.w, v2.x, c) ? find_bin(E, c, dig) : -1;
+                    const int b3 = atom_value_f32(g, v2.y, v2.z, v2.w, c) ? find_bin(E, c, dig) : -1;
+                    deposit(b0, fixed(w0)); deposit(b1, fixed(w1)); deposit(b2, fixed(w2)); deposit(b3, fixed(w3));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < HC_PER; ++s) {
+                const long long j = tile * HC_TILE + s * HC_THREADS + t;
+                if (j < n) deposit(bin_generic(j), fixed(w[j]));
+            }
+        }
+        if (++since_fold == HC_FOLD_TILES) {
+            __syncthreads();
+            fold();
+            __syncthreads();
+            since_fold = 0;
+        }
+    }
+    __syncthreads();
+    fold();
+    __syncthreads();
+
+    // owners flush their bins into the 128-bit global accumulators
+    for (int b = t; b < nb; b += HC_THREADS) {
+        unsigned int s0, s1, s2, cn;
+        lds_acc(s_acc + 16u * (unsigned int)b, s0, s1, s2, cn);
+        if (!cn) continue;
+        atomicAdd(&gc[b], (unsigned long long)cn);
+        const unsigned long long lo64 = ((unsigned long long)s1 << 32) | s0;
+        const unsigned long long old = atomicAdd(&glo[b], lo64);
+        const unsigned long long hi = (unsigned long long)s2 + ((old + lo64) < old ? 1ull : 0ull);
+        if (hi) atomicAdd(&ghi[b], hi);
+    }
+}
+
 // out_w = (acc - count * 2^52) * Q  (exact in __int128), or the float64 fallback sums
 __global__ void k_hist_merge(HistParams p, int fixed_point, double *__restrict__ out_w, long long *__restrict__ out_c,
                              long long total) {
@@ -767,6 +983,17 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
         dim3 grid(bx, (unsigned)F);
         if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
         if (mode == 0 && ctx->hist_mode == 0) {
+            // chunked non-returning atomics: one or two resident CTAs of 512 threads per SM, the grid fills them once
+            const size_t csm = NB * 16 + (NB + 1) * 8 + NB * 16 + 16;
+            if (!ctx->hc_attr_set) {
+                MB_CUDA(cudaFuncSetAttribute(k_hist_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                ctx->hc_attr_set = true;
+            }
+            const long long slots = (long long)ctx->n_sm * (csm <= 112 * 1024 ? 2 : 1);
+            const long long n_tiles = (long long)((N + HC_TILE - 1) / HC_TILE);
+            const unsigned cbx = (unsigned)std::max<long long>(1, std::min(n_tiles, std::max<long long>(1, slots / (long long)F)));
+            k_hist_chunk<<<dim3(cbx, (unsigned)F), HC_THREADS, csm, ctx->stream>>>(p);
+        } else if (mode == 0 && ctx->hist_mode == 2) {
             // counting-sort kernel: one or two resident CTAs of 512 threads per SM, the grid fills them once
             const size_t ssm = NB * 16 + (size_t)HS_TILE * 8 + (NB + 1) * 8 + (NB + 1) * 4 + 64 + 16;
             const long long slots = (long long)ctx->n_sm * (ssm <= 112 * 1024 ? 2 : 1);
@@ -825,7 +1052,8 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
 
 extern "C" int mb200_ctx_set_hist_mode(mb200_ctx *ctx, int mode) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
-    if (mode < 0 || mode > 1) return fail(MB200_EINVAL, "histogram mode must be 0 (counting sort) or 1 (three atomics)");
+    if (mode < 0 || mode > 2)
+        return fail(MB200_EINVAL, "histogram mode must be 0 (chunked atomics), 1 (three returning atomics) or 2 (counting sort)");
     ctx->hist_mode = mode;
     return MB200_OK;
 }

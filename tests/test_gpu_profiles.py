@@ -120,13 +120,14 @@ def test_sorted_kernel_bitwise_equals_atomics_kernel(n_bins):
         for geom, p, dim, ww, e, c, z, dig in cases:
             ctx.set_hist_mode("atomics")
             ref_w, ref_c = profile_hist(geom, np.ascontiguousarray(p), dim, np.ascontiguousarray(ww), e, c, z, digitize=dig)
-            ctx.set_hist_mode("sorted")
-            hw, hc = profile_hist(geom, np.ascontiguousarray(p), dim, np.ascontiguousarray(ww), e, c, z, digitize=dig)
-            assert_array_equal(hc, ref_c)
-            assert_array_equal(hw, ref_w)
+            for other in ("sorted", "chunks"):  # counting-sort tiles; chunked non-returning atomics (the default)
+                ctx.set_hist_mode(other)
+                hw, hc = profile_hist(geom, np.ascontiguousarray(p), dim, np.ascontiguousarray(ww), e, c, z, digitize=dig)
+                assert_array_equal(hc, ref_c)
+                assert_array_equal(hw, ref_w)
             assert hc.sum() > 0
     finally:
-        ctx.set_hist_mode("sorted")
+        ctx.set_hist_mode("chunks")
     # and against numpy for the linspace case
     hw, hc = profile_hist(0, pos32, 2, w, lin)
     for f in range(F):
