@@ -769,7 +769,12 @@ __global__ void __launch_bounds__(HC_THREADS, 2) k_hist_chunk(HistParams p) {
     }
 
     long long a0 = 0, n_quads = 0;
-    const bool fast = p.geometry != MB200_GEOM_SCALAR && p.is_f32 && (((unsigned long long)(uintptr_t)p.pos) & 3ull) == 0;
+    // float32 [n][3] frames.  Slab profiles need ONE coordinate per atom: consecutive lanes read it from consecutive atoms
+    // (stride 12 B: a warp touches three cache lines per load, every fetched sector is used by the neighbouring lanes'
+    // other loads) -- the three float4 per four atoms of the radial geometries cost three times the L1 wavefronts
+    // (ncu on the first version of this kernel: L1TEX pipe 83 % busy, 64 % excessive sectors).
+    const bool planar32 = p.geometry == MB200_GEOM_PLANAR && p.is_f32 && !dig;
+    const bool fast = !planar32 && p.geometry != MB200_GEOM_SCALAR && p.is_f32 && (((unsigned long long)(uintptr_t)p.pos) & 3ull) == 0;
     const float *fbase = reinterpret_cast<const float *>(p.pos) + (size_t)f * n * 3;
     if (fast) {
         const unsigned long long addr = (unsigned long long)(uintptr_t)fbase;
@@ -795,7 +800,22 @@ __global__ void __launch_bounds__(HC_THREADS, 2) k_hist_chunk(HistParams p) {
 
     int since_fold = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (fast) {
+        if (planar32) {
+            float zv[HC_PER];
+            double wv[HC_PER];
+            const float *zb = fbase + g.d0;
+#pragma unroll
+            for (int s = 0; s < HC_PER; ++s) {  // all loads of the tile first: eight independent pairs in flight per thread
+                const long long j = tile * HC_TILE + s * HC_THREADS + t;
+                zv[s] = j < n ? __ldg(zb + 3 * j) : 0.f;
+                wv[s] = j < n ? __ldg(w + j) : 0.0;
+            }
+#pragma unroll
+            for (int s = 0; s < HC_PER; ++s) {
+                const long long j = tile * HC_TILE + s * HC_THREADS + t;
+                if (j < n) deposit(find_bin(E, (double)zv[s], 0), fixed(wv[s]));
+            }
+        } else if (fast) {
             const float4 *vb = reinterpret_cast<const float4 *>(fbase + a0 * 3);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
