@@ -52,9 +52,9 @@ FP64_DMMA_PEAK_TFLOPS_FALLBACK = 37.0
 I8_PEAK_TOPS_FALLBACK = 4359.0
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the contraction kernel from the committed `ncu --set full`
 # capture of `bench.py --steps 2 --warmup 1` (40 frames per launch); see profiles/ for the round's capture
-NCU_TRAFFIC_BYTES = {"i8x5": 5.238e9 + 0.256e9, "fp64": 17.944e9 + 0.093e9}
+NCU_TRAFFIC_BYTES = {"i8x5": 5.228e9 + 0.263e9, "fp64": 17.944e9 + 0.093e9}
 NCU_TRAFFIC_FRAMES = 40
-NCU_TRAFFIC_SOURCE = "profiles/r01_tc_atm_ncu_details.txt"
+NCU_TRAFFIC_SOURCE = {"i8x5": "profiles/r02_tc_atm_ncu_details.txt (round-2 build)", "fp64": "profiles/r01_contract_v2_ncu_details.txt"}
 
 
 def parse():
@@ -374,9 +374,12 @@ def main():
     f64_peak = peaks["fp64_dmma_tflops"] if peaks.get("fp64_dmma_tflops", 0) > 0 else FP64_DMMA_PEAK_TFLOPS_FALLBACK
     common = {"kernel_ms_per_launch": kern_s / max(kern_launches, 1) * 1e3, "kernel_share_of_step": kern_s / (ms * 1e-3),
               "traffic": NCU_TRAFFIC_BYTES[args.precision] * B / NCU_TRAFFIC_FRAMES,
-              "traffic_note": f"DRAM bytes per launch from the committed ncu capture {NCU_TRAFFIC_SOURCE} (not measured in this "
-                              "run): the tables are re-read from HBM by every row tile; the kernel is compute-side bound "
-                              "(DRAM < 10 % of peak)",
+              "traffic_note": f"DRAM bytes per launch from the committed ncu capture {NCU_TRAFFIC_SOURCE[args.precision]} (not "
+                              "measured in this run).  It equals the size of the phase tables + Z image of the batch (5.2 GB for 40 "
+                              "frames x 100k atoms x 1296 B): k_sf_tables writes them once, the contraction reads every byte once "
+                              "from HBM (the seven row tiles of an atom range run concurrently and share it through L2, hit rate "
+                              "73 %); the 48 MB of positions are the algorithmic input.  DRAM is at 9 % of its peak during the "
+                              "contraction: the kernel is bound on the SM side",
               "hbm_gbs_measured_peak": peaks_file.get("hbm_gbs"),
               "fp64_equivalent_tflops": FLOP_PER_ATOMQ * atomq_per_launch * kern_launches / kern_s / 1e12 if kern_s > 0 else None,
               "fp64_dmma_peak_tflops": f64_peak,
