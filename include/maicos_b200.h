@@ -186,6 +186,15 @@ int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const double *we
  * the trajectory reader's buffer (MDAnalysis `ts.positions`) into the pinned batch buffer faster than one core copies. */
 int mb200_host_copy(void *dst, const void *src, size_t bytes, int n_threads);
 
+/* Frame statistics of a batch, host only (no device needed): running mean, standard error of the mean and sum of a
+ * per-frame observable, frame after frame with the reference's own recurrences
+ * (src/maicos/core/base.py:460-480, src/maicos/lib/math.py:325-459), bitwise what the per-frame Python code gives.
+ *   x_f64 / x_i64 : [n_frames][size], exactly one of them non-NULL;  n0 >= 1 frames are already in the statistics
+ *   mean, sem     : float64 [size], updated in place;  sum_f64 / sum_i64 : [size], the one matching x
+ *   scalar_pow    : the observable is a float scalar in the Python frame loop, whose `sem ** 2` is libm's pow(sem, 2) */
+int mb200_running_stats(int64_t n0, int64_t n_frames, int64_t size, int scalar_pow, const double *x_f64,
+                        const int64_t *x_i64, double *mean, double *sem, double *sum_f64, int64_t *sum_i64);
+
 /* ---- per-frame compound prologue ------------------------------------ */
 
 /* Plain device buffers for intermediate results that stay on the GPU between two entry points. */

@@ -41,6 +41,11 @@ SIGNATURES = {
     "mb200_host_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
     "mb200_plan_describe": (ctypes.c_int, [c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                            ctypes.c_int32, c_i64_p]),
+    "mb200_running_stats": (
+        ctypes.c_int,
+        [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
+    ),
     "mb200_sfactor_maxn": (ctypes.c_int, [c_double_p, ctypes.c_double, c_i32_p]),
     "mb200_structure_factor": (
         ctypes.c_int,

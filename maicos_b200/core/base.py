@@ -666,10 +666,73 @@ class AnalysisBase(_Runner):
         t0 = time.perf_counter()
         staged, out = fut.result()  # re-raises worker exceptions
         self.timings["wait_device_s"] += time.perf_counter() - t0
-        for (slot, _), (obs, value) in zip(staged, out):
+        start = 0
+        if not hasattr(self, "means") and staged:  # the first frame of the run initialises the statistics
+            (slot, _), (obs, value) = staged[0], out[0]
             obs = Results(obs)
             self._accumulate(slot, value, obs)
             self._frame_index, self._obs = slot, obs
+            start = 1
+        if start < len(staged) and not self._accumulate_batch(staged[start:], out[start:]):
+            for (slot, _), (obs, value) in zip(staged[start:], out[start:]):
+                obs = Results(obs)
+                self._accumulate(slot, value, obs)
+                self._frame_index, self._obs = slot, obs
+
+    def _accumulate_batch(self, staged: list, out: list) -> bool:
+        """The statistics recurrences of ``_accumulate`` for a whole batch in one host call per observable
+        (``mb200_running_stats``: the same operations, frame after frame -- bitwise the per-frame result).  Returns False
+        (nothing done) when the batch needs the per-frame path: ``concfreq`` checkpoints, observables that are not float64 /
+        int64 arrays or float scalars, or shapes that changed."""
+        from .. import _cabi
+
+        if self.concfreq or not out:
+            return False
+        keys = list(self.means.keys())
+        plan = []
+        for key in keys:
+            first = out[0][0].get(key)
+            m = self.means[key]
+            if first is None or any(key not in o for o, _ in out):
+                return False
+            if isinstance(first, np.ndarray) and isinstance(m, np.ndarray) and first.dtype in (np.float64, np.int64) \
+                    and first.shape == m.shape and m.dtype in (np.float64, np.int64) \
+                    and np.asarray(self.sums[key]).dtype == first.dtype:
+                if any(not isinstance(o[key], np.ndarray) or o[key].shape != first.shape or o[key].dtype != first.dtype
+                       for o, _ in out):
+                    return False
+                plan.append((key, "array", first.dtype))
+            elif type(first) in (float, np.float64) and type(m) in (float, np.float64):
+                if any(type(o[key]) not in (float, np.float64) for o, _ in out):
+                    return False
+                plan.append((key, "scalar", np.dtype(np.float64)))
+            else:
+                return False
+        if any(len(o) != len(keys) for o, _ in out):
+            return False
+        lib, n0, F = _cabi.load(), self._n_local, len(out)
+        for key, kind, dtype in plan:
+            x = np.ascontiguousarray(np.stack([o[key] for o, _ in out]) if kind == "array"
+                                     else np.array([o[key] for o, _ in out], dtype=np.float64))
+            size = int(x.size // F)
+            mean = np.ascontiguousarray(self.means[key], dtype=np.float64).reshape(-1).copy()
+            sem = np.ascontiguousarray(self.sems[key], dtype=np.float64).reshape(-1).copy()
+            total = np.ascontiguousarray(self.sums[key]).reshape(-1).copy()
+            is_int = dtype == np.int64
+            _cabi.check(lib.mb200_running_stats(
+                n0, F, size, int(kind == "scalar"), None if is_int else _cabi.ptr(x), _cabi.ptr(x) if is_int else None,
+                _cabi.ptr(mean), _cabi.ptr(sem), None if is_int else _cabi.ptr(total), _cabi.ptr(total) if is_int else None))
+            if kind == "array":
+                shape = np.shape(self.means[key])
+                self.means[key], self.sems[key], self.sums[key] = mean.reshape(shape), sem.reshape(shape), total.reshape(shape)
+            else:
+                self.means[key], self.sems[key], self.sums[key] = np.float64(mean[0]), np.float64(sem[0]), np.float64(total[0])
+        for (slot, _), (obs, value) in zip(staged, out):
+            self.timeseries[slot] = np.nan if value is None else value
+        self._n_local += F
+        self._index = self._n_local
+        self._frame_index, self._obs = staged[-1][0], Results(out[-1][0])
+        return True
 
     def _call_single_frame(self, ts, current_frame_index) -> None:
         """Serial entry point with the reference's signature (one frame, statistics updated)."""

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <thread>
 
 namespace mb200 {
@@ -167,5 +168,39 @@ extern "C" int mb200_host_copy(void *dst, const void *src, size_t bytes, int n_t
     }
     std::memcpy(dst, src, std::min(chunk, bytes));
     for (auto &w : workers) w.join();
+    return MB200_OK;
+}
+
+// Running mean / standard error / sum of per-frame observables for a whole batch of frames, host only.  Restates the
+// recurrences of the reference frame loop (src/maicos/core/base.py:460-480 with lib/math.py:325-459: new_mean,
+// new_variance) operation by operation, frame after frame, so that the result is bitwise what the per-frame Python
+// code gives -- a 40-frame batch costs microseconds instead of 40 x 3 x ~10 small NumPy calls:
+//   old_var = sem^2 (n - 1);  mean_n = ((n - 1) mean + x) / n;  s = old_var (n - 1) + (x - mean_old)(x - mean_n), s < 0 -> 0;
+//   sem_n = sqrt(s / n / n);  sum += x.
+// x: [n_frames][size] float64 (x_f64) or int64 (x_i64: means / sems see it as float64, the sum stays int64).
+// n0 = frames already in the statistics (>= 1: the first frame initialises them on the caller's side); scalar_pow: the
+// observable is a Python / NumPy float scalar (see below).
+extern "C" int mb200_running_stats(int64_t n0, int64_t n_frames, int64_t size, int scalar_pow, const double *x_f64,
+                                   const int64_t *x_i64, double *mean, double *sem, double *sum_f64, int64_t *sum_i64) {
+    if (n0 < 1 || n_frames < 0 || size < 0 || (!x_f64 && !x_i64) || !mean || !sem || (x_f64 && !sum_f64) || (x_i64 && !sum_i64))
+        return fail(MB200_EINVAL, "invalid argument to mb200_running_stats");
+    for (int64_t f = 0; f < n_frames; ++f) {
+        const double n = (double)(n0 + f + 1), nm1 = (double)(n0 + f);
+        for (int64_t i = 0; i < size; ++i) {
+            const double x = x_f64 ? x_f64[f * size + i] : (double)x_i64[f * size + i];
+            const double old_mean = mean[i];
+            // sem ** 2: NumPy squares arrays with a multiplication, Python / NumPy float scalars go through libm's pow
+            const double old_var = (scalar_pow ? std::pow(sem[i], 2.0) : sem[i] * sem[i]) * nm1;
+            const double t = nm1 * old_mean;
+            const double new_mean = (t + x) / n;
+            const double a = old_var * nm1, b = (x - old_mean) * (x - new_mean);
+            double sv = a + b;
+            if (sv < 0) sv = 0;
+            mean[i] = new_mean;
+            sem[i] = std::sqrt((sv / n) / n);
+            if (x_f64) sum_f64[i] = sum_f64[i] + x;
+            else sum_i64[i] = sum_i64[i] + x_i64[f * size + i];
+        }
+    }
     return MB200_OK;
 }

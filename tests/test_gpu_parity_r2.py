@@ -502,3 +502,38 @@ def test_single_process_device_round_robin_equals_single_device(precision):
         for key in b.sems:
             assert_array_equal(np.asarray(a.sems[key]), np.asarray(b.sems[key]), err_msg=f"{type(a).__name__}.{key}")
         assert_array_equal(a.timeseries, b.timeseries)
+
+
+def test_batched_statistics_equal_the_per_frame_path_bitwise(monkeypatch, precision):
+    """Per-frame observables of a batch enter means / sems / sums through ``mb200_running_stats`` (one host call per
+    observable) -- bit for bit what the per-frame recurrences of ``_accumulate`` give (arrays, counts and the float
+    scalars of the profile geometry)."""
+    import maicos_b200.core.base as base
+
+    u, frames, vel, topo = _water_with_velocities(n_mol=400, L=24.0, F=29, seed=3)
+
+    def run_all():
+        return [mb.Saxs(u.atoms, qmax=2.0, dq=0.1).run(), mb.DiporderStructureFactor(u.atoms, qmax=2.0, dq=0.1).run(),
+                mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.7).run(), mb.VelocityPlanar(u.atoms, bin_width=0.9).run()]
+
+    calls = []
+    real = base.AnalysisBase._accumulate_batch
+
+    def counting(self, staged, out):
+        done = real(self, staged, out)
+        calls.append(done)
+        return done
+
+    monkeypatch.setattr(base.AnalysisBase, "_accumulate_batch", counting)
+    batched = run_all()
+    assert calls and all(calls), "every batch of these classes should take the batched statistics"
+    monkeypatch.setattr(base.AnalysisBase, "_accumulate_batch", lambda self, staged, out: False)
+    serial = run_all()
+    for a, b in zip(batched, serial):
+        assert a._index == b._index == 29
+        for name in ("sums", "means", "sems"):
+            for key, v in getattr(b, name).items():
+                got = getattr(a, name)[key]
+                assert_array_equal(np.asarray(got), np.asarray(v), err_msg=f"{type(a).__name__}.{name}.{key}")
+                assert np.asarray(got).dtype == np.asarray(v).dtype, f"{type(a).__name__}.{name}.{key}"
+        assert_array_equal(a.timeseries, b.timeseries)
