@@ -541,6 +541,11 @@ class AnalysisBase(_Runner):
             else:
                 self.ref_weights = self.refgroup.masses
         self._prepare()
+        # a streaming reader that decodes into a ring of page-locked frame buffers (mdshim.TRRTrajectory(pinned_ring=k)):
+        # rows handed to the device must not be overwritten while a batch is in flight
+        ring = int(getattr(self._trajectory, "ring_len", 0) or 0)
+        if ring:
+            self._batch_size = int(max(1, min(self._batch_size, ring // (len(self._run_devices()) + 2))))
         if logging.getLogger().isEnabledFor(logging.INFO):  # the headers scan every atom: only when shown
             if self.refgroup is not None:
                 logging.info(

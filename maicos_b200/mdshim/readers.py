@@ -12,7 +12,7 @@ from pathlib import Path
 
 import numpy as np
 
-from .universe import MemoryTrajectory, Universe
+from .universe import MemoryTrajectory, Timestep, Universe
 
 #: atomic masses (u) for elements met in the water / slab inputs
 MASSES = {"H": 1.008, "C": 12.011, "N": 14.007, "O": 15.999, "NA": 22.98977, "CL": 35.45, "S": 32.06}
@@ -100,7 +100,176 @@ def read_trr(path) -> dict:
     }
 
 
-def universe_from_gro(gro_path, trr_path=None, charges=None) -> Universe:
+def _scan_trr(mm) -> list[dict]:
+    """Frame index of a TRR file from its headers alone: byte offsets of the x / v blocks, box, time, precision."""
+    frames, off, size = [], 0, len(mm)
+    while off < size:
+        magic, _slen = struct.unpack_from(">ii", mm, off)
+        if magic != 1993:
+            raise ValueError(f"not a TRR frame at byte {off} (magic {magic})")
+        off += 8
+        (strlen,) = struct.unpack_from(">i", mm, off)
+        off += 4 + (strlen + 3) // 4 * 4
+        _ir, _e, box, vir, pres, _top, _sym, xs, vs, fs, natoms, _step, _nre = struct.unpack_from(">13i", mm, off)
+        off += 52
+        real = box // 9 if box else (xs // (3 * natoms) if xs else (vs or fs) // (3 * natoms))
+        fmt = ">f4" if real == 4 else ">f8"
+        t = float(np.frombuffer(mm, dtype=fmt, count=1, offset=off)[0])
+        off += 2 * real
+        dims = None
+        if box:
+            b = np.frombuffer(mm, dtype=fmt, count=9, offset=off).reshape(3, 3)
+            dims = [b[0, 0] * 10, b[1, 1] * 10, b[2, 2] * 10, 90, 90, 90]
+        off += box + vir + pres
+        frames.append({"x": off if xs else None, "v": off + xs if vs else None, "n": natoms, "fmt": fmt, "time": t, "dims": dims})
+        off += xs + vs + fs
+    return frames
+
+
+class TRRTrajectory:
+    """Streaming ``.trr`` reader: the file is memory-mapped and indexed once (headers only), a frame is decoded when it
+    is visited -- big-endian XDR reals -> native float32, nm -> Å, ONE pass over the frame's bytes.
+
+    ``pinned_ring=k`` decodes into a ring of ``k`` page-locked frame buffers and serves those rows through
+    ``pinned_row`` (the protocol of :class:`MemoryTrajectory`): the batched analyses then hand the decoded frames to the
+    device where the reader put them, without a staging copy.  An analysis keeps at most ``(devices + 2) x batch``
+    frames alive; ``AnalysisBase`` shrinks its batch to fit the ring.
+    """
+
+    def __init__(self, path, pinned_ring: int = 0):
+        import mmap
+
+        self._file = open(path, "rb")
+        self._mm = mmap.mmap(self._file.fileno(), 0, access=mmap.ACCESS_READ)
+        self._index = _scan_trr(self._mm)
+        if not self._index or any(fr["x"] is None for fr in self._index):
+            raise ValueError("every TRR frame needs coordinates")
+        self.n_frames = len(self._index)
+        self.n_atoms = int(self._index[0]["n"])
+        if any(fr["n"] != self.n_atoms for fr in self._index):
+            raise ValueError("the number of atoms changes inside the trajectory")
+        have_box = all(fr["dims"] is not None for fr in self._index)
+        self.dimensions = np.asarray([fr["dims"] for fr in self._index], dtype=np.float32) if have_box else None
+        self.times = np.asarray([fr["time"] for fr in self._index])
+        self.velocities = True if all(fr["v"] is not None for fr in self._index) else None  # decoded per frame
+        self.dt = float(self.times[1] - self.times[0]) if self.n_frames > 1 else 1.0
+        self.coordinates = None
+        self.ring_len = 0
+        self._ring = self._ring_block = None
+        self._ring_frame: list[int] = []
+        if pinned_ring > 0:
+            from .. import _cabi
+
+            self.ring_len = int(min(pinned_ring, self.n_frames))
+            nbytes = self.ring_len * self.n_atoms * 12
+            if _cabi.device_count() > 0:
+                self._ring_block = _cabi._PinnedBlock(max(nbytes, 1))
+                self._ring = np.frombuffer(self._ring_block.buf, dtype=np.float32, count=self.ring_len * self.n_atoms * 3)
+                self._ring = self._ring.reshape(self.ring_len, self.n_atoms, 3)
+            else:
+                self._ring = np.empty((self.ring_len, self.n_atoms, 3), dtype=np.float32)
+            self._ring_frame = [-1] * self.ring_len
+        self.ts = None
+        self._goto(0)
+
+    def _decode(self, offset: int, fmt: str, out: np.ndarray) -> np.ndarray:
+        src = np.frombuffer(self._mm, dtype=fmt, count=3 * self.n_atoms, offset=offset).reshape(self.n_atoms, 3)
+        np.multiply(src, 10.0, out=out, casting="unsafe")  # byte order, precision and unit in one pass
+        return out
+
+    def _goto(self, f: int) -> Timestep:
+        if f < 0:
+            f += self.n_frames
+        if not 0 <= f < self.n_frames:
+            raise IndexError(f"frame {f} out of range (0..{self.n_frames - 1})")
+        fr = self._index[f]
+        if self._ring is not None:
+            slot = f % self.ring_len
+            if self._ring_frame[slot] != f:
+                self._decode(fr["x"], fr["fmt"], self._ring[slot])
+                self._ring_frame[slot] = f
+            pos = self._ring[slot].view()
+        else:
+            pos = self._decode(fr["x"], fr["fmt"], np.empty((self.n_atoms, 3), dtype=np.float32))
+        pos.flags.writeable = False  # copy-on-write, like MemoryTrajectory (Timestep.writable_positions)
+        vel = None
+        if fr["v"] is not None and self.velocities is not None:
+            vel = self._decode(fr["v"], fr["fmt"], np.empty((self.n_atoms, 3), dtype=np.float32))
+        dims = None if self.dimensions is None else np.array(self.dimensions[f], dtype=np.float32)
+        self.ts = Timestep(pos, dims, f, float(fr["time"]), vel)
+        return self.ts
+
+    def pinned_row(self, f: int):
+        """``(ring block, row)`` when frame ``f`` is the one currently held by its ring slot, else ``None``."""
+        if self._ring_block is None:
+            return None
+        slot = int(f) % self.ring_len
+        return (self._ring, slot) if self._ring_frame[slot] == int(f) else None
+
+    def __len__(self):
+        return self.n_frames
+
+    def __iter__(self):
+        for f in range(self.n_frames):
+            yield self._goto(f)
+
+    def __getitem__(self, item):
+        from .universe import _FrameIterator
+
+        if isinstance(item, (int, np.integer)):
+            return self._goto(int(item))
+        if isinstance(item, slice):
+            return _FrameIterator(self, np.arange(self.n_frames)[item])
+        item = np.asarray(item)
+        if item.dtype == bool:
+            item = np.nonzero(item)[0]
+        return _FrameIterator(self, item)
+
+    def close(self) -> None:
+        block, self._ring_block = self._ring_block, None
+        self._ring = None
+        if block is not None:
+            block.free()
+        if getattr(self, "_mm", None) is not None:
+            self.ts = None
+            try:
+                self._mm.close()
+            except BufferError:  # a decoded view is still alive somewhere: the map goes with the last reference
+                pass
+            self._mm = None
+            self._file.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def write_trr(path, positions, dimensions, times=None, velocities=None) -> None:
+    """Write float32 frames (Å) as a single-precision GROMACS ``.trr`` (orthorhombic box, x and optionally v blocks): the
+    inverse of the readers above, used to put synthetic trajectories on disk."""
+    positions = np.asarray(positions, dtype=np.float32)
+    n_frames, n_atoms = positions.shape[:2]
+    dimensions = np.broadcast_to(np.asarray(dimensions, dtype=np.float32), (n_frames, np.shape(dimensions)[-1]))
+    version = b"GMX_trn_file"
+    with open(path, "wb") as fh:
+        for f in range(n_frames):
+            xs = 12 * n_atoms
+            vs = xs if velocities is not None else 0
+            fh.write(struct.pack(">ii", 1993, len(version) + 1))
+            fh.write(struct.pack(">i", len(version)) + version + b"\0" * (-len(version) % 4))
+            fh.write(struct.pack(">13i", 0, 0, 36, 0, 0, 0, 0, xs, vs, 0, n_atoms, f, 0))
+            fh.write(struct.pack(">ff", float(times[f]) if times is not None else float(f), 0.0))
+            box = np.zeros((3, 3), dtype=">f4")
+            box[0, 0], box[1, 1], box[2, 2] = dimensions[f, 0] / 10, dimensions[f, 1] / 10, dimensions[f, 2] / 10
+            fh.write(box.tobytes())
+            fh.write((positions[f] / np.float32(10)).astype(">f4").tobytes())
+            if velocities is not None:
+                fh.write((np.asarray(velocities[f], dtype=np.float32) / np.float32(10)).astype(">f4").tobytes())
+
+
+def universe_from_gro(gro_path, trr_path=None, charges=None, stream: bool = False, pinned_ring: int = 0) -> Universe:
     """Universe with the topology order of a ``.gro`` file and, optionally, a ``.trr`` trajectory."""
     g = read_gro(gro_path)
     n = len(g["names"])
@@ -110,6 +279,10 @@ def universe_from_gro(gro_path, trr_path=None, charges=None) -> Universe:
     if trr_path is None:
         traj = MemoryTrajectory(g["positions"][None], g["dimensions"],
                                 None if g["velocities"] is None else g["velocities"][None])
+    elif stream or pinned_ring:  # frames are decoded from the memory-mapped file when they are visited
+        traj = TRRTrajectory(trr_path, pinned_ring=pinned_ring)
+        if traj.n_atoms != n:
+            raise ValueError("topology and trajectory disagree on the number of atoms")
     else:
         t = read_trr(trr_path)
         if t["positions"].shape[1] != n:

@@ -599,3 +599,32 @@ def test_structure_factors_agree_with_the_fourier_transform_of_the_rdf(water_fra
     sel = q >= 0.5  # "low q values converge very slowly" (test_diporderstructurefactor.py:62-64)
     assert np.max(np.abs(s_direct - s_rdf)[sel]) < 0.3
     assert np.median(np.abs(s_direct - s_rdf)[sel]) < 0.04
+
+
+def test_streaming_trr_with_pinned_ring_feeds_the_device_without_staging_copies(tmp_path, precision):
+    """A trajectory on disk read by ``mdshim.TRRTrajectory(pinned_ring=k)``: frames are decoded from the memory-mapped file
+    into a ring of page-locked buffers and the device reads them there.  Results = the in-memory trajectory's, bit for
+    bit; the batch is shrunk to fit the ring."""
+    from maicos_b200.mdshim import MemoryTrajectory, TRRTrajectory, Universe, read_trr, write_trr
+
+    n_mol, L, F = 700, 27.5, 41
+    frames = mb.synthetic.spce_water_frames(n_mol, L, 17, n_frames=F)
+    dims = np.float32([L, L, L, 90, 90, 90])
+    path = tmp_path / "water.trr"
+    write_trr(path, frames, dims)
+    on_disk = read_trr(path)["positions"]  # what the file holds (nm in float32 and back)
+    topo = mb.synthetic.spce_topology(n_mol)
+    ref_s = mb.Saxs(Universe(3 * n_mol, MemoryTrajectory(on_disk, dims), **topo).atoms, qmax=2.5).run()
+    ref_d = mb.DensityPlanar(Universe(3 * n_mol, MemoryTrajectory(on_disk, dims), **topo).atoms, dens="mass", bin_width=0.5,
+                             unwrap=False, pack=False).run()
+    for ring in (0, 12):
+        u = Universe(3 * n_mol, TRRTrajectory(path, pinned_ring=ring), **topo)
+        s = mb.Saxs(u.atoms, qmax=2.5).run()
+        d = mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.5, unwrap=False, pack=False).run()
+        if ring:
+            assert s._batch_size <= ring // 3 and d._batch_size <= ring // 3
+        for a, b in ((s, ref_s), (d, ref_d)):
+            assert a._index == F
+            for key in b.sums:
+                assert_array_equal(np.asarray(a.sums[key]), np.asarray(b.sums[key]), err_msg=f"{type(a).__name__}.{key}")
+        u.trajectory.close()
