@@ -258,9 +258,11 @@ def main():
     launches0 = ctx.launch_count()
     kern_ns, kern_launches = 0, 0
     ev0.record(stream)
+    mma_count = 0
     for k in range(K):
         st = step(W + k)
         kern_ns += st["contract_ns"]; kern_launches += 1
+        mma_count += st["dmma_steps"]
     parallel.allreduce_sum(acc)  # the single end-of-run merge of the binned accumulators
     ev1.record(stream)
     torch.cuda.synchronize(); parallel.barrier()
@@ -407,6 +409,7 @@ def main():
             "peak_source": "tcgen05 kind::i8 dense rate probed in this run (mb200_probe_peaks: 148 CTAs x 128x256x32 MMAs from "
                            "shared memory); nominal 4500" if peaks.get("i8_tops", 0) > 0 else "fallback: profiles/r01_umma_i8.log",
             "algorithmic_int8_ops_per_atomq": I8_OPS_PER_ATOMQ,
+            "shared_pipe_bound": shared_pipe_bound(mma_count, kern_s, wl, peaks, i8_peak),
             "algorithmic_unit_note": "SURVEY 8(d) counts 8 FP64 flop per atom*q; fp64_equivalent_tflops restates the kernel in "
                                      "that unit against the FP64 DMMA ceiling (a ratio > 1 is what the split-precision path buys)",
             **common}
@@ -752,6 +755,27 @@ def run_configs(args, ctx, lib, torch, rank, world, peaks):
             with parallel.local_only():  # a single-process job while the other ranks wait at the next barrier
                 fn()
     return out
+
+
+def shared_pipe_bound(mma_count, kern_s, wl, peaks, i8_peak):
+    """The bound that applies to k_sf_contract_tc: on a B200 SM the FP64 pipe (the generators that form the A operand) and the
+    tensor pipe do not run at the same time (tools/microbench/fp64_vs_umma.cu, profiles/r02_fp64_vs_umma.log: combined time
+    = sum of the two), so a K-step of 16 atoms costs at least its MMA time plus its FP64 time."""
+    if not mma_count or kern_s <= 0:
+        return None
+    k_steps = mma_count / 15.0                      # fifteen digit products per K-step
+    np_cols = 2 * ((wl["maxn"][2] + 7) // 8 * 8)    # accumulator columns per digit group (re / im of the l tile)
+    int8_ops = mma_count * 2.0 * 128 * np_cols * 32  # issued, dead cells of the tiles included
+    fp64_lane_instr = k_steps * 8 * 64 * 32          # 8 generator tasks x 64 FP64 warp instructions per K-step
+    f64 = peaks.get("fp64_fma_tflops") or 33.0
+    t_tensor = int8_ops / (i8_peak * 1e12)
+    t_fp64 = fp64_lane_instr * 2.0 / (f64 * 1e12)
+    return {"note": "FP64 FMA and tcgen05 MMA work of an SM serialise (measured: profiles/r02_fp64_vs_umma.log); bound = issued int8 "
+                    "ops / probed kind::i8 rate + generator FP64 instructions / probed FP64 FMA rate",
+            "issued_int8_ops_total": int8_ops, "generator_fp64_flop_equiv_total": fp64_lane_instr * 2.0,
+            "fp64_fma_tflops_probed": peaks.get("fp64_fma_tflops"),
+            "tensor_seconds": t_tensor, "fp64_seconds": t_fp64, "measured_seconds": kern_s,
+            "frac_of_serialised_bound": (t_tensor + t_fp64) / kern_s}
 
 
 def path2_summary(ctx, lib, torch, peaks=None):

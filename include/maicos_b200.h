@@ -78,7 +78,7 @@ int mb200_ctx_set_precision(mb200_ctx *ctx, int mode);
  * (a few milliseconds each, best of three):
  *   out[0] = tcgen05 kind::i8 dense rate in TOP/s (M = 128, N = 256, K = 32 from shared memory on every SM),
  *   out[1] = FP64 DMMA rate in TFLOP/s (mma.sync m8n8k4), out[2] = device-to-device copy rate in GB/s
- *   (read + write bytes of a 512 MiB copy), out[3] = 0 (reserved). */
+ *   (read + write bytes of a 512 MiB copy), out[3] = scalar FP64 FMA rate in TFLOP/s. */
 int mb200_probe_peaks(mb200_ctx *ctx, double out[4]);
 /* Total kernels launched by this context since creation. */
 int64_t mb200_ctx_launch_count(mb200_ctx *ctx);

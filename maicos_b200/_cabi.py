@@ -210,10 +210,12 @@ class Context:
         _check(load().mb200_ctx_set_hist_mode(self._h, {"chunks": 0, "atomics": 1, "sorted": 2}[mode]))
 
     def probe_peaks(self) -> dict:
-        """Measured ceilings of this device, in this process: ``i8_tops``, ``fp64_dmma_tflops``, ``hbm_copy_gbs``."""
+        """Measured ceilings of this device, in this process: ``i8_tops``, ``fp64_dmma_tflops``, ``hbm_copy_gbs``,
+        ``fp64_fma_tflops``."""
         out = (ctypes.c_double * 4)()
         _check(load().mb200_probe_peaks(self._h, out))
-        return {"i8_tops": float(out[0]), "fp64_dmma_tflops": float(out[1]), "hbm_copy_gbs": float(out[2])}
+        return {"i8_tops": float(out[0]), "fp64_dmma_tflops": float(out[1]), "hbm_copy_gbs": float(out[2]),
+                "fp64_fma_tflops": float(out[3])}
 
     def launch_count(self) -> int:
         return int(load().mb200_ctx_launch_count(self._h))

@@ -4,6 +4,7 @@
 //     pair (operands resident, accumulator in TMEM) -- the ceiling of k_sf_contract_tc's pipe;
 //   * FP64 DMMA rate: mma.sync.m8n8k4.f64 on register operands, 8 independent accumulator tiles per warp -- the
 //     ceiling of k_sf_contract's pipe;
+//   * scalar FP64 FMA rate -- the generators of k_sf_contract_tc run on it, and an SM cannot run it and the tensor pipe at once;
 //   * HBM copy rate: device-to-device copy of 1 GiB (read + write bytes) -- the ceiling of the histogram path.
 // Not product compute: nothing here touches user data.
 #include "common.cuh"
@@ -81,6 +82,20 @@ __global__ void __launch_bounds__(256) k_probe_dmma(double *out, int iters, doub
     if (s == 123.456) out[0] = s;
 }
 
+__global__ void __launch_bounds__(256) k_probe_dfma(double *out, int iters, double a, double b) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456) out[0] = s;
+}
+
 }  // namespace mb200
 
 using namespace mb200;
@@ -131,6 +146,22 @@ extern "C" int mb200_probe_peaks(mb200_ctx *ctx, double out[4]) {
         }
         out[1] = best;
     }
+    // scalar FP64 FMA pipe (the generators of k_sf_contract_tc; it does NOT overlap with the tensor pipe on an SM:
+    // tools/microbench/fp64_vs_umma.cu)
+    {
+        const int iters = 10000, grid = ctx->n_sm * 4;
+        k_probe_dfma<<<grid, 256, 0, ctx->stream>>>(flag.as<double>() + 16, 100, 1.000001, 1e-9);
+        double best = 0.0;
+        for (int rep = 0; rep < 3; ++rep) {
+            MB_CUDA(cudaEventRecord(e0, ctx->stream));
+            k_probe_dfma<<<grid, 256, 0, ctx->stream>>>(flag.as<double>() + 16, iters, 1.000001, 1e-9);
+            MB_CUDA(cudaEventRecord(e1, ctx->stream));
+            MB_CUDA(cudaEventSynchronize(e1));
+            MB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::max(best, 2.0 * 16 * (double)iters * 256.0 * grid / (ms * 1e-3) / 1e12);
+        }
+        out[3] = best;
+    }
     // HBM copy
     {
         const size_t half = (size_t)512 << 20;
@@ -147,7 +178,7 @@ extern "C" int mb200_probe_peaks(mb200_ctx *ctx, double out[4]) {
         }
         out[2] = best;
     }
-    ctx->launches += 8;
+    ctx->launches += 12;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return MB200_OK;
