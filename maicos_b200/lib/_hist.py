@@ -29,6 +29,14 @@ def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights:
     ``device_positions = (pointer, F, n)``: float64 ``[F, n, 3]`` already in HBM (output of the
     compound prologue); ``device_weights = (pointer, per_frame)`` likewise.
     Returns ``(hist_w float64 [F, n_bins] or None, hist_c int64 [F, n_bins])``.
+
+    Accuracy of the weighted sums: every weight is quantised to ``Q = 2^(k - 52)`` with ``2^k >= max|w|`` of the frame
+    (of the array, for static weights) and the sums are exact integers, so a bin's sum carries an ABSOLUTE error of at
+    most ``count * max|w| * 2^-53`` -- what float64 accumulation has once its running sum reaches ``max|w|``, and
+    independent of the summation order (bitwise reproducible).  A bin that holds only weights many orders of magnitude
+    below ``max|w|`` therefore has a larger *relative* error than numpy's float64 sum of that bin alone (e.g. 1e-12
+    relative needs ``|w| >= 1e-4 max|w|`` in the bin); counts are always exact.  Frames with non-finite weights and
+    histograms with more than 4096 bins are accumulated in float64.
     """
     if device_positions is not None:
         pos_ptr, F, n = device_positions
