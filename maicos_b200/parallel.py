@@ -77,7 +77,14 @@ def use_devices(devices=None) -> list[int] | None:
 
 
 def devices() -> list[int] | None:
-    """Devices of the single-process multi-GPU mode (``None``: the process default device only)."""
+    """Devices of the single-process multi-GPU mode (``None``: the process default device only).  The environment
+    variable ``MAICOS_B200_DEVICES`` (``all`` or a comma-separated list) selects them for the CLI; it is ignored in
+    processes started by ``torchrun`` (one process per GPU)."""
+    if _state["devices"] is None and not _state.get("devices_env_read"):
+        _state["devices_env_read"] = True
+        spec = os.environ.get("MAICOS_B200_DEVICES", "").strip()
+        if spec and int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+            use_devices("all" if spec.lower() == "all" else [int(x) for x in spec.split(",") if x.strip()])
     return _state["devices"]
 
 
