@@ -168,6 +168,19 @@ int mb200_saxs_frames_groups(mb200_ctx *ctx, const float *positions, int positio
                              int32_t block, int32_t n_blocks, double *s_binned, double *i_binned,
                              int64_t *bincount);
 
+/* Saxs with bin_spectrum=False (src/maicos/modules/saxs.py:188-189, 238-239: the raw cubes of all element groups are
+ * summed per frame) for a batch of frames of ONE cell: per frame and group the structure factors of the accepted q
+ * vectors as a compact list in C order of the reciprocal cube -- one tables launch and one contraction launch per batch
+ * instead of one mb200_structure_factor call (dense cube back, host scatter) per frame and group.
+ *   box      : host float32 [3], the cell of every frame (the class refuses a changing cell, saxs.py:182-186)
+ *   n_valid  : number of accepted q vectors = mb200_plan_describe(..., n_bins = 0) out[0] (checked)
+ * outputs (host): cells int32 [n_valid] (h * maxn1 * maxn2 + k * maxn2 + l) and scattering_vectors float64 [n_valid]
+ *   (either may be NULL), s_values float64 [n_frames][n_groups][n_valid]. */
+int mb200_saxs_frames_cells(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                            const float box[3], const mb200_groups *groups, double qmin, double qmax,
+                            double thetamin, double thetamax, int pack_atoms, int64_t n_valid,
+                            int32_t *cells, double *scattering_vectors, double *s_values);
+
 /* Fused DiporderStructureFactor frame body (replaces
  * src/maicos/modules/diporderstructurefactor.py:105-150): three weight sets on identical
  * positions share one set of phase tables; per frame and component S is binned by |q|.

@@ -39,8 +39,8 @@ SIGNATURES = {
     "mb200_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mb200_host_free": (None, [ctypes.c_void_p]),
     "mb200_host_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
-    "mb200_plan_describe": (ctypes.c_int, [c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
-                                           ctypes.c_int32, c_i64_p]),
+    "mb200_plan_describe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                           ctypes.c_int32, ctypes.c_void_p]),
     "mb200_running_stats": (
         ctypes.c_int,
         [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -76,6 +76,12 @@ SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
          ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_int, ctypes.c_int32,
          ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "mb200_saxs_frames_cells": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+         ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_void_p],
     ),
     "mb200_dev_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mb200_dev_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

@@ -1751,6 +1751,82 @@ static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int position
     return MB200_OK;
 }
 
+// Saxs with bin_spectrum = False (saxs.py:188-189, 238-239): the per-cell structure factors of every frame and element
+// group as compact lists over the accepted q vectors of the (constant) cell, in C order of the reciprocal cube.  One
+// tables launch and one contraction launch per batch instead of one mb200_structure_factor call per frame and group.
+extern "C" int mb200_saxs_frames_cells(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                                       const float box[3], const mb200_groups *groups, double qmin, double qmax,
+                                       double thetamin, double thetamax, int pack_atoms, int64_t n_valid,
+                                       int32_t *cells, double *scattering_vectors, double *s_values) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
+    if (!groups || !box || n_frames < 0 || n_valid < 0 || (n_frames && n_valid && !s_values) ||
+        (groups->n_atoms_total && n_frames && !positions))
+        return fail(MB200_EINVAL, "invalid argument to mb200_saxs_frames_cells");
+    if (groups->device != ctx->device) return fail(MB200_EINVAL, "groups belong to another device");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const double dims[3] = {(double)box[0], (double)box[1], (double)box[2]};
+    std::shared_ptr<SfPlan> plan;
+    MB_TRY(get_plan(ctx, dims, qmin, qmax, thetamin, thetamax, 0, plan));
+    const size_t nv = plan->cell.size();
+    if ((int64_t)nv != n_valid)
+        return fail(MB200_EINVAL, "n_valid = %lld, the cell has %zu accepted q vectors (mb200_plan_describe out[0])", (long long)n_valid, nv);
+    for (size_t e = 0; e < nv; ++e) {
+        if (cells) cells[e] = plan->cell[e];
+        if (scattering_vectors) scattering_vectors[e] = plan->qrr[e];
+    }
+    const int n_groups = (int)groups->ptr.size() - 1;
+    if (n_frames == 0 || n_groups <= 0 || nv == 0) return MB200_OK;
+    const size_t frame_elems = (size_t)groups->n_atoms_total * 3;
+    size_t done = 0;
+    while (done < (size_t)n_frames) {
+        size_t fb = 0;  // table bytes of one frame
+        for (int gi = 0; gi < n_groups; ++gi) {
+            const size_t ld = ((size_t)(groups->ptr[gi + 1] - groups->ptr[gi]) + KT - 1) / KT * KT;
+            fb += ld * (size_t)(plan->rows[0] + plan->rows[1] + plan->rows[2]) * 16;
+        }
+        const size_t chunk = std::max<size_t>(1, std::min<size_t>({(size_t)n_frames - done, ((size_t)12 << 30) / std::max<size_t>(fb, 1), (size_t)256}));
+        const float *dpos;
+        if (positions_on_device) {
+            dpos = positions + done * frame_elems;
+        } else {
+            MB_TRY(ctx->d_pos.ensure(std::max<size_t>(chunk * frame_elems, 1) * 4));
+            if (frame_elems)
+                MB_CUDA(cudaMemcpyAsync(ctx->d_pos.p, positions + done * frame_elems, chunk * frame_elems * 4, cudaMemcpyHostToDevice,
+                                        ctx->stream));
+            dpos = ctx->d_pos.as<float>();
+        }
+        std::vector<SegSpec> specs(chunk * n_groups);
+        for (size_t f = 0; f < chunk; ++f)
+            for (int gi = 0; gi < n_groups; ++gi) {
+                SegSpec &sp = specs[f * n_groups + gi];
+                sp.plan = plan.get(); sp.share_yz_with = -1; sp.ff2_group = -1;
+                std::memset(&sp.job, 0, sizeof(TableJob));
+                sp.job.wscale = 1.0;
+                sp.job.pos = dpos + f * frame_elems;
+                sp.job.index = groups->idx.as<int32_t>() + groups->ptr[gi];
+                sp.job.weights = nullptr;
+                sp.job.stride_atom = 3; sp.job.stride_xyz = 1;
+                for (int d = 0; d < 3; ++d) { sp.job.boxf[d] = box[d]; sp.job.box[d] = dims[d]; }
+                sp.job.n = (int32_t)(groups->ptr[gi + 1] - groups->ptr[gi]);
+                sp.job.is_f32 = 1; sp.job.wrap_mode = pack_atoms ? 2 : 1;
+            }
+        std::vector<SegDesc> segs;
+        MB_TRY(run_segments(ctx, specs, 0, 1, segs));
+        const size_t ns = specs.size();
+        MB_TRY(ctx->d_sval.ensure(ns * nv * 8));
+        k_sf_svalues<<<dim3((unsigned)((nv + 255) / 256), (unsigned)ns), 256, 0, ctx->stream>>>(ctx->d_segs.as<SegDesc>(),
+                                                                                              ctx->d_sval.as<double>(), (int)nv);
+        MB_CUDA(cudaGetLastError());
+        ctx->launches += 1; ctx->stats[0] += 1;
+        MB_CUDA(cudaMemcpyAsync(s_values + done * (size_t)n_groups * nv, ctx->d_sval.p, ns * nv * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MB_CUDA(cudaStreamSynchronize(ctx->stream));
+        MB_TRY(finish_timing(ctx));
+        done += chunk;
+    }
+    return MB200_OK;
+}
+
 extern "C" int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const double *weights, int inputs_on_device,
                                   int64_t n_frames, int64_t n, const double *boxes, double qmin, double qmax, int32_t n_bins,
                                   int32_t block, int32_t n_blocks, double *s_binned, int64_t *bincount) {

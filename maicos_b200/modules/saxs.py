@@ -21,7 +21,7 @@ import numpy as np
 from .. import _cabi, parallel
 from ..core.base import AnalysisBase, gather_rows
 from ..lib import tables
-from ..lib.math import atomic_form_factor, structure_factor
+from ..lib.math import atomic_form_factor
 from ..lib.util import cell_diagonal, is_orthorhombic
 
 
@@ -206,6 +206,9 @@ class Saxs(AnalysisBase):
             self.box = cell_diagonal(self._universe.dimensions)
             self.scattering_vector_factors = 2 * np.pi / self.box
             self.max_n = np.ceil(self.qmax / self.scattering_vector_factors).astype(int)
+            self._cells = None
+            # two float64 cubes per frame come back from a batch: at most ~256 MB of them
+            self._batch_size = int(max(1, min(self._batch_size, (256 << 20) // max(1, 16 * int(np.prod(self.max_n))))))
 
     # ---- frame body ------------------------------------------------------------------------
     def _stage_frame(self):
@@ -222,7 +225,6 @@ class Saxs(AnalysisBase):
         if self.bin_spectrum:
             self._announce_rows([(st[0], st[1]) for st in staged])
 
-
     def _device_packs(self) -> bool:
         # the kernel's pack is the orthorhombic ``x -= floor(x / L) L``; a triclinic cell is packed by the host
         # (``atoms.wrap`` in ``_transform_frame``) before the frame is staged
@@ -230,7 +232,7 @@ class Saxs(AnalysisBase):
 
     def _compute_staged(self, staged: list) -> list:
         if not self.bin_spectrum:
-            return [self._unbinned_frame(buf[row].copy(), box) for buf, row, box in staged]
+            return self._compute_unbinned(staged)
         F, n, G = len(staged), self.atomgroup.n_atoms, len(self.groups)
         pos = self._gather_staged([(st[0], st[1]) for st in staged])  # a view of the staging buffer / pinned trajectory
         boxes = np.array([st[2] for st in staged], dtype=np.float32)
@@ -239,19 +241,7 @@ class Saxs(AnalysisBase):
         c = np.zeros((F, G, self.n_bins), dtype=np.int64)
         block, n_blocks = parallel.q_block()
         ctx = _cabi.context()
-        handle = self._groups_handles.get(ctx.device)
-        if handle is None:  # the selection goes to a device once per run
-            import ctypes
-
-            import weakref
-
-            handle = ctypes.c_void_p()
-            _cabi.check(_cabi.load().mb200_groups_create(ctx.handle, _cabi.ptr(self._group_flat), _cabi.ptr(self._group_ptr), G, n,
-                                                         ctypes.byref(handle)))
-            # kept with the universe's prepared selection (further analyses of the same selection reuse it), destroyed
-            # with the universe
-            self._groups_handles[ctx.device] = handle
-            weakref.finalize(self._universe, _destroy_groups, ctx.device, handle)
+        handle = self._groups_on(ctx)
         _cabi.check(
             _cabi.load().mb200_saxs_frames_groups(
                 ctx.handle, _cabi.ptr(pos), 0, F, _cabi.ptr(boxes), handle, _cabi.ptr(self._cm),
@@ -274,21 +264,71 @@ class Saxs(AnalysisBase):
         last = s[:, G - 1, -1].tolist()
         return [({"structure_factors": sf[f], "scattering_intensities": si[f], "bincount": bc[f]}, last[f]) for f in range(F)]
 
-    def _unbinned_frame(self, positions: np.ndarray, box: np.ndarray):
-        """``bin_spectrum=False``: raw cubes summed over element groups (saxs.py:188-189, 238-239)."""
-        if self._device_packs():
-            positions = positions - np.floor(positions / box) * box
-        sf = np.zeros(self.max_n)
-        si = np.zeros(self.max_n)
-        s_last = None
-        for idx, element in zip(self._group_index, self.elements):
-            p = positions[idx]
-            p = p - box * np.round(p / box)
-            q, s_last = structure_factor(np.double(p), np.double(box), self.qmin, self.qmax, self.thetamin,
-                                         self.thetamax, np.ones(len(idx)))
-            sf += s_last
-            si += atomic_form_factor(q, str(element)) ** 2 * s_last
-        return {"structure_factors": sf, "scattering_intensities": si}, s_last.flatten()[-1]
+    def _groups_on(self, ctx):
+        """Handle of the element groups' index lists on ``ctx``'s device (uploaded once per selection and device)."""
+        handle = self._groups_handles.get(ctx.device)
+        if handle is None:
+            import ctypes
+            import weakref
+
+            handle = ctypes.c_void_p()
+            _cabi.check(_cabi.load().mb200_groups_create(ctx.handle, _cabi.ptr(self._group_flat), _cabi.ptr(self._group_ptr),
+                                                         len(self._group_index), self.atomgroup.n_atoms, ctypes.byref(handle)))
+            # kept with the universe's prepared selection (further analyses of the same selection reuse it), destroyed
+            # with the universe
+            self._groups_handles[ctx.device] = handle
+            weakref.finalize(self._universe, _destroy_groups, ctx.device, handle)
+        return handle
+
+    def _compute_unbinned(self, staged: list) -> list:
+        """``bin_spectrum=False``: raw cubes summed over element groups (saxs.py:188-189, 238-239), a batch of frames per
+        device call (``mb200_saxs_frames_cells``): the device returns S of the accepted q vectors only, the cubes are
+        filled here."""
+        lib = _cabi.load()
+        F, G = len(staged), len(self.groups)
+        box = np.ascontiguousarray(self.box, dtype=np.float32)
+        if self._cells is None:  # constant cell: one q-plan per run
+            desc = np.zeros(16, dtype=np.int64)
+            dims = np.array(box, dtype=np.float64)  # named: the pointer must outlive the call
+            _cabi.check(lib.mb200_plan_describe(_cabi.ptr(dims), float(self.qmin), float(self.qmax),
+                                                float(self.thetamin), float(self.thetamax), 0, _cabi.ptr(desc)))
+            if tuple(desc[1:4]) != tuple(self.max_n):
+                # the kernel's cube uses the float32 q factor (_cmath.pyx:93-96), `max_n` the float64 one (saxs.py:150-153);
+                # where they differ the reference fails on the cube shapes (saxs.py:238)
+                raise ValueError(f"operands could not be broadcast together with shapes {tuple(self.max_n)} {tuple(desc[1:4])}")
+            nv = int(desc[0])
+            self._cells = (np.zeros(nv, dtype=np.int32), np.zeros(nv), None)
+        cells, q, ff2 = self._cells
+        nv = len(cells)
+        pos = self._gather_staged([(st[0], st[1]) for st in staged])
+        s = np.zeros((F, G, nv))
+        ctx = _cabi.context()
+        _cabi.check(
+            lib.mb200_saxs_frames_cells(
+                ctx.handle, _cabi.ptr(pos), 0, F, _cabi.ptr(box), self._groups_on(ctx), float(self.qmin), float(self.qmax),
+                float(self.thetamin), float(self.thetamax), int(self._device_packs()), nv, _cabi.ptr(cells), _cabi.ptr(q),
+                _cabi.ptr(s),
+            )
+        )
+        if ff2 is None:
+            ff2 = np.stack([atomic_form_factor(q, str(el)) ** 2 for el in self.elements]) if nv else np.zeros((G, 0))
+            self._cells = (cells, q, ff2)
+        n_cells = int(np.prod(self.max_n))
+        at_end = nv > 0 and int(cells[-1]) == n_cells - 1  # the correlation scalar is the last cell of the last cube
+        out = []
+        for f in range(F):
+            sf = np.zeros(n_cells)
+            si = np.zeros(n_cells)
+            acc_s = np.zeros(nv)
+            acc_i = np.zeros(nv)
+            for g in range(G):  # same order of additions as the reference's loop over groups
+                acc_s += s[f, g]
+                acc_i += ff2[g] * s[f, g]
+            sf[cells] = acc_s
+            si[cells] = acc_i
+            last = float(s[f, G - 1, -1]) if at_end else 0.0
+            out.append(({"structure_factors": sf.reshape(self.max_n), "scattering_intensities": si.reshape(self.max_n)}, last))
+        return out
 
     _single_frame = AnalysisBase._single_frame_from_batch
 
@@ -301,7 +341,7 @@ class Saxs(AnalysisBase):
             dsf = self.sems.structure_factors
             dsi = self.sems.scattering_intensities
         else:
-            miller = np.array(list(np.ndindex(tuple(self.max_n))))
+            miller = np.indices(tuple(self.max_n)).reshape(3, -1).T  # == np.array(list(np.ndindex(max_n))), saxs.py:256
             q = np.linalg.norm(miller * self.scattering_vector_factors[np.newaxis, :], axis=1)
             order = np.argsort(q)
             q, miller = q[order], miller[order]

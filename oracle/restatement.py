@@ -104,6 +104,38 @@ def saxs_single_frame(positions, box, elements, qmin, qmax, thetamin, thetamax, 
     return obs, last.flatten()[-1]  # :241
 
 
+def saxs_single_frame_unbinned(positions, box, elements, qmin, qmax, thetamin, thetamax, max_n, sfactor=None):
+    """modules/saxs.py:175-241 with ``bin_spectrum=False``: the raw cubes of all element groups summed (:188-189,
+    :238-239).  ``max_n`` is the class's float64 cube shape (:173); a kernel cube of another shape fails in ``+=`` as it
+    does in the reference.  Returns ``(obs dict, correlation scalar)``."""
+    sfactor = sfactor or kernel.structure_factor
+    positions = np.asarray(positions, dtype=np.float32)
+    box = np.asarray(box, dtype=np.float32)
+    obs = {"structure_factors": np.zeros(max_n), "scattering_intensities": np.zeros(max_n)}  # :188-189
+    s = None
+    for element in np.unique(elements):
+        p = positions[np.asarray(elements) == element]
+        p = p - box * np.round(p / box)  # :193-195
+        q, s = sfactor(np.double(p), np.double(box), qmin, qmax, thetamin, thetamax, np.ones(len(p)))  # :197-205
+        obs["structure_factors"] += s  # :238
+        obs["scattering_intensities"] += atomic_form_factor(q, str(element)) ** 2 * s  # :207-210, :239
+    return obs, s.flatten()[-1]  # :241
+
+
+def saxs_conclude_unbinned(means, n_atoms, box, max_n):
+    """modules/saxs.py:255-300 with ``bin_spectrum=False``: Miller indices sorted by |q|."""
+    factors = 2 * np.pi / np.asarray(box)  # :172
+    miller = np.array(list(np.ndindex(tuple(max_n))))  # :256
+    q = np.linalg.norm(miller * factors[np.newaxis, :], axis=1)  # :257-259
+    order = np.argsort(q)  # :260
+    q, miller = q[order], miller[order]
+    s = means["structure_factors"].flatten()[order]  # :264-268
+    i = means["scattering_intensities"].flatten()[order]
+    keep = np.invert(np.isnan(s))  # :277
+    return {"scattering_vectors": q[keep], "miller_indices": miller[keep], "structure_factors": s[keep] / n_atoms,
+            "scattering_intensities": i[keep] / n_atoms}
+
+
 def saxs_conclude(sums, sems, n_atoms, qmin, qmax, dq):
     """modules/saxs.py:243-300 (``bin_spectrum=True``)."""
     q = np.arange(qmin, qmax, dq) + 0.5 * dq  # :245-247

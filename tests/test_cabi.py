@@ -133,9 +133,9 @@ def test_q_plan_host_side(L, qmax, n_bins, window, monkeypatch):
     qmin, tmin, tmax = window
 
     def describe():
-        out = (ctypes.c_int64 * 16)()
-        _cabi.check(lib.mb200_plan_describe(dims.ctypes.data_as(_cabi.c_double_p), qmin, qmax, tmin, tmax, n_bins, out))
-        return list(out)
+        out = np.zeros(16, dtype=np.int64)
+        _cabi.check(lib.mb200_plan_describe(_cabi.ptr(dims), qmin, qmax, tmin, tmax, n_bins, _cabi.ptr(out)))
+        return out.tolist()
 
     monkeypatch.setenv("MAICOS_B200_HOST_THREADS", "1")
     serial = describe()

@@ -628,3 +628,78 @@ def test_streaming_trr_with_pinned_ring_feeds_the_device_without_staging_copies(
             for key in b.sums:
                 assert_array_equal(np.asarray(a.sums[key]), np.asarray(b.sums[key]), err_msg=f"{type(a).__name__}.{key}")
         u.trajectory.close()
+
+
+# ---- Saxs with bin_spectrum=False: a batch of frames per device call ------------------------------------------------
+@pytest.mark.parametrize("theta", [(0, 180), (20, 110)])
+@pytest.mark.parametrize("pack", [True, False])
+def test_saxs_unbinned_batches_equal_the_restated_frame_body(theta, pack, precision, monkeypatch):
+    """saxs.py:188-189, 238-241, 255-300: raw cubes summed over element groups, their means over the frames, the
+    correlation scalar (last cell of the last group's cube) and the |q|-sorted Miller list, against the oracle."""
+    n_mol, L, F = 400, 24.0, 5
+    frames = mb.synthetic.spce_water_frames(n_mol, L, 77, n_frames=F)
+    frames = frames + np.float32(3.0)  # some atoms outside [0, L): pack matters
+    elements = np.tile(np.array(["O", "H", "H"], dtype=object), n_mol)
+    dims = np.array([L, L + 1.5, L - 2.0, 90, 90, 90], dtype=np.float32)
+    u = water_universe(frames, dims, elements)
+    qmax = 2.3
+    monkeypatch.setattr(mb.Saxs, "_batch_size", 2)  # batches of 2, 2 and 1 frames
+    ana = mb.Saxs(u.atoms, bin_spectrum=False, qmax=qmax, qmin=0.1, thetamin=theta[0], thetamax=theta[1], pack=pack).run()
+    box = dims[:3]
+    tmin, tmax = np.deg2rad(theta[0]), np.deg2rad(theta[1])
+    stats = restatement.RunningStats()
+    series = []
+    for f in range(F):
+        pos = restatement.wrap_atoms_f32(frames[f], box) if pack else frames[f]
+        obs, val = restatement.saxs_single_frame_unbinned(pos, box, elements, 0.1, qmax, tmin, tmax, tuple(ana.max_n))
+        stats.update(obs)
+        series.append(val)
+    ref = restatement.saxs_conclude_unbinned(stats.means, len(elements), ana.box, ana.max_n)
+    for k in ("structure_factors", "scattering_intensities"):
+        cube, want = ana.means[k], stats.means[k]
+        assert cube.shape == tuple(ana.max_n)
+        assert_array_equal(cube != 0, want != 0)
+        assert_allclose(cube, want, rtol=RTOL, atol=0)
+    assert_allclose(ana.timeseries, series, rtol=RTOL, atol=0)
+    assert_array_equal(ana.results.miller_indices, ref["miller_indices"])
+    assert_array_equal(ana.results.scattering_vectors, ref["scattering_vectors"])
+    assert_allclose(ana.results.structure_factors, ref["structure_factors"], rtol=RTOL, atol=0)
+    assert_allclose(ana.results.scattering_intensities, ref["scattering_intensities"], rtol=RTOL, atol=0)
+
+
+def test_saxs_frames_cells_lists_equal_the_dense_cube(precision):
+    """``mb200_saxs_frames_cells``: cell numbers, |q| and S of the accepted vectors equal the nonzero cells of the oracle's
+    dense cube; a wrong ``n_valid`` is refused."""
+    rng = np.random.default_rng(91)
+    n, F = 3000, 3
+    box = np.array([21.0, 19.5, 23.0], dtype=np.float32)
+    pos = rng.uniform(0, 1, (F, n, 3)).astype(np.float32) * box
+    flat = rng.permutation(n).astype(np.int32)
+    ptr = np.array([0, 1000, 1001, n], dtype=np.int64)  # a group of one atom in the middle
+    lib, ctx = _cabi.load(), _cabi.context()
+    handle = ctypes.c_void_p()
+    _cabi.check(lib.mb200_groups_create(ctx.handle, _cabi.ptr(flat), _cabi.ptr(ptr), 3, n, ctypes.byref(handle)))
+    try:
+        desc = np.zeros(16, dtype=np.int64)
+        args = (0.3, 2.5, 0.2, 2.4)
+        dims = box.astype(np.float64)
+        _cabi.check(lib.mb200_plan_describe(_cabi.ptr(dims), *args, 0, _cabi.ptr(desc)))
+        nv = int(desc[0])
+        cells, q, s = np.zeros(nv, dtype=np.int32), np.zeros(nv), np.zeros((F, 3, nv))
+        _cabi.check(lib.mb200_saxs_frames_cells(ctx.handle, _cabi.ptr(pos), 0, F, _cabi.ptr(box), handle, *args, 0, nv,
+                                                _cabi.ptr(cells), _cabi.ptr(q), _cabi.ptr(s)))
+        assert lib.mb200_saxs_frames_cells(ctx.handle, _cabi.ptr(pos), 0, F, _cabi.ptr(box), handle, *args, 0, nv + 1,
+                                           _cabi.ptr(cells), _cabi.ptr(q), _cabi.ptr(s)) != 0
+        for f in range(F):
+            for g in range(3):
+                p = pos[f][flat[ptr[g]:ptr[g + 1]]]
+                p = p - box * np.round(p / box)
+                q1, s1 = kernel.structure_factor(np.double(p), np.double(box), *args, np.ones(len(p)))
+                assert tuple(desc[1:4]) == s1.shape
+                nz = np.flatnonzero(s1.ravel())
+                if len(nz) == nv:  # no accepted cell cancels exactly
+                    assert_array_equal(cells, nz)
+                assert_array_equal(q, q1.ravel()[cells])
+                assert_allclose(s[f, g], s1.ravel()[cells], rtol=RTOL, atol=0)
+    finally:
+        lib.mb200_groups_destroy(ctx.handle, handle)

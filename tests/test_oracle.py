@@ -113,6 +113,27 @@ def test_saxs_one_frame_golden(water_gro):
         assert_allclose(res[k], g[k], rtol=1e-9)
 
 
+def test_saxs_unbinned_restatement_bins_to_the_binned_one(water_gro):
+    """``bin_spectrum=False`` (saxs.py:188-189, 238-239) keeps every Miller vector; histogramming its cubes by |q| per
+    group is the binned frame body, so the summed cubes binned over their nonzero cells give the binned observables when
+    every accepted S is nonzero (one frame of water.gro, qmax = 2; tests/modules/test_saxs.py:90-107 is structural)."""
+    pos = restatement.wrap_atoms_f32(water_gro["positions"], water_gro["dimensions"][:3])
+    box = np.asarray(water_gro["dimensions"][:3], dtype=np.float32)
+    el = water_gro["elements"]
+    max_n = tuple(np.ceil(2 / (2 * np.pi / np.double(box))).astype(int))
+    cubes, last = restatement.saxs_single_frame_unbinned(pos, box, el, 0, 2, 0, np.pi, max_n)
+    binned, _ = restatement.saxs_single_frame(pos, box, el, 0, 2, 0, np.pi, 20)
+    q, s_h = kernel.structure_factor(np.double(pos[el == "O"]), np.double(box), 0, 2, 0, np.pi, np.ones((el == "O").sum()))
+    assert cubes["structure_factors"].shape == q.shape and last == s_h.flatten()[-1]  # O sorts last: H, O
+    nz = cubes["structure_factors"].flatten() != 0
+    for k in ("structure_factors", "scattering_intensities"):
+        h, _ = np.histogram(q.flatten()[nz], bins=20, range=(0, 2), weights=cubes[k].flatten()[nz])
+        assert_allclose(h, binned[k], rtol=1e-12)
+    res = restatement.saxs_conclude_unbinned(cubes, len(el), box, max_n)
+    assert_array_equal(res["scattering_vectors"], np.sort(res["scattering_vectors"]))
+    assert len(res["miller_indices"]) == int(np.prod(max_n)) and res["structure_factors"][0] == 0  # q = 0 is rejected
+
+
 def test_saxs_npt_frames_golden(water_frames, water_gro):
     res, stats, series = restatement.run_saxs(water_frames["positions"], water_frames["dimensions"][:, :3],
                                               water_gro["elements"])
