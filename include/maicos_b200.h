@@ -85,8 +85,17 @@ int64_t mb200_ctx_launch_count(mb200_ctx *ctx);
 /* Announce the host buffer the NEXT mb200_saxs_frames call will read its positions from: the frames are copied to
  * the device on a separate copy stream while the current call computes (host staging -> PCIe -> HBM overlap across
  * calls).  The next call recognises the pointer and skips its own copy.  May be called from another thread than the
- * one inside a compute call; at most two announcements are kept.  The buffer must stay untouched until that call. */
+ * one inside a compute call; at most four announcements are kept, and a slot a running call still reads is never
+ * overwritten.  The buffer must stay untouched until that call. */
 int mb200_prefetch_frames(mb200_ctx *ctx, const void *host_frames, size_t bytes);
+/* The same for frames that several analyses of one frame loop read (AnalysisCollection, src/maicos/core/base.py:602-718:
+ * every instance sees the same untransformed frame): announcements with equal (host_frames, bytes, tag), tag != 0, share
+ * ONE host -> device copy, and the slot serves as many compute calls as announced it.  The caller's tag must identify the
+ * content (e.g. run number and first frame of the batch): a buffer refilled with other frames needs another tag.
+ * mb200_ctx_prefetch_stats: out[0] = announced copies issued since the context was created, out[1] = copies saved by
+ * sharing, out[2] = announcements not copied ahead because every slot was being read (the call copies by itself). */
+int mb200_prefetch_frames_shared(mb200_ctx *ctx, const void *host_frames, size_t bytes, uint64_t tag);
+int mb200_ctx_prefetch_stats(mb200_ctx *ctx, int64_t out[3]);
 /* Page-locked host memory for frame staging (full-rate asynchronous H2D / D2H).  Any host pointer
  * is accepted by the compute calls; pinned ones avoid the driver's bounce buffer. */
 int mb200_host_alloc(size_t bytes, void **out);

@@ -23,6 +23,7 @@ sharded over ranks and merged by one allreduce at the end.
 from __future__ import annotations
 
 import collections
+import itertools
 import logging
 import time
 import warnings
@@ -284,6 +285,10 @@ class VelocityWeights:
             pass
 
 
+#: numbers the runs of AnalysisCollection (tags of shared frame announcements, ``mb200_prefetch_frames_shared``)
+_collection_runs = itertools.count(1)
+
+
 class _Runner:
     """Shared ``run`` machinery of :class:`AnalysisBase` and :class:`AnalysisCollection`."""
 
@@ -293,11 +298,19 @@ class _Runner:
         logging.getLogger(__name__).setLevel(logging.INFO if verbose else logging.WARNING)
         if frames is not None and not all(opt is None for opt in [start, stop, step]):
             raise ValueError("start/stop/step cannot be combined with frames")
+        share_run = next(_collection_runs) if len(analysis_instances) > 1 else 0
         for a in analysis_instances:
             a._run_locals = self._run_locals
+            a._share_run = share_run
             a._setup_frames(a._trajectory, start=start, stop=stop, step=step, frames=frames)
         for a in analysis_instances:
             a._call_prepare()
+        if len(analysis_instances) > 1:
+            # members of a collection stage the same number of frames per device call, so that those reading the frames
+            # where the trajectory holds them announce identical blocks and share one host -> device copy
+            batched = [a for a in analysis_instances if getattr(type(a)._single_frame, "_from_batch", False)]
+            for a in batched:
+                a._batch_size = min(b._batch_size for b in batched)
 
         if progressbar_kwargs:
             logging.getLogger(__name__).info("progressbar_kwargs are accepted for API compatibility and ignored "
@@ -401,6 +414,8 @@ class AnalysisBase(_Runner):
         self._pools = None            # device -> single-worker executor of the device calls
         self._inflight_q = collections.deque()
         self._batch_device = None     # device of the batch being announced / submitted
+        self._batch_tag = 0           # content tag of the batch being announced (shared frames of a collection)
+        self._share_run = 0           # number of the collection run this instance is part of, 0 = on its own
         self._stage_parity = 0
         self.timings = {"stage_s": 0.0, "wait_device_s": 0.0, "device_call_s": 0.0}
 
@@ -506,7 +521,9 @@ class AnalysisBase(_Runner):
             return  # not one run of rows: the call gathers and copies by itself
         block = buf[rows[0][1]:rows[0][1] + len(rows)]
         ctx = _cabi.context(self._batch_device)  # the device this batch is about to be submitted to
-        _cabi.check(_cabi.load().mb200_prefetch_frames(ctx.handle, block.ctypes.data, block.nbytes))
+        # in a collection the analyses that read the frames where the trajectory holds them announce the same block with
+        # the same tag (run, first frame of the batch): one host -> device copy serves them all
+        _cabi.check(_cabi.load().mb200_prefetch_frames_shared(ctx.handle, block.ctypes.data, block.nbytes, self._batch_tag))
 
     def _staging_rows(self, shape, dtype, tag: str) -> tuple[np.ndarray, int]:
         """``(pinned batch buffer [batch, *shape], row)`` for the frame being staged.
@@ -646,6 +663,7 @@ class AnalysisBase(_Runner):
                     max_workers=1, thread_name_prefix=f"mb200-batch-{device}", initializer=_cabi.set_thread_device,
                     initargs=(device,))
             self._batch_device = device
+            self._batch_tag = ((self._share_run << 32) | (int(staged[0][0]) + 1)) if self._share_run else 0
             self._announce_staged([st for _, st in staged])
             self._inflight_q.append(pool.submit(self._device_batch, staged))
             # the next batch is staged into the next pinned buffer: one more buffer than batches in flight

@@ -121,7 +121,20 @@ inline void parallel_chunks(size_t n, size_t min_parallel, F fn) {
 #define MB_LOCK(ctx) std::lock_guard<std::recursive_mutex> _mb_call_lock((ctx)->call_mutex)
 
 struct SfPlan;  // sfactor.cu
-const void *take_prefetched(mb200_ctx *ctx, const void *host, size_t bytes);  // context.cu
+// The prefetch slot a compute call reads (context.cu).  take(): device copy of `host` if it was announced with
+// mb200_prefetch_frames[_shared] (the compute stream is made to wait for the copy), else nullptr.  release(): every kernel
+// that reads the slot has been queued -- records the slot's "done" event on the compute stream; until then the slot is
+// busy and no announcement overwrites it.  The destructor releases on every exit path.
+struct PrefetchRead {
+    mb200_ctx *ctx;
+    int slot = -1;
+    explicit PrefetchRead(mb200_ctx *c) : ctx(c) {}
+    PrefetchRead(const PrefetchRead &) = delete;
+    PrefetchRead &operator=(const PrefetchRead &) = delete;
+    const void *take(const void *host, size_t bytes);
+    void release();
+    ~PrefetchRead() { release(); }
+};
 
 }  // namespace mb200
 
@@ -146,17 +159,23 @@ struct mb200_ctx {
     mb200::DevBuf d_hpos, d_hw, d_hw2, d_hedges, d_hpar, d_hout, d_ctopo;
     // host -> device prefetch of the next batch of frames (mb200_prefetch_frames): copy stream, two buffers
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t pref_ev[2] = {nullptr, nullptr};
-    mb200::DevBuf d_pref[2];
-    const void *pref_src[2] = {nullptr, nullptr};
-    size_t pref_bytes[2] = {0, 0};
-    int pref_next = 0;
+    static constexpr int N_PREF = 4;  // a collection of two analyses keeps four announcements alive (2 each)
+    cudaEvent_t pref_ev[N_PREF] = {};
+    mb200::DevBuf d_pref[N_PREF];
+    const void *pref_src[N_PREF] = {};   // host pointer while announcements of the slot are still to be taken
+    size_t pref_bytes[N_PREF] = {};
+    const void *pref_host[N_PREF] = {};  // what the slot holds (pref_src is cleared by its last reader)
+    uint64_t pref_tag[N_PREF] = {};      // content tag of a shared announcement, 0 = not shared
+    int pref_readers[N_PREF] = {};       // announcements of the slot not taken yet
+    int pref_busy[N_PREF] = {};          // compute calls that took the slot and have not queued their last reader yet
+    uint64_t pref_seq[N_PREF] = {};      // announcement number of the slot's content (oldest is overwritten first)
+    uint64_t pref_counter = 0;
+    int64_t pref_copies = 0, pref_saved = 0, pref_skipped = 0;  // copies issued / saved by sharing / not issued (no free slot)
     std::mutex pref_mutex;
-    // the device copy of a prefetch slot may be overwritten only after the call that consumed it has read it: recorded on
-    // the compute stream when the slot's last reader (k_sf_tables) has been queued, waited for by the copy stream
-    cudaEvent_t pref_done_ev[2] = {nullptr, nullptr};
-    bool pref_done_set[2] = {false, false};
-    int pref_taken = -1;  // slot taken by the compute call in progress (under call_mutex)
+    // the device copy of a prefetch slot may be overwritten only after the calls that consumed it have read it: recorded on
+    // the compute stream when a call's last reader has been queued (PrefetchRead::release), waited for by the copy stream
+    cudaEvent_t pref_done_ev[N_PREF] = {};
+    bool pref_done_set[N_PREF] = {};
     // Every compute entry point holds this for its whole duration: the workspaces above and the stream are shared by all
     // callers of the context (several analysis instances each drive their own worker thread, AnalysisCollection).
     std::recursive_mutex call_mutex;

@@ -14,9 +14,9 @@ mb200_ctx::~mb200_ctx() {
     plans.clear();
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < N_PREF; ++i)
         if (pref_ev[i]) cudaEventDestroy(pref_ev[i]);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < N_PREF; ++i)
         if (pref_done_ev[i]) cudaEventDestroy(pref_done_ev[i]);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (stream) cudaStreamDestroy(stream);
@@ -54,8 +54,8 @@ extern "C" int mb200_ctx_create(int device, mb200_ctx **out) {
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->pref_ev[i], cudaEventDisableTiming);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->pref_done_ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < mb200_ctx::N_PREF && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->pref_ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < mb200_ctx::N_PREF && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->pref_done_ev[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete ctx;
         return fail(MB200_ECUDA, "context creation failed: %s", cudaGetErrorString(e));
@@ -94,37 +94,89 @@ extern "C" int mb200_ctx_set_timing(mb200_ctx *ctx, int enable) {
 
 extern "C" int64_t mb200_ctx_launch_count(mb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-extern "C" int mb200_prefetch_frames(mb200_ctx *ctx, const void *host_frames, size_t bytes) {
+extern "C" int mb200_prefetch_frames_shared(mb200_ctx *ctx, const void *host_frames, size_t bytes, uint64_t tag) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context");
     if (!host_frames || bytes == 0) return MB200_OK;
     MB_CUDA(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> lock(ctx->pref_mutex);
-    const int slot = ctx->pref_next;
-    ctx->pref_next ^= 1;
-    ctx->pref_src[slot] = nullptr;
-    if (ctx->pref_done_set[slot])  // the slot's previous content may still be read by a queued compute call
+    // MAICOS_B200_PREF_SLOTS (developer aid): use fewer than N_PREF slots
+    static const int NP = std::getenv("MAICOS_B200_PREF_SLOTS")
+                              ? std::min(std::max(std::atoi(std::getenv("MAICOS_B200_PREF_SLOTS")), 1), (int)mb200_ctx::N_PREF)
+                              : (int)mb200_ctx::N_PREF;
+    if (tag != 0)  // the same frames announced again by another analysis of a collection: one more reader, no second copy
+        for (int slot = 0; slot < NP; ++slot)
+            if (ctx->pref_tag[slot] == tag && ctx->pref_host[slot] == host_frames && ctx->pref_bytes[slot] == bytes) {
+                ctx->pref_readers[slot] += 1;
+                ctx->pref_src[slot] = host_frames;
+                ctx->pref_saved += 1;
+                return MB200_OK;
+            }
+    // a slot no running call reads: one whose announcements were all taken if there is any, else the oldest content
+    // (an announcement nobody took -- its call copies by itself)
+    // (measured: a single analysis that rotates through all four buffers instead of alternating between the first two
+    // has runs 1.5 - 3x slower now and then, tools/r2_c4_probe.py -- hence the LOWEST free slot, not the oldest)
+    int slot = -1;
+    for (int i = 0; i < NP && slot < 0; ++i)
+        if (ctx->pref_busy[i] == 0 && ctx->pref_readers[i] <= 0) slot = i;
+    for (int i = 0; i < NP; ++i) {
+        if (slot >= 0 && ctx->pref_readers[slot] <= 0) break;
+        if (ctx->pref_busy[i] == 0 && (slot < 0 || ctx->pref_seq[i] < ctx->pref_seq[slot])) slot = i;
+    }
+    if (slot < 0) {  // every slot is being read: the call copies its frames by itself
+        ctx->pref_skipped += 1;
+        return MB200_OK;
+    }
+    ctx->pref_src[slot] = ctx->pref_host[slot] = nullptr;
+    ctx->pref_tag[slot] = 0;
+    ctx->pref_readers[slot] = 0;
+    if (ctx->pref_done_set[slot])  // the slot's previous content may still be read by a queued kernel
         MB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pref_done_ev[slot], 0));
     MB_TRY(ctx->d_pref[slot].ensure(bytes));
     MB_CUDA(cudaMemcpyAsync(ctx->d_pref[slot].p, host_frames, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
     MB_CUDA(cudaEventRecord(ctx->pref_ev[slot], ctx->copy_stream));
-    ctx->pref_src[slot] = host_frames;
+    ctx->pref_src[slot] = ctx->pref_host[slot] = host_frames;
     ctx->pref_bytes[slot] = bytes;
+    ctx->pref_tag[slot] = tag;
+    ctx->pref_readers[slot] = 1;
+    ctx->pref_seq[slot] = ++ctx->pref_counter;
+    ctx->pref_copies += 1;
+    return MB200_OK;
+}
+
+extern "C" int mb200_prefetch_frames(mb200_ctx *ctx, const void *host_frames, size_t bytes) {
+    return mb200_prefetch_frames_shared(ctx, host_frames, bytes, 0);
+}
+
+extern "C" int mb200_ctx_prefetch_stats(mb200_ctx *ctx, int64_t out[3]) {
+    if (!ctx || !out) return fail(MB200_EINVAL, "invalid argument to mb200_ctx_prefetch_stats");
+    std::lock_guard<std::mutex> lock(ctx->pref_mutex);
+    out[0] = ctx->pref_copies;
+    out[1] = ctx->pref_saved;
+    out[2] = ctx->pref_skipped;
     return MB200_OK;
 }
 
 namespace mb200 {
-// Device copy of `host` if it was announced with mb200_prefetch_frames (the compute stream is made to wait for the
-// copy), else nullptr.  A slot is consumed by the first call that takes it.
-const void *take_prefetched(mb200_ctx *ctx, const void *host, size_t bytes) {
+const void *PrefetchRead::take(const void *host, size_t bytes) {
+    if (!host || slot >= 0) return nullptr;
     std::lock_guard<std::mutex> lock(ctx->pref_mutex);
-    for (int slot = 0; slot < 2; ++slot)
-        if (ctx->pref_src[slot] == host && ctx->pref_bytes[slot] >= bytes && host) {
-            ctx->pref_src[slot] = nullptr;
-            if (cudaStreamWaitEvent(ctx->stream, ctx->pref_ev[slot], 0) != cudaSuccess) return nullptr;
-            ctx->pref_taken = slot;
-            return ctx->d_pref[slot].p;
+    for (int i = 0; i < mb200_ctx::N_PREF; ++i)
+        if (ctx->pref_src[i] == host && ctx->pref_bytes[i] >= bytes) {
+            if (cudaStreamWaitEvent(ctx->stream, ctx->pref_ev[i], 0) != cudaSuccess) return nullptr;
+            if (--ctx->pref_readers[i] <= 0) ctx->pref_src[i] = nullptr;  // every announcement is taken once
+            ctx->pref_busy[i] += 1;
+            slot = i;
+            return ctx->d_pref[i].p;
         }
     return nullptr;
+}
+
+void PrefetchRead::release() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(ctx->pref_mutex);
+    if (cudaEventRecord(ctx->pref_done_ev[slot], ctx->stream) == cudaSuccess) ctx->pref_done_set[slot] = true;
+    ctx->pref_busy[slot] -= 1;
+    slot = -1;
 }
 }  // namespace mb200
 

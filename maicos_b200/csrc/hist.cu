@@ -29,6 +29,8 @@
 // warp-private variant using __match_any_sync + plain read-modify-write (2x slower: MATCH latency,
 // 12.5 % occupancy at 2154 bins).
 #include "common.cuh"
+#include <chrono>
+#include <cstdlib>
 
 namespace mb200 {
 
@@ -920,15 +922,23 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
     const size_t esz = pos_is_f32 ? 4 : 8;
     const size_t ncomp = geometry == MB200_GEOM_SCALAR ? 1 : 3;  // values per element in `positions`
 
+    // developer aid: MAICOS_B200_TRACE_HOST=1 prints the host-side time of every phase of the call to stderr
+    static const bool trace_host = std::getenv("MAICOS_B200_TRACE_HOST") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!trace_host) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[mb200_profile_hist] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    mark("entry");
     HistParams p;
     std::memset(&p, 0, sizeof(p));
-    int pref_slot = -1;
+    PrefetchRead pref_read(ctx);
     if (positions_on_device || N == 0) {
         p.pos = positions;
-    } else if (const void *pref = take_prefetched(ctx, positions, F * N * ncomp * esz)) {
+    } else if (const void *pref = pref_read.take(positions, F * N * ncomp * esz)) {
         p.pos = pref;  // announced with mb200_prefetch_frames: copied on the copy stream under the previous call
-        pref_slot = ctx->pref_taken;
-        ctx->pref_taken = -1;
     } else {
         MB_TRY(ctx->d_hpos.ensure(F * N * ncomp * esz));
         MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * ncomp * esz, cudaMemcpyHostToDevice, ctx->stream));
@@ -1045,11 +1055,8 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
     MB_CUDA(cudaGetLastError());
     ctx->launches += 1;
     }
-    if (pref_slot >= 0) {  // the prefetch slot this call read may be refilled from here on
-        std::lock_guard<std::mutex> lock(ctx->pref_mutex);
-        MB_CUDA(cudaEventRecord(ctx->pref_done_ev[pref_slot], ctx->stream));
-        ctx->pref_done_set[pref_slot] = true;
-    }
+    mark(pref_read.slot >= 0 ? "queued (prefetched)" : "queued (own copy)");
+    pref_read.release();  // the prefetch slot this call read may be refilled from here on
     // results: ONE device -> pinned copy of (weighted | counts), then into the caller's (pageable) arrays
     MB_TRY(ctx->h_out.ensure(F * NB * 16));
     char *hres = ctx->h_out.as<char>();
@@ -1059,6 +1066,7 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
         MB_CUDA(cudaMemcpyAsync(hres + F * NB * 8, d_oc, F * NB * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    mark("device (wait)");
     if (hist_w) std::memcpy(hist_w, hres, F * NB * 8);
     std::memcpy(hist_c, hres + F * NB * 8, F * NB * 8);
     ctx->stats[5] = 0;

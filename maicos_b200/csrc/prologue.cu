@@ -10,6 +10,8 @@
 // image about the first atom of a compound, float64 sequential sums in atom order, centre-of-mass
 // wrap), so the device prologue and the host prologue agree bit for bit; one thread owns one compound.
 #include "common.cuh"
+#include <chrono>
+#include <cstdlib>
 
 namespace mb200 {
 
@@ -301,15 +303,23 @@ extern "C" int mb200_compound_prologue_topo(mb200_ctx *ctx, const float *positio
     if (n_frames > 65535) return fail(MB200_EINVAL, "at most 65535 frames per call");
     MB_CUDA(cudaSetDevice(ctx->device));
     const size_t F = (size_t)n_frames, N = (size_t)topo->n_atoms, NC = (size_t)topo->n_c;
+    // developer aid: MAICOS_B200_TRACE_HOST=1 prints the host-side time of every phase of the call to stderr
+    static const bool trace_host = std::getenv("MAICOS_B200_TRACE_HOST") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!trace_host) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[mb200_compound_prologue] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    mark("entry");
     CompoundParams p;
     std::memset(&p, 0, sizeof(p));
-    int pref_slot = -1;
+    PrefetchRead pref_read(ctx);
     if (positions_on_device) {
         p.pos = positions;
-    } else if (const void *pref = take_prefetched(ctx, positions, F * N * 12)) {
+    } else if (const void *pref = pref_read.take(positions, F * N * 12)) {
         p.pos = reinterpret_cast<const float *>(pref);  // copied on the copy stream under the previous call
-        pref_slot = ctx->pref_taken;
-        ctx->pref_taken = -1;
     } else {
         MB_TRY(ctx->d_hpos.ensure(F * N * 12));
         MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * 12, cudaMemcpyHostToDevice, ctx->stream));
@@ -327,12 +337,10 @@ extern "C" int mb200_compound_prologue_topo(mb200_ctx *ctx, const float *positio
     k_compound<<<grid, 128, 0, ctx->stream>>>(p);
     MB_CUDA(cudaGetLastError());
     ctx->launches += 1;
-    if (pref_slot >= 0) {
-        std::lock_guard<std::mutex> lock(ctx->pref_mutex);
-        MB_CUDA(cudaEventRecord(ctx->pref_done_ev[pref_slot], ctx->stream));
-        ctx->pref_done_set[pref_slot] = true;
-    }
+    mark(pref_read.slot >= 0 ? "queued (prefetched)" : "queued (own copy)");
+    pref_read.release();
     MB_CUDA(cudaStreamSynchronize(ctx->stream));  // `positions` / `boxes` may be reused by the caller
+    mark("device (wait)");
     return MB200_OK;
 }
 

@@ -1666,6 +1666,7 @@ static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int position
     size_t done = 0;
     const float *pref = nullptr;
     bool pref_checked = false;
+    PrefetchRead pref_read(ctx);
     while (done < (size_t)n_frames) {
         // chunk size: keep tables under ~12 GB
         size_t chunk = 0, tab_bytes = 0;
@@ -1694,7 +1695,7 @@ static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int position
         if (positions_on_device) {
             dpos = positions + done * frame_elems;
         } else if (!pref_checked && (pref = reinterpret_cast<const float *>(
-                                         take_prefetched(ctx, positions, (size_t)n_frames * frame_elems * 4))) != nullptr) {
+                                         pref_read.take(positions, (size_t)n_frames * frame_elems * 4))) != nullptr) {
             pref_checked = true;
             dpos = pref + done * frame_elems;  // the whole call was copied ahead by mb200_prefetch_frames
         } else if (pref != nullptr) {
@@ -1742,12 +1743,7 @@ static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int position
         MB_TRY(finish_timing(ctx));
         done += chunk;
     }
-    if (ctx->pref_taken >= 0) {  // the prefetch slot this call read may be refilled from here on
-        std::lock_guard<std::mutex> lock(ctx->pref_mutex);
-        MB_CUDA(cudaEventRecord(ctx->pref_done_ev[ctx->pref_taken], ctx->stream));
-        ctx->pref_done_set[ctx->pref_taken] = true;
-        ctx->pref_taken = -1;
-    }
+    pref_read.release();  // the prefetch slot this call read may be refilled from here on
     return MB200_OK;
 }
 

@@ -703,3 +703,51 @@ def test_saxs_frames_cells_lists_equal_the_dense_cube(precision):
                 assert_allclose(s[f, g], s1.ravel()[cells], rtol=RTOL, atol=0)
     finally:
         lib.mb200_groups_destroy(ctx.handle, handle)
+
+
+# ---- one device-resident frame for all members of a collection ------------------------
+def test_collection_members_share_one_copy_of_the_frames(precision):
+    """Saxs + DensityPlanar + DiporderPlanar on the whole universe of a page-locked trajectory: every member reads the
+    frames where the trajectory holds them, announces the same block with the same tag, and the library copies it to
+    the device ONCE (``mb200_prefetch_frames_shared``).  Results equal the members' solo runs bit for bit."""
+    from maicos_b200.mdshim import MemoryTrajectory, Universe
+
+    n_mol, F = 1500, 48
+    L = mb.synthetic.cubic_box_for(n_mol)
+    fr = mb.synthetic.spce_water_frames(n_mol, L, 11, n_frames=F)
+    topo = mb.synthetic.spce_topology(n_mol)
+
+    def universe():
+        return Universe(fr.shape[1], MemoryTrajectory(fr, np.float32([L, L, L, 90, 90, 90]), pinned=True), **topo)
+
+    def members(u):
+        out = [mb.Saxs(u.atoms, qmax=2.0, dq=0.1),
+               mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.2, unwrap=False, pack=False),
+               mb.DiporderPlanar(u.atoms, bin_width=0.5, unwrap=False, pack=False)]
+        return out
+
+    lib, ctx = _cabi.load(), _cabi.context()
+    keep = {c: c._batch_size for c in (mb.Saxs, mb.DensityPlanar, mb.DiporderPlanar)}
+    try:
+        for c in keep:
+            c._batch_size = 8
+        before = np.zeros(3, dtype=np.int64)
+        _cabi.check(lib.mb200_ctx_prefetch_stats(ctx.handle, _cabi.ptr(before)))
+        together = members(universe())
+        mb.AnalysisCollection(*together).run()
+        after = np.zeros(3, dtype=np.int64)
+        _cabi.check(lib.mb200_ctx_prefetch_stats(ctx.handle, _cabi.ptr(after)))
+        solo = members(universe())
+        for m in solo:
+            m.run()
+    finally:
+        for c, b in keep.items():
+            c._batch_size = b
+    copies, saved, skipped = (after - before).tolist()
+    # batches of 2, 4, 8, ... frames: 8 batches per member; one copy per batch, two members ride along
+    assert copies > 0 and saved == 2 * copies, (copies, saved, skipped)
+    for a, b in zip(together, solo):
+        for key in b.sums:
+            assert_array_equal(np.asarray(a.sums[key]), np.asarray(b.sums[key]), err_msg=f"{type(a).__name__}.{key}")
+        for key in b.means:
+            assert_array_equal(np.asarray(a.means[key]), np.asarray(b.means[key]), err_msg=f"{type(a).__name__}.{key}")
