@@ -267,6 +267,12 @@ int mb200_compound_prologue_topo(mb200_ctx *ctx, const float *positions, int pos
                                  int64_t n_frames, const float *boxes, const mb200_topology *topo,
                                  int make_whole, int wrap_center, int weight_mode, int pdim,
                                  int uv_mode, int uv_dim, double *centers_dev, double *weights_dev);
+/* The same with the topology's atoms being the window [first_atom, first_atom + n_atoms) of whole frames of n_total
+ * atoms (see mb200_profile_hist_window). */
+int mb200_compound_prologue_window(mb200_ctx *ctx, const float *positions, int positions_on_device,
+                                   int64_t n_frames, int64_t n_total, int64_t first_atom, const float *boxes,
+                                   const mb200_topology *topo, int make_whole, int wrap_center, int weight_mode,
+                                   int pdim, int uv_mode, int uv_dim, double *centers_dev, double *weights_dev);
 
 /* Velocity-derived weights from the raw velocities of a batch of frames; replaces the per-frame host calls
  *   velocity_weights(ag, grouping, vdim)     src/maicos/lib/weights.py:195-225
@@ -331,6 +337,16 @@ int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *positions, int 
                        const double *weights, int weights_per_frame, int weights_on_device,
                        const double *edges, int32_t n_bins, const double *center,
                        const double *zrange, double *hist_w, int64_t *hist_c);
+/* The same for a group that is a WINDOW of whole frames: `positions` holds [n_frames][n_total][3] (or [n_frames][n_total]
+ * for MB200_GEOM_SCALAR) and the group is atoms [first_atom, first_atom + n) of every frame -- a contiguous selection (the
+ * water of a slab system) is binned where the trajectory holds the frames, without a gather on the host, and frames
+ * announced with mb200_prefetch_frames[_shared] as whole frames serve every analysis of a collection.  Weights are
+ * per group atom ([n] or [n_frames][n]) as before. */
+int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const void *positions, int pos_is_f32,
+                              int positions_on_device, int64_t n_frames, int64_t n_total, int64_t first_atom,
+                              int64_t n, int dim, const double *weights, int weights_per_frame,
+                              int weights_on_device, const double *edges, int32_t n_bins, const double *center,
+                              const double *zrange, double *hist_w, int64_t *hist_c);
 
 #ifdef __cplusplus
 }

@@ -197,18 +197,24 @@ class CompoundPrologue:
             st = self._dev[ctx.device] = (ctx, topo, _cabi.DeviceBuffer(ctx), _cabi.DeviceBuffer(ctx))
         return st
 
-    def run(self, positions: np.ndarray, boxes: np.ndarray):
-        """positions float32 [F, n_atoms, 3] (pinned), boxes float32 [F, 3] -> device pointers (centres, weights)."""
+    def run(self, positions: np.ndarray, boxes: np.ndarray, window=None):
+        """positions float32 [F, n_atoms, 3] (pinned), boxes float32 [F, 3] -> device pointers (centres, weights).
+
+        ``window = (n_total, first)``: ``positions`` holds whole frames ``[F, n_total, 3]`` and the group is atoms
+        ``first .. first + n_atoms`` of each (``AnalysisBase._frame_window``)."""
         from .. import _cabi
 
         ctx, topo, centers, weights = self._on_device()
         F = positions.shape[0]
+        n_total, first = window if window is not None else (self.n_atoms, 0)
+        if positions.shape[1] != n_total:
+            raise ValueError(f"frames of {positions.shape[1]} atoms, expected {n_total}")
         c_ptr = centers.ensure(F * self.n_c * 24)
         n_w = {0: 0, 1: 1, 2: 1, 3: 1, 4: 3}[self.weight_mode]
         w_ptr = weights.ensure(F * self.n_c * 8 * n_w) if n_w else None
         boxes = np.ascontiguousarray(boxes, dtype=np.float32)
-        _cabi.check(_cabi.load().mb200_compound_prologue_topo(
-            ctx.handle, _cabi.ptr(positions), 0, F, _cabi.ptr(boxes), topo, int(self.make_whole),
+        _cabi.check(_cabi.load().mb200_compound_prologue_window(
+            ctx.handle, _cabi.ptr(positions), 0, F, int(n_total), int(first), _cabi.ptr(boxes), topo, int(self.make_whole),
             int(self.wrap_center), self.weight_mode, self.pdim, self.uv_mode, self.uv_dim, c_ptr, w_ptr))
         return c_ptr, w_ptr
 
@@ -415,6 +421,7 @@ class AnalysisBase(_Runner):
         self._inflight_q = collections.deque()
         self._batch_device = None     # device of the batch being announced / submitted
         self._batch_tag = 0           # content tag of the batch being announced (shared frames of a collection)
+        self._window_state = None     # see ``_frame_window``
         self._share_run = 0           # number of the collection run this instance is part of, 0 = on its own
         self._stage_parity = 0
         self.timings = {"stage_s": 0.0, "wait_device_s": 0.0, "device_call_s": 0.0}
@@ -487,11 +494,16 @@ class AnalysisBase(_Runner):
         frame, the row IS the trajectory's: no host copy, the device reads the frame where the reader put it."""
         ag = self.atomgroup
         pinned_row = getattr(self._trajectory, "pinned_row", None)
-        if pinned_row is not None and getattr(ag, "_all", False):
+        window = self._frame_window()
+        if pinned_row is not None and (getattr(ag, "_all", False) or window is not None):
             ts = self._universe.trajectory.ts
             where = pinned_row(ts.frame)
             if where is not None and where[0][where[1]].ctypes.data == ts.positions.ctypes.data:
                 return where
+        if window is not None:  # a frame that is not where the trajectory holds it: the whole frame is staged all the same
+            buf, row = self._staging_rows((window[0], 3), np.float32, tag)
+            np.copyto(buf[row], self._universe.trajectory.ts.positions)
+            return buf, row
         buf, row = self._staging_rows((ag.n_atoms, 3), np.float32, tag)
         positions_into(ag, buf[row])
         return buf, row
@@ -557,6 +569,7 @@ class AnalysisBase(_Runner):
                 self.ref_weights = np.ones(self.refgroup.n_atoms)
             else:
                 self.ref_weights = self.refgroup.masses
+        self._window_state = False  # decided on first use (``_frame_window``), after ``_prepare``
         self._prepare()
         # a streaming reader that decodes into a ring of page-locked frame buffers (mdshim.TRRTrajectory(pinned_ring=k)):
         # rows handed to the device must not be overwritten while a batch is in flight
@@ -586,6 +599,37 @@ class AnalysisBase(_Runner):
                 delattr(self, name)
         logging.info(f"Analysing {self.n_frames} trajectory frames.")
         logging.debug(f"Module input: {get_module_input_str(self)}")
+
+    def _host_transforms(self) -> bool:
+        """True when ``_transform_frame`` may rewrite the frame on the host (same conditions, asked once per run)."""
+        device_compounds = getattr(self, "_prologue", None) is not None
+        if (self.unwrap and not device_compounds) or self.refgroup is not None or self.jitter != 0.0:
+            return True
+        return bool(self.pack and self._universe.dimensions is not None and not device_compounds and not (
+            self._device_pack and self.wrap_compound == "atoms" and is_orthorhombic(self._universe.dimensions)))
+
+    def _frame_window(self):
+        """``(n_total, first)`` when the device calls of this run read the atom group out of WHOLE frames, else ``None``.
+
+        A group that is not the whole universe normally has its atoms gathered into the staging buffer frame by frame
+        (one host pass over the selection).  When the trajectory lives in page-locked memory and nothing transforms the
+        frames on the host, classes that can address their atoms inside a whole frame (``_window_capable``: ``"range"`` --
+        a contiguous selection, as the water of a slab system; ``"indices"`` -- any selection, Saxs gathers by index on
+        the device anyway) stage the trajectory's own rows instead: no host copy, and in a collection the frames reach the
+        device once for all members.  ``first`` is ``None`` for ``"indices"``."""
+        if self._window_state is False:
+            self._window_state = None
+            mode = getattr(self, "_window_capable", None)
+            ag = self.atomgroup
+            if (mode and not getattr(ag, "_all", False) and getattr(self._trajectory, "has_pinned_frames", False)
+                    and hasattr(ag, "indices") and not self._host_transforms()):
+                idx = np.asarray(ag.indices)
+                n_total = int(self._universe.atoms.n_atoms)
+                if mode == "indices":
+                    self._window_state = (n_total, None)
+                elif len(idx) and int(idx[-1]) - int(idx[0]) + 1 == len(idx) and (len(idx) < 2 or bool(np.all(np.diff(idx) == 1))):
+                    self._window_state = (n_total, int(idx[0]))
+        return self._window_state
 
     def _transform_frame(self, ts) -> None:
         """unwrap -> refgroup centring -> wrap -> jitter, in the reference's order (base.py:436-451)."""
@@ -944,6 +988,8 @@ class ProfileBase:
 
     #: set by modules whose weights depend on topology only (masses, charges, counts)
     _static_weights = False
+    #: a contiguous selection is read out of whole frames of a page-locked trajectory (``AnalysisBase._frame_window``)
+    _window_capable = "range"
 
     def __init__(self, atomgroup, grouping: str, bin_method: str, output: str, weighting_function: Callable,
                  weighting_function_kwargs: None | dict, normalization: str) -> None:
@@ -1005,6 +1051,9 @@ class ProfileBase:
                                                  prologue=self._prologue)
             except ValueError:
                 self._velocity = None
+        win = self._frame_window()  # whole frames of a page-locked trajectory travel: size the batches by them
+        if win is not None:
+            self._batch_size = int(max(1, min(64, (128 << 20) // max(1, win[0] * 12))))
 
     # geometry classes provide these two
     def _hist_geometry(self) -> dict:
@@ -1111,21 +1160,23 @@ class ProfileBase:
         if self._velocity is not None:
             vel_w = (self._velocity.run(self._gather_staged([s["velocities"] for s in staged], tag="velg")), True)
         if self._prologue is not None:
-            c_ptr, w_ptr = self._prologue.run(pos, np.stack([s["box"] for s in staged]))
+            c_ptr, w_ptr = self._prologue.run(pos, np.stack([s["box"] for s in staged]), window=self._frame_window())
             dev_w = (w_ptr, True) if w_ptr else vel_w
             if self._static_weights and not w_ptr:
                 dev_w = (self._static_weights_on_device(g0["weights"]), False)
             hw, hc = profile_hist(g0["geometry"], None, g0["dim"], None, edges, center, zrange,
                                   device_positions=(c_ptr, len(staged), self._prologue.n_c), device_weights=dev_w)
         else:
+            win = self._frame_window() if self.grouping == "atoms" else None  # else: centres formed on the host
+            win = None if win is None else (win[1], self.atomgroup.n_atoms)  # atoms [first, first + n) of whole frames
             if self._static_weights:
-                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange,
+                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange, window=win,
                                       device_weights=(self._static_weights_on_device(g0["weights"]), False))
             elif vel_w is not None:
-                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange, device_weights=vel_w)
+                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange, device_weights=vel_w, window=win)
             else:
                 w = self._gather_rows([s["weights"] for s in staged])
-                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], w, edges, center, zrange)
+                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], w, edges, center, zrange, window=win)
         out = []
         for f, s in enumerate(staged):
             obs = s["obs"]

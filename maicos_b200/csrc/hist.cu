@@ -49,6 +49,7 @@ struct HistParams {
     double *acc_f;                        // [F][n_bins] float64 fallback sums
     unsigned long long *acc_c;            // [F][n_bins] counts
     long long n;
+    long long fstride;     // elements of `pos` between two frames (n * 3, n for scalars; more when the group is a window of whole frames)
     int n_bins, dim, geometry, is_f32, w_per_frame, digitize;
 };
 
@@ -196,14 +197,14 @@ __global__ void __launch_bounds__(H_THREADS) k_hist(HistParams p) {
     if (p.geometry == MB200_GEOM_SCALAR) {  // the binned coordinate itself, [F][n]
         const long long gtid = (long long)blockIdx.x * H_THREADS + threadIdx.x, gstride = (long long)gridDim.x * H_THREADS;
         if (p.is_f32) {
-            const float *base = reinterpret_cast<const float *>(p.pos) + (size_t)f * n;
+            const float *base = reinterpret_cast<const float *>(p.pos) + (size_t)f * p.fstride;
             for (long long j = gtid; j < n; j += gstride) deposit(scalar_bin(g, (double)base[j], edges), j);
         } else {
-            const double *base = reinterpret_cast<const double *>(p.pos) + (size_t)f * n;
+            const double *base = reinterpret_cast<const double *>(p.pos) + (size_t)f * p.fstride;
             for (long long j = gtid; j < n; j += gstride) deposit(scalar_bin(g, base[j], edges), j);
         }
     } else if (p.is_f32) {
-        const float *base = reinterpret_cast<const float *>(p.pos) + (size_t)f * n * 3;
+        const float *base = reinterpret_cast<const float *>(p.pos) + (size_t)f * p.fstride;
         // scalar head up to 16-byte alignment, float4 body (4 atoms = 3 x float4), scalar tail
         const unsigned long long addr = (unsigned long long)(uintptr_t)base;
         long long a0 = (addr & 3ull) ? n : 0;  // not even float aligned: all scalar
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(H_THREADS) k_hist(HistParams p) {
         for (long long j = tail0 + gtid; j < n; j += gstride)
             deposit(atom_bin(g, (double)base[j * 3], (double)base[j * 3 + 1], (double)base[j * 3 + 2], edges), j);
     } else {
-        const double *base = reinterpret_cast<const double *>(p.pos) + (size_t)f * n * 3;
+        const double *base = reinterpret_cast<const double *>(p.pos) + (size_t)f * p.fstride;
         for (long long j = (long long)blockIdx.x * H_THREADS + threadIdx.x; j < n; j += (long long)gridDim.x * H_THREADS)
             deposit(atom_bin(g, base[j * 3], base[j * 3 + 1], base[j * 3 + 2], edges), j);
     }
@@ -433,15 +434,15 @@ __global__ void __launch_bounds__(HS_THREADS, 2) k_hist_sorted(HistParams p) {
     auto bin_generic = [&](long long j) -> int {
         double v;
         if (p.geometry == MB200_GEOM_SCALAR) {
-            v = p.is_f32 ? (double)(reinterpret_cast<const float *>(p.pos) + (size_t)f * n)[j]
-                         : (reinterpret_cast<const double *>(p.pos) + (size_t)f * n)[j];
+            v = p.is_f32 ? (double)(reinterpret_cast<const float *>(p.pos) + (size_t)f * p.fstride)[j]
+                         : (reinterpret_cast<const double *>(p.pos) + (size_t)f * p.fstride)[j];
         } else {
             double x, y, z;
             if (p.is_f32) {
-                const float *b = reinterpret_cast<const float *>(p.pos) + ((size_t)f * n + j) * 3;
+                const float *b = reinterpret_cast<const float *>(p.pos) + (size_t)f * p.fstride + (size_t)j * 3;
                 x = (double)b[0]; y = (double)b[1]; z = (double)b[2];
             } else {
-                const double *b = reinterpret_cast<const double *>(p.pos) + ((size_t)f * n + j) * 3;
+                const double *b = reinterpret_cast<const double *>(p.pos) + (size_t)f * p.fstride + (size_t)j * 3;
                 x = b[0]; y = b[1]; z = b[2];
             }
             if (!atom_value(g, x, y, z, v)) return -1;
@@ -466,7 +467,7 @@ __global__ void __launch_bounds__(HS_THREADS, 2) k_hist_sorted(HistParams p) {
     long long a0 = 0, n_quads = 0;
     const bool fast = p.geometry != MB200_GEOM_SCALAR && p.is_f32 &&
                       (((unsigned long long)(uintptr_t)p.pos) & 3ull) == 0;
-    const float *fbase = reinterpret_cast<const float *>(p.pos) + (size_t)f * n * 3;
+    const float *fbase = reinterpret_cast<const float *>(p.pos) + (size_t)f * p.fstride;
     if (fast) {
         const unsigned long long addr = (unsigned long long)(uintptr_t)fbase;
         while (a0 < n && ((addr + (unsigned long long)a0 * 12ull) & 15ull)) ++a0;
@@ -715,15 +716,15 @@ __global__ void __launch_bounds__(HC_THREADS, 2) k_hist_chunk(HistParams p) {
     auto bin_generic = [&](long long j) -> int {
         double v;
         if (p.geometry == MB200_GEOM_SCALAR) {
-            v = p.is_f32 ? (double)(reinterpret_cast<const float *>(p.pos) + (size_t)f * n)[j]
-                         : (reinterpret_cast<const double *>(p.pos) + (size_t)f * n)[j];
+            v = p.is_f32 ? (double)(reinterpret_cast<const float *>(p.pos) + (size_t)f * p.fstride)[j]
+                         : (reinterpret_cast<const double *>(p.pos) + (size_t)f * p.fstride)[j];
         } else {
             double x, y, z;
             if (p.is_f32) {
-                const float *b = reinterpret_cast<const float *>(p.pos) + ((size_t)f * n + j) * 3;
+                const float *b = reinterpret_cast<const float *>(p.pos) + (size_t)f * p.fstride + (size_t)j * 3;
                 x = (double)b[0]; y = (double)b[1]; z = (double)b[2];
             } else {
-                const double *b = reinterpret_cast<const double *>(p.pos) + ((size_t)f * n + j) * 3;
+                const double *b = reinterpret_cast<const double *>(p.pos) + (size_t)f * p.fstride + (size_t)j * 3;
                 x = b[0]; y = b[1]; z = b[2];
             }
             if (!atom_value(g, x, y, z, v)) return -1;
@@ -777,7 +778,7 @@ __global__ void __launch_bounds__(HC_THREADS, 2) k_hist_chunk(HistParams p) {
     // (ncu on the first version of this kernel: L1TEX pipe 83 % busy, 64 % excessive sectors).
     const bool planar32 = p.geometry == MB200_GEOM_PLANAR && p.is_f32 && !dig;
     const bool fast = !planar32 && p.geometry != MB200_GEOM_SCALAR && p.is_f32 && (((unsigned long long)(uintptr_t)p.pos) & 3ull) == 0;
-    const float *fbase = reinterpret_cast<const float *>(p.pos) + (size_t)f * n * 3;
+    const float *fbase = reinterpret_cast<const float *>(p.pos) + (size_t)f * p.fstride;
     if (fast) {
         const unsigned long long addr = (unsigned long long)(uintptr_t)fbase;
         while (a0 < n && ((addr + (unsigned long long)a0 * 12ull) & 15ull)) ++a0;
@@ -905,12 +906,21 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
                                   int positions_on_device, int64_t n_frames, int64_t n, int dim, const double *weights,
                                   int weights_per_frame, int weights_on_device, const double *edges, int32_t n_bins,
                                   const double *center, const double *zrange, double *hist_w, int64_t *hist_c) {
+    return mb200_profile_hist_window(ctx, geometry, positions, pos_is_f32, positions_on_device, n_frames, n, 0, n, dim, weights,
+                                     weights_per_frame, weights_on_device, edges, n_bins, center, zrange, hist_w, hist_c);
+}
+
+extern "C" int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const void *positions, int pos_is_f32,
+                                         int positions_on_device, int64_t n_frames, int64_t n_total, int64_t first_atom,
+                                         int64_t n, int dim, const double *weights, int weights_per_frame,
+                                         int weights_on_device, const double *edges, int32_t n_bins, const double *center,
+                                         const double *zrange, double *hist_w, int64_t *hist_c) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
     MB_LOCK(ctx);
     const int digitize = (geometry & MB200_BIN_DIGITIZE) ? 1 : 0;
     geometry &= ~MB200_BIN_DIGITIZE;
     if (geometry < 0 || geometry > 3 || n_frames < 0 || n < 0 || n_bins <= 0 || dim < 0 || dim > 2 || !edges || !hist_c ||
-        (n && !positions) || (weights && !hist_w))
+        (n && !positions) || (weights && !hist_w) || first_atom < 0 || first_atom + n > n_total)
         return fail(MB200_EINVAL, "invalid argument to mb200_profile_hist");
     if ((geometry == MB200_GEOM_CYLINDER || geometry == MB200_GEOM_SPHERE) && !center)
         return fail(MB200_EINVAL, "center required for radial geometries");
@@ -935,14 +945,25 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
     HistParams p;
     std::memset(&p, 0, sizeof(p));
     PrefetchRead pref_read(ctx);
+    // the group is atoms [first_atom, first_atom + n) of whole frames of n_total atoms (a window; n_total = n: the frames
+    // hold the group only)
+    const size_t NT = (size_t)n_total, win = (size_t)first_atom * ncomp * esz;
+    p.fstride = (long long)(NT * ncomp);
     if (positions_on_device || N == 0) {
-        p.pos = positions;
-    } else if (const void *pref = pref_read.take(positions, F * N * ncomp * esz)) {
-        p.pos = pref;  // announced with mb200_prefetch_frames: copied on the copy stream under the previous call
+        p.pos = reinterpret_cast<const char *>(positions) + win;
+    } else if (const void *pref = pref_read.take(positions, F * NT * ncomp * esz)) {
+        // announced with mb200_prefetch_frames: copied on the copy stream under the previous call
+        p.pos = reinterpret_cast<const char *>(pref) + win;
     } else {
         MB_TRY(ctx->d_hpos.ensure(F * N * ncomp * esz));
-        MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * ncomp * esz, cudaMemcpyHostToDevice, ctx->stream));
+        if (NT == N) {
+            MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * ncomp * esz, cudaMemcpyHostToDevice, ctx->stream));
+        } else {  // only the window travels
+            MB_CUDA(cudaMemcpy2DAsync(ctx->d_hpos.p, N * ncomp * esz, reinterpret_cast<const char *>(positions) + win,
+                                      NT * ncomp * esz, N * ncomp * esz, F, cudaMemcpyHostToDevice, ctx->stream));
+        }
         p.pos = ctx->d_hpos.p;
+        p.fstride = (long long)(N * ncomp);
     }
     const bool weighted = weights && N;
     const size_t Fw = weights_per_frame ? F : 1;

@@ -25,6 +25,7 @@ struct CompoundParams {
     double *centers;         // [F][n_c][3]
     double *weights;         // [F][n_c] or [F][3][n_c] or null
     long long n_atoms, n_c;
+    long long fstride;       // floats between two frames of `pos` (n_atoms * 3, more for a window of whole frames)
     int make_whole, wrap_center, weight_mode, pdim;
     // unit vector the dipole is projected on: 0 Cartesian e_pdim (lib/util.py:684-706), 1 radial direction of a cylinder
     // with axis uv_dim about the box centre (util.py:710-756), 2 radial direction of a sphere about the box centre (760-786)
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(128) k_compound(CompoundParams p) {
     if (c >= p.n_c) return;
     const long long a0 = p.ptr[c], a1 = p.ptr[c + 1];
     const int m = (int)(a1 - a0);
-    const float *q = p.pos + ((size_t)f * p.n_atoms + a0) * 3;
+    const float *q = p.pos + (size_t)f * p.fstride + (size_t)a0 * 3;
     const float bx = p.boxes[f * 3], by = p.boxes[f * 3 + 1], bz = p.boxes[f * 3 + 2];
 
     // pass 1: make whole (float32, about the first atom) and the mass-weighted centre for wrapping
@@ -291,8 +292,18 @@ extern "C" int mb200_compound_prologue_topo(mb200_ctx *ctx, const float *positio
                                             int64_t n_frames, const float *boxes, const mb200_topology *topo,
                                             int make_whole, int wrap_center, int weight_mode, int pdim,
                                             int uv_mode, int uv_dim, double *centers_dev, double *weights_dev) {
+    return mb200_compound_prologue_window(ctx, positions, positions_on_device, n_frames, topo ? topo->n_atoms : 0, 0, boxes, topo,
+                                          make_whole, wrap_center, weight_mode, pdim, uv_mode, uv_dim, centers_dev, weights_dev);
+}
+
+extern "C" int mb200_compound_prologue_window(mb200_ctx *ctx, const float *positions, int positions_on_device,
+                                              int64_t n_frames, int64_t n_total, int64_t first_atom, const float *boxes,
+                                              const mb200_topology *topo, int make_whole, int wrap_center, int weight_mode,
+                                              int pdim, int uv_mode, int uv_dim, double *centers_dev, double *weights_dev) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
     MB_LOCK(ctx);
+    if (topo && (first_atom < 0 || first_atom + topo->n_atoms > n_total))
+        return fail(MB200_EINVAL, "the window [first_atom, first_atom + n_atoms) does not fit the frames");
     if (!topo || n_frames < 0 || !boxes || !centers_dev || (topo->n_atoms && !positions) || weight_mode < 0 || weight_mode > 4 ||
         pdim < 0 || pdim > 2 || uv_mode < 0 || uv_mode > 2 || uv_dim < 0 || uv_dim > 2 || !topo->ptr)
         return fail(MB200_EINVAL, "invalid argument to mb200_compound_prologue");
@@ -316,14 +327,23 @@ extern "C" int mb200_compound_prologue_topo(mb200_ctx *ctx, const float *positio
     CompoundParams p;
     std::memset(&p, 0, sizeof(p));
     PrefetchRead pref_read(ctx);
+    // the topology's atoms are [first_atom, first_atom + N) of whole frames of n_total atoms
+    const size_t NT = (size_t)n_total;
+    p.fstride = (long long)(NT * 3);
     if (positions_on_device) {
-        p.pos = positions;
-    } else if (const void *pref = pref_read.take(positions, F * N * 12)) {
-        p.pos = reinterpret_cast<const float *>(pref);  // copied on the copy stream under the previous call
+        p.pos = positions + (size_t)first_atom * 3;
+    } else if (const void *pref = pref_read.take(positions, F * NT * 12)) {
+        p.pos = reinterpret_cast<const float *>(pref) + (size_t)first_atom * 3;  // copied on the copy stream under the previous call
     } else {
         MB_TRY(ctx->d_hpos.ensure(F * N * 12));
-        MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * 12, cudaMemcpyHostToDevice, ctx->stream));
+        if (NT == N) {
+            MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * 12, cudaMemcpyHostToDevice, ctx->stream));
+        } else {  // only the window travels
+            MB_CUDA(cudaMemcpy2DAsync(ctx->d_hpos.p, N * 12, positions + (size_t)first_atom * 3, NT * 12, N * 12, F,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        }
         p.pos = ctx->d_hpos.as<float>();
+        p.fstride = (long long)(N * 3);
     }
     MB_TRY(ctx->d_ctopo.ensure(F * 12 + 64));
     MB_CUDA(cudaMemcpyAsync(ctx->d_ctopo.p, boxes, F * 12, cudaMemcpyHostToDevice, ctx->stream));

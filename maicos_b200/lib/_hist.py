@@ -19,7 +19,8 @@ DIGITIZE = 0x10  # or-ed into the geometry: np.digitize(x, edges[1:-1]) semantic
 
 def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights: np.ndarray | None, edges: np.ndarray,
                  center: np.ndarray | None = None, zrange: np.ndarray | None = None, device: int | None = None,
-                 device_positions: tuple | None = None, device_weights: tuple | None = None, digitize: bool = False):
+                 device_positions: tuple | None = None, device_weights: tuple | None = None, digitize: bool = False,
+                 window: tuple | None = None):
     """Histogram ``positions [F, n, 3]`` (float32 or float64) into ``edges [F, n_bins + 1]``.
 
     ``geometry = SCALAR``: ``positions [F, n]`` is the binned coordinate itself.  ``digitize=True``: the bin is
@@ -28,6 +29,8 @@ def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights:
     ``weights``: ``None`` (counts only), ``[1, n]`` (same for all frames) or ``[F, n]``.
     ``device_positions = (pointer, F, n)``: float64 ``[F, n, 3]`` already in HBM (output of the
     compound prologue); ``device_weights = (pointer, per_frame)`` likewise.
+    ``window = (first, n)``: ``positions`` holds whole frames ``[F, n_total, 3]`` and the group is atoms
+    ``first .. first + n`` of each (``mb200_profile_hist_window``); weights are per group atom.
     Returns ``(hist_w float64 [F, n_bins] or None, hist_c int64 [F, n_bins])``.
 
     Accuracy of the weighted sums: every weight is quantised to ``Q = 2^(k - 52)`` with ``2^k >= max|w|`` of the frame
@@ -52,6 +55,11 @@ def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights:
             raise ValueError("positions must be float32 or float64")
         F, n = positions.shape[0], positions.shape[1]
         pos_ptr, pos_is_f32, pos_on_dev = _cabi.ptr(positions), int(positions.dtype == np.float32), 0
+    n_total, first = n, 0
+    if window is not None:
+        first, n = int(window[0]), int(window[1])
+        if first < 0 or first + n > n_total:
+            raise ValueError(f"window [{first}, {first + n}) does not fit frames of {n_total} atoms")
     edges = np.ascontiguousarray(edges, dtype=np.float64)
     if edges.shape[0] != F:
         raise ValueError("edges must have one row per frame")
@@ -74,8 +82,8 @@ def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights:
     hist_w = np.zeros((F, n_bins), dtype=np.float64) if weights is not None else None
     ctx = _cabi.context(device)
     _cabi.check(
-        _cabi.load().mb200_profile_hist(
-            ctx.handle, int(geometry) | (DIGITIZE if digitize else 0), pos_ptr, pos_is_f32, pos_on_dev, F, n, int(dim),
+        _cabi.load().mb200_profile_hist_window(
+            ctx.handle, int(geometry) | (DIGITIZE if digitize else 0), pos_ptr, pos_is_f32, pos_on_dev, F, n_total, first, n, int(dim),
             w_ptr, per_frame, w_on_dev, _cabi.ptr(edges), n_bins, _cabi.ptr(center), _cabi.ptr(zrange),
             _cabi.ptr(hist_w), _cabi.ptr(hist_c),
         )

@@ -199,6 +199,11 @@ class TRRTrajectory:
         self.ts = Timestep(pos, dims, f, float(fr["time"]), vel)
         return self.ts
 
+    @property
+    def has_pinned_frames(self) -> bool:
+        """True when frames are decoded into a ring of page-locked buffers (``pinned_ring=k``)."""
+        return self._ring_block is not None
+
     def pinned_row(self, f: int):
         """``(ring block, row)`` when frame ``f`` is the one currently held by its ring slot, else ``None``."""
         if self._ring_block is None:

@@ -154,6 +154,11 @@ class MemoryTrajectory:
         self.ts = Timestep(np.ascontiguousarray(pos, dtype=np.float32), dims, f, float(t), vel)
         return self.ts
 
+    @property
+    def has_pinned_frames(self) -> bool:
+        """True when the frames live in page-locked memory (``pinned_row`` can answer)."""
+        return self._pinned_rows is not None or self._pinned_block is not None
+
     def pinned_row(self, f: int):
         """``(page-locked float32 block [*, n_atoms, 3], row)`` holding frame ``f``, or ``None``."""
         if self._pinned_rows is not None:

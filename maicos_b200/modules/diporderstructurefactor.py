@@ -29,6 +29,8 @@ class DiporderStructureFactor(AnalysisBase):
     """
 
     _batch_size = 16
+    #: a contiguous selection is read out of whole frames of a page-locked trajectory (``AnalysisBase._frame_window``)
+    _window_capable = "range"
 
     def __init__(self, atomgroup, bin_method: str = "com", grouping: str = "molecules", refgroup=None,
                  unwrap: bool = True, pack: bool = True, jitter: float = 0.0, concfreq: int = 0, qmin: float = 0,
@@ -56,7 +58,9 @@ class DiporderStructureFactor(AnalysisBase):
                                                   weight_mode=4)
             except ValueError:
                 self._prologue = None
-        self._batch_size = int(max(1, min(type(self)._batch_size, (128 << 20) // max(1, self.atomgroup.n_atoms * 12))))
+        window = self._frame_window() if self._prologue is not None else None  # whole frames of a page-locked trajectory
+        n_staged = window[0] if window is not None else self.atomgroup.n_atoms
+        self._batch_size = int(max(1, min(type(self)._batch_size, (128 << 20) // max(1, n_staged * 12))))
 
     def _stage_frame(self):
         box = np.double(np.array(cell_diagonal(self._ts.dimensions), dtype=np.float32))  # diporderstructurefactor.py:94
@@ -83,7 +87,7 @@ class DiporderStructureFactor(AnalysisBase):
         on_device = 0
         if self._prologue is not None:
             raw = self._gather_staged([(st[0], st[1]) for st in staged])
-            pos, w = self._prologue.run(raw, boxes.astype(np.float32))
+            pos, w = self._prologue.run(raw, boxes.astype(np.float32), window=self._frame_window())
             n, on_device = self._prologue.n_c, 1
         else:
             n = staged[0][0].shape[0]

@@ -154,6 +154,8 @@ class Saxs(AnalysisBase):
 
     _batch_size = 32
     _device_pack = True
+    #: any selection is gathered by index on the device: with a page-locked trajectory whole frames are staged as they are
+    _window_capable = "indices"
 
     def __init__(self, atomgroup, unwrap: bool = False, pack: bool = True, refgroup=None, jitter: float = 0.0,
                  concfreq: int = 0, bin_spectrum: bool = True, qmin: float = 0, qmax: float = 6, dq: float = 0.1,
@@ -186,20 +188,25 @@ class Saxs(AnalysisBase):
         unique, inverse = _element_groups(self.atomgroup)
         universe = self.atomgroup.universe
         cache = universe.__dict__.setdefault("_mb200_saxs_groups", {}) if hasattr(universe, "__dict__") else {}
-        prepared = cache.get(id(inverse))  # `inverse` lives in the element-group cache: same selection, same object
+        window = self._frame_window()  # whole frames staged: the groups index the universe's atoms, not the selection's
+        key = (id(inverse), window is not None)
+        prepared = cache.get(key)  # `inverse` lives in the element-group cache: same selection, same object
         if prepared is None or prepared[0] is not inverse:
             index = [np.flatnonzero(inverse == g).astype(np.int32) for g in range(len(unique))]
             ptr = np.concatenate([[0], np.cumsum([len(i) for i in index])]).astype(np.int64)
             flat = np.ascontiguousarray(np.concatenate(index), dtype=np.int32)
+            if window is not None:
+                flat = np.ascontiguousarray(np.asarray(self.atomgroup.indices)[flat], dtype=np.int32)
             cm = np.ascontiguousarray(np.stack([tables.cm_packed(str(el)) for el in unique]))
-            prepared = cache[id(inverse)] = (inverse, index, ptr, flat, cm, {})
+            prepared = cache[key] = (inverse, index, ptr, flat, cm, {})
         _, self._group_index, self._group_ptr, self._group_flat, self._cm, self._groups_handles = prepared
+        self._n_staged_atoms = window[0] if window is not None else self.atomgroup.n_atoms
         self.elements = list(unique)
         self.groups = _GroupList(self.atomgroup, self._group_index)
         self.weights = _OnesList(self._group_index)
 
         # frames per device call: bounded by ~128 MB of staged positions (and by the table workspace)
-        self._batch_size = int(max(1, min(type(self)._batch_size, (128 << 20) // max(1, self.atomgroup.n_atoms * 12))))
+        self._batch_size = int(max(1, min(type(self)._batch_size, (128 << 20) // max(1, self._n_staged_atoms * 12))))
         if self.bin_spectrum:
             self.n_bins = int(np.ceil((self.qmax - self.qmin) / self.dq))
         else:
@@ -273,7 +280,7 @@ class Saxs(AnalysisBase):
 
             handle = ctypes.c_void_p()
             _cabi.check(_cabi.load().mb200_groups_create(ctx.handle, _cabi.ptr(self._group_flat), _cabi.ptr(self._group_ptr),
-                                                         len(self._group_index), self.atomgroup.n_atoms, ctypes.byref(handle)))
+                                                         len(self._group_index), self._n_staged_atoms, ctypes.byref(handle)))
             # kept with the universe's prepared selection (further analyses of the same selection reuse it), destroyed
             # with the universe
             self._groups_handles[ctx.device] = handle

@@ -751,3 +751,56 @@ def test_collection_members_share_one_copy_of_the_frames(precision):
             assert_array_equal(np.asarray(a.sums[key]), np.asarray(b.sums[key]), err_msg=f"{type(a).__name__}.{key}")
         for key in b.means:
             assert_array_equal(np.asarray(a.means[key]), np.asarray(b.means[key]), err_msg=f"{type(a).__name__}.{key}")
+
+
+# ---- selections read out of whole frames of a page-locked trajectory (no gather on the host) ------------------------
+def test_selections_are_read_out_of_whole_pinned_frames(precision):
+    """A contiguous selection (the water of a slab system) and, for Saxs, any selection: with the trajectory in page-locked
+    memory the analyses stage the trajectory's own rows (whole frames) and address their atoms on the device
+    (``mb200_profile_hist_window``, ``mb200_compound_prologue_window``, group indices into the universe).  Results equal the
+    runs from a pageable trajectory (selection gathered on the host) bit for bit, and in a collection the frames travel
+    once for all members."""
+    from maicos_b200.mdshim import MemoryTrajectory, Universe
+
+    fr, topo = mb.synthetic.confined_slab_frames(1200, 300, 30.0, 30.0, 40.0, 24.0, 5, n_frames=40)
+    dims = np.float32([30, 30, 40, 90, 90, 90])
+    u_pg = Universe(fr.shape[1], MemoryTrajectory(fr.copy(), dims), **topo)
+    u_pin = Universe(fr.shape[1], MemoryTrajectory(fr.copy(), dims, pinned=True), **topo)
+
+    def members(u):
+        water = u.select_atoms("element O H")
+        oxygen = u.select_atoms("element O")          # every third atom of the water: not contiguous
+        assert water.n_atoms == 3600 and water.indices[0] == 300
+        return [mb.DensityPlanar(water, dens="mass", bin_width=0.2, unwrap=False, pack=False),
+                mb.DensityPlanar(u.atoms, dens="number", bin_width=0.2, unwrap=False, pack=False),
+                mb.DiporderPlanar(water, bin_width=0.5, unwrap=False, pack=False),
+                mb.DensityCylinder(water, dens="charge", bin_width=0.5, unwrap=False, pack=False),
+                mb.Saxs(water, qmax=2.0, dq=0.1),
+                mb.Saxs(oxygen, qmax=2.0, dq=0.1),
+                mb.DiporderStructureFactor(water, qmax=2.0, dq=0.1)]
+
+    pinned, pageable = members(u_pin), members(u_pg)
+    for m in pinned + pageable:
+        m.run()
+    windows = [m._frame_window() for m in pinned]
+    assert windows[0] == (3900, 300) and windows[1] is None and windows[2] == (3900, 300) and windows[3] == (3900, 300)
+    assert windows[4] == (3900, None) and windows[5] == (3900, None) and windows[6] == (3900, 300)
+    assert all(m._frame_window() is None for m in pageable)
+    for a, b in zip(pinned, pageable):
+        for key in b.sums:
+            assert_array_equal(np.asarray(a.sums[key]), np.asarray(b.sums[key]), err_msg=f"{type(a).__name__}.{key}")
+        for key in b.means:
+            assert_array_equal(np.asarray(a.means[key]), np.asarray(b.means[key]), err_msg=f"{type(a).__name__}.{key}")
+
+    # in one collection: every member reads the same whole frames -> one host -> device copy per batch
+    lib, ctx = _cabi.load(), _cabi.context()
+    before, after = np.zeros(3, dtype=np.int64), np.zeros(3, dtype=np.int64)
+    _cabi.check(lib.mb200_ctx_prefetch_stats(ctx.handle, _cabi.ptr(before)))
+    together = members(u_pin)
+    mb.AnalysisCollection(*together).run()
+    _cabi.check(lib.mb200_ctx_prefetch_stats(ctx.handle, _cabi.ptr(after)))
+    copies, saved, _ = (after - before).tolist()
+    assert copies > 0 and saved == 6 * copies, (copies, saved)
+    for a, b in zip(together, pageable):
+        for key in b.means:
+            assert_array_equal(np.asarray(a.means[key]), np.asarray(b.means[key]), err_msg=f"collection {type(a).__name__}.{key}")

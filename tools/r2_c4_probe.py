@@ -19,6 +19,7 @@ fr, topo = confined_slab_frames(300_000, 100_000, *box, 200.0, 20261021, n_frame
 u_pg = Universe(fr.shape[1], MemoryTrajectory(fr, np.float32([*box, 90, 90, 90])), **topo)
 u = Universe(fr.shape[1], MemoryTrajectory(fr, np.float32([*box, 90, 90, 90]), pinned=True), **topo)
 lib, ctx = _cabi.load(), _cabi.context()
+WATER = {id(u): u.select_atoms("element O H"), id(u_pg): u_pg.select_atoms("element O H")}
 
 
 def pstat():
@@ -34,7 +35,7 @@ def run(uu, label, cls=None, **kw):
     if cls is None:
         a = mb.DensityPlanar(uu.atoms, dens="mass", bin_width=0.1, unwrap=False, pack=False).run(**kw)
     else:
-        a = cls(uu.select_atoms("element O H"), bin_width=0.1, unwrap=False, pack=False).run(**kw)
+        a = cls(WATER[id(uu)], bin_width=0.1, unwrap=False, pack=False).run(**kw)
     dt = time.perf_counter() - t
     print(f"{label:10s} {a.n_frames / dt:8.0f} fps  {dt * 1e3:7.1f} ms  prefetch {(pstat() - p0).tolist()}  "
           + " ".join(f"{k}={v * 1e3:.1f}" for k, v in a.timings.items()), flush=True)
@@ -51,6 +52,17 @@ for i in range(3):
     run(u, "pinned")
 for i in range(4):
     run(u, "diporder", cls=mb.DiporderPlanar)
+for i in range(3):
+    run(u_pg, "diporder pg", cls=mb.DiporderPlanar)
 import os  # noqa: E402
 if os.environ.get("MAICOS_B200_TRACE_HOST"):
     print("traced run above", flush=True)
+if os.environ.get("MB200_PROFILE"):
+    import cProfile
+    import pstats
+    water = u.select_atoms("element O H")
+    pr = cProfile.Profile()
+    pr.enable()
+    mb.DiporderPlanar(water, bin_width=0.1, unwrap=False, pack=False).run()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
