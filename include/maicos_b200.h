@@ -341,10 +341,14 @@ int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *positions, int 
  * for MB200_GEOM_SCALAR) and the group is atoms [first_atom, first_atom + n) of every frame -- a contiguous selection (the
  * water of a slab system) is binned where the trajectory holds the frames, without a gather on the host, and frames
  * announced with mb200_prefetch_frames[_shared] as whole frames serve every analysis of a collection.  Weights are
- * per group atom ([n] or [n_frames][n]) as before. */
+ * per group atom ([n] or [n_frames][n]) as before.
+ *   pack_boxes : NULL, or host float32 [n_frames][3] cell lengths -- the float32 positions are first wrapped into the
+ *                primary cell on the device, x -= floor(x / L) * L in float32, which is what the reference's frame loop does
+ *                on the host for every frame with pack=True and atoms grouping (src/maicos/core/base.py:446-448,
+ *                `universe.atoms.wrap(compound="atoms")`). */
 int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const void *positions, int pos_is_f32,
                               int positions_on_device, int64_t n_frames, int64_t n_total, int64_t first_atom,
-                              int64_t n, int dim, const double *weights, int weights_per_frame,
+                              int64_t n, const float *pack_boxes, int dim, const double *weights, int weights_per_frame,
                               int weights_on_device, const double *edges, int32_t n_bins, const double *center,
                               const double *zrange, double *hist_w, int64_t *hist_c);
 

@@ -1051,6 +1051,15 @@ class ProfileBase:
                                                  prologue=self._prologue)
             except ValueError:
                 self._velocity = None
+        # atoms grouping with pack=True: the reference wraps every atom of the universe on the host in every frame
+        # (base.py:446-448); when nothing else needs the wrapped coordinates (weights from the topology or the velocities)
+        # the float32 wrap runs on the device in front of the histogram (``pack_boxes`` of mb200_profile_hist_window)
+        dims = self.atomgroup.universe.dimensions
+        self._device_pack = bool(
+            self.grouping == "atoms" and getattr(self, "pack", False) and not getattr(self, "jitter", 0.0)
+            and (self._static_weights or self._velocity is not None)
+            and getattr(type(self)._single_frame, "_from_batch", False)
+            and dims is not None and is_orthorhombic(dims))
         win = self._frame_window()  # whole frames of a page-locked trajectory travel: size the batches by them
         if win is not None:
             self._batch_size = int(max(1, min(64, (128 << 20) // max(1, win[0] * 12))))
@@ -1110,6 +1119,8 @@ class ProfileBase:
             return st
         if self.grouping == "atoms":
             buf, row = self._stage_positions()
+            if self._device_pack:
+                st["box"] = np.array(self._universe.dimensions[:3], dtype=np.float32)
         else:
             centres = get_center(self.atomgroup, bin_method=self.bin_method, compound=self.grouping)
             buf, row = self._staging_rows(centres.shape, np.float64, "pos")
@@ -1169,11 +1180,13 @@ class ProfileBase:
         else:
             win = self._frame_window() if self.grouping == "atoms" else None  # else: centres formed on the host
             win = None if win is None else (win[1], self.atomgroup.n_atoms)  # atoms [first, first + n) of whole frames
+            boxes = np.stack([s["box"] for s in staged]) if (self._device_pack and self.grouping == "atoms") else None
             if self._static_weights:
-                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange, window=win,
+                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange, window=win, pack_boxes=boxes,
                                       device_weights=(self._static_weights_on_device(g0["weights"]), False))
             elif vel_w is not None:
-                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange, device_weights=vel_w, window=win)
+                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange, device_weights=vel_w, window=win,
+                                      pack_boxes=boxes)
             else:
                 w = self._gather_rows([s["weights"] for s in staged])
                 hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], w, edges, center, zrange, window=win)

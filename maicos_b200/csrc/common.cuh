@@ -156,7 +156,7 @@ struct mb200_ctx {
     mb200::DevBuf d_pos, d_w, d_idx, d_tables, d_amp, d_sval, d_jobs, d_segs, d_items, d_out, d_ff2, d_counter, d_bimg, d_tcdesc, d_owned;
     mb200::PinBuf h_stage, h_out;
     // histogram workspaces
-    mb200::DevBuf d_hpos, d_hw, d_hw2, d_hedges, d_hpar, d_hout, d_ctopo;
+    mb200::DevBuf d_hpos, d_hpack, d_hw, d_hw2, d_hedges, d_hpar, d_hout, d_ctopo;
     // host -> device prefetch of the next batch of frames (mb200_prefetch_frames): copy stream, two buffers
     cudaStream_t copy_stream = nullptr;
     static constexpr int N_PREF = 4;  // a collection of two analyses keeps four announcements alive (2 each)

@@ -103,6 +103,21 @@ __global__ void __launch_bounds__(256) k_hist_wmax(const double *__restrict__ w,
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out + blockIdx.y, m);
 }
 
+// AtomGroup.wrap(compound="atoms") of float32 positions -- x -= floor(x / L) * L, every operation rounded to float32 as
+// numpy does it (core/base.py:446-448 of the reference calls it on the host for every frame) -- from a window of whole
+// frames into a dense [F][n][3] buffer
+__global__ void __launch_bounds__(256) k_pack_atoms(const float *__restrict__ src, long long src_fstride, float *__restrict__ dst,
+                                                    const float *__restrict__ boxes, long long n3) {
+    const long long f = blockIdx.y;
+    const float *s = src + (size_t)f * src_fstride;
+    float *d = dst + (size_t)f * n3;
+    const float L[3] = {boxes[f * 3], boxes[f * 3 + 1], boxes[f * 3 + 2]};
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n3; e += (long long)gridDim.x * blockDim.x) {
+        const float l = L[e % 3], x = s[e];
+        d[e] = __fsub_rn(x, __fmul_rn(floorf(__fdiv_rn(x, l)), l));
+    }
+}
+
 struct FrameGeom {
     double cx, cy, cz, zlo, zhi, first, last, inv_width;
     int d0, d1, d2, geometry, nb, digitize;
@@ -906,13 +921,13 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
                                   int positions_on_device, int64_t n_frames, int64_t n, int dim, const double *weights,
                                   int weights_per_frame, int weights_on_device, const double *edges, int32_t n_bins,
                                   const double *center, const double *zrange, double *hist_w, int64_t *hist_c) {
-    return mb200_profile_hist_window(ctx, geometry, positions, pos_is_f32, positions_on_device, n_frames, n, 0, n, dim, weights,
-                                     weights_per_frame, weights_on_device, edges, n_bins, center, zrange, hist_w, hist_c);
+    return mb200_profile_hist_window(ctx, geometry, positions, pos_is_f32, positions_on_device, n_frames, n, 0, n, nullptr, dim,
+                                     weights, weights_per_frame, weights_on_device, edges, n_bins, center, zrange, hist_w, hist_c);
 }
 
 extern "C" int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const void *positions, int pos_is_f32,
                                          int positions_on_device, int64_t n_frames, int64_t n_total, int64_t first_atom,
-                                         int64_t n, int dim, const double *weights, int weights_per_frame,
+                                         int64_t n, const float *pack_boxes, int dim, const double *weights, int weights_per_frame,
                                          int weights_on_device, const double *edges, int32_t n_bins, const double *center,
                                          const double *zrange, double *hist_w, int64_t *hist_c) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
@@ -922,6 +937,8 @@ extern "C" int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const voi
     if (geometry < 0 || geometry > 3 || n_frames < 0 || n < 0 || n_bins <= 0 || dim < 0 || dim > 2 || !edges || !hist_c ||
         (n && !positions) || (weights && !hist_w) || first_atom < 0 || first_atom + n > n_total)
         return fail(MB200_EINVAL, "invalid argument to mb200_profile_hist");
+    if (pack_boxes && (!pos_is_f32 || geometry == MB200_GEOM_SCALAR))
+        return fail(MB200_EINVAL, "pack_boxes wraps float32 atom positions (as AtomGroup.wrap does)");
     if ((geometry == MB200_GEOM_CYLINDER || geometry == MB200_GEOM_SPHERE) && !center)
         return fail(MB200_EINVAL, "center required for radial geometries");
     if (geometry == MB200_GEOM_CYLINDER && !zrange && !digitize) return fail(MB200_EINVAL, "zrange required for cylinder geometry");
@@ -977,7 +994,8 @@ extern "C" int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const voi
         }
     }
     // small per-frame parameters: edges | center | zrange | wmax bits -- gathered in the pinned staging block, ONE copy
-    const size_t n_par = F * (NB + 1) + F * 3 + F * 2 + F;
+    const size_t n_box = pack_boxes ? (F * 3 + 1) / 2 : 0;  // float32 [F][3] in units of doubles
+    const size_t n_par = F * (NB + 1) + F * 3 + F * 2 + n_box + F;
     MB_TRY(ctx->d_hpar.ensure(n_par * 8));
     MB_TRY(ctx->h_stage.ensure(n_par * 8));  // the previous call synchronised the stream before it returned
     double *dpar = ctx->d_hpar.as<double>();
@@ -992,8 +1010,21 @@ extern "C" int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const voi
         std::memcpy(hpar + F * (NB + 1) + F * 3, zrange, F * 16);
         p.zrange = dpar + F * (NB + 1) + F * 3;
     }
-    MB_CUDA(cudaMemcpyAsync(dpar, hpar, (F * (NB + 1) + F * 5) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    unsigned long long *d_wmax = reinterpret_cast<unsigned long long *>(dpar + F * (NB + 1) + F * 5);
+    if (pack_boxes) std::memcpy(hpar + F * (NB + 1) + F * 5, pack_boxes, F * 12);
+    MB_CUDA(cudaMemcpyAsync(dpar, hpar, (F * (NB + 1) + F * 5 + n_box) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long *d_wmax = reinterpret_cast<unsigned long long *>(dpar + F * (NB + 1) + F * 5 + n_box);
+    if (pack_boxes && N) {  // wrap into the primary cell on the device: dense float32 copy of the group, then binned as usual
+        MB_TRY(ctx->d_hpack.ensure(F * N * 12));
+        const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((N * 3 + 256 * 8 - 1) / (256 * 8), (size_t)ctx->n_sm * 8 / F + 1));
+        k_pack_atoms<<<dim3(gx, (unsigned)F), 256, 0, ctx->stream>>>(reinterpret_cast<const float *>(p.pos), p.fstride,
+                                                                     ctx->d_hpack.as<float>(),
+                                                                     reinterpret_cast<const float *>(dpar + F * (NB + 1) + F * 5),
+                                                                     (long long)(N * 3));
+        MB_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        p.pos = ctx->d_hpack.p;
+        p.fstride = (long long)(N * 3);
+    }
     p.wmax_bits = d_wmax;
     // accumulators [F][NB]: lo, hi, f64, count + outputs [F][NB] (w, c)
     const size_t acc = F * NB;

@@ -20,7 +20,7 @@ DIGITIZE = 0x10  # or-ed into the geometry: np.digitize(x, edges[1:-1]) semantic
 def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights: np.ndarray | None, edges: np.ndarray,
                  center: np.ndarray | None = None, zrange: np.ndarray | None = None, device: int | None = None,
                  device_positions: tuple | None = None, device_weights: tuple | None = None, digitize: bool = False,
-                 window: tuple | None = None):
+                 window: tuple | None = None, pack_boxes: np.ndarray | None = None):
     """Histogram ``positions [F, n, 3]`` (float32 or float64) into ``edges [F, n_bins + 1]``.
 
     ``geometry = SCALAR``: ``positions [F, n]`` is the binned coordinate itself.  ``digitize=True``: the bin is
@@ -31,6 +31,8 @@ def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights:
     compound prologue); ``device_weights = (pointer, per_frame)`` likewise.
     ``window = (first, n)``: ``positions`` holds whole frames ``[F, n_total, 3]`` and the group is atoms
     ``first .. first + n`` of each (``mb200_profile_hist_window``); weights are per group atom.
+    ``pack_boxes``: float32 ``[F, 3]`` cell lengths -- float32 positions are wrapped into the primary cell on the device
+    first (``AtomGroup.wrap(compound="atoms")``: ``x -= floor(x / L) * L`` in float32).
     Returns ``(hist_w float64 [F, n_bins] or None, hist_c int64 [F, n_bins])``.
 
     Accuracy of the weighted sums: every weight is quantised to ``Q = 2^(k - 52)`` with ``2^k >= max|w|`` of the frame
@@ -78,12 +80,17 @@ def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights:
         center = np.ascontiguousarray(center, dtype=np.float64)
     if zrange is not None:
         zrange = np.ascontiguousarray(zrange, dtype=np.float64)
+    if pack_boxes is not None:
+        pack_boxes = np.ascontiguousarray(pack_boxes, dtype=np.float32)
+        if pack_boxes.shape != (F, 3):
+            raise ValueError("pack_boxes must have shape (n_frames, 3)")
     hist_c = np.zeros((F, n_bins), dtype=np.int64)
     hist_w = np.zeros((F, n_bins), dtype=np.float64) if weights is not None else None
     ctx = _cabi.context(device)
     _cabi.check(
         _cabi.load().mb200_profile_hist_window(
-            ctx.handle, int(geometry) | (DIGITIZE if digitize else 0), pos_ptr, pos_is_f32, pos_on_dev, F, n_total, first, n, int(dim),
+            ctx.handle, int(geometry) | (DIGITIZE if digitize else 0), pos_ptr, pos_is_f32, pos_on_dev, F, n_total, first, n,
+            _cabi.ptr(pack_boxes), int(dim),
             w_ptr, per_frame, w_on_dev, _cabi.ptr(edges), n_bins, _cabi.ptr(center), _cabi.ptr(zrange),
             _cabi.ptr(hist_w), _cabi.ptr(hist_c),
         )

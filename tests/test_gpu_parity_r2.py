@@ -804,3 +804,54 @@ def test_selections_are_read_out_of_whole_pinned_frames(precision):
     for a, b in zip(together, pageable):
         for key in b.means:
             assert_array_equal(np.asarray(a.means[key]), np.asarray(b.means[key]), err_msg=f"collection {type(a).__name__}.{key}")
+
+
+# ---- pack=True with atoms grouping: the float32 wrap of base.py:446-448 runs in front of the histogram on the device ----
+@pytest.mark.parametrize("pinned", [False, True])
+def test_profiles_with_default_pack_wrap_the_atoms_on_the_device(pinned, precision):
+    """``DensityPlanar / DensityCylinder / DensitySphere`` and ``VelocityPlanar`` with the reference's default ``pack=True``:
+    atoms far outside the cell (and on either side of 0 and L) are wrapped with numpy's float32 arithmetic,
+    ``x - floor(x / L) * L``, before they are binned; counts and weighted sums equal the oracle's histogram of the
+    host-wrapped frame, and the host loop no longer touches the coordinates (whole frames of a page-locked trajectory are
+    staged as they are, also for the water selection)."""
+    from maicos_b200.mdshim import MemoryTrajectory, Universe
+
+    fr, topo = mb.synthetic.confined_slab_frames(900, 240, 30.0, 28.0, 40.0, 24.0, 9, n_frames=6)
+    rng = np.random.default_rng(4)
+    fr = (fr + rng.integers(-3, 4, size=(fr.shape[0], fr.shape[1], 3)).astype(np.float32) * np.float32([30.0, 28.0, 40.0])
+          + np.float32(1e-3)).astype(np.float32)
+    fr[:, :5] = np.float32([[0.0, 28.0, 40.0], [30.0, 0.0, -0.0], [-1e-6, 27.999998, 39.999996], [29.999998, -28.0, 80.0],
+                            [1e-30, -1e-30, 120.0]])
+    dims = np.float32([30, 28, 40, 90, 90, 90])
+    vel = rng.normal(size=fr.shape).astype(np.float32)
+    u = Universe(fr.shape[1], MemoryTrajectory(fr.copy(), dims, velocities=vel, pinned=pinned), **topo)
+    water = u.select_atoms("element O H")
+    box = dims[:3]
+    wrapped = [restatement.wrap_atoms_f32(f, box) for f in fr]
+    first = int(water.indices[0])
+
+    dens = mb.DensityPlanar(water, dens="mass", bin_width=0.25).run()
+    assert dens._device_pack and (dens._frame_window() == (fr.shape[1], first)) == pinned
+    nb = dens.n_bins
+    vol = restatement.planar_geometry(np.double(box), 2, nb)[2]["bin_volume"]
+    ref_c = np.sum([restatement.hist_planar(w[first:], None, 2, nb, 0.0, np.float64(box[2])) for w in wrapped], axis=0)
+    ref_w = np.mean([restatement.hist_planar(w[first:], water.masses, 2, nb, 0.0, np.float64(box[2])) for w in wrapped], axis=0)
+    assert_array_equal(dens.sums.bincount, ref_c)
+    assert_allclose(dens.means.profile * vol, ref_w, rtol=1e-12, atol=1e-12)
+    assert dens.sums.bincount.sum() == len(fr) * water.n_atoms  # every atom is inside after the wrap
+
+    cyl = mb.DensityCylinder(u.atoms, dens="number", bin_width=0.5).run()
+    assert cyl._device_pack
+    centre = np.double(box) / 2
+    rc = np.sum([restatement.hist_cylinder(np.double(w), None, 2, cyl.n_bins, 0.0, cyl.rmax, 0.0, np.float64(box[2]), centre)
+                 for w in wrapped], axis=0)
+    assert_array_equal(cyl.sums.bincount, rc)
+
+    sph = mb.DensitySphere(water, dens="charge", bin_width=0.5).run()
+    rs = np.sum([restatement.hist_sphere(np.double(w[first:]), None, sph.n_bins, 0.0, sph.rmax, centre) for w in wrapped], axis=0)
+    assert_array_equal(sph.sums.bincount, rs)
+
+    velp = mb.VelocityPlanar(u.atoms, bin_width=0.5, vdim=0).run()
+    assert velp._device_pack
+    rv = np.sum([restatement.hist_planar(w, None, 2, velp.n_bins, 0.0, np.float64(box[2])) for w in wrapped], axis=0)
+    assert_array_equal(velp.sums.bincount, rv)
