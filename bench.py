@@ -639,6 +639,17 @@ def run_configs(args, ctx, lib, torch, rank, world, peaks):
                        "bincount_equal": bool(np.array_equal(one.sums.bincount, ref_c)),
                        "max_rel_err_profile": float(np.max(np.abs(one.means.profile[nzw] * geo["bin_volume"][nzw] / ref_w[nzw] - 1))),
                        "tolerance": "counts exact, weighted sums rel <= 1e-12"}}
+        # the reference's default arguments (pack=True: `universe.atoms.wrap()` on the host in every frame, base.py:446-448):
+        # the float32 wrap runs on the device in front of the histogram
+        run_dp = lambda: mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.1).run()  # noqa: E731
+        run_dp()
+        a_dp, dt_dp, _ = timed(run_dp, passes=3)
+        wr0 = restatement.wrap_atoms_f32(fr[0], np.float32(box))
+        one_dp = mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.1).run(stop=1)
+        out["C4_densityplanar_1M"]["default_arguments_pack_true"] = {
+            "frames_per_s": a_dp.n_frames / dt_dp, "e2e_seconds": dt_dp, "host_timings_s": a_dp.timings,
+            "parity": {"checked": "frame 0 vs np.histogram of the host-wrapped frame (x - floor(x / L) L in float32)",
+                       "bincount_equal": bool(np.array_equal(one_dp.sums.bincount, restatement.hist_planar(wr0, None, 2, a.n_bins, zmin, zmax)))}}
         # C4 as BASELINE.json words it -- DensityPlanar + DiporderPlanar over the same trajectory -- in ONE frame loop
         # (AnalysisCollection, core/base.py:602-718): the members (the whole system, and the water as a window of the whole
         # frames) read the frames where the page-locked trajectory holds them and share one host -> device copy per batch
