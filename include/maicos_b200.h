@@ -342,13 +342,16 @@ int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *positions, int 
  * water of a slab system) is binned where the trajectory holds the frames, without a gather on the host, and frames
  * announced with mb200_prefetch_frames[_shared] as whole frames serve every analysis of a collection.  Weights are
  * per group atom ([n] or [n_frames][n]) as before.
+ *   selection  : NULL, or one group of n atom indices into the whole frames (mb200_groups_create with n_groups = 1 and
+ *                n_atoms_total = n_total; first_atom = 0): ANY selection ("type OW") is gathered on the device.
  *   pack_boxes : NULL, or host float32 [n_frames][3] cell lengths -- the float32 positions are first wrapped into the
  *                primary cell on the device, x -= floor(x / L) * L in float32, which is what the reference's frame loop does
  *                on the host for every frame with pack=True and atoms grouping (src/maicos/core/base.py:446-448,
  *                `universe.atoms.wrap(compound="atoms")`). */
 int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const void *positions, int pos_is_f32,
                               int positions_on_device, int64_t n_frames, int64_t n_total, int64_t first_atom,
-                              int64_t n, const float *pack_boxes, int dim, const double *weights, int weights_per_frame,
+                              int64_t n, const mb200_groups *selection, const float *pack_boxes, int dim,
+                              const double *weights, int weights_per_frame,
                               int weights_on_device, const double *edges, int32_t n_bins, const double *center,
                               const double *zrange, double *hist_w, int64_t *hist_c);
 

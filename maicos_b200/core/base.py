@@ -615,20 +615,22 @@ class AnalysisBase(_Runner):
         (one host pass over the selection).  When the trajectory lives in page-locked memory and nothing transforms the
         frames on the host, classes that can address their atoms inside a whole frame (``_window_capable``: ``"range"`` --
         a contiguous selection, as the water of a slab system; ``"indices"`` -- any selection, Saxs gathers by index on
-        the device anyway) stage the trajectory's own rows instead: no host copy, and in a collection the frames reach the
-        device once for all members.  ``first`` is ``None`` for ``"indices"``."""
+        the device anyway, the profiles of single atoms copy them out of the frame in front of the histogram) stage the
+        trajectory's own rows instead: no host copy, and in a collection the frames reach the device once for all
+        members.  ``first`` is ``None`` for a selection that is not one contiguous range."""
         if self._window_state is False:
             self._window_state = None
             mode = getattr(self, "_window_capable", None)
+            mode = mode() if callable(mode) else mode
             ag = self.atomgroup
             if (mode and not getattr(ag, "_all", False) and getattr(self._trajectory, "has_pinned_frames", False)
                     and hasattr(ag, "indices") and not self._host_transforms()):
                 idx = np.asarray(ag.indices)
                 n_total = int(self._universe.atoms.n_atoms)
-                if mode == "indices":
-                    self._window_state = (n_total, None)
-                elif len(idx) and int(idx[-1]) - int(idx[0]) + 1 == len(idx) and (len(idx) < 2 or bool(np.all(np.diff(idx) == 1))):
+                if len(idx) and int(idx[-1]) - int(idx[0]) + 1 == len(idx) and (len(idx) < 2 or bool(np.all(np.diff(idx) == 1))):
                     self._window_state = (n_total, int(idx[0]))
+                elif mode == "indices":
+                    self._window_state = (n_total, None)
         return self._window_state
 
     def _transform_frame(self, ts) -> None:
@@ -916,6 +918,9 @@ class AnalysisBase(_Runner):
         from .. import _cabi
 
         _cabi.release_pinned(self._slot_prefix())  # staging buffers live for one run
+        release_selection = getattr(self, "_release_selection", None)
+        if release_selection is not None:
+            release_selection()
 
     def run(self, start=None, stop=None, step=None, frames=None, verbose=None, progressbar_kwargs=None):
         """Iterate over the trajectory (same arguments as ``maicos.core.AnalysisBase.run``)."""
@@ -988,8 +993,10 @@ class ProfileBase:
 
     #: set by modules whose weights depend on topology only (masses, charges, counts)
     _static_weights = False
-    #: a contiguous selection is read out of whole frames of a page-locked trajectory (``AnalysisBase._frame_window``)
-    _window_capable = "range"
+    def _window_capable(self) -> str:
+        """A selection is read out of whole frames of a page-locked trajectory (``AnalysisBase._frame_window``): single
+        atoms by index, compounds (device prologue) when they form one contiguous range."""
+        return "indices" if self.grouping == "atoms" else "range"
 
     def __init__(self, atomgroup, grouping: str, bin_method: str, output: str, weighting_function: Callable,
                  weighting_function_kwargs: None | dict, normalization: str) -> None:
@@ -1145,6 +1152,29 @@ class ProfileBase:
         if staged and (self._prologue is not None or self.grouping == "atoms"):
             self._announce_rows([s["positions"] for s in staged])
 
+    def _selection_on_device(self):
+        """Handle of the atom group's indices into whole frames on the calling thread's device (uploaded once per run)."""
+        import ctypes
+
+        from .. import _cabi
+
+        ctx = _cabi.context()
+        handles = self.__dict__.setdefault("_selection_handles", {})
+        if ctx.device not in handles:
+            idx = np.ascontiguousarray(self.atomgroup.indices, dtype=np.int32)
+            ptr = np.array([0, len(idx)], dtype=np.int64)
+            handle = ctypes.c_void_p()
+            _cabi.check(_cabi.load().mb200_groups_create(ctx.handle, _cabi.ptr(idx), _cabi.ptr(ptr), 1,
+                                                         int(self._universe.atoms.n_atoms), ctypes.byref(handle)))
+            handles[ctx.device] = (ctx, handle)
+        return handles[ctx.device][1]
+
+    def _release_selection(self) -> None:
+        from .. import _cabi
+
+        for ctx, handle in self.__dict__.pop("_selection_handles", {}).values():
+            _cabi.load().mb200_groups_destroy(ctx.handle, handle)
+
     def _static_weights_on_device(self, weights: np.ndarray) -> int:
         """Topology-only weights (masses, charges, ones) are uploaded once per run, not with every batch."""
         from .. import _cabi
@@ -1179,17 +1209,20 @@ class ProfileBase:
                                   device_positions=(c_ptr, len(staged), self._prologue.n_c), device_weights=dev_w)
         else:
             win = self._frame_window() if self.grouping == "atoms" else None  # else: centres formed on the host
+            sel = None
+            if win is not None and win[1] is None:  # not one range: gathered by index on the device
+                sel, win = (self._selection_on_device(), self.atomgroup.n_atoms), None
             win = None if win is None else (win[1], self.atomgroup.n_atoms)  # atoms [first, first + n) of whole frames
             boxes = np.stack([s["box"] for s in staged]) if (self._device_pack and self.grouping == "atoms") else None
             if self._static_weights:
                 hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange, window=win, pack_boxes=boxes,
-                                      device_weights=(self._static_weights_on_device(g0["weights"]), False))
+                                      selection=sel, device_weights=(self._static_weights_on_device(g0["weights"]), False))
             elif vel_w is not None:
                 hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], None, edges, center, zrange, device_weights=vel_w, window=win,
-                                      pack_boxes=boxes)
+                                      pack_boxes=boxes, selection=sel)
             else:
                 w = self._gather_rows([s["weights"] for s in staged])
-                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], w, edges, center, zrange, window=win)
+                hw, hc = profile_hist(g0["geometry"], pos, g0["dim"], w, edges, center, zrange, window=win, selection=sel)
         out = []
         for f, s in enumerate(staged):
             obs = s["obs"]

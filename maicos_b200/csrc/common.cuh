@@ -187,3 +187,11 @@ struct mb200_ctx {
     std::list<std::shared_ptr<mb200::SfPlan>> plans;  // small LRU cache keyed by box + q window
     ~mb200_ctx();
 };
+
+// index lists of atom groups inside whole frames, resident on one device (mb200_groups_create, sfactor.cu)
+struct mb200_groups {
+    mb200::DevBuf idx;          // int32, the groups' lists back to back
+    std::vector<int64_t> ptr;   // [n_groups + 1] offsets into idx
+    int64_t n_atoms_total = 0;  // atoms per frame
+    int device = 0;
+};

@@ -103,18 +103,27 @@ __global__ void __launch_bounds__(256) k_hist_wmax(const double *__restrict__ w,
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out + blockIdx.y, m);
 }
 
-// AtomGroup.wrap(compound="atoms") of float32 positions -- x -= floor(x / L) * L, every operation rounded to float32 as
-// numpy does it (core/base.py:446-448 of the reference calls it on the host for every frame) -- from a window of whole
-// frames into a dense [F][n][3] buffer
+// Dense float32 copy [F][n][3] of a group of atoms of whole frames, in front of the histogram:
+//   index != null : the group is index[0 .. n) (any selection), else atoms 0 .. n of `src` (a window);
+//   boxes != null : AtomGroup.wrap(compound="atoms"), x -= floor(x / L) * L with every operation rounded to float32 as
+//                   numpy does it (core/base.py:446-448 of the reference calls it on the host for every frame).
 __global__ void __launch_bounds__(256) k_pack_atoms(const float *__restrict__ src, long long src_fstride, float *__restrict__ dst,
-                                                    const float *__restrict__ boxes, long long n3) {
+                                                    const float *__restrict__ boxes, const int32_t *__restrict__ index,
+                                                    long long n3) {
     const long long f = blockIdx.y;
     const float *s = src + (size_t)f * src_fstride;
     float *d = dst + (size_t)f * n3;
-    const float L[3] = {boxes[f * 3], boxes[f * 3 + 1], boxes[f * 3 + 2]};
+    float L[3] = {1.f, 1.f, 1.f};
+    if (boxes) { L[0] = boxes[f * 3]; L[1] = boxes[f * 3 + 1]; L[2] = boxes[f * 3 + 2]; }
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n3; e += (long long)gridDim.x * blockDim.x) {
-        const float l = L[e % 3], x = s[e];
-        d[e] = __fsub_rn(x, __fmul_rn(floorf(__fdiv_rn(x, l)), l));
+        const long long i = e / 3;
+        const int c = (int)(e - i * 3);
+        float x = index ? s[(size_t)index[i] * 3 + c] : s[e];
+        if (boxes) {
+            const float l = L[c];
+            x = __fsub_rn(x, __fmul_rn(floorf(__fdiv_rn(x, l)), l));
+        }
+        d[e] = x;
     }
 }
 
@@ -921,13 +930,15 @@ extern "C" int mb200_profile_hist(mb200_ctx *ctx, int geometry, const void *posi
                                   int positions_on_device, int64_t n_frames, int64_t n, int dim, const double *weights,
                                   int weights_per_frame, int weights_on_device, const double *edges, int32_t n_bins,
                                   const double *center, const double *zrange, double *hist_w, int64_t *hist_c) {
-    return mb200_profile_hist_window(ctx, geometry, positions, pos_is_f32, positions_on_device, n_frames, n, 0, n, nullptr, dim,
-                                     weights, weights_per_frame, weights_on_device, edges, n_bins, center, zrange, hist_w, hist_c);
+    return mb200_profile_hist_window(ctx, geometry, positions, pos_is_f32, positions_on_device, n_frames, n, 0, n, nullptr,
+                                     nullptr, dim, weights, weights_per_frame, weights_on_device, edges, n_bins, center, zrange,
+                                     hist_w, hist_c);
 }
 
 extern "C" int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const void *positions, int pos_is_f32,
                                          int positions_on_device, int64_t n_frames, int64_t n_total, int64_t first_atom,
-                                         int64_t n, const float *pack_boxes, int dim, const double *weights, int weights_per_frame,
+                                         int64_t n, const mb200_groups *selection, const float *pack_boxes, int dim,
+                                         const double *weights, int weights_per_frame,
                                          int weights_on_device, const double *edges, int32_t n_bins, const double *center,
                                          const double *zrange, double *hist_w, int64_t *hist_c) {
     if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
@@ -937,8 +948,11 @@ extern "C" int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const voi
     if (geometry < 0 || geometry > 3 || n_frames < 0 || n < 0 || n_bins <= 0 || dim < 0 || dim > 2 || !edges || !hist_c ||
         (n && !positions) || (weights && !hist_w) || first_atom < 0 || first_atom + n > n_total)
         return fail(MB200_EINVAL, "invalid argument to mb200_profile_hist");
-    if (pack_boxes && (!pos_is_f32 || geometry == MB200_GEOM_SCALAR))
-        return fail(MB200_EINVAL, "pack_boxes wraps float32 atom positions (as AtomGroup.wrap does)");
+    if ((pack_boxes || selection) && (!pos_is_f32 || geometry == MB200_GEOM_SCALAR))
+        return fail(MB200_EINVAL, "pack_boxes / selection apply to float32 atom positions");
+    if (selection && (selection->device != ctx->device || selection->ptr.size() != 2 || selection->ptr[1] != n ||
+                      selection->n_atoms_total != n_total || first_atom != 0))
+        return fail(MB200_EINVAL, "selection must be one group of n atoms of frames of n_total atoms on this device");
     if ((geometry == MB200_GEOM_CYLINDER || geometry == MB200_GEOM_SPHERE) && !center)
         return fail(MB200_EINVAL, "center required for radial geometries");
     if (geometry == MB200_GEOM_CYLINDER && !zrange && !digitize) return fail(MB200_EINVAL, "zrange required for cylinder geometry");
@@ -972,15 +986,15 @@ extern "C" int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const voi
         // announced with mb200_prefetch_frames: copied on the copy stream under the previous call
         p.pos = reinterpret_cast<const char *>(pref) + win;
     } else {
-        MB_TRY(ctx->d_hpos.ensure(F * N * ncomp * esz));
-        if (NT == N) {
-            MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * N * ncomp * esz, cudaMemcpyHostToDevice, ctx->stream));
+        MB_TRY(ctx->d_hpos.ensure(F * (selection ? NT : N) * ncomp * esz));
+        if (NT == N || selection) {  // (a selection is gathered on the device: its whole frames travel)
+            MB_CUDA(cudaMemcpyAsync(ctx->d_hpos.p, positions, F * NT * ncomp * esz, cudaMemcpyHostToDevice, ctx->stream));
         } else {  // only the window travels
             MB_CUDA(cudaMemcpy2DAsync(ctx->d_hpos.p, N * ncomp * esz, reinterpret_cast<const char *>(positions) + win,
                                       NT * ncomp * esz, N * ncomp * esz, F, cudaMemcpyHostToDevice, ctx->stream));
         }
         p.pos = ctx->d_hpos.p;
-        p.fstride = (long long)(N * ncomp);
+        p.fstride = (long long)((selection ? NT : N) * ncomp);
     }
     const bool weighted = weights && N;
     const size_t Fw = weights_per_frame ? F : 1;
@@ -1013,12 +1027,13 @@ extern "C" int mb200_profile_hist_window(mb200_ctx *ctx, int geometry, const voi
     if (pack_boxes) std::memcpy(hpar + F * (NB + 1) + F * 5, pack_boxes, F * 12);
     MB_CUDA(cudaMemcpyAsync(dpar, hpar, (F * (NB + 1) + F * 5 + n_box) * 8, cudaMemcpyHostToDevice, ctx->stream));
     unsigned long long *d_wmax = reinterpret_cast<unsigned long long *>(dpar + F * (NB + 1) + F * 5 + n_box);
-    if (pack_boxes && N) {  // wrap into the primary cell on the device: dense float32 copy of the group, then binned as usual
+    if ((pack_boxes || selection) && N) {  // gather / wrap into the primary cell on the device: dense float32 copy of the group
         MB_TRY(ctx->d_hpack.ensure(F * N * 12));
         const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((N * 3 + 256 * 8 - 1) / (256 * 8), (size_t)ctx->n_sm * 8 / F + 1));
         k_pack_atoms<<<dim3(gx, (unsigned)F), 256, 0, ctx->stream>>>(reinterpret_cast<const float *>(p.pos), p.fstride,
                                                                      ctx->d_hpack.as<float>(),
-                                                                     reinterpret_cast<const float *>(dpar + F * (NB + 1) + F * 5),
+                                                                     pack_boxes ? reinterpret_cast<const float *>(dpar + F * (NB + 1) + F * 5) : nullptr,
+                                                                     selection ? selection->idx.as<int32_t>() : nullptr,
                                                                      (long long)(N * 3));
         MB_CUDA(cudaGetLastError());
         ctx->launches += 1;

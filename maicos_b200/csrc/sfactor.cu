@@ -157,24 +157,34 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
     double2 *tab = jb.tab[axis];
     if (tab == nullptr) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= jb.ld) return;
+    // every field the row loop needs goes to registers up front: the job lives in global memory and the loop's stores
+    // would otherwise force the compiler to reload it in every iteration (ncu: half of all stall cycles on those loads)
+    const int ld = jb.ld, n_atoms = jb.n;
+    if (j >= ld) return;
     const int rows = jb.rows[axis];
     // split-precision mode, z axis: digits of Z = Ez[l] straight into the image of the tensor-core kernel, rows
     // 2 l (real part of A: (Zr, -Zi)) and 2 l + 1 (imaginary part: (Zi, Zr)) of l tile l / L_t, K position 2 (j % 16)
     const bool to_image = axis == 2 && jb.bimg != nullptr;
     const bool masked = axis == 1 && jb.use_y_mask != 0;
-    auto wanted = [&](int r) -> bool { return !masked || ((jb.y_mask[(r >> 6) & 3] >> (r & 63)) & 1ull); };
-    const int np = 2 * jb.img_lt;
+    const unsigned long long ym0 = masked ? jb.y_mask[0] : ~0ull, ym1 = masked ? jb.y_mask[1] : ~0ull,
+                             ym2 = masked ? jb.y_mask[2] : ~0ull, ym3 = masked ? jb.y_mask[3] : ~0ull;
+    auto wanted = [&](int r) -> bool {
+        const int wd = (r >> 6) & 3;
+        const unsigned long long m = wd == 0 ? ym0 : (wd == 1 ? ym1 : (wd == 2 ? ym2 : ym3));
+        return (m >> (r & 63)) & 1ull;
+    };
+    const int img_lt = jb.img_lt, img_maxn = jb.img_maxn, img_rows = jb.img_n_lt * jb.img_lt;
+    const int np = 2 * img_lt;
     int8_t *img = nullptr;
     if (to_image) img = jb.bimg + (size_t)(j / TC_KA) * (size_t)(TC_S * np * 32) + tc_canon(0, 2 * (j % TC_KA));
-    const size_t img_tile = (size_t)(jb.ld / TC_KA) * (size_t)(TC_S * np * 32);
+    const size_t img_tile = (size_t)(ld / TC_KA) * (size_t)(TC_S * np * 32);
     auto put_image = [&](int l, double zr, double zi) {
         unsigned rlo, rhi, ilo, ihi, nlo, nhi;
         tc_digits(zr, rlo, rhi);
         tc_digits(zi, ilo, ihi);
         tc_digits(-zi, nlo, nhi);
-        int8_t *b = img + (size_t)(l / jb.img_lt) * img_tile;
-        const int li = l % jb.img_lt;
+        int8_t *b = img + (size_t)(l / img_lt) * img_tile;
+        const int li = l % img_lt;
         const int o0 = tc_canon(2 * li, 0), o1 = tc_canon(2 * li + 1, 0);
 #pragma unroll
         for (int t = 1; t <= TC_S; ++t) {
@@ -183,9 +193,9 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
             b += np * 32;
         }
     };
-    if (j >= jb.n) {  // zero padding up to the leading dimension
+    if (j >= n_atoms) {  // zero padding up to the leading dimension
         if (to_image) {
-            for (int l = 0; l < jb.img_n_lt * jb.img_lt; ++l) put_image(l, 0.0, 0.0);
+            for (int l = 0; l < img_rows; ++l) put_image(l, 0.0, 0.0);
             return;
         }
         for (int r = 0; r < rows; ++r)
@@ -197,9 +207,10 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
     if (jb.is_f32) {
         float p = reinterpret_cast<const float *>(jb.pos)[a * jb.stride_atom + axis * jb.stride_xyz];
         const float L = jb.boxf[axis];
-        if (jb.wrap_mode == 2)  // AtomGroup.wrap(compound="atoms"): x -= floor(x/L)*L in float32
+        const int wrap_mode = jb.wrap_mode;
+        if (wrap_mode == 2)  // AtomGroup.wrap(compound="atoms"): x -= floor(x/L)*L in float32
             p = __fsub_rn(p, __fmul_rn(floorf(__fdiv_rn(p, L)), L));
-        if (jb.wrap_mode >= 1)  // saxs.py:193-195: pos - box*round(pos/box), float32 arithmetic
+        if (wrap_mode >= 1)  // saxs.py:193-195: pos - box*round(pos/box), float32 arithmetic
             p = __fsub_rn(p, __fmul_rn(L, rintf(__fdiv_rn(p, L))));
         u = (double)p / (double)L;
     } else {
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
             sincospi(2.0 * t, &ci, &cr);
         }
         if (to_image) {
-            if (r < jb.img_maxn) put_image(r, cr, ci);  // the z axis never carries weights
+            if (r < img_maxn) put_image(r, cr, ci);  // the z axis never carries weights
         } else if (wanted(r)) {
             tab[tab_index(j, r, rows)] = make_double2(w * cr, w * ci);
         }
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
         ci = ni;
     }
     if (to_image)  // l values of the last tile beyond the cube edge
-        for (int l = jb.img_maxn; l < jb.img_n_lt * jb.img_lt; ++l) put_image(l, 0.0, 0.0);
+        for (int l = img_maxn; l < img_rows; ++l) put_image(l, 0.0, 0.0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1535,13 +1546,6 @@ extern "C" int mb200_structure_factor(mb200_ctx *ctx, const double *positions, i
 }
 
 // Element groups of a Saxs analysis, resident on the device for the whole run (mb200_groups_create).
-struct mb200_groups {
-    mb200::DevBuf idx;
-    std::vector<int64_t> ptr;
-    int64_t n_atoms_total = 0;
-    int device = 0;
-};
-
 static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
                             int64_t n_atoms_total, const float *boxes, const int32_t *d_group_index,
                             const int64_t *group_ptr, int32_t n_groups, const double *cm_params, double qmin,

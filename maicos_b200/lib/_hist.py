@@ -20,7 +20,7 @@ DIGITIZE = 0x10  # or-ed into the geometry: np.digitize(x, edges[1:-1]) semantic
 def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights: np.ndarray | None, edges: np.ndarray,
                  center: np.ndarray | None = None, zrange: np.ndarray | None = None, device: int | None = None,
                  device_positions: tuple | None = None, device_weights: tuple | None = None, digitize: bool = False,
-                 window: tuple | None = None, pack_boxes: np.ndarray | None = None):
+                 window: tuple | None = None, pack_boxes: np.ndarray | None = None, selection=None):
     """Histogram ``positions [F, n, 3]`` (float32 or float64) into ``edges [F, n_bins + 1]``.
 
     ``geometry = SCALAR``: ``positions [F, n]`` is the binned coordinate itself.  ``digitize=True``: the bin is
@@ -31,6 +31,8 @@ def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights:
     compound prologue); ``device_weights = (pointer, per_frame)`` likewise.
     ``window = (first, n)``: ``positions`` holds whole frames ``[F, n_total, 3]`` and the group is atoms
     ``first .. first + n`` of each (``mb200_profile_hist_window``); weights are per group atom.
+    ``selection = (handle, n)``: ``positions`` holds whole frames and the group is the ``n`` atoms listed in the device
+    index list ``handle`` (``mb200_groups_create`` with one group), gathered on the device.
     ``pack_boxes``: float32 ``[F, 3]`` cell lengths -- float32 positions are wrapped into the primary cell on the device
     first (``AtomGroup.wrap(compound="atoms")``: ``x -= floor(x / L) * L`` in float32).
     Returns ``(hist_w float64 [F, n_bins] or None, hist_c int64 [F, n_bins])``.
@@ -58,7 +60,10 @@ def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights:
         F, n = positions.shape[0], positions.shape[1]
         pos_ptr, pos_is_f32, pos_on_dev = _cabi.ptr(positions), int(positions.dtype == np.float32), 0
     n_total, first = n, 0
-    if window is not None:
+    sel_handle = None
+    if selection is not None:
+        sel_handle, n = selection[0], int(selection[1])
+    elif window is not None:
         first, n = int(window[0]), int(window[1])
         if first < 0 or first + n > n_total:
             raise ValueError(f"window [{first}, {first + n}) does not fit frames of {n_total} atoms")
@@ -90,7 +95,7 @@ def profile_hist(geometry: int, positions: np.ndarray | None, dim: int, weights:
     _cabi.check(
         _cabi.load().mb200_profile_hist_window(
             ctx.handle, int(geometry) | (DIGITIZE if digitize else 0), pos_ptr, pos_is_f32, pos_on_dev, F, n_total, first, n,
-            _cabi.ptr(pack_boxes), int(dim),
+            sel_handle, _cabi.ptr(pack_boxes), int(dim),
             w_ptr, per_frame, w_on_dev, _cabi.ptr(edges), n_bins, _cabi.ptr(center), _cabi.ptr(zrange),
             _cabi.ptr(hist_w), _cabi.ptr(hist_c),
         )

@@ -777,14 +777,17 @@ def test_selections_are_read_out_of_whole_pinned_frames(precision):
                 mb.DensityCylinder(water, dens="charge", bin_width=0.5, unwrap=False, pack=False),
                 mb.Saxs(water, qmax=2.0, dq=0.1),
                 mb.Saxs(oxygen, qmax=2.0, dq=0.1),
-                mb.DiporderStructureFactor(water, qmax=2.0, dq=0.1)]
+                mb.DiporderStructureFactor(water, qmax=2.0, dq=0.1),
+                mb.DensityPlanar(oxygen, dens="number", bin_width=0.2),                      # by index, wrapped on the device
+                mb.DensitySphere(oxygen, dens="mass", bin_width=0.5, unwrap=False, pack=False)]
 
     pinned, pageable = members(u_pin), members(u_pg)
     for m in pinned + pageable:
         m.run()
     windows = [m._frame_window() for m in pinned]
     assert windows[0] == (3900, 300) and windows[1] is None and windows[2] == (3900, 300) and windows[3] == (3900, 300)
-    assert windows[4] == (3900, None) and windows[5] == (3900, None) and windows[6] == (3900, 300)
+    assert windows[4] == (3900, 300) and windows[5] == (3900, None) and windows[6] == (3900, 300)
+    assert windows[7] == (3900, None) and windows[8] == (3900, None)
     assert all(m._frame_window() is None for m in pageable)
     for a, b in zip(pinned, pageable):
         for key in b.sums:
@@ -800,7 +803,7 @@ def test_selections_are_read_out_of_whole_pinned_frames(precision):
     mb.AnalysisCollection(*together).run()
     _cabi.check(lib.mb200_ctx_prefetch_stats(ctx.handle, _cabi.ptr(after)))
     copies, saved, _ = (after - before).tolist()
-    assert copies > 0 and saved == 6 * copies, (copies, saved)
+    assert copies > 0 and saved == 8 * copies, (copies, saved)
     for a, b in zip(together, pageable):
         for key in b.means:
             assert_array_equal(np.asarray(a.means[key]), np.asarray(b.means[key]), err_msg=f"collection {type(a).__name__}.{key}")
