@@ -116,6 +116,15 @@ int mb200_sfactor_maxn(const double dimensions[3], double qmax, int32_t maxn[3])
 int mb200_plan_describe(const double dimensions[3], double qmin, double qmax, double thetamin, double thetamax,
                         int32_t n_bins, int64_t out[16]);
 
+/* Build the q-plans of the frames of the NEXT *_frames call ahead of it (host work only, no device call): an NPT trajectory
+ * has a new cell, hence a new plan (about a millisecond of host time at maxn = 32), in every frame.  Called from the thread
+ * that stages the frames while the previous batch computes; the plans of cells that are neither cached nor built already
+ * are constructed side by side on the host threads and picked up by the compute call.
+ *   boxes : host float64 [n_frames][3] (Saxs: its float32 cell lengths converted to double, as the call does)
+ *   n_bins, thetamin / thetamax, cm_params / n_groups : those of the call (DiporderStructureFactor: 0, pi, NULL, 0) */
+int mb200_plans_ahead(mb200_ctx *ctx, const double *boxes, int64_t n_frames, double qmin, double qmax, double thetamin,
+                      double thetamax, int32_t n_bins, const double *cm_params, int32_t n_groups);
+
 /* Drop-in for `_cmath.structure_factor` (src/maicos/lib/_cmath.pyx:21-126, re-exported
  * at src/maicos/lib/math.py:15; callers saxs.py:197-205, diporderstructurefactor.py:121-129).
  *   positions : host float64, element (j, d) at positions[j*stride_atom + d*stride_xyz]

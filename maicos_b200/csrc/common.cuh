@@ -120,7 +120,8 @@ inline void parallel_chunks(size_t n, size_t min_parallel, F fn) {
 
 #define MB_LOCK(ctx) std::lock_guard<std::recursive_mutex> _mb_call_lock((ctx)->call_mutex)
 
-struct SfPlan;  // sfactor.cu
+struct SfPlan;    // sfactor.cu
+struct PlanPool;  // sfactor.cu: retired q-plans whose host vectors and device buffers the next plan reuses
 // The prefetch slot a compute call reads (context.cu).  take(): device copy of `host` if it was announced with
 // mb200_prefetch_frames[_shared] (the compute stream is made to wait for the copy), else nullptr.  release(): every kernel
 // that reads the slot has been queued -- records the slot's "done" event on the compute stream; until then the slot is
@@ -185,6 +186,10 @@ struct mb200_ctx {
     unsigned long long idx_fp = 0;
     int64_t idx_natoms = 0;
     std::list<std::shared_ptr<mb200::SfPlan>> plans;  // small LRU cache keyed by box + q window
+    size_t plan_cap = 64;                              // entries kept (raised to the frames of a call: NPT trajectories)
+    std::shared_ptr<mb200::PlanPool> plan_pool;        // created with the first plan
+    std::mutex plan_mutex;                             // guards plans / plans_ahead (mb200_plans_ahead runs beside a compute call)
+    std::vector<std::shared_ptr<mb200::SfPlan>> plans_ahead;  // built by mb200_plans_ahead, not uploaded yet
     ~mb200_ctx();
 };
 

@@ -32,6 +32,7 @@
 #include <map>
 
 #include "common.cuh"
+#include <array>
 #include "sfactor_digits.cuh"
 
 namespace mb200 {
@@ -632,6 +633,37 @@ struct SfPlan {
     DevBuf d_tgs, d_ent_amp, d_bin_start, d_ff2, d_tc_rows, d_ent_amp_tc;
     std::vector<double> ff2_key;  // cm params the cached ff2 was built for
     int32_t ff2_groups = 0;
+    std::vector<double> ff2_host;      // squared form factors computed ahead (prepare_plans), uploaded by plan_ff2
+    std::vector<double> ff2_host_key;
+
+    // a retired plan becomes the next one: vectors and device buffers keep their capacity (no cudaMalloc / cudaFree --
+    // which synchronises the device -- per frame of an NPT trajectory)
+    void reset() {
+        cell.clear(); qrr.clear(); ent_amp.clear(); bin_start.clear(); tgs.clear(); tc_rows.clear(); ent_amp_tc.clear();
+        tc_tile_used.clear(); ff2_key.clear(); ff2_host.clear(); ff2_host_key.clear();
+        n_wt = 0; n_mma_tiles = 0; tc_n_rt = tc_n_lt = tc_lt = tc_n_pairs = tc_n_used = 0; tc_ok = false; ff2_groups = 0;
+        for (auto &m : tc_ymask) m = 0ull;
+    }
+};
+
+struct PlanPool {
+    std::mutex m;
+    std::vector<SfPlan *> free;
+    SfPlan *take() {
+        std::lock_guard<std::mutex> lock(m);
+        if (free.empty()) return nullptr;
+        SfPlan *p = free.back();
+        free.pop_back();
+        return p;
+    }
+    void give(SfPlan *p) {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            if (free.size() < 320) { free.push_back(p); return; }
+        }
+        delete p;
+    }
+    ~PlanPool() { for (SfPlan *p : free) delete p; }
 };
 
 static void sfactor_maxn_host(const double *dims, double qmax, int32_t *maxn) {
@@ -654,8 +686,15 @@ static inline int32_t numpy_bin(double x, double first, double last, int32_t n, 
 }
 
 static int build_plan(const double *dims, double qmin, double qmax, double thmin, double thmax, int32_t n_bins,
-                      std::shared_ptr<SfPlan> &out) {
-    auto pl = std::make_shared<SfPlan>();
+                      std::shared_ptr<SfPlan> &out, const std::shared_ptr<PlanPool> &pool = nullptr) {
+    std::shared_ptr<SfPlan> pl;
+    if (pool) {  // the plan goes back to the pool when its last holder lets go of it
+        SfPlan *raw = pool->take();
+        if (raw) raw->reset(); else raw = new SfPlan();
+        pl = std::shared_ptr<SfPlan>(raw, [pool](SfPlan *p) { pool->give(p); });
+    } else {
+        pl = std::make_shared<SfPlan>();
+    }
     for (int i = 0; i < 3; ++i) pl->dims[i] = dims[i];
     pl->qmin = qmin; pl->qmax = qmax; pl->thmin = thmin; pl->thmax = thmax; pl->n_bins = n_bins;
     sfactor_maxn_host(dims, qmax, pl->maxn);
@@ -669,6 +708,14 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
     double qf[3];
     for (int i = 0; i < 3; ++i) qf[i] = 2 * M_PI / dims[i];
 
+    static const bool trace_plan = std::getenv("MAICOS_B200_TRACE_PLAN") != nullptr;  // developer aid: phase times to stderr
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!trace_plan) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[build_plan] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     const size_t cells = (size_t)m0 * m1 * m2;
     std::vector<double> qcube(cells, 0.0);  // 0 = rejected
     const bool need_theta = !(thmin <= 0.0 && thmax >= 1.5707963267948968);
@@ -692,6 +739,7 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
             }
         }
     });
+    mark("q cube");
     // warp tiles: (quad, l-pair) with at least one valid q; DMMA-tile validity mask
     const int nqh = pl->rows[0] / QH, nqk = pl->rows[1] / QK, nlp = pl->rows[2] / NL;
     std::vector<int32_t> wt_of((size_t)nqh * nqk * nlp, -1);
@@ -749,6 +797,7 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
         }
         pl->tgs.push_back(tg);
     }
+    mark("dmma tiles");
     // entries
     std::vector<int32_t> cell; std::vector<double> qv; std::vector<int32_t> amp;
     {
@@ -781,6 +830,7 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
         });
     }
     const size_t nv = cell.size();
+    mark("entries");
     if (n_bins > 0) {
         // np.histogram(a=|q|, bins=n_bins, range=(qmin, qmax)) -- saxs.py:222-233
         double first = qmin, last = qmax;
@@ -806,6 +856,7 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
     } else {
         pl->cell.swap(cell); pl->qrr.swap(qv); pl->ent_amp.swap(amp);
     }
+    mark("bins");
     // tensor-core tiling: (h,k) pairs with at least one valid l, packed in quads (h, k0 .. k0 + 3) -- the generators form the
     // four rows of a quad from one seed product -- 32 quads = 128 rows per row tile, l tiles of <= 48 values
     if (m0 <= 255 && m1 <= 255 && m2 >= 1 && nv > 0) {
@@ -880,6 +931,7 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
         for (uint8_t u : pl->tc_tile_used) pl->tc_n_used += u;
         pl->tc_ok = true;
     }
+    mark("tc tiling");
     out = pl;
     return MB200_OK;
 }
@@ -907,37 +959,142 @@ static int upload_plan(mb200_ctx *ctx, SfPlan &pl) {
         MB_CUDA(cudaMemcpyAsync(pl.d_ent_amp_tc.p, pl.ent_amp_tc.data(), pl.ent_amp_tc.size() * 4, cudaMemcpyHostToDevice,
                                 ctx->stream));
     }
-    MB_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors may be read again only after this
+    // no synchronisation: the sources are pageable, cudaMemcpyAsync returns once it has staged them
     return MB200_OK;
 }
 
+static inline bool plan_is(const SfPlan &p, const double *d, double qmin, double qmax, double thmin, double thmax, int32_t n_bins) {
+    return p.dims[0] == d[0] && p.dims[1] == d[1] && p.dims[2] == d[2] && p.qmin == qmin && p.qmax == qmax && p.thmin == thmin &&
+           p.thmax == thmax && p.n_bins == n_bins;
+}
+
+static std::shared_ptr<PlanPool> plan_pool_of(mb200_ctx *ctx) {
+    std::lock_guard<std::mutex> lock(ctx->plan_mutex);
+    if (!ctx->plan_pool) ctx->plan_pool = std::make_shared<PlanPool>();
+    return ctx->plan_pool;
+}
+
+// (called under the context's call mutex; plan_mutex only guards the lists against mb200_plans_ahead on another thread)
 static int get_plan(mb200_ctx *ctx, const double *dims, double qmin, double qmax, double thmin, double thmax,
                     int32_t n_bins, std::shared_ptr<SfPlan> &out) {
-    for (auto it = ctx->plans.begin(); it != ctx->plans.end(); ++it) {
-        SfPlan &p = **it;
-        if (p.dims[0] == dims[0] && p.dims[1] == dims[1] && p.dims[2] == dims[2] && p.qmin == qmin &&
-            p.qmax == qmax && p.thmin == thmin && p.thmax == thmax && p.n_bins == n_bins) {
-            out = *it;
-            ctx->plans.splice(ctx->plans.begin(), ctx->plans, it);
-            return MB200_OK;
-        }
+    {
+        std::lock_guard<std::mutex> lock(ctx->plan_mutex);
+        for (auto it = ctx->plans.begin(); it != ctx->plans.end(); ++it)
+            if (plan_is(**it, dims, qmin, qmax, thmin, thmax, n_bins)) {
+                out = *it;
+                ctx->plans.splice(ctx->plans.begin(), ctx->plans, it);
+                return MB200_OK;
+            }
+        for (auto it = ctx->plans_ahead.begin(); it != ctx->plans_ahead.end(); ++it)
+            if (plan_is(**it, dims, qmin, qmax, thmin, thmax, n_bins)) {  // built ahead, not uploaded yet
+                out = *it;
+                ctx->plans_ahead.erase(it);
+                break;
+            }
     }
-    MB_TRY(build_plan(dims, qmin, qmax, thmin, thmax, n_bins, out));
+    if (!out) MB_TRY(build_plan(dims, qmin, qmax, thmin, thmax, n_bins, out, plan_pool_of(ctx)));
     MB_TRY(upload_plan(ctx, *out));
-    ctx->plans.push_front(out);
-    while (ctx->plans.size() > 64) ctx->plans.pop_back();
+    std::vector<std::shared_ptr<SfPlan>> retired;  // released outside the lock
+    {
+        std::lock_guard<std::mutex> lock(ctx->plan_mutex);
+        ctx->plans.push_front(out);
+        while (ctx->plans.size() > ctx->plan_cap) { retired.push_back(ctx->plans.back()); ctx->plans.pop_back(); }
+    }
+    return MB200_OK;
+}
+
+static void compute_ff2(const SfPlan &pl, const double *cm, int n_groups, std::vector<double> &ff2, bool threads);
+
+// The q-plans of all frames of a call, built ahead: an NPT trajectory has a new cell -- a new plan -- in every frame, and
+// one plan costs about a millisecond of host time (maxn = 32).  Boxes that are not cached are built on the host threads
+// side by side (with their squared form factors when `cm` is given), then uploaded one after the other; the calls'
+// get_plan lookups then hit the cache.  dims_of(f, d[3]) yields the cell of frame f.
+// Boxes of `n_frames` frames that have no plan yet -- neither cached nor built ahead -- each listed once.
+template <typename DimsOf>
+static std::vector<std::array<double, 3>> missing_plans(mb200_ctx *ctx, size_t n_frames, DimsOf dims_of, double qmin, double qmax,
+                                                        double thmin, double thmax, int32_t n_bins) {
+    std::vector<std::array<double, 3>> miss;
+    std::lock_guard<std::mutex> lock(ctx->plan_mutex);
+    double last[3] = {-1.0, -1.0, -1.0};
+    for (size_t f = 0; f < n_frames; ++f) {
+        double d[3];
+        dims_of(f, d);
+        if (d[0] == last[0] && d[1] == last[1] && d[2] == last[2]) continue;  // NVT: one look-up per call
+        last[0] = d[0]; last[1] = d[1]; last[2] = d[2];
+        bool known = false;
+        for (const auto &sp : ctx->plans)
+            if (plan_is(*sp, d, qmin, qmax, thmin, thmax, n_bins)) { known = true; break; }
+        for (size_t i = 0; i < ctx->plans_ahead.size() && !known; ++i)
+            known = plan_is(*ctx->plans_ahead[i], d, qmin, qmax, thmin, thmax, n_bins);
+        for (size_t i = 0; i < miss.size() && !known; ++i) known = miss[i][0] == d[0] && miss[i][1] == d[1] && miss[i][2] == d[2];
+        if (!known) miss.push_back({d[0], d[1], d[2]});
+    }
+    return miss;
+}
+
+// Host side of the plans of `miss`, side by side on the host threads (with their squared form factors when `cm` is given).
+static int build_plans(mb200_ctx *ctx, const std::vector<std::array<double, 3>> &miss, double qmin, double qmax, double thmin,
+                       double thmax, int32_t n_bins, const double *cm, int n_groups, std::vector<std::shared_ptr<SfPlan>> &built) {
+    const std::shared_ptr<PlanPool> pool = plan_pool_of(ctx);
+    built.assign(miss.size(), nullptr);
+    std::vector<int> rc(miss.size(), MB200_OK);
+    parallel_chunks(miss.size(), 2, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            rc[i] = build_plan(miss[i].data(), qmin, qmax, thmin, thmax, n_bins, built[i], pool);
+            if (rc[i] == MB200_OK && cm && n_groups > 0) {
+                compute_ff2(*built[i], cm, n_groups, built[i]->ff2_host, false);
+                built[i]->ff2_host_key.assign(cm, cm + (size_t)n_groups * 20);
+            }
+        }
+    });
+    for (int r : rc)
+        if (r != MB200_OK) return r;
+    return MB200_OK;
+}
+
+// The q-plans of all frames of a call: an NPT trajectory has a new cell -- a new plan -- in every frame, and one plan
+// costs about a millisecond of host time (maxn = 32).  Plans that mb200_plans_ahead did not build already (on the
+// staging thread, under the previous call) are built here side by side; the calls' get_plan lookups then find them.
+// dims_of(f, d[3]) yields the cell of frame f.
+template <typename DimsOf>
+static int prepare_plans(mb200_ctx *ctx, size_t n_frames, DimsOf dims_of, double qmin, double qmax, double thmin, double thmax,
+                         int32_t n_bins, const double *cm, int n_groups) {
+    {
+        std::lock_guard<std::mutex> lock(ctx->plan_mutex);
+        ctx->plan_cap = std::max<size_t>(ctx->plan_cap, std::min<size_t>(n_frames + 16, 288));
+    }
+    const auto miss = missing_plans(ctx, n_frames, dims_of, qmin, qmax, thmin, thmax, n_bins);
+    if (miss.size() < 2) return MB200_OK;  // a single new cell: get_plan builds it (with its own threads if it is large)
+    std::vector<std::shared_ptr<SfPlan>> built;
+    MB_TRY(build_plans(ctx, miss, qmin, qmax, thmin, thmax, n_bins, cm, n_groups, built));
+    std::lock_guard<std::mutex> lock(ctx->plan_mutex);
+    for (auto &pl : built) ctx->plans_ahead.push_back(pl);  // uploaded by get_plan when their frame comes up
+    return MB200_OK;
+}
+
+extern "C" int mb200_plans_ahead(mb200_ctx *ctx, const double *boxes, int64_t n_frames, double qmin, double qmax, double thetamin,
+                                 double thetamax, int32_t n_bins, const double *cm_params, int32_t n_groups) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    if (!boxes || n_frames < 0 || n_bins < 0 || (n_groups > 0 && !cm_params)) return fail(MB200_EINVAL, "invalid argument to mb200_plans_ahead");
+    // host work only, and NOT under the call mutex: it runs beside the compute call of the previous batch
+    const auto miss = missing_plans(ctx, (size_t)n_frames, [&](size_t f, double *d) { for (int i = 0; i < 3; ++i) d[i] = boxes[f * 3 + i]; },
+                                    qmin, qmax, thetamin, thetamax, n_bins);
+    if (miss.empty()) return MB200_OK;
+    std::vector<std::shared_ptr<SfPlan>> built;
+    MB_TRY(build_plans(ctx, miss, qmin, qmax, thetamin, thetamax, n_bins, cm_params, n_groups, built));
+    std::lock_guard<std::mutex> lock(ctx->plan_mutex);
+    for (auto &pl : built) ctx->plans_ahead.push_back(pl);
+    while (ctx->plans_ahead.size() > 512) ctx->plans_ahead.erase(ctx->plans_ahead.begin());  // announced, never computed
     return MB200_OK;
 }
 
 // Squared form factor per entry and group (lib/math.py:692-700): f = sum_i a_i exp(-b_i (q/4pi)^2) + c,
 // up to two element sets per group for united atoms (math.py:671-684).
-static int plan_ff2(mb200_ctx *ctx, SfPlan &pl, const double *cm, int n_groups) {
-    std::vector<double> key(cm, cm + (size_t)n_groups * 20);
-    if (pl.ff2_groups == n_groups && pl.ff2_key == key) return MB200_OK;
+static void compute_ff2(const SfPlan &pl, const double *cm, int n_groups, std::vector<double> &ff2, bool threads) {
     const size_t nv = pl.qrr.size();
-    std::vector<double> ff2((size_t)n_groups * nv);
+    ff2.resize((size_t)n_groups * nv);
     for (int gidx = 0; gidx < n_groups; ++gidx)
-        parallel_chunks(nv, 50000, [&](size_t e_lo, size_t e_hi) {
+        parallel_chunks(nv, threads ? (size_t)50000 : nv + 1, [&](size_t e_lo, size_t e_hi) {
         for (size_t e = e_lo; e < e_hi; ++e) {
             const double q = pl.qrr[e] / (4 * M_PI);
             const double q2 = q * q;
@@ -952,10 +1109,19 @@ static int plan_ff2(mb200_ctx *ctx, SfPlan &pl, const double *cm, int n_groups) 
             ff2[(size_t)gidx * nv + e] = f * f;
         }
         });
-    if (!ff2.empty()) {
-        MB_TRY(pl.d_ff2.ensure(ff2.size() * 8));
-        MB_CUDA(cudaMemcpyAsync(pl.d_ff2.p, ff2.data(), ff2.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-        MB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+static int plan_ff2(mb200_ctx *ctx, SfPlan &pl, const double *cm, int n_groups) {
+    std::vector<double> key(cm, cm + (size_t)n_groups * 20);
+    if (pl.ff2_groups == n_groups && pl.ff2_key == key) return MB200_OK;
+    if (pl.ff2_host_key != key) {  // not computed ahead by prepare_plans
+        compute_ff2(pl, cm, n_groups, pl.ff2_host, true);
+        pl.ff2_host_key = key;
+    }
+    if (!pl.ff2_host.empty()) {
+        MB_TRY(pl.d_ff2.ensure(pl.ff2_host.size() * 8));
+        // (pageable source: the call returns once it has staged the data)
+        MB_CUDA(cudaMemcpyAsync(pl.d_ff2.p, pl.ff2_host.data(), pl.ff2_host.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
     pl.ff2_key.swap(key);
     pl.ff2_groups = n_groups;
@@ -1671,6 +1837,10 @@ static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int position
     const float *pref = nullptr;
     bool pref_checked = false;
     PrefetchRead pref_read(ctx);
+    MB_TRY(prepare_plans(ctx, (size_t)n_frames,
+                         [&](size_t f, double *d) { for (int i = 0; i < 3; ++i) d[i] = (double)boxes[f * 3 + i]; },
+                         qmin, qmax, thetamin, thetamax, n_bins, cm_params, n_groups));
+    mark("plans ahead");
     while (done < (size_t)n_frames) {
         // chunk size: keep tables under ~12 GB
         size_t chunk = 0, tab_bytes = 0;
@@ -1838,6 +2008,9 @@ extern "C" int mb200_dipsf_frames(mb200_ctx *ctx, const double *positions, const
     MB_CUDA(cudaSetDevice(ctx->device));
     const size_t nn = (size_t)n;
     size_t done = 0;
+    MB_TRY(prepare_plans(ctx, (size_t)n_frames,
+                         [&](size_t f, double *d) { for (int i = 0; i < 3; ++i) d[i] = boxes[f * 3 + i]; },
+                         qmin, qmax, 0.0, M_PI, n_bins, nullptr, 0));
     while (done < (size_t)n_frames) {
         size_t chunk = 0, tab_bytes = 0;
         std::vector<std::shared_ptr<SfPlan>> plans;

@@ -80,6 +80,11 @@ class DiporderStructureFactor(AnalysisBase):
     def _announce_staged(self, staged: list) -> None:
         if self._prologue is not None:
             self._announce_rows([(st[0], st[1]) for st in staged])
+        boxes = np.array([st[2] for st in staged], dtype=np.float64)  # NPT: the frames' q-plans are built ahead (see Saxs)
+        if len(boxes) > 1 and not np.all(boxes == boxes[0]):
+            ctx = _cabi.context(self._batch_device)
+            _cabi.check(_cabi.load().mb200_plans_ahead(ctx.handle, _cabi.ptr(boxes), len(boxes), float(self.qmin), float(self.qmax),
+                                                       0.0, float(np.pi), self.n_bins, None, 0))
 
     def _compute_staged(self, staged: list) -> list:
         F = len(staged)

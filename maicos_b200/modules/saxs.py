@@ -231,6 +231,14 @@ class Saxs(AnalysisBase):
     def _announce_staged(self, staged: list) -> None:
         if self.bin_spectrum:
             self._announce_rows([(st[0], st[1]) for st in staged])
+            # NPT: every frame has its own cell and needs its own q-plan; they are built here, on the staging thread, while
+            # the previous batch computes (constant cell: the one plan is cached after the first batch)
+            boxes = np.array([st[2] for st in staged], dtype=np.float64)
+            if len(boxes) > 1 and not np.all(boxes == boxes[0]):
+                ctx = _cabi.context(self._batch_device)
+                _cabi.check(_cabi.load().mb200_plans_ahead(
+                    ctx.handle, _cabi.ptr(boxes), len(boxes), float(self.qmin), float(self.qmax), float(self.thetamin),
+                    float(self.thetamax), self.n_bins, _cabi.ptr(self._cm), len(self._group_index)))
 
     def _device_packs(self) -> bool:
         # the kernel's pack is the orthorhombic ``x -= floor(x / L) L``; a triclinic cell is packed by the host
