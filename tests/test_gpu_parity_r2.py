@@ -858,3 +858,48 @@ def test_profiles_with_default_pack_wrap_the_atoms_on_the_device(pinned, precisi
     assert velp._device_pack
     rv = np.sum([restatement.hist_planar(w, None, 2, velp.n_bins, 0.0, np.float64(box[2])) for w in wrapped], axis=0)
     assert_array_equal(velp.sums.bincount, rv)
+
+
+# ---- NPT: a new cell, hence a new q-plan, in every frame ----------------------------------------------------------------
+def test_saxs_and_dipsf_on_an_npt_trajectory_with_plans_built_ahead(precision, monkeypatch):
+    """40 frames with 40 different cells (a barostat's breathing, anisotropic): the q-plans of a batch are built side by side
+    on the host threads, ahead of the call (``mb200_plans_ahead``), picked up by the compute call, recycled afterwards.
+    Saxs against the restated run, frame by frame statistics included; DiporderStructureFactor against its per-frame
+    restatement; a second run over the same trajectory (plans partly cached, partly recycled) gives the same bits."""
+    from maicos_b200.mdshim import MemoryTrajectory, Universe
+
+    n_mol, F = 400, 40
+    L = mb.synthetic.cubic_box_for(n_mol)
+    fr = mb.synthetic.spce_water_frames(n_mol, L, 21, n_frames=F)
+    topo = mb.synthetic.spce_topology(n_mol)
+    k = np.arange(F)[:, None]
+    lengths = np.float32(L * (1.0 + 2e-3 * np.sin(0.7 * k + np.array([0.0, 1.0, 2.0]))))
+    dims = np.concatenate([lengths, np.full((F, 3), 90, np.float32)], axis=1)
+    assert len({tuple(r) for r in lengths.tolist()}) == F
+    u = Universe(fr.shape[1], MemoryTrajectory(fr, dims), **topo)
+    monkeypatch.setattr(mb.Saxs, "_batch_size", 8)
+    monkeypatch.setattr(mb.DiporderStructureFactor, "_batch_size", 8)
+    elements = np.asarray(topo["elements"])
+
+    saxs = mb.Saxs(u.atoms, qmax=3.0, dq=0.1).run()
+    res, stats, series = restatement.run_saxs(fr, lengths, elements, qmax=3.0, dq=0.1)
+    assert_array_equal(saxs.sums.bincount, stats.sums["bincount"])
+    assert_allclose(saxs.results.scattering_intensities, res["scattering_intensities"], rtol=RTOL)
+    assert_allclose(saxs.results.dstructure_factors, res["dstructure_factors"], rtol=1e-5, atol=1e-12)
+    assert_allclose(saxs.timeseries, series, rtol=RTOL)
+    again = mb.Saxs(u.atoms, qmax=3.0, dq=0.1).run()
+    for key in saxs.means:
+        assert_array_equal(np.asarray(again.means[key]), np.asarray(saxs.means[key]))
+
+    dip = mb.DiporderStructureFactor(u.atoms, qmax=3.0, dq=0.1, grouping="residues").run()
+    st = restatement.RunningStats()
+    for f in range(F):
+        u.trajectory[f]
+        u.atoms.unwrap(compound="residues")
+        u.atoms.wrap(compound="residues")
+        centres = np.double(u.atoms.center(u.atoms.masses, compound="residues"))
+        mu = u.atoms.dipole_vector(compound="residues")
+        unit = np.ascontiguousarray((mu / np.linalg.norm(mu, axis=1)[:, None]).T)
+        obs, _ = restatement.dipsf_single_frame(centres, unit, np.double(lengths[f]), 0, 3.0, dip.n_bins)
+        st.update(obs)
+    assert_allclose(dip.means.structure_factors, st.means["structure_factors"], rtol=RTOL, atol=1e-12)
