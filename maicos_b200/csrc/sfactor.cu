@@ -150,22 +150,111 @@ __host__ __device__ __forceinline__ size_t tab_index(int atom, int row, int rows
 
 // ------------------------------------------------------------------------------------------
 // k_sf_tables: phase tables
-//   grid = (ceil(ld/128), 3, n_jobs); thread = one atom on one axis.
+//   grid = (3 ceil(ld/128), 1, n_jobs); thread = one atom on one axis (axis = blockIdx.x % 3).
 // ------------------------------------------------------------------------------------------
+//   LT: l values per l tile of the digit image known at compile time (32 / 40 / 48), 0: taken from the job.
+//
+//   Split-precision mode, z axis (tables_z_image): the digits of Z = Ez[l] go straight into the image the tensor-core
+//   kernel reads -- rows 2 l (real part of A: (Zr, -Zi)) and 2 l + 1 (imaginary part: (Zi, Zr)) of l tile l / L_t, K position
+//   2 (j % 16), five digit slices.  A thread owns an atom and walks l by recurrence; its ten 2-byte digit pairs per l would
+//   be ten 2-byte global stores (measured: the image half of the kernel's bytes then moves at 2.8 TB/s against 6.2 TB/s for the
+//   16-byte stores of the FP64 rows).  Instead the CTA (128 atoms = 8 K-steps) collects four l values -- one 8-row group of
+//   the canonical layout: 256 contiguous bytes per (K-step, slice) -- in shared memory and writes them out with 16-byte
+//   stores, 256-byte runs; two buffers, one barrier per group.
+template <int LT>
+__device__ __forceinline__ void tables_z_image(const TableJob &jb, int j, double u) {
+    __shared__ __align__(16) unsigned char s_img[2][8 * TC_S * 256];
+    const int ld = jb.ld, n_atoms = jb.n;
+    const int img_lt = LT ? LT : jb.img_lt, img_maxn = jb.img_maxn, img_rows = jb.img_n_lt * img_lt;
+    const int np = 2 * img_lt;
+    const size_t kstep_bytes = (size_t)(TC_S * np * 32);
+    const size_t img_tile = (size_t)(ld / TC_KA) * kstep_bytes;
+    const int ks = threadIdx.x >> 4, a = threadIdx.x & 15;
+    const int kstep0 = ((blockIdx.x / 3) * blockDim.x) / TC_KA, n_ksteps = ld / TC_KA;
+    const bool real = j < n_atoms;  // j in [n, ld): zero padding up to the leading dimension
+    double s1 = 0.0, c1 = 1.0;
+    if (real) {
+        const double t = u - rint(u);
+        sincospi(2.0 * t, &s1, &c1);
+    }
+    double cr = 1.0, ci = 0.0;
+    unsigned char *mine = &s_img[0][0] + ks * (TC_S * 256) + (a >> 3) * 128 + (a & 7) * 2;
+    for (int l0 = 0; l0 < img_rows; l0 += 4) {
+        unsigned char *buf = mine + ((l0 >> 2) & 1) * (8 * TC_S * 256);
+#pragma unroll
+        for (int dl = 0; dl < 4; ++dl) {
+            const int l = l0 + dl;
+            if (real && (l & 7) == 0) {  // exact re-seed: limits recurrence drift to 7 steps
+                double t = (double)l * u;
+                t -= rint(t);
+                sincospi(2.0 * t, &ci, &cr);
+            }
+            const bool in = real && l < img_maxn;  // l values of the last tile beyond the cube edge are zero rows
+            unsigned rlo, rhi, ilo, ihi, nlo, nhi;
+            tc_digits(in ? cr : 0.0, rlo, rhi);
+            tc_digits(in ? ci : 0.0, ilo, ihi);
+            tc_digits(in ? -ci : 0.0, nlo, nhi);
+#pragma unroll
+            for (int t = 1; t <= TC_S; ++t) {
+                *reinterpret_cast<uint16_t *>(buf + (t - 1) * 256 + (2 * dl) * 16) = (uint16_t)tc_pair(t, rlo, rhi, nlo, nhi);
+                *reinterpret_cast<uint16_t *>(buf + (t - 1) * 256 + (2 * dl + 1) * 16) = (uint16_t)tc_pair(t, ilo, ihi, rlo, rhi);
+            }
+            const double nr = cr * c1 - ci * s1;
+            const double ni = cr * s1 + ci * c1;
+            cr = nr;
+            ci = ni;
+        }
+        __syncthreads();
+        // 8 K-steps x 5 slices x 256 bytes = 640 chunks of 16 bytes
+        const unsigned char *src = &s_img[(l0 >> 2) & 1][0];
+        int8_t *dst = jb.bimg + (size_t)(l0 / img_lt) * img_tile + (size_t)((l0 % img_lt) >> 2) * 256;
+#pragma unroll
+        for (int i = 0; i < TC_S; ++i) {
+            const int c = threadIdx.x + 128 * i;
+            const int cks = c / (TC_S * 16), rem = c - cks * (TC_S * 16), t = rem >> 4, w = rem & 15;
+            if (kstep0 + cks < n_ksteps)
+                *reinterpret_cast<uint4 *>(dst + (size_t)(kstep0 + cks) * kstep_bytes + (size_t)t * (np * 32) + w * 16) =
+                    *reinterpret_cast<const uint4 *>(src + c * 16);
+        }
+    }
+}
+
+template <int LT>
 __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ jobs) {
     const TableJob &jb = jobs[blockIdx.z];
-    const int axis = blockIdx.y;
+    // the axis is the fastest block index: CTAs of the write-heavy x rows, the light y rows and the compute-heavy z digits
+    // of the same atoms are resident side by side instead of one phase after the other
+    const int axis = blockIdx.x % 3;
     double2 *tab = jb.tab[axis];
     if (tab == nullptr) return;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (blockIdx.x / 3) * blockDim.x + threadIdx.x;
     // every field the row loop needs goes to registers up front: the job lives in global memory and the loop's stores
-    // would otherwise force the compiler to reload it in every iteration (ncu: half of all stall cycles on those loads)
+    // would otherwise force the compiler to reload it in every iteration
     const int ld = jb.ld, n_atoms = jb.n;
-    if (j >= ld) return;
+    const bool to_image = axis == 2 && jb.bimg != nullptr;  // uniform over the CTA
+    if (j >= ld && !to_image) return;
+    double u = 0.0;
+    if (j < n_atoms) {
+        const int64_t a = jb.index ? (int64_t)jb.index[j] : (int64_t)j;
+        if (jb.is_f32) {
+            float p = reinterpret_cast<const float *>(jb.pos)[a * jb.stride_atom + axis * jb.stride_xyz];
+            const float L = jb.boxf[axis];
+            const int wrap_mode = jb.wrap_mode;
+            if (wrap_mode == 2)  // AtomGroup.wrap(compound="atoms"): x -= floor(x/L)*L in float32
+                p = __fsub_rn(p, __fmul_rn(floorf(__fdiv_rn(p, L)), L));
+            if (wrap_mode >= 1)  // saxs.py:193-195: pos - box*round(pos/box), float32 arithmetic
+                p = __fsub_rn(p, __fmul_rn(L, rintf(__fdiv_rn(p, L))));
+            u = (double)p / (double)L;
+        } else {
+            double p = reinterpret_cast<const double *>(jb.pos)[a * jb.stride_atom + axis * jb.stride_xyz];
+            u = p / jb.box[axis];
+        }
+    }
+    if (to_image) {  // every thread of the CTA takes part (block barriers), also those beyond ld
+        tables_z_image<LT>(jb, j, u);
+        return;
+    }
     const int rows = jb.rows[axis];
-    // split-precision mode, z axis: digits of Z = Ez[l] straight into the image of the tensor-core kernel, rows
-    // 2 l (real part of A: (Zr, -Zi)) and 2 l + 1 (imaginary part: (Zi, Zr)) of l tile l / L_t, K position 2 (j % 16)
-    const bool to_image = axis == 2 && jb.bimg != nullptr;
     const bool masked = axis == 1 && jb.use_y_mask != 0;
     const unsigned long long ym0 = masked ? jb.y_mask[0] : ~0ull, ym1 = masked ? jb.y_mask[1] : ~0ull,
                              ym2 = masked ? jb.y_mask[2] : ~0ull, ym3 = masked ? jb.y_mask[3] : ~0ull;
@@ -174,49 +263,10 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
         const unsigned long long m = wd == 0 ? ym0 : (wd == 1 ? ym1 : (wd == 2 ? ym2 : ym3));
         return (m >> (r & 63)) & 1ull;
     };
-    const int img_lt = jb.img_lt, img_maxn = jb.img_maxn, img_rows = jb.img_n_lt * jb.img_lt;
-    const int np = 2 * img_lt;
-    int8_t *img = nullptr;
-    if (to_image) img = jb.bimg + (size_t)(j / TC_KA) * (size_t)(TC_S * np * 32) + tc_canon(0, 2 * (j % TC_KA));
-    const size_t img_tile = (size_t)(ld / TC_KA) * (size_t)(TC_S * np * 32);
-    auto put_image = [&](int l, double zr, double zi) {
-        unsigned rlo, rhi, ilo, ihi, nlo, nhi;
-        tc_digits(zr, rlo, rhi);
-        tc_digits(zi, ilo, ihi);
-        tc_digits(-zi, nlo, nhi);
-        int8_t *b = img + (size_t)(l / img_lt) * img_tile;
-        const int li = l % img_lt;
-        const int o0 = tc_canon(2 * li, 0), o1 = tc_canon(2 * li + 1, 0);
-#pragma unroll
-        for (int t = 1; t <= TC_S; ++t) {
-            *reinterpret_cast<uint16_t *>(b + o0) = (uint16_t)tc_pair(t, rlo, rhi, nlo, nhi);
-            *reinterpret_cast<uint16_t *>(b + o1) = (uint16_t)tc_pair(t, ilo, ihi, rlo, rhi);
-            b += np * 32;
-        }
-    };
     if (j >= n_atoms) {  // zero padding up to the leading dimension
-        if (to_image) {
-            for (int l = 0; l < img_rows; ++l) put_image(l, 0.0, 0.0);
-            return;
-        }
         for (int r = 0; r < rows; ++r)
             if (wanted(r)) tab[tab_index(j, r, rows)] = make_double2(0.0, 0.0);
         return;
-    }
-    const int64_t a = jb.index ? (int64_t)jb.index[j] : (int64_t)j;
-    double u;
-    if (jb.is_f32) {
-        float p = reinterpret_cast<const float *>(jb.pos)[a * jb.stride_atom + axis * jb.stride_xyz];
-        const float L = jb.boxf[axis];
-        const int wrap_mode = jb.wrap_mode;
-        if (wrap_mode == 2)  // AtomGroup.wrap(compound="atoms"): x -= floor(x/L)*L in float32
-            p = __fsub_rn(p, __fmul_rn(floorf(__fdiv_rn(p, L)), L));
-        if (wrap_mode >= 1)  // saxs.py:193-195: pos - box*round(pos/box), float32 arithmetic
-            p = __fsub_rn(p, __fmul_rn(L, rintf(__fdiv_rn(p, L))));
-        u = (double)p / (double)L;
-    } else {
-        double p = reinterpret_cast<const double *>(jb.pos)[a * jb.stride_atom + axis * jb.stride_xyz];
-        u = p / jb.box[axis];
     }
     const double w = (axis == 0 && jb.weights) ? jb.weights[j] * jb.wscale : 1.0;
     double s1, c1;
@@ -231,18 +281,12 @@ __global__ void __launch_bounds__(128) k_sf_tables(const TableJob *__restrict__ 
             t -= rint(t);
             sincospi(2.0 * t, &ci, &cr);
         }
-        if (to_image) {
-            if (r < img_maxn) put_image(r, cr, ci);  // the z axis never carries weights
-        } else if (wanted(r)) {
-            tab[tab_index(j, r, rows)] = make_double2(w * cr, w * ci);
-        }
+        if (wanted(r)) tab[tab_index(j, r, rows)] = make_double2(w * cr, w * ci);
         const double nr = cr * c1 - ci * s1;
         const double ni = cr * s1 + ci * c1;
         cr = nr;
         ci = ni;
     }
-    if (to_image)  // l values of the last tile beyond the cube edge
-        for (int l = img_maxn; l < img_rows; ++l) put_image(l, 0.0, 0.0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1128,6 +1172,22 @@ static int plan_ff2(mb200_ctx *ctx, SfPlan &pl, const double *cm, int n_groups) 
     return MB200_OK;
 }
 
+// launches k_sf_tables with the l-tile size of the jobs' digit images as a compile-time constant when they agree on one
+static void launch_tables(mb200_ctx *ctx, dim3 grid, const TableJob *d_jobs, const std::vector<int> &img_lts) {
+    int lt = -1;
+    for (int v : img_lts) {
+        if (v <= 0) continue;  // no digit image in this job
+        lt = (lt < 0 || lt == v) ? v : 0;
+        if (lt == 0) break;
+    }
+    switch (lt) {
+        case 32: k_sf_tables<32><<<grid, 128, 0, ctx->stream>>>(d_jobs); break;
+        case 40: k_sf_tables<40><<<grid, 128, 0, ctx->stream>>>(d_jobs); break;
+        case 48: k_sf_tables<48><<<grid, 128, 0, ctx->stream>>>(d_jobs); break;
+        default: k_sf_tables<0><<<grid, 128, 0, ctx->stream>>>(d_jobs); break;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host: engine
 // ------------------------------------------------------------------------------------------
@@ -1350,7 +1410,9 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
     for (int s = 0; s < ns; ++s) max_ld = std::max(max_ld, specs[s].job.ld);
     int64_t launched = 0;
     if (max_ld > 0) {
-        k_sf_tables<<<dim3((max_ld + 127) / 128, 3, ns), 128, 0, ctx->stream>>>(ctx->d_jobs.as<TableJob>());
+        std::vector<int> lts(ns);
+        for (int s = 0; s < ns; ++s) lts[s] = specs[s].job.bimg ? specs[s].job.img_lt : 0;
+        launch_tables(ctx, dim3(3 * ((max_ld + 127) / 128), 1, ns), ctx->d_jobs.as<TableJob>(), lts);
         MB_CUDA(cudaGetLastError());
         ++launched;
     }
@@ -1518,8 +1580,8 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
     for (int s = 0; s < ns; ++s) max_ld = std::max(max_ld, specs[s].job.ld);
     int64_t launched = 0;
     if (max_ld > 0) {
-        dim3 grid((max_ld + 127) / 128, 3, ns);
-        k_sf_tables<<<grid, 128, 0, ctx->stream>>>(ctx->d_jobs.as<TableJob>());
+        dim3 grid(3 * ((max_ld + 127) / 128), 1, ns);
+        launch_tables(ctx, grid, ctx->d_jobs.as<TableJob>(), std::vector<int>());  // FP64 mode: no digit images
         MB_CUDA(cudaGetLastError());
         ++launched;
     }
