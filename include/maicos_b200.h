@@ -96,6 +96,12 @@ int mb200_prefetch_frames(mb200_ctx *ctx, const void *host_frames, size_t bytes)
  * sharing, out[2] = announcements not copied ahead because every slot was being read (the call copies by itself). */
 int mb200_prefetch_frames_shared(mb200_ctx *ctx, const void *host_frames, size_t bytes, uint64_t tag);
 int mb200_ctx_prefetch_stats(mb200_ctx *ctx, int64_t out[3]);
+/* One frame of a GROMACS .xtc file (compressed coordinates), host only.  `data` / `size`: the (memory-mapped) file, `offset`:
+ * where the frame starts.  Outputs (each may be NULL): atom count, step, time (ps), box (3 x 3, nm), positions float32
+ * [natoms][3] multiplied by `scale` (10: nm -> Angstrom) -- NULL positions only scans the header -- and the offset of the
+ * next frame.  Replaces the XTC reader MDAnalysis brings (xdrfile, third party) on the trajectory-ingest side of the path. */
+int mb200_xtc_frame(const void *data, size_t size, size_t offset, int64_t *natoms, int32_t *step, float *time,
+                    float box[9], float *positions, double scale, size_t *next_offset);
 /* Page-locked host memory for frame staging (full-rate asynchronous H2D / D2H).  Any host pointer
  * is accepted by the compute calls; pinned ones avoid the driver's bounce buffer. */
 int mb200_host_alloc(size_t bytes, void **out);

@@ -1,4 +1,4 @@
-"""Hand-written GROMACS ``.gro`` and ``.trr`` readers (orthorhombic cells, lengths converted nm -> Å).
+"""Hand-written GROMACS ``.gro``, ``.trr`` and ``.xtc`` readers (lengths converted nm -> Å).
 
 These stand in for the MDAnalysis readers the reference relies on (third-party, not installable
 here).  They cover what configuration 1 needs: the topology order of ``water.gro`` and the
@@ -126,14 +126,16 @@ def _scan_trr(mm) -> list[dict]:
     return frames
 
 
-class TRRTrajectory:
-    """Streaming ``.trr`` reader: the file is memory-mapped and indexed once (headers only), a frame is decoded when it
-    is visited -- big-endian XDR reals -> native float32, nm -> Å, ONE pass over the frame's bytes.
+class _StreamingTrajectory:
+    """A trajectory file that is memory-mapped and indexed once (headers only); a frame is decoded when it is visited.
 
     ``pinned_ring=k`` decodes into a ring of ``k`` page-locked frame buffers and serves those rows through
     ``pinned_row`` (the protocol of :class:`MemoryTrajectory`): the batched analyses then hand the decoded frames to the
     device where the reader put them, without a staging copy.  An analysis keeps at most ``(devices + 2) x batch``
     frames alive; ``AnalysisBase`` shrinks its batch to fit the ring.
+
+    Subclasses provide ``_scan(mm) -> [dict(n, time, dims, v)]`` and ``_decode_x(frame index entry, out)`` (and
+    ``_decode_v`` when the format carries velocities).
     """
 
     def __init__(self, path, pinned_ring: int = 0):
@@ -141,9 +143,9 @@ class TRRTrajectory:
 
         self._file = open(path, "rb")
         self._mm = mmap.mmap(self._file.fileno(), 0, access=mmap.ACCESS_READ)
-        self._index = _scan_trr(self._mm)
-        if not self._index or any(fr["x"] is None for fr in self._index):
-            raise ValueError("every TRR frame needs coordinates")
+        self._index = self._scan(self._mm)
+        if not self._index:
+            raise ValueError("no frames in the trajectory")
         self.n_frames = len(self._index)
         self.n_atoms = int(self._index[0]["n"])
         if any(fr["n"] != self.n_atoms for fr in self._index):
@@ -151,7 +153,7 @@ class TRRTrajectory:
         have_box = all(fr["dims"] is not None for fr in self._index)
         self.dimensions = np.asarray([fr["dims"] for fr in self._index], dtype=np.float32) if have_box else None
         self.times = np.asarray([fr["time"] for fr in self._index])
-        self.velocities = True if all(fr["v"] is not None for fr in self._index) else None  # decoded per frame
+        self.velocities = True if all(fr.get("v") is not None for fr in self._index) else None  # decoded per frame
         self.dt = float(self.times[1] - self.times[0]) if self.n_frames > 1 else 1.0
         self.coordinates = None
         self.ring_len = 0
@@ -172,10 +174,14 @@ class TRRTrajectory:
         self.ts = None
         self._goto(0)
 
-    def _decode(self, offset: int, fmt: str, out: np.ndarray) -> np.ndarray:
-        src = np.frombuffer(self._mm, dtype=fmt, count=3 * self.n_atoms, offset=offset).reshape(self.n_atoms, 3)
-        np.multiply(src, 10.0, out=out, casting="unsafe")  # byte order, precision and unit in one pass
-        return out
+    def _scan(self, mm) -> list[dict]:
+        raise NotImplementedError
+
+    def _decode_x(self, fr: dict, out: np.ndarray) -> np.ndarray:
+        raise NotImplementedError
+
+    def _decode_v(self, fr: dict, out: np.ndarray) -> np.ndarray:
+        raise NotImplementedError
 
     def _goto(self, f: int) -> Timestep:
         if f < 0:
@@ -186,15 +192,16 @@ class TRRTrajectory:
         if self._ring is not None:
             slot = f % self.ring_len
             if self._ring_frame[slot] != f:
-                self._decode(fr["x"], fr["fmt"], self._ring[slot])
+                self._ring_frame[slot] = -1
+                self._decode_x(fr, self._ring[slot])
                 self._ring_frame[slot] = f
             pos = self._ring[slot].view()
         else:
-            pos = self._decode(fr["x"], fr["fmt"], np.empty((self.n_atoms, 3), dtype=np.float32))
+            pos = self._decode_x(fr, np.empty((self.n_atoms, 3), dtype=np.float32))
         pos.flags.writeable = False  # copy-on-write, like MemoryTrajectory (Timestep.writable_positions)
         vel = None
-        if fr["v"] is not None and self.velocities is not None:
-            vel = self._decode(fr["v"], fr["fmt"], np.empty((self.n_atoms, 3), dtype=np.float32))
+        if fr.get("v") is not None and self.velocities is not None:
+            vel = self._decode_v(fr, np.empty((self.n_atoms, 3), dtype=np.float32))
         dims = None if self.dimensions is None else np.array(self.dimensions[f], dtype=np.float32)
         self.ts = Timestep(pos, dims, f, float(fr["time"]), vel)
         return self.ts
@@ -251,6 +258,78 @@ class TRRTrajectory:
             pass
 
 
+class TRRTrajectory(_StreamingTrajectory):
+    """Streaming ``.trr`` reader: big-endian XDR reals -> native float32, nm -> Å, ONE pass over the frame's bytes."""
+
+    def _scan(self, mm) -> list[dict]:
+        index = _scan_trr(mm)
+        if any(fr["x"] is None for fr in index):
+            raise ValueError("every TRR frame needs coordinates")
+        return index
+
+    def _decode(self, offset: int, fmt: str, out: np.ndarray) -> np.ndarray:
+        src = np.frombuffer(self._mm, dtype=fmt, count=3 * self.n_atoms, offset=offset).reshape(self.n_atoms, 3)
+        np.multiply(src, 10.0, out=out, casting="unsafe")  # byte order, precision and unit in one pass
+        return out
+
+    def _decode_x(self, fr: dict, out: np.ndarray) -> np.ndarray:
+        return self._decode(fr["x"], fr["fmt"], out)
+
+    def _decode_v(self, fr: dict, out: np.ndarray) -> np.ndarray:
+        return self._decode(fr["v"], fr["fmt"], out)
+
+
+def box_to_dimensions(box: np.ndarray) -> np.ndarray:
+    """``[lx, ly, lz, alpha, beta, gamma]`` (Å, degrees; float32) of a 3 x 3 matrix of cell vectors in nm."""
+    box = np.asarray(box, dtype=np.float64).reshape(3, 3) * 10.0
+    lengths = np.linalg.norm(box, axis=1)
+    if not np.all(lengths > 0):
+        return np.zeros(6, dtype=np.float32)
+    a, b, c = box
+
+    def angle(u, v):
+        return float(np.degrees(np.arccos(np.clip(np.dot(u, v) / (np.linalg.norm(u) * np.linalg.norm(v)), -1.0, 1.0))))
+
+    off = box - np.diag(np.diag(box))
+    angles = [90.0, 90.0, 90.0] if not off.any() else [angle(b, c), angle(a, c), angle(a, b)]
+    return np.array([*lengths, *angles], dtype=np.float32)
+
+
+class XTCTrajectory(_StreamingTrajectory):
+    """Streaming ``.xtc`` reader (compressed coordinates, no velocities): frames are indexed from their headers and decoded
+    by ``mb200_xtc_frame`` (C++ in ``libmaicos_b200``, host only) when they are visited, nm -> Å."""
+
+    def _scan(self, mm) -> list[dict]:
+        import ctypes
+
+        from .. import _cabi
+
+        lib = _cabi.load()
+        self._bytes = np.frombuffer(mm, dtype=np.uint8)
+        size, off, index = len(self._bytes), 0, []
+        nat, step, t, nxt = ctypes.c_int64(), ctypes.c_int32(), ctypes.c_float(), ctypes.c_size_t()
+        box = np.zeros(9, dtype=np.float32)
+        while off < size:
+            _cabi.check(lib.mb200_xtc_frame(_cabi.ptr(self._bytes), size, off, ctypes.byref(nat), ctypes.byref(step),
+                                            ctypes.byref(t), _cabi.ptr(box), None, 10.0, ctypes.byref(nxt)))
+            index.append({"offset": off, "n": int(nat.value), "time": float(t.value), "step": int(step.value),
+                          "dims": box_to_dimensions(box), "v": None})
+            off = int(nxt.value)
+        return index
+
+    def _decode_x(self, fr: dict, out: np.ndarray) -> np.ndarray:
+        from .. import _cabi
+
+        assert out.flags.c_contiguous and out.dtype == np.float32
+        _cabi.check(_cabi.load().mb200_xtc_frame(_cabi.ptr(self._bytes), len(self._bytes), fr["offset"], None, None, None, None,
+                                                 _cabi.ptr(out), 10.0, None))
+        return out
+
+    def close(self) -> None:
+        self._bytes = None
+        super().close()
+
+
 def write_trr(path, positions, dimensions, times=None, velocities=None) -> None:
     """Write float32 frames (Å) as a single-precision GROMACS ``.trr`` (orthorhombic box, x and optionally v blocks): the
     inverse of the readers above, used to put synthetic trajectories on disk."""
@@ -274,8 +353,21 @@ def write_trr(path, positions, dimensions, times=None, velocities=None) -> None:
                 fh.write((np.asarray(velocities[f], dtype=np.float32) / np.float32(10)).astype(">f4").tobytes())
 
 
+def read_xtc(path) -> dict:
+    """Decode every frame of an ``.xtc`` -> dict(positions [F,n,3] f32 Å, velocities None, dimensions [F,6], times)."""
+    traj = XTCTrajectory(path)
+    try:
+        pos = np.empty((traj.n_frames, traj.n_atoms, 3), dtype=np.float32)
+        for f, fr in enumerate(traj._index):
+            traj._decode_x(fr, pos[f])
+        return {"positions": pos, "velocities": None, "dimensions": None if traj.dimensions is None else traj.dimensions.copy(),
+                "times": traj.times.copy()}
+    finally:
+        traj.close()
+
+
 def universe_from_gro(gro_path, trr_path=None, charges=None, stream: bool = False, pinned_ring: int = 0) -> Universe:
-    """Universe with the topology order of a ``.gro`` file and, optionally, a ``.trr`` trajectory."""
+    """Universe with the topology order of a ``.gro`` file and, optionally, a ``.trr`` or ``.xtc`` trajectory."""
     g = read_gro(gro_path)
     n = len(g["names"])
     elements = np.array([guess_element(nm) for nm in g["names"]], dtype=object)
@@ -285,11 +377,12 @@ def universe_from_gro(gro_path, trr_path=None, charges=None, stream: bool = Fals
         traj = MemoryTrajectory(g["positions"][None], g["dimensions"],
                                 None if g["velocities"] is None else g["velocities"][None])
     elif stream or pinned_ring:  # frames are decoded from the memory-mapped file when they are visited
-        traj = TRRTrajectory(trr_path, pinned_ring=pinned_ring)
+        reader = XTCTrajectory if str(trr_path).lower().endswith(".xtc") else TRRTrajectory
+        traj = reader(trr_path, pinned_ring=pinned_ring)
         if traj.n_atoms != n:
             raise ValueError("topology and trajectory disagree on the number of atoms")
     else:
-        t = read_trr(trr_path)
+        t = read_xtc(trr_path) if str(trr_path).lower().endswith(".xtc") else read_trr(trr_path)
         if t["positions"].shape[1] != n:
             raise ValueError("topology and trajectory disagree on the number of atoms")
         traj = MemoryTrajectory(t["positions"], t["dimensions"], t["velocities"], times=t["times"])

@@ -903,3 +903,32 @@ def test_saxs_and_dipsf_on_an_npt_trajectory_with_plans_built_ahead(precision, m
         obs, _ = restatement.dipsf_single_frame(centres, unit, np.double(lengths[f]), 0, 3.0, dip.n_bins)
         st.update(obs)
     assert_allclose(dip.means.structure_factors, st.means["structure_factors"], rtol=RTOL, atol=1e-12)
+
+
+def test_streaming_xtc_with_pinned_ring_feeds_the_device(precision):
+    """The reference's compressed ``cntwater.xtc`` (first two frames, ``tests/golden``) decoded by ``mb200_xtc_frame`` into a
+    ring of page-locked buffers and binned where the decoder put it: number density along z = numpy's histogram of the
+    decoded (and float32-wrapped) frames; the same from the whole-file reader."""
+    from pathlib import Path
+
+    from maicos_b200.mdshim import MemoryTrajectory, Universe, XTCTrajectory, read_xtc
+
+    path = Path(__file__).resolve().parent / "golden" / "xtc_cntwater_2frames.xtc"
+    x = read_xtc(path)
+    n = x["positions"].shape[1]
+    topo = dict(names=np.array(["X"] * n, dtype=object), masses=np.ones(n), charges=np.zeros(n), resindices=np.arange(n))
+    box = x["dimensions"][0, :3]
+    results = []
+    for traj in (XTCTrajectory(path, pinned_ring=2), XTCTrajectory(path), MemoryTrajectory(x["positions"], x["dimensions"])):
+        u = Universe(n, traj, **topo)
+        d = mb.DensityPlanar(u.atoms, dens="number", bin_width=0.5).run()
+        assert d.n_frames == 2
+        results.append(d)
+        if hasattr(traj, "close"):
+            traj.close()
+    nb = results[0].n_bins
+    ref = np.sum([restatement.hist_planar(restatement.wrap_atoms_f32(p, box), None, 2, nb, 0.0, np.float64(box[2]))
+                  for p in x["positions"]], axis=0)
+    for d in results:
+        assert_array_equal(d.sums.bincount, ref)
+        assert_array_equal(d.means.profile, results[0].means.profile)
