@@ -32,3 +32,16 @@ gro = read_gro(REF / "cntwater.gro")
 np.savez_compressed(OUT / "xtc_cntwater_frame0.npz", gro_positions=gro["positions"], dimensions=gro["dimensions"],
                     times=np.array([0.0, 0.5]), n_frames_in_file=51)
 print("wrote", cuts[-1], "bytes of XTC and", gro["positions"].shape, "reference coordinates")
+
+# a second, geometric check of the decoder on a file that is too large to commit: every O-H bond of every frame of the
+# reference's examples/water_nvt.xtc (512 SPC/E molecules, 201 frames) has its model length
+from maicos_b200.mdshim import read_xtc  # noqa: E402
+
+w = read_xtc("/root/reference/examples/water_nvt.xtc")
+L = w["dimensions"][:, None, :3]
+for h in (1, 2):
+    v = w["positions"][:, h::3] - w["positions"][:, 0::3]
+    v -= np.round(v / L) * L
+    d = np.linalg.norm(v, axis=2)
+    assert 0.98 < d.min() and d.max() < 1.02, (d.min(), d.max())
+print("water_nvt.xtc:", w["positions"].shape, "all O-H bonds within", float(d.min()), float(d.max()))
