@@ -163,7 +163,11 @@ __host__ __device__ __forceinline__ size_t tab_index(int atom, int row, int rows
 //   stores, 256-byte runs; two buffers, one barrier per group.
 template <int LT>
 __device__ __forceinline__ void tables_z_image(const TableJob &jb, int j, double u) {
-    __shared__ __align__(16) unsigned char s_img[2][8 * TC_S * 256];
+    // shared layout of one 4-l group: [K-step 8][slice 5][K chunk 2][row 8][16 B], padded (K chunk stride 160 B, slice
+    // 320 B, K-step 1600 B = 64 mod 128) so that the four 16-byte chunks a warp's 2-byte stores touch (two K-steps x two
+    // K chunks) fall into four different bank groups -- unpadded they collide four ways and the L1 pipe saturates (ncu 93 %)
+    constexpr int Z_KC = 160, Z_T = 2 * Z_KC, Z_KS = TC_S * Z_T, Z_BUF = 8 * Z_KS;
+    __shared__ __align__(16) unsigned char s_img[2][Z_BUF];
     const int ld = jb.ld, n_atoms = jb.n;
     const int img_lt = LT ? LT : jb.img_lt, img_maxn = jb.img_maxn, img_rows = jb.img_n_lt * img_lt;
     const int np = 2 * img_lt;
@@ -178,9 +182,9 @@ __device__ __forceinline__ void tables_z_image(const TableJob &jb, int j, double
         sincospi(2.0 * t, &s1, &c1);
     }
     double cr = 1.0, ci = 0.0;
-    unsigned char *mine = &s_img[0][0] + ks * (TC_S * 256) + (a >> 3) * 128 + (a & 7) * 2;
+    unsigned char *mine = &s_img[0][0] + ks * Z_KS + (a >> 3) * Z_KC + (a & 7) * 2;
     for (int l0 = 0; l0 < img_rows; l0 += 4) {
-        unsigned char *buf = mine + ((l0 >> 2) & 1) * (8 * TC_S * 256);
+        unsigned char *buf = mine + ((l0 >> 2) & 1) * Z_BUF;
 #pragma unroll
         for (int dl = 0; dl < 4; ++dl) {
             const int l = l0 + dl;
@@ -196,8 +200,8 @@ __device__ __forceinline__ void tables_z_image(const TableJob &jb, int j, double
             tc_digits(in ? -ci : 0.0, nlo, nhi);
 #pragma unroll
             for (int t = 1; t <= TC_S; ++t) {
-                *reinterpret_cast<uint16_t *>(buf + (t - 1) * 256 + (2 * dl) * 16) = (uint16_t)tc_pair(t, rlo, rhi, nlo, nhi);
-                *reinterpret_cast<uint16_t *>(buf + (t - 1) * 256 + (2 * dl + 1) * 16) = (uint16_t)tc_pair(t, ilo, ihi, rlo, rhi);
+                *reinterpret_cast<uint16_t *>(buf + (t - 1) * Z_T + (2 * dl) * 16) = (uint16_t)tc_pair(t, rlo, rhi, nlo, nhi);
+                *reinterpret_cast<uint16_t *>(buf + (t - 1) * Z_T + (2 * dl + 1) * 16) = (uint16_t)tc_pair(t, ilo, ihi, rlo, rhi);
             }
             const double nr = cr * c1 - ci * s1;
             const double ni = cr * s1 + ci * c1;
@@ -214,7 +218,7 @@ __device__ __forceinline__ void tables_z_image(const TableJob &jb, int j, double
             const int cks = c / (TC_S * 16), rem = c - cks * (TC_S * 16), t = rem >> 4, w = rem & 15;
             if (kstep0 + cks < n_ksteps)
                 *reinterpret_cast<uint4 *>(dst + (size_t)(kstep0 + cks) * kstep_bytes + (size_t)t * (np * 32) + w * 16) =
-                    *reinterpret_cast<const uint4 *>(src + c * 16);
+                    *reinterpret_cast<const uint4 *>(src + cks * Z_KS + t * Z_T + (w >> 3) * Z_KC + (w & 7) * 16);
         }
     }
 }
@@ -1889,7 +1893,10 @@ static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int position
     auto mark = [&](const char *what) {
         if (!trace_host) return;
         const auto now = std::chrono::steady_clock::now();
-        std::fprintf(stderr, "[mb200_saxs_frames] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        static const auto t_zero = now;  // absolute time of the first traced call: shows the gaps between calls as well
+        std::fprintf(stderr, "[mb200_saxs_frames] %-28s %8.3f ms   @ %10.3f ms\n", what,
+                     std::chrono::duration<double, std::milli>(now - t_last).count(),
+                     std::chrono::duration<double, std::milli>(now - t_zero).count());
         t_last = now;
     };
     mark("entry");
