@@ -232,11 +232,18 @@ def main():
     s_b = np.zeros((B, G, n_bins)); i_b = np.zeros((B, G, n_bins)); c_b = np.zeros((B, G, n_bins), dtype=np.int64)
     acc = np.zeros(3 * n_bins)
 
+    # the element groups go to the device once, as in Saxs.run() (mb200_groups_create; the array form of the call would
+    # fingerprint the 100k indices in every step)
+    import ctypes
+
+    groups_handle = ctypes.c_void_p()
+    _cabi.check(lib.mb200_groups_create(ctx.handle, _cabi.ptr(gflat), _cabi.ptr(gptr), G, n, ctypes.byref(groups_handle)))
+
     def step(k):
         ptr_dev = d_pool.data_ptr() + (k % P) * B * n * 12
-        _cabi.check(lib.mb200_saxs_frames(ctx.handle, ptr_dev, 1, B, n, _cabi.ptr(boxes), _cabi.ptr(gflat),
-                                          _cabi.ptr(gptr), G, _cabi.ptr(cm), 0.0, QMAX, 0.0, float(np.pi), n_bins, 1,
-                                          0, 1, _cabi.ptr(s_b), _cabi.ptr(i_b), _cabi.ptr(c_b)))
+        _cabi.check(lib.mb200_saxs_frames_groups(ctx.handle, ptr_dev, 1, B, _cabi.ptr(boxes), groups_handle, _cabi.ptr(cm),
+                                                 0.0, QMAX, 0.0, float(np.pi), n_bins, 1, 0, 1, _cabi.ptr(s_b), _cabi.ptr(i_b),
+                                                 _cabi.ptr(c_b)))
         acc[:n_bins] += s_b.sum((0, 1)); acc[n_bins:2 * n_bins] += i_b.sum((0, 1)); acc[2 * n_bins:] += c_b[:, -1].sum(0)
         return ctx.stats()
 
