@@ -239,13 +239,33 @@ def main():
     groups_handle = ctypes.c_void_p()
     _cabi.check(lib.mb200_groups_create(ctx.handle, _cabi.ptr(gflat), _cabi.ptr(gptr), G, n, ctypes.byref(groups_handle)))
 
-    def step(k):
+    # a step is submitted behind the one that is running and collected afterwards (mb200_saxs_frames_submit / _collect, the
+    # pair Saxs.run() uses): every step's kernels, results and host-side accumulation lie inside the timed region
+    def submit(k):
         ptr_dev = d_pool.data_ptr() + (k % P) * B * n * 12
-        _cabi.check(lib.mb200_saxs_frames_groups(ctx.handle, ptr_dev, 1, B, _cabi.ptr(boxes), groups_handle, _cabi.ptr(cm),
-                                                 0.0, QMAX, 0.0, float(np.pi), n_bins, 1, 0, 1, _cabi.ptr(s_b), _cabi.ptr(i_b),
-                                                 _cabi.ptr(c_b)))
+        ticket = ctypes.c_int32(-1)
+        _cabi.check(lib.mb200_saxs_frames_submit(ctx.handle, ptr_dev, 1, B, _cabi.ptr(boxes), groups_handle, _cabi.ptr(cm),
+                                                 0.0, QMAX, 0.0, float(np.pi), n_bins, 1, 0, 1, ctypes.byref(ticket)))
+        return int(ticket.value)
+
+    def collect(ticket):
+        _cabi.check(lib.mb200_saxs_frames_collect(ctx.handle, ticket, _cabi.ptr(s_b), _cabi.ptr(i_b), _cabi.ptr(c_b)))
         acc[:n_bins] += s_b.sum((0, 1)); acc[n_bins:2 * n_bins] += i_b.sum((0, 1)); acc[2 * n_bins:] += c_b[:, -1].sum(0)
         return ctx.stats()
+
+    def step(k):
+        return collect(submit(k))
+
+    def steps(first, count):
+        """`count` steps, each queued behind its predecessor; yields the statistics of every step."""
+        waiting = None
+        for k in range(first, first + count):
+            ticket = submit(k)
+            if waiting is not None:
+                yield collect(waiting)
+            waiting = ticket
+        if waiting is not None:
+            yield collect(waiting)
 
     stream = torch.cuda.ExternalStream(int(lib.mb200_ctx_stream(ctx.handle)), device=local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -266,8 +286,7 @@ def main():
     kern_ns, kern_launches = 0, 0
     ev0.record(stream)
     mma_count = 0
-    for k in range(K):
-        st = step(W + k)
+    for st in steps(W, K):
         kern_ns += st["contract_ns"]; kern_launches += 1
         mma_count += st["dmma_steps"]
     parallel.allreduce_sum(acc)  # the single end-of-run merge of the binned accumulators
@@ -295,8 +314,8 @@ def main():
     o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     o0.record(stream)
     o_ns = 0
-    for k in range(K):
-        o_ns += step(W + k)["contract_ns"]
+    for st in steps(W, K):
+        o_ns += st["contract_ns"]
     o1.record(stream)
     torch.cuda.synchronize()
     o_ms = o0.elapsed_time(o1)

@@ -34,6 +34,7 @@ extern "C" {
 #define MB200_ENODEVICE (-2)
 #define MB200_ECUDA (-3)
 #define MB200_ENOMEM (-4)
+#define MB200_EBUSY (-5) /* no free slot for a deferred batch (mb200_saxs_frames_submit) */
 
 typedef struct mb200_ctx mb200_ctx;
 
@@ -191,6 +192,19 @@ int mb200_saxs_frames_groups(mb200_ctx *ctx, const float *positions, int positio
                              double qmax, double thetamin, double thetamax, int32_t n_bins, int pack_atoms,
                              int32_t block, int32_t n_blocks, double *s_binned, double *i_binned,
                              int64_t *bincount);
+
+/* Deferred form of mb200_saxs_frames_groups: _submit prepares and queues the batch and returns a ticket (0 or 1) while
+ * the kernels run -- or wait behind the previous batch -- so that the host side of the next batch (plan look-up,
+ * descriptors, launches) overlaps with the device work of this one; _collect waits for the batch and hands out its results
+ * (same layout as mb200_saxs_frames_groups).  Up to four batches of a context may wait at a time (MB200_EBUSY beyond that:
+ * collect one, or use the synchronous call).  `boxes` is read before _submit returns; page-locked host `positions` that
+ * were not announced with mb200_prefetch_frames are copied by the stream when their turn comes, so they must stay
+ * untouched until _collect. */
+int mb200_saxs_frames_submit(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                             const float *boxes, const mb200_groups *groups, const double *cm_params, double qmin,
+                             double qmax, double thetamin, double thetamax, int32_t n_bins, int pack_atoms,
+                             int32_t block, int32_t n_blocks, int32_t *ticket);
+int mb200_saxs_frames_collect(mb200_ctx *ctx, int32_t ticket, double *s_binned, double *i_binned, int64_t *bincount);
 
 /* Saxs with bin_spectrum=False (src/maicos/modules/saxs.py:188-189, 238-239: the raw cubes of all element groups are
  * summed per frame) for a batch of frames of ONE cell: per frame and group the structure factors of the accepted q

@@ -15,6 +15,7 @@ import numpy as np
 
 _LIB_PATH = Path(os.environ.get("MAICOS_B200_LIB") or Path(__file__).resolve().parent / "_lib" / "libmaicos_b200.so")
 
+EBUSY = -5  # MB200_EBUSY: no free slot for a deferred batch
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_float_p = ctypes.POINTER(ctypes.c_float)
 c_i32_p = ctypes.POINTER(ctypes.c_int32)
@@ -83,6 +84,13 @@ SIGNATURES = {
          ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_int, ctypes.c_int32,
          ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
     ),
+    "mb200_saxs_frames_submit": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_int, ctypes.c_int32,
+         ctypes.c_int32, ctypes.c_void_p],
+    ),
+    "mb200_saxs_frames_collect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "mb200_saxs_frames_cells": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,

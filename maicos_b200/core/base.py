@@ -421,6 +421,7 @@ class AnalysisBase(_Runner):
         self._inflight_q = collections.deque()
         self._batch_device = None     # device of the batch being announced / submitted
         self._batch_tag = 0           # content tag of the batch being announced (shared frames of a collection)
+        self._pending = {}            # device -> (staged batch, future of its submission) waiting to be collected
         self._window_state = None     # see ``_frame_window``
         self._share_run = 0           # number of the collection run this instance is part of, 0 = on its own
         self._stage_parity = 0
@@ -592,6 +593,7 @@ class AnalysisBase(_Runner):
         self._n_flushed = 0
         self._staged = []
         self._inflight_q = collections.deque()
+        self._pending = {}
         #: host-side time split of the last run: staging, waiting for the device, inside the C-ABI call
         self.timings = {"stage_s": 0.0, "wait_device_s": 0.0, "device_call_s": 0.0}
         for name in ("sums", "means", "sems"):
@@ -711,21 +713,52 @@ class AnalysisBase(_Runner):
             self._batch_device = device
             self._batch_tag = ((self._share_run << 32) | (int(staged[0][0]) + 1)) if self._share_run else 0
             self._announce_staged([st for _, st in staged])
-            self._inflight_q.append(pool.submit(self._device_batch, staged))
+            deferred = self._defers_batches()
+            if deferred:
+                # submit / collect (mb200_saxs_frames_submit): the worker queues this batch behind the one that is running and
+                # only then waits for the older one -- the device never idles between two batches
+                ticket = pool.submit(self._submit_batch, staged)
+                older = self._pending.get(device)
+                if older is not None:
+                    self._inflight_q.append(pool.submit(self._collect_batch, *older))
+                self._pending[device] = (staged, ticket)
+            else:
+                self._inflight_q.append(pool.submit(self._device_batch, staged))
             # the next batch is staged into the next pinned buffer: one more buffer than batches in flight
-            self._stage_parity = (self._stage_parity + 1) % (len(devs) + 1)
+            self._stage_parity = (self._stage_parity + 1) % (len(devs) + 1 + int(deferred))
             while len(self._inflight_q) > len(devs):
                 self._finish_batch(self._inflight_q.popleft())
         if wait:
             self._drain()
 
     def _drain(self) -> None:
+        # batches still waiting on the device: collected in the order they were submitted (= frame order)
+        for device, older in sorted(self._pending.items(), key=lambda kv: kv[1][0][0][0]):
+            self._inflight_q.append(self._pools[device].submit(self._collect_batch, *older))
+        self._pending = {}
         while self._inflight_q:
             self._finish_batch(self._inflight_q.popleft())
+
+    def _defers_batches(self) -> bool:
+        """True when the class splits its device call into ``_submit_staged`` / ``_collect_staged``."""
+        return False
 
     def _device_batch(self, staged: list):
         t0 = time.perf_counter()
         out = self._compute_staged([s for _, s in staged])
+        self.timings["device_call_s"] += time.perf_counter() - t0
+        return staged, out
+
+    def _submit_batch(self, staged: list):
+        t0 = time.perf_counter()
+        state = self._submit_staged([s for _, s in staged])
+        self.timings["device_call_s"] += time.perf_counter() - t0
+        return state
+
+    def _collect_batch(self, staged: list, ticket):
+        state = ticket.result()  # re-raises what the submission raised
+        t0 = time.perf_counter()
+        out = self._collect_staged([s for _, s in staged], state)
         self.timings["device_call_s"] += time.perf_counter() - t0
         return staged, out
 
@@ -906,6 +939,12 @@ class AnalysisBase(_Runner):
         """End of a run, also when a frame raised: wait for the batch in flight, stop the worker thread and hand the
         pinned staging blocks (keyed by ``id(self)``) back, so that no later instance can be given a slot that a device
         call still reads."""
+        for device, older in list(getattr(self, "_pending", {}).items()):  # submitted, never collected: free the ticket
+            try:
+                self._pools[device].submit(self._collect_batch, *older).result()
+            except Exception:
+                pass
+        self._pending = {}
         while self._inflight_q:
             try:
                 self._inflight_q.popleft().result()

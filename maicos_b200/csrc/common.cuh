@@ -144,6 +144,27 @@ struct mb200_ctx {
     int n_sm = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // split-precision contraction: descriptor staging in two alternating page-locked buffers (a call may be queued behind a
+    // running one: mb200_saxs_frames_submit), each guarded by the event recorded behind the copies that read it
+    mb200::PinBuf h_tc_stage[2];
+    cudaEvent_t tc_stage_ev[2] = {nullptr, nullptr};
+    bool tc_stage_used[2] = {false, false};
+    cudaEvent_t tc_ev0[2] = {nullptr, nullptr}, tc_ev1[2] = {nullptr, nullptr};  // kernel timing per staging parity
+    int tc_parity = 0;
+    mb200::PrefetchRead *release_after_tables = nullptr;  // the prefetch slot whose last reader is the next k_sf_tables launch
+    cudaEvent_t t_ev0 = nullptr, t_ev1 = nullptr;  // events around the last contraction launch (finish_timing)
+    int t_parity = -1;
+    // deferred Saxs batches (mb200_saxs_frames_submit / _collect): results wait in page-locked memory
+    struct Pending {
+        bool open = false;
+        size_t n_out = 0;        // doubles per output array
+        int parity = 0;          // staging parity (timing events) of the batch
+        int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaEvent_t done = nullptr;
+    };
+    static constexpr int N_PENDING = 4;  // several analyses of a collection may each have a batch waiting
+    Pending pending[N_PENDING];
+    mb200::PinBuf h_res[N_PENDING];
     bool timing = false;
     bool sf_attr_set = false, hist_attr_set = false, tc_attr_set = false, hc_attr_set = false;
     unsigned hs_attr_set = 0;  // k_hist_sorted<B> instantiations whose shared-memory limit is raised

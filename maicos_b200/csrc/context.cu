@@ -14,6 +14,13 @@ mb200_ctx::~mb200_ctx() {
     plans.clear();
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    for (int i = 0; i < 2; ++i) {
+        if (tc_stage_ev[i]) cudaEventDestroy(tc_stage_ev[i]);
+        if (tc_ev0[i]) cudaEventDestroy(tc_ev0[i]);
+        if (tc_ev1[i]) cudaEventDestroy(tc_ev1[i]);
+    }
+    for (int i = 0; i < N_PENDING; ++i)
+        if (pending[i].done) cudaEventDestroy(pending[i].done);
     for (int i = 0; i < N_PREF; ++i)
         if (pref_ev[i]) cudaEventDestroy(pref_ev[i]);
     for (int i = 0; i < N_PREF; ++i)
@@ -53,6 +60,13 @@ extern "C" int mb200_ctx_create(int device, mb200_ctx **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&ctx->tc_stage_ev[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->tc_ev0[i]);
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->tc_ev1[i]);
+    }
+    for (int i = 0; i < mb200_ctx::N_PENDING && e == cudaSuccess; ++i)
+        e = cudaEventCreateWithFlags(&ctx->pending[i].done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < mb200_ctx::N_PREF && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->pref_ev[i], cudaEventDisableTiming);
     for (int i = 0; i < mb200_ctx::N_PREF && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->pref_done_ev[i], cudaEventDisableTiming);

@@ -1177,6 +1177,8 @@ static int plan_ff2(mb200_ctx *ctx, SfPlan &pl, const double *cm, int n_groups) 
 }
 
 // launches k_sf_tables with the l-tile size of the jobs' digit images as a compile-time constant when they agree on one
+// (the positions of a batch are read by this launch only: a prefetch slot they came from is released right behind it, so
+// that the next batch's host -> device copy runs under the contraction -- also when the batch after is already queued)
 static void launch_tables(mb200_ctx *ctx, dim3 grid, const TableJob *d_jobs, const std::vector<int> &img_lts) {
     int lt = -1;
     for (int v : img_lts) {
@@ -1189,6 +1191,10 @@ static void launch_tables(mb200_ctx *ctx, dim3 grid, const TableJob *d_jobs, con
         case 40: k_sf_tables<40><<<grid, 128, 0, ctx->stream>>>(d_jobs); break;
         case 48: k_sf_tables<48><<<grid, 128, 0, ctx->stream>>>(d_jobs); break;
         default: k_sf_tables<0><<<grid, 128, 0, ctx->stream>>>(d_jobs); break;
+    }
+    if (ctx->release_after_tables) {
+        ctx->release_after_tables->release();
+        ctx->release_after_tables = nullptr;
     }
 }
 
@@ -1386,9 +1392,13 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
                  b_tsegs = ((size_t)ns * sizeof(TcSeg) + 15) / 16 * 16 + (size_t)ns * sizeof(FoldDesc),  // TcSeg[ns] | FoldDesc[ns]
                  b_fold_off = ((size_t)ns * sizeof(TcSeg) + 15) / 16 * 16, b_items = items.size() * sizeof(TcItem);
     const size_t b_owned = (owned_host.size() + 15) / 16 * 16;
-    MB_TRY(ctx->h_stage.ensure(b_jobs + b_segs + b_tsegs + b_items + b_owned + 64));
-    MB_CUDA(cudaStreamSynchronize(ctx->stream));
-    char *hs = ctx->h_stage.as<char>();
+    // two staging buffers alternate, so that this call can be prepared while the previous one still runs (its copies out
+    // of the other buffer may not have executed yet); a buffer is rewritten once the copies that read it are done
+    const int par = ctx->tc_parity;
+    ctx->tc_parity ^= 1;
+    if (ctx->tc_stage_used[par]) MB_CUDA(cudaEventSynchronize(ctx->tc_stage_ev[par]));
+    MB_TRY(ctx->h_tc_stage[par].ensure(b_jobs + b_segs + b_tsegs + b_items + b_owned + 64));
+    char *hs = ctx->h_tc_stage[par].as<char>();
     for (int s = 0; s < ns; ++s) std::memcpy(hs + (size_t)s * sizeof(TableJob), &specs[s].job, sizeof(TableJob));
     std::memcpy(hs + b_jobs, segs_host.data(), b_segs);
     std::memcpy(hs + b_jobs + b_segs, tsegs.data(), (size_t)ns * sizeof(TcSeg));
@@ -1409,6 +1419,8 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
     MB_CUDA(cudaMemcpyAsync(ctx->d_tcdesc.p, hs + b_jobs + b_segs, b_tsegs, cudaMemcpyHostToDevice, ctx->stream));
     if (b_items)
         MB_CUDA(cudaMemcpyAsync(ctx->d_items.p, hs + b_jobs + b_segs + b_tsegs, b_items, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(cudaEventRecord(ctx->tc_stage_ev[par], ctx->stream));
+    ctx->tc_stage_used[par] = true;
     // ---- launches
     int max_ld = 0;
     for (int s = 0; s < ns; ++s) max_ld = std::max(max_ld, specs[s].job.ld);
@@ -1429,7 +1441,7 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
         // l tiles of at most 32 values leave room in tensor memory for the generated A operand (sfactor_tc.cuh)
         bool a_in_tmem = ctx->tc_a_tmem;
         for (int s = 0; s < ns; ++s) a_in_tmem = a_in_tmem && specs[s].plan->tc_lt <= TC_ATM_MAX_LT;
-        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->tc_ev0[par], ctx->stream));
         MB_CUDA(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
         const unsigned n_cta = (unsigned)std::min<size_t>(items.size(), (size_t)ctx->n_sm);
         if (a_in_tmem)
@@ -1439,9 +1451,10 @@ static int run_segments_tc(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t 
             k_sf_contract_tc<false><<<n_cta, TC_THREADS, TC_SMEM, ctx->stream>>>(ctx->d_items.as<TcItem>(), (int)items.size(),
                                                                                 ctx->d_tcdesc.as<TcSeg>(), ctx->d_counter.as<int>());
         MB_CUDA(cudaGetLastError());
-        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->tc_ev1[par], ctx->stream));
         ++launched;
     }
+    ctx->t_ev0 = ctx->tc_ev0[par]; ctx->t_ev1 = ctx->tc_ev1[par]; ctx->t_parity = par;
     if (any_fold) {
         long long max_stride = 0;
         for (int s = 0; s < ns; ++s)
@@ -1601,6 +1614,7 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
                                                                    ctx->d_segs.as<SegDesc>(), ctx->d_counter.as<int>());
         MB_CUDA(cudaGetLastError());
         if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        ctx->t_ev0 = ctx->ev0; ctx->t_ev1 = ctx->ev1; ctx->t_parity = -1;
         ++launched;
     }
     ctx->launches += launched;
@@ -1638,10 +1652,10 @@ static int launch_binned(mb200_ctx *ctx, const std::vector<SegSpec> &specs, doub
 
 static int finish_timing(mb200_ctx *ctx) {
     ctx->stats[5] = 0;
-    if (ctx->timing && ctx->stats[2] > 0) {
+    if (ctx->timing && ctx->stats[2] > 0 && ctx->t_ev0 && ctx->t_ev1) {
         float ms = 0.f;
-        MB_CUDA(cudaEventSynchronize(ctx->ev1));
-        MB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        MB_CUDA(cudaEventSynchronize(ctx->t_ev1));
+        MB_CUDA(cudaEventElapsedTime(&ms, ctx->t_ev0, ctx->t_ev1));
         ctx->stats[5] = (int64_t)(ms * 1.0e6);
     }
     return MB200_OK;
@@ -1782,7 +1796,8 @@ static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int position
                             int64_t n_atoms_total, const float *boxes, const int32_t *d_group_index,
                             const int64_t *group_ptr, int32_t n_groups, const double *cm_params, double qmin,
                             double qmax, double thetamin, double thetamax, int32_t n_bins, int pack_atoms,
-                            int32_t block, int32_t n_blocks, double *s_binned, double *i_binned, int64_t *bincount);
+                            int32_t block, int32_t n_blocks, double *s_binned, double *i_binned, int64_t *bincount,
+                            int32_t *ticket = nullptr);
 
 extern "C" int mb200_groups_create(mb200_ctx *ctx, const int32_t *group_index, const int64_t *group_ptr, int32_t n_groups,
                                    int64_t n_atoms_total, mb200_groups **out) {
@@ -1837,6 +1852,47 @@ extern "C" int mb200_saxs_frames_groups(mb200_ctx *ctx, const float *positions, 
                             thetamin, thetamax, n_bins, pack_atoms, block, n_blocks, s_binned, i_binned, bincount);
 }
 
+// Deferred form of mb200_saxs_frames_groups: the batch is prepared and queued, the call returns while its kernels run (or
+// wait behind the previous batch), so that the host side of batch k + 1 -- plan look-up, descriptors, the launches
+// themselves -- overlaps with the device work of batch k.  At most two batches wait at a time.
+extern "C" int mb200_saxs_frames_submit(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
+                                        const float *boxes, const mb200_groups *groups, const double *cm_params, double qmin,
+                                        double qmax, double thetamin, double thetamax, int32_t n_bins, int pack_atoms,
+                                        int32_t block, int32_t n_blocks, int32_t *ticket) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    MB_LOCK(ctx);
+    if (!groups || !ticket) return fail(MB200_EINVAL, "null groups handle or ticket");
+    if (groups->device != ctx->device) return fail(MB200_EINVAL, "groups belong to another device");
+    return saxs_frames_impl(ctx, positions, positions_on_device, n_frames, groups->n_atoms_total, boxes,
+                            groups->idx.as<int32_t>(), groups->ptr.data(), (int32_t)groups->ptr.size() - 1, cm_params, qmin, qmax,
+                            thetamin, thetamax, n_bins, pack_atoms, block, n_blocks, nullptr, nullptr, nullptr, ticket);
+}
+
+extern "C" int mb200_saxs_frames_collect(mb200_ctx *ctx, int32_t ticket, double *s_binned, double *i_binned, int64_t *bincount) {
+    if (!ctx) return fail(MB200_ENODEVICE, "no CUDA context (there is no CPU fallback)");
+    if (ticket < 0 || ticket >= mb200_ctx::N_PENDING || !s_binned || !i_binned || !bincount)
+        return fail(MB200_EINVAL, "invalid argument to mb200_saxs_frames_collect");
+    mb200_ctx::Pending &pd = ctx->pending[ticket];
+    if (!pd.open) return fail(MB200_EINVAL, "no deferred batch waits under ticket %d", (int)ticket);
+    // the wait happens outside the call mutex: the next batch may be submitted meanwhile
+    MB_CUDA(cudaSetDevice(ctx->device));
+    MB_CUDA(cudaEventSynchronize(pd.done));
+    MB_LOCK(ctx);
+    const double *h_s = ctx->h_res[ticket].as<double>();
+    std::memcpy(s_binned, h_s, pd.n_out * 8);
+    std::memcpy(i_binned, h_s + pd.n_out, pd.n_out * 8);
+    std::memcpy(bincount, h_s + 2 * pd.n_out, pd.n_out * 8);
+    for (int i = 0; i < 8; ++i) ctx->stats[i] = pd.stats[i];
+    ctx->stats[5] = 0;
+    if (ctx->timing && pd.parity >= 0 && pd.stats[2] > 0) {
+        float ms = 0.f;
+        MB_CUDA(cudaEventElapsedTime(&ms, ctx->tc_ev0[pd.parity], ctx->tc_ev1[pd.parity]));
+        ctx->stats[5] = (int64_t)(ms * 1.0e6);
+    }
+    pd.open = false;
+    return MB200_OK;
+}
+
 extern "C" int mb200_saxs_frames(mb200_ctx *ctx, const float *positions, int positions_on_device, int64_t n_frames,
                                  int64_t n_atoms_total, const float *boxes, const int32_t *group_index,
                                  const int64_t *group_ptr, int32_t n_groups, const double *cm_params, double qmin,
@@ -1881,12 +1937,37 @@ static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int position
                             int64_t n_atoms_total, const float *boxes, const int32_t *d_group_index,
                             const int64_t *group_ptr, int32_t n_groups, const double *cm_params, double qmin,
                             double qmax, double thetamin, double thetamax, int32_t n_bins, int pack_atoms,
-                            int32_t block, int32_t n_blocks, double *s_binned, double *i_binned, int64_t *bincount) {
-    if (n_frames < 0 || n_groups < 0 || n_bins <= 0 || !boxes || !group_ptr || !cm_params || !s_binned || !i_binned ||
-        !bincount || (n_atoms_total && !positions))
+                            int32_t block, int32_t n_blocks, double *s_binned, double *i_binned, int64_t *bincount,
+                            int32_t *ticket) {
+    // ticket != null: deferred -- the results of the (last chunk of the) batch stay in page-locked memory and the call returns
+    // with its kernels still queued; mb200_saxs_frames_collect(ticket) waits for them and hands the results out
+    const bool deferred = ticket != nullptr;
+    if (n_frames < 0 || n_groups < 0 || n_bins <= 0 || !boxes || !group_ptr || !cm_params ||
+        (!deferred && (!s_binned || !i_binned || !bincount)) || (n_atoms_total && !positions))
         return fail(MB200_EINVAL, "invalid argument to mb200_saxs_frames");
-    if (n_frames == 0 || n_groups == 0) return MB200_OK;
     MB_CUDA(cudaSetDevice(ctx->device));
+    int slot = -1;
+    double *h_s = nullptr, *h_i = nullptr;
+    int64_t *h_c = nullptr;
+    if (deferred) {
+        for (int i = 0; i < mb200_ctx::N_PENDING && slot < 0; ++i)
+            if (!ctx->pending[i].open) slot = i;
+        if (slot < 0) return fail(MB200_EBUSY, "every deferred-batch slot is taken: collect one first (or use the synchronous call)");
+        const size_t n_out = (size_t)n_frames * (size_t)n_groups * (size_t)n_bins;
+        MB_TRY(ctx->h_res[slot].ensure(std::max<size_t>(n_out, 1) * 24));
+        h_s = ctx->h_res[slot].as<double>(); h_i = h_s + n_out; h_c = reinterpret_cast<int64_t *>(h_i + n_out);
+        s_binned = h_s; i_binned = h_i; bincount = h_c;
+        ctx->pending[slot].n_out = n_out;
+        *ticket = slot;
+    }
+    if (n_frames == 0 || n_groups == 0) {
+        if (deferred) {
+            ctx->pending[slot].open = true;
+            ctx->pending[slot].parity = -1;
+            MB_CUDA(cudaEventRecord(ctx->pending[slot].done, ctx->stream));
+        }
+        return MB200_OK;
+    }
     // developer aid: MAICOS_B200_TRACE_HOST=1 prints the host-side time of every phase of the call to stderr
     static const bool trace_host = std::getenv("MAICOS_B200_TRACE_HOST") != nullptr;
     auto t_last = std::chrono::steady_clock::now();
@@ -1969,7 +2050,10 @@ static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int position
             }
         std::vector<SegDesc> segs;
         mark("positions + specs");
-        MB_TRY(run_segments(ctx, specs, block, n_blocks, segs));
+        if (done + chunk == (size_t)n_frames) ctx->release_after_tables = &pref_read;  // last reader of the prefetched frames
+        const int rc_seg = run_segments(ctx, specs, block, n_blocks, segs);
+        ctx->release_after_tables = nullptr;
+        MB_TRY(rc_seg);
         mark("run_segments (host side)");
         const size_t ns = specs.size();
         const size_t ob = ns * (size_t)n_bins;
@@ -1981,12 +2065,21 @@ static int saxs_frames_impl(mb200_ctx *ctx, const float *positions, int position
         MB_CUDA(cudaMemcpyAsync(s_binned + oo, d_s, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
         MB_CUDA(cudaMemcpyAsync(i_binned + oo, d_i, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
         MB_CUDA(cudaMemcpyAsync(bincount + oo, d_c, ob * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        done += chunk;
+        if (deferred && done == (size_t)n_frames) break;  // the last chunk is waited for by the collect call
         MB_CUDA(cudaStreamSynchronize(ctx->stream));
         mark("device (wait)");
         MB_TRY(finish_timing(ctx));
-        done += chunk;
     }
     pref_read.release();  // the prefetch slot this call read may be refilled from here on
+    if (deferred) {
+        mb200_ctx::Pending &pd = ctx->pending[slot];
+        MB_CUDA(cudaEventRecord(pd.done, ctx->stream));
+        pd.open = true;
+        pd.parity = ctx->t_parity;
+        for (int i = 0; i < 8; ++i) pd.stats[i] = ctx->stats[i];
+        mark("queued (deferred)");
+    }
     return MB200_OK;
 }
 

@@ -245,10 +245,46 @@ class Saxs(AnalysisBase):
         # (``atoms.wrap`` in ``_transform_frame``) before the frame is staged
         return bool(self.pack and self._universe.dimensions is not None and is_orthorhombic(self._universe.dimensions))
 
+    def _defers_batches(self) -> bool:
+        # MAICOS_B200_DEFER=0: one synchronous call per batch (for A/B measurements)
+        import os
+
+        return bool(self.bin_spectrum) and os.environ.get("MAICOS_B200_DEFER", "1") != "0"
+
+    def _submit_staged(self, staged: list):
+        """Queue a batch (``mb200_saxs_frames_submit``) and return at once; ``_collect_staged`` waits for it."""
+        import ctypes
+
+        F = len(staged)
+        pos = self._gather_staged([(st[0], st[1]) for st in staged])  # a view of the staging buffer / pinned trajectory
+        boxes = np.array([st[2] for st in staged], dtype=np.float32)
+        block, n_blocks = parallel.q_block()
+        ctx = _cabi.context()
+        ticket = ctypes.c_int32(-1)
+        rc = _cabi.load().mb200_saxs_frames_submit(
+            ctx.handle, _cabi.ptr(pos), 0, F, _cabi.ptr(boxes), self._groups_on(ctx), _cabi.ptr(self._cm),
+            float(self.qmin), float(self.qmax), float(self.thetamin), float(self.thetamax), self.n_bins,
+            int(self._device_packs()), block, n_blocks, ctypes.byref(ticket))
+        if rc == _cabi.EBUSY:  # every slot of the context is taken (many analyses share it): the synchronous call
+            return ("done", self._compute_staged(staged))
+        _cabi.check(rc)
+        return ("ticket", ctx, int(ticket.value), pos)  # `pos` stays referenced until the batch is collected
+
+    def _collect_staged(self, staged: list, state) -> list:
+        if state[0] == "done":
+            return state[1]
+        _, ctx, ticket, _pos = state
+        F, G = len(staged), len(self.groups)
+        s = np.zeros((F, G, self.n_bins))
+        i = np.zeros((F, G, self.n_bins))
+        c = np.zeros((F, G, self.n_bins), dtype=np.int64)
+        _cabi.check(_cabi.load().mb200_saxs_frames_collect(ctx.handle, ticket, _cabi.ptr(s), _cabi.ptr(i), _cabi.ptr(c)))
+        return self._binned_observables(s, i, c)
+
     def _compute_staged(self, staged: list) -> list:
         if not self.bin_spectrum:
             return self._compute_unbinned(staged)
-        F, n, G = len(staged), self.atomgroup.n_atoms, len(self.groups)
+        F, G = len(staged), len(self.groups)
         pos = self._gather_staged([(st[0], st[1]) for st in staged])  # a view of the staging buffer / pinned trajectory
         boxes = np.array([st[2] for st in staged], dtype=np.float32)
         s = np.zeros((F, G, self.n_bins))
@@ -264,6 +300,11 @@ class Saxs(AnalysisBase):
                 int(self._device_packs()), block, n_blocks, _cabi.ptr(s), _cabi.ptr(i), _cabi.ptr(c),
             )
         )
+        return self._binned_observables(s, i, c)
+
+    def _binned_observables(self, s: np.ndarray, i: np.ndarray, c: np.ndarray) -> list:
+        """Per-frame observables of a batch from the binned per-group sums ``[F, G, n_bins]``."""
+        F, G = s.shape[0], s.shape[1]
         if parallel.q_sharded():
             packed = np.concatenate([s.reshape(-1), i.reshape(-1), c.reshape(-1).astype(np.float64)])
             parallel.allreduce_sum(packed)

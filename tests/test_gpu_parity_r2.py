@@ -932,3 +932,52 @@ def test_streaming_xtc_with_pinned_ring_feeds_the_device(precision):
     for d in results:
         assert_array_equal(d.sums.bincount, ref)
         assert_array_equal(d.means.profile, results[0].means.profile)
+
+
+# ---- deferred batches: mb200_saxs_frames_submit / _collect ---------------------------------------------------------------
+def test_saxs_deferred_batches_equal_the_synchronous_calls(precision, monkeypatch):
+    """``Saxs.run()`` queues batch k + 1 behind batch k (``mb200_saxs_frames_submit``) and collects batch k afterwards; the
+    results, the per-frame statistics and the time series equal the synchronous path's bit for bit -- constant cell, NPT,
+    a selection, and two Saxs instances plus a profile in one collection (tickets of one context shared by two workers)."""
+    from maicos_b200.mdshim import MemoryTrajectory, Universe
+
+    n_mol, F = 500, 37
+    L = mb.synthetic.cubic_box_for(n_mol)
+    fr = mb.synthetic.spce_water_frames(n_mol, L, 3, n_frames=F)
+    topo = mb.synthetic.spce_topology(n_mol)
+    lengths = np.float32(L * (1.0 + 1e-3 * np.cos(np.arange(F))[:, None] * np.array([1.0, 0.5, -1.0])))
+    npt = np.concatenate([lengths, np.full((F, 3), 90, np.float32)], axis=1)
+    monkeypatch.setattr(mb.Saxs, "_batch_size", 4)
+
+    def run(dims, pinned, deferred, select=None):
+        u = Universe(fr.shape[1], MemoryTrajectory(fr, dims, pinned=pinned), **topo)
+        ag = u.atoms if select is None else u.select_atoms(select)
+        a = mb.Saxs(ag, qmax=2.5, dq=0.05)
+        if not deferred:
+            a._defers_batches = lambda: False
+        return a.run()
+
+    for dims, pinned, select in ((np.float32([L, L, L, 90, 90, 90]), True, None), (npt, False, None),
+                                 (np.float32([L, L, L, 90, 90, 90]), True, "element O")):
+        a, b = run(dims, pinned, True, select), run(dims, pinned, False, select)
+        assert a._defers_batches() and not b._defers_batches()
+        for key in b.sums:
+            assert_array_equal(np.asarray(a.sums[key]), np.asarray(b.sums[key]))
+            assert_array_equal(np.asarray(a.sems[key]), np.asarray(b.sems[key]))
+        assert_array_equal(a.timeseries, b.timeseries)
+
+    u = Universe(fr.shape[1], MemoryTrajectory(fr, np.float32([L, L, L, 90, 90, 90]), pinned=True), **topo)
+    members = [mb.Saxs(u.atoms, qmax=2.5, dq=0.05), mb.Saxs(u.select_atoms("element H"), qmax=2.0, dq=0.1),
+               mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.5)]
+    mb.AnalysisCollection(*members).run()
+    solo = [mb.Saxs(u.atoms, qmax=2.5, dq=0.05).run(), mb.Saxs(u.select_atoms("element H"), qmax=2.0, dq=0.1).run(),
+            mb.DensityPlanar(u.atoms, dens="mass", bin_width=0.5).run()]
+    for a, b in zip(members, solo):
+        for key in b.means:
+            assert_array_equal(np.asarray(a.means[key]), np.asarray(b.means[key]), err_msg=f"{type(a).__name__}.{key}")
+
+    # the C ABI on its own: tickets, the busy code, collect of an unknown ticket
+    lib, ctx = _cabi.load(), _cabi.context()
+    assert lib.mb200_saxs_frames_collect(ctx.handle, 0, _cabi.ptr(np.zeros(1)), _cabi.ptr(np.zeros(1)),
+                                         _cabi.ptr(np.zeros(1, dtype=np.int64))) != 0
+    assert b"no deferred batch" in lib.mb200_last_error()
