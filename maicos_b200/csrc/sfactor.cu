@@ -1607,14 +1607,16 @@ static int run_segments(mb200_ctx *ctx, std::vector<SegSpec> &specs, int32_t blo
             MB_CUDA(cudaFuncSetAttribute(k_sf_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
             ctx->sf_attr_set = true;
         }
-        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        const int tpar = ctx->tc_parity;  // timing events alternate like the split-precision path's (deferred batches)
+        ctx->tc_parity ^= 1;
+        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->tc_ev0[tpar], ctx->stream));
         MB_CUDA(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
         const unsigned n_cta = (unsigned)std::min<size_t>(items.size(), (size_t)ctx->n_sm * 3);
         k_sf_contract<<<n_cta, NTHREADS, SMEM_TOTAL, ctx->stream>>>(ctx->d_items.as<ItemDesc>(), (int)items.size(),
                                                                    ctx->d_segs.as<SegDesc>(), ctx->d_counter.as<int>());
         MB_CUDA(cudaGetLastError());
-        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-        ctx->t_ev0 = ctx->ev0; ctx->t_ev1 = ctx->ev1; ctx->t_parity = -1;
+        if (ctx->timing) MB_CUDA(cudaEventRecord(ctx->tc_ev1[tpar], ctx->stream));
+        ctx->t_ev0 = ctx->tc_ev0[tpar]; ctx->t_ev1 = ctx->tc_ev1[tpar]; ctx->t_parity = tpar;
         ++launched;
     }
     ctx->launches += launched;
