@@ -422,6 +422,7 @@ class AnalysisBase(_Runner):
         self._batch_device = None     # device of the batch being announced / submitted
         self._batch_tag = 0           # content tag of the batch being announced (shared frames of a collection)
         self._pending = {}            # device -> (staged batch, future of its submission) waiting to be collected
+        self._stage_bufs = {}         # (tag, parity, rows, shape, dtype) -> pinned staging array of this run
         self._window_state = None     # see ``_frame_window``
         self._share_run = 0           # number of the collection run this instance is part of, 0 = on its own
         self._stage_parity = 0
@@ -544,10 +545,16 @@ class AnalysisBase(_Runner):
         Two buffers alternate per batch: one is read by the in-flight device call while the host
         fills the other, so frames go trajectory -> pinned memory -> HBM with one host copy.
         """
-        from .. import _cabi
-
         rows = max(1, self._batch_size)
-        buf = _cabi.pinned_empty((rows, *shape), dtype, slot=f"{self._slot_prefix()}{tag}:{self._stage_parity}")
+        key = (tag, self._stage_parity, rows, shape, dtype)
+        buf = self._stage_bufs.get(key)
+        if buf is None:  # one look-up per (buffer, run) instead of one per frame
+            from .. import _cabi
+
+            buf = _cabi.pinned_empty((rows, *shape), dtype, slot=f"{self._slot_prefix()}{tag}:{self._stage_parity}")
+            for k in [k for k in self._stage_bufs if k[:2] == key[:2]]:  # the slot's previous array is invalid now
+                del self._stage_bufs[k]
+            self._stage_bufs[key] = buf
         return buf, len(self._staged) % rows
 
     def _compute_staged(self, staged: list) -> list:
@@ -594,6 +601,7 @@ class AnalysisBase(_Runner):
         self._staged = []
         self._inflight_q = collections.deque()
         self._pending = {}
+        self._stage_bufs = {}
         #: host-side time split of the last run: staging, waiting for the device, inside the C-ABI call
         self.timings = {"stage_s": 0.0, "wait_device_s": 0.0, "device_call_s": 0.0}
         for name in ("sums", "means", "sems"):
@@ -957,6 +965,7 @@ class AnalysisBase(_Runner):
         from .. import _cabi
 
         _cabi.release_pinned(self._slot_prefix())  # staging buffers live for one run
+        self._stage_bufs = {}
         release_selection = getattr(self, "_release_selection", None)
         if release_selection is not None:
             release_selection()
