@@ -518,7 +518,10 @@ class AnalysisBase(_Runner):
         buf, base = rows[0][0], rows[0][0].ctypes.data
         if all(r[0].ctypes.data == base and r[1] == rows[0][1] + i for i, r in enumerate(rows)):
             return buf[rows[0][1]:rows[0][1] + len(rows)]
-        out = _cabi.pinned_empty((len(rows), *buf.shape[1:]), buf.dtype, slot=f"{self._slot_prefix()}{tag}")
+        # three buffers in turn: with deferred batches (mb200_saxs_frames_submit) the copy of batch k out of its buffer may
+        # still be queued on the device when batch k + 1 is gathered
+        self._gather_turn = (getattr(self, "_gather_turn", -1) + 1) % 3
+        out = _cabi.pinned_empty((len(rows), *buf.shape[1:]), buf.dtype, slot=f"{self._slot_prefix()}{tag}:{self._gather_turn}")
         for i, (b, r) in enumerate(rows):
             _cabi.host_copy(out[i], b[r])
         return out
@@ -583,7 +586,7 @@ class AnalysisBase(_Runner):
         # rows handed to the device must not be overwritten while a batch is in flight
         ring = int(getattr(self._trajectory, "ring_len", 0) or 0)
         if ring:
-            self._batch_size = int(max(1, min(self._batch_size, ring // (len(self._run_devices()) + 2))))
+            self._batch_size = int(max(1, min(self._batch_size, ring // (len(self._run_devices()) + 2 + int(self._defers_batches())))))
         if logging.getLogger().isEnabledFor(logging.INFO):  # the headers scan every atom: only when shown
             if self.refgroup is not None:
                 logging.info(

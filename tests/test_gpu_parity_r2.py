@@ -981,3 +981,30 @@ def test_saxs_deferred_batches_equal_the_synchronous_calls(precision, monkeypatc
     assert lib.mb200_saxs_frames_collect(ctx.handle, 0, _cabi.ptr(np.zeros(1)), _cabi.ptr(np.zeros(1)),
                                          _cabi.ptr(np.zeros(1, dtype=np.int64))) != 0
     assert b"no deferred batch" in lib.mb200_last_error()
+
+
+def test_deferred_batches_with_gathered_rows(precision, monkeypatch):
+    """A strided frame selection of a page-locked trajectory: the rows of a batch are not consecutive, every batch is
+    gathered into a page-locked buffer and copied by the stream when its turn comes -- with batch k + 1 already gathered
+    and queued.  Results equal the synchronous path's and the oracle's frame selection."""
+    from maicos_b200.mdshim import MemoryTrajectory, Universe
+
+    n_mol, F = 3000, 60
+    L = mb.synthetic.cubic_box_for(n_mol)
+    fr = mb.synthetic.spce_water_frames(n_mol, L, 8, n_frames=F)
+    topo = mb.synthetic.spce_topology(n_mol)
+    dims = np.float32([L, L, L, 90, 90, 90])
+    monkeypatch.setattr(mb.Saxs, "_batch_size", 4)
+    u = Universe(fr.shape[1], MemoryTrajectory(fr, dims, pinned=True), **topo)
+    a = mb.Saxs(u.atoms, qmax=2.0, dq=0.05).run(step=3)
+    b = mb.Saxs(u.atoms, qmax=2.0, dq=0.05)
+    b._defers_batches = lambda: False
+    b.run(step=3)
+    assert a.n_frames == 20
+    for key in b.sums:
+        assert_array_equal(np.asarray(a.sums[key]), np.asarray(b.sums[key]))
+    assert_array_equal(a.timeseries, b.timeseries)
+    sel = fr[::3]
+    res, _, _ = restatement.run_saxs(sel[:3], np.tile(dims[:3], (3, 1)), np.asarray(topo["elements"]), qmax=2.0, dq=0.05)
+    three = mb.Saxs(u.atoms, qmax=2.0, dq=0.05).run(step=3, stop=9)
+    assert_allclose(three.results.scattering_intensities, res["scattering_intensities"], rtol=RTOL)
