@@ -768,21 +768,30 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
     std::vector<double> qcube(cells, 0.0);  // 0 = rejected
     const bool need_theta = !(thmin <= 0.0 && thmax >= 1.5707963267948968);
     const size_t par_h = cells >= 200000 ? 2 : (size_t)m0 + 1;  // threads only for big cubes
+    // the acceptance test is the reference's (sqrt, then the comparisons with qmin / qmax); cells whose q^2 lies clearly
+    // outside [qmin^2, qmax^2] skip the square root -- the margin is far wider than the rounding of q^2 and of the root
+    const double q2_hi = qmax > 0.0 ? qmax * qmax * (1.0 + 1e-12) : 0.0, q2_lo = qmin > 0.0 ? qmin * qmin * (1.0 - 1e-12) : -1.0;
+    std::vector<double> qz_of(m2), qz2_of(m2);
+    for (int l = 0; l < m2; ++l) { qz_of[l] = l * qf[2]; qz2_of[l] = qz_of[l] * qz_of[l]; }
     parallel_chunks((size_t)m0, par_h, [&](size_t h_lo, size_t h_hi) {
         for (int h = (int)h_lo; h < (int)h_hi; ++h) {
             const double qx = h * qf[0];
             for (int k = 0; k < m1; ++k) {
                 const double qy = k * qf[1];
-                for (int l = 0; l < m2; ++l) {
-                    if (h + k + l == 0) continue;
-                    const double qz = l * qf[2];
-                    const double qrr = std::sqrt(qx * qx + qy * qy + qz * qz);
+                const double qxy2 = qx * qx + qy * qy;  // (qx qx + qy qy) + qz qz: the reference's order of additions
+                if (qxy2 > q2_hi) continue;
+                double *row = qcube.data() + ((size_t)h * m1 + k) * m2;
+                for (int l = (h + k == 0) ? 1 : 0; l < m2; ++l) {
+                    const double q2 = qxy2 + qz2_of[l];
+                    if (q2 > q2_hi) break;  // q grows with l
+                    if (q2 < q2_lo) continue;
+                    const double qrr = std::sqrt(q2);
                     if (!(qrr >= qmin && qrr <= qmax)) continue;
                     if (need_theta) {
-                        const double theta = std::acos(qz / qrr);
+                        const double theta = std::acos(qz_of[l] / qrr);
                         if (!(theta >= thmin && theta <= thmax)) continue;
                     }
-                    qcube[((size_t)h * m1 + k) * m2 + l] = qrr;
+                    row[l] = qrr;
                 }
             }
         }
@@ -848,6 +857,8 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
     mark("dmma tiles");
     // entries
     std::vector<int32_t> cell; std::vector<double> qv; std::vector<int32_t> amp;
+    std::vector<uint32_t> hkl, hkl_sorted;  // (h << 20 | k << 10 | l) of every entry when it fits: spares the tilings' divisions
+    const bool pack_hkl = m0 <= 1023 && m1 <= 1023 && m2 <= 1023;
     {
         std::vector<size_t> h_start((size_t)m0 + 1, 0);  // entries are listed in C order of the cube: offsets per h slab
         parallel_chunks((size_t)m0, par_h, [&](size_t h_lo, size_t h_hi) {
@@ -861,19 +872,26 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
         for (int h = 0; h < m0; ++h) h_start[h + 1] += h_start[h];
         const size_t total = h_start[m0];
         cell.resize(total); qv.resize(total); amp.resize(total);
+        if (pack_hkl) hkl.resize(total);
         parallel_chunks((size_t)m0, par_h, [&](size_t h_lo, size_t h_hi) {
             for (int h = (int)h_lo; h < (int)h_hi; ++h) {
                 size_t o = h_start[h];
-                for (int k = 0; k < m1; ++k)
+                for (int k = 0; k < m1; ++k) {
+                    const size_t ci0 = ((size_t)h * m1 + k) * m2;
+                    const size_t wt0 = ((size_t)(h / QH) * nqk + (k / QK)) * nlp;
+                    const int32_t amp_hk = (h % QH) * 8 + (k % QK);
+                    const uint32_t hk_bits = ((uint32_t)h << 20) | ((uint32_t)k << 10);
                     for (int l = 0; l < m2; ++l) {
-                        const size_t ci = ((size_t)h * m1 + k) * m2 + l;
+                        const size_t ci = ci0 + l;
                         if (qcube[ci] == 0.0) continue;
-                        const int32_t wt = wt_of[((size_t)(h / QH) * nqk + (k / QK)) * nlp + (l / NL)];
+                        const int32_t wt = wt_of[wt0 + (l / NL)];
                         cell[o] = (int32_t)ci;
                         qv[o] = qcube[ci];
-                        amp[o] = (wt * 32 + (h % QH) * 8 + (k % QK)) * 16 + (l % NL);
+                        amp[o] = (wt * 32 + amp_hk) * 16 + (l % NL);
+                        if (pack_hkl) hkl[o] = hk_bits | (uint32_t)l;
                         ++o;
                     }
+                }
             }
         });
     }
@@ -897,10 +915,13 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
         pl->bin_start = count;
         std::vector<int32_t> pos(count.begin(), count.end() - 1);
         pl->cell.resize(nv); pl->qrr.resize(nv); pl->ent_amp.resize(nv);
+        if (pack_hkl) hkl_sorted.resize(nv);
         for (size_t e = 0; e < nv; ++e) {  // stable counting sort by bin
             const int32_t d = pos[bin[e]]++;
             pl->cell[d] = cell[e]; pl->qrr[d] = qv[e]; pl->ent_amp[d] = amp[e];
+            if (pack_hkl) hkl_sorted[d] = hkl[e];
         }
+        hkl.swap(hkl_sorted);
     } else {
         pl->cell.swap(cell); pl->qrr.swap(qv); pl->ent_amp.swap(amp);
     }
@@ -964,14 +985,27 @@ static int build_plan(const double *dims, double qmin, double qmax, double thmin
         }
         pl->ent_amp_tc.resize(nv);
         pl->tc_tile_used.assign((size_t)pl->tc_n_rt * n_lt, 0);
+        // row of every (h,k) pair in the packed tiling, l tile and position inside it of every l: per entry only look-ups
+        std::vector<int32_t> row_of((size_t)m0 * m1, -1);
+        for (size_t hk = 0; hk < row_of.size(); ++hk) {
+            const int32_t qi = quad_of[hk];
+            if (qi >= 0) row_of[hk] = slot_of[qi] * 4 + ((int)(hk % (size_t)m1) - (int)quads[qi].k0);
+        }
+        std::vector<int32_t> lt_of(m2), lin_of(m2);
+        for (int l = 0; l < m2; ++l) { lt_of[l] = l / lt_size; lin_of[l] = l % lt_size; }
         parallel_chunks(nv, 100000, [&](size_t e_lo, size_t e_hi) {
             for (size_t e = e_lo; e < e_hi; ++e) {
-                const int32_t ci = pl->cell[e];
-                const int l = ci % m2, k = (ci / m2) % m1, h = ci / (m2 * m1);
-                const int32_t qi = quad_of[(size_t)h * m1 + k];
-                const int32_t pp = slot_of[qi] * 4 + (k - (int)quads[qi].k0);
-                const int32_t tile = (pp / TC_M) * n_lt + l / lt_size;
-                pl->ent_amp_tc[e] = (tile * TC_M + pp % TC_M) * lt_size + l % lt_size;
+                int h, k, l;
+                if (pack_hkl) {
+                    const uint32_t v = hkl[e];
+                    h = (int)(v >> 20); k = (int)((v >> 10) & 1023u); l = (int)(v & 1023u);
+                } else {
+                    const int32_t ci = pl->cell[e];
+                    l = ci % m2; k = (ci / m2) % m1; h = ci / (m2 * m1);
+                }
+                const int32_t pp = row_of[(size_t)h * m1 + k];
+                const int32_t tile = (pp / TC_M) * n_lt + lt_of[l];
+                pl->ent_amp_tc[e] = (tile * TC_M + pp % TC_M) * lt_size + lin_of[l];
             }
         });
         for (size_t e = 0; e < nv; ++e) pl->tc_tile_used[pl->ent_amp_tc[e] / (TC_M * lt_size)] = 1;
