@@ -1912,8 +1912,12 @@ extern "C" int mb200_saxs_frames_collect(mb200_ctx *ctx, int32_t ticket, double 
     if (!pd.open) return fail(MB200_EINVAL, "no deferred batch waits under ticket %d", (int)ticket);
     // the wait happens outside the call mutex: the next batch may be submitted meanwhile
     MB_CUDA(cudaSetDevice(ctx->device));
-    MB_CUDA(cudaEventSynchronize(pd.done));
+    const cudaError_t waited = cudaEventSynchronize(pd.done);
     MB_LOCK(ctx);
+    if (waited != cudaSuccess) {  // the batch failed on the device: the ticket is spent all the same
+        pd.open = false;
+        return fail(MB200_ECUDA, "deferred batch %d failed: %s", (int)ticket, cudaGetErrorString(waited));
+    }
     const double *h_s = ctx->h_res[ticket].as<double>();
     std::memcpy(s_binned, h_s, pd.n_out * 8);
     std::memcpy(i_binned, h_s + pd.n_out, pd.n_out * 8);
